@@ -1,0 +1,101 @@
+"""ctypes binding of libb2f.so (include/b2f.h).  No fallback: if the library is missing or a
+compute call finds no GPU, the error is raised, never swallowed."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+B2F_MAX_IF = 32
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb2f.so")
+
+POL_P0, POL_P1, POL_I, POL_I2, POL_COHERENCE, POL_IQUV, POL_PPQQ = range(7)
+K_VALIDATE, K_COLUMN, K_EPS, K_ROW, K_STATS, K_QUANT, K_DECODE = range(7)
+KERNEL_NAMES = ["validate", "column", "eps", "row", "stats", "quant", "decode"]
+
+EINVAL, ECUDA, ENOMEM, ESTATE, EUNSUPPORTED = -1, -2, -3, -4, -5
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("device", C.c_int32), ("nif", C.c_int32), ("nchan", C.c_int32),
+        ("freq_res", C.c_int32), ("tscrunch", C.c_int32), ("pol_mode", C.c_int32), ("out_nbit", C.c_int32),
+        ("in_nbit", C.c_int32), ("frame_bytes", C.c_int32), ("header_bytes", C.c_int32),
+        ("frame_time_mode", C.c_int32), ("mask_faults", C.c_int32), ("keep_bandpass", C.c_int32),
+        ("splice_pol_major", C.c_int32), ("chunk_units", C.c_int32), ("rescale_interval_s", C.c_double),
+        ("bw_mhz", C.c_double * B2F_MAX_IF), ("freq_mhz", C.c_double * B2F_MAX_IF),
+        ("if_order", C.c_int32 * B2F_MAX_IF), ("dm", C.c_double), ("coherent", C.c_int32),
+        ("profile", C.c_int32), ("stream", C.c_void_p),
+    ]
+
+
+class Geometry(C.Structure):
+    _fields_ = [
+        ("unit_frames", C.c_int64), ("unit_blocks", C.c_int64), ("chunk_frames", C.c_int64),
+        ("chunk_rows", C.c_int64), ("block_samples", C.c_int64), ("samples_per_frame", C.c_int64),
+        ("row_bytes", C.c_int64), ("nprod", C.c_int32), ("freq_res", C.c_int32), ("tsamp_s", C.c_double),
+        ("interval_rows", C.c_int64),
+    ]
+
+
+class Counters(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in (
+        "frames_ok", "frames_invalid", "frames_with_fill", "fill_words", "frames_dropped",
+        "frames_misplaced", "frames_badhdr", "slots_missing", "rows_produced", "rows_emitted",
+        "blocks_dirty")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+#: every symbol include/b2f.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "b2f_version": (C.c_int, []),
+    "b2f_last_error": (C.c_char_p, []),
+    "b2f_device_count": (C.c_int, []),
+    "b2f_plan_create": (C.c_int, [C.POINTER(Params), C.POINTER(C.c_void_p)]),
+    "b2f_plan_destroy": (C.c_int, [C.c_void_p]),
+    "b2f_get_geometry": (C.c_int, [C.c_void_p, C.POINTER(Geometry)]),
+    "b2f_push": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int64, C.c_int]),
+    "b2f_flush": (C.c_int, [C.c_void_p]),
+    "b2f_pull": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_int64)]),
+    "b2f_sync": (C.c_int, [C.c_void_p]),
+    "b2f_reset": (C.c_int, [C.c_void_p]),
+    "b2f_get_counters": (C.c_int, [C.c_void_p, C.POINTER(Counters)]),
+    "b2f_get_rescale": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b2f_kernel_time": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "b2f_reset_timers": (C.c_int, [C.c_void_p]),
+    "b2f_decode": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                             C.c_void_p, C.c_int, C.c_int, C.POINTER(Counters)]),
+    "b2f_debug_copy": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+}
+
+_lib = None
+
+
+class B2FError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"libb2f error {code}: {message}")
+        self.code = code
+        self.message = message
+
+
+def lib() -> C.CDLL:
+    """Load libb2f.so (built in-tree by `make -C frb-baseband_b200/csrc` / __graft_entry__.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise OSError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback)")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise B2FError(rc, lib().b2f_last_error().decode(errors="replace"))

@@ -1,0 +1,789 @@
+// libb2f.so: plan object, streaming state machine and the C ABI declared in include/b2f.h.
+// Host side of the path /root/reference/process_vdif.py:142-199 (run_digifil) and
+// /root/reference/base2fil.sh:404-448 (fan-out + splice) drive today with two executables.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "b2f_kernels.cuh"
+
+using namespace b2f;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CU(x)                                                                                   \
+    do {                                                                                        \
+        cudaError_t e__ = (x);                                                                  \
+        if (e__ != cudaSuccess) {                                                               \
+            return fail(B2F_ECUDA, std::string(#x) + ": " + cudaGetErrorString(e__));          \
+        }                                                                                       \
+    } while (0)
+
+bool is_pow2(int64_t v) { return v > 0 && (v & (v - 1)) == 0; }
+
+struct TimedLaunch {
+    int kid;
+    cudaEvent_t a, b;
+};
+
+}  // namespace
+
+struct b2f_plan {
+    b2f_params prm{};
+    int R = 0, N = 0, L = 0, D = 0, nprod = 0, nstrips = 0, num_sms = 0;
+    int64_t M = 0, spf = 0, fps = 0, payload = 0, groups_per_slot = 0;
+    int64_t unit_frames = 0, unit_blocks = 0, chunk_frames = 0, chunk_blocks = 0, chunk_rows = 0;
+    int64_t interval_rows = 0, F_cap_rows = 0;
+    int out_elem_bits = 8;
+    int64_t row_elems = 0, row_bytes = 0;
+
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    bool own_stream = false;
+    cudaEvent_t ev_stage_free[2]{}, ev_h2d_done[2]{};
+    int stage_idx = 0;
+
+    uint8_t* d_stage[2]{};
+    size_t stage_if_stride = 0;
+    uint8_t *d_compact = nullptr, *d_wmask = nullptr, *d_fstat = nullptr, *d_blkdirty = nullptr;
+    size_t compact_stride = 0, wmask_stride = 0, fstat_stride = 0;
+    float2 *d_inter = nullptr, *d_colsum = nullptr, *d_eps = nullptr;
+    float* d_F = nullptr;
+    int64_t F_if_stride = 0;
+    float *d_mean = nullptr, *d_scale = nullptr;
+    double2* d_partial = nullptr;
+    float2 *d_tab_g = nullptr, *d_tab_h = nullptr, *d_tab_w = nullptr, *d_tab_r = nullptr;
+    unsigned long long* d_counters = nullptr;
+    uint8_t* d_out_stage = nullptr;
+    size_t out_stage_bytes = 0;
+
+    // state
+    int64_t rows_base = 0;         // rows already emitted and dropped from the front of F
+    int64_t rows_off = 0;          // offset inside F of the first held row
+    int64_t rows_held = 0;
+    int64_t rows_produced = 0, rows_emitted = 0;
+    bool stats_ready = false, flushed = false, have_base = false;
+    int64_t frames_pushed = 0;
+    uint32_t base_sec0[B2F_MAX_IF]{}, base_fnum0[B2F_MAX_IF]{};
+    int64_t last_nblk = 0, last_nframes = 0;
+    unsigned long long blocks_dirty = 0;
+
+    std::vector<TimedLaunch> pending;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+    double k_ms[B2F_K_COUNT]{};
+    int64_t k_n[B2F_K_COUNT]{};
+};
+
+namespace {
+
+static const int kStatSplit = 64;
+
+template <class Fn>
+int timed(b2f_plan* pl, int kid, Fn&& fn) {
+    if (!pl->prm.profile) {
+        fn();
+        pl->k_n[kid]++;
+        CU(cudaGetLastError());
+        return 0;
+    }
+    std::pair<cudaEvent_t, cudaEvent_t> ev;
+    if (!pl->ev_pool.empty()) {
+        ev = pl->ev_pool.back();
+        pl->ev_pool.pop_back();
+    } else {
+        CU(cudaEventCreate(&ev.first));
+        CU(cudaEventCreate(&ev.second));
+    }
+    CU(cudaEventRecord(ev.first, pl->stream));
+    fn();
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(ev.second, pl->stream));
+    pl->pending.push_back({kid, ev.first, ev.second});
+    return 0;
+}
+
+int collect_times(b2f_plan* pl) {
+    if (pl->pending.empty()) return 0;
+    CU(cudaStreamSynchronize(pl->stream));
+    for (auto& t : pl->pending) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, t.a, t.b));
+        pl->k_ms[t.kid] += ms;
+        pl->k_n[t.kid]++;
+        pl->ev_pool.emplace_back(t.a, t.b);
+    }
+    pl->pending.clear();
+    return 0;
+}
+
+int nprod_of(int mode) {
+    switch (mode) {
+        case B2F_POL_P0: case B2F_POL_P1: case B2F_POL_I: case B2F_POL_I2: return 1;
+        case B2F_POL_PPQQ: return 2;
+        case B2F_POL_COHERENCE: case B2F_POL_IQUV: return 4;
+        default: return 0;
+    }
+}
+
+template <int TR, int PT>
+int launch_kb_np(b2f_plan* pl, const KBParams& kp, int grid) {
+    auto go = [&](auto kern, size_t smem) -> int {
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        return timed(pl, B2F_K_ROW, [&] { kern<<<grid, kKBThreads, smem, pl->stream>>>(kp); });
+    };
+    switch (pl->nprod) {
+        case 1: return go(kb_row_pass<TR, PT, 1>, KBSmem<TR, PT, 1>::kBytes);
+        case 2: return go(kb_row_pass<TR, PT, 2>, KBSmem<TR, PT, 2>::kBytes);
+        default: return go(kb_row_pass<TR, PT, 4>, KBSmem<TR, PT, 4>::kBytes);
+    }
+}
+
+int launch_kb(b2f_plan* pl, const KBParams& kp, int grid) {
+    switch (pl->R) {
+        case 16: return launch_kb_np<4, 4>(pl, kp, grid);
+        case 32: return launch_kb_np<4, 8>(pl, kp, grid);
+        case 64: return launch_kb_np<8, 8>(pl, kp, grid);
+        case 128: return launch_kb_np<8, 16>(pl, kp, grid);
+        case 256: return launch_kb_np<16, 16>(pl, kp, grid);
+        case 512: return launch_kb_np<16, 32>(pl, kp, grid);
+    }
+    return fail(B2F_EUNSUPPORTED, "row length");
+}
+
+void kb_shape(int R, int* TR, int* PT) {
+    switch (R) {
+        case 16: *TR = 4; *PT = 4; break;
+        case 32: *TR = 4; *PT = 8; break;
+        case 64: *TR = 8; *PT = 8; break;
+        case 128: *TR = 8; *PT = 16; break;
+        case 256: *TR = 16; *PT = 16; break;
+        default: *TR = 16; *PT = 32; break;
+    }
+}
+
+int upload_tables(b2f_plan* pl) {
+    const int R = pl->R;
+    const double M = (double)pl->M;
+    std::vector<float2> g(16 * R), h(32 * R), w(32 * 16);
+    for (int q = 0; q < 16; ++q)
+        for (int n1 = 0; n1 < R; ++n1) {
+            const double ph = -2.0 * M_PI * (double)((int64_t)q * n1) / M;
+            g[q * R + n1] = make_float2((float)cos(ph), (float)sin(ph));
+        }
+    for (int p = 0; p < 32; ++p)
+        for (int n1 = 0; n1 < R; ++n1) {
+            const double ph = -2.0 * M_PI * (double)((int64_t)16 * p * n1) / M;
+            h[p * R + n1] = make_float2((float)cos(ph), (float)sin(ph));
+        }
+    for (int l = 0; l < 32; ++l)
+        for (int q = 0; q < 16; ++q) {
+            const double ph = -2.0 * M_PI * (double)(l * q) / 512.0;
+            w[l * 16 + q] = make_float2((float)cos(ph), (float)sin(ph));
+        }
+    int TR, PT;
+    kb_shape(R, &TR, &PT);
+    std::vector<float2> r(PT * TR);
+    for (int q = 0; q < PT; ++q)
+        for (int s = 0; s < TR; ++s) {
+            const double ph = -2.0 * M_PI * (double)(s * q) / (double)R;
+            r[q * TR + s] = make_float2((float)cos(ph), (float)sin(ph));
+        }
+    CU(cudaMalloc(&pl->d_tab_g, g.size() * sizeof(float2)));
+    CU(cudaMalloc(&pl->d_tab_h, h.size() * sizeof(float2)));
+    CU(cudaMalloc(&pl->d_tab_w, w.size() * sizeof(float2)));
+    CU(cudaMalloc(&pl->d_tab_r, r.size() * sizeof(float2)));
+    CU(cudaMemcpy(pl->d_tab_g, g.data(), g.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(pl->d_tab_h, h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(pl->d_tab_w, w.data(), w.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(pl->d_tab_r, r.data(), r.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int launch_k0(b2f_plan* pl, const K0Params& kp, cudaStream_t st, bool profile_ok) {
+    const bool vec = (kp.payload_bytes % 32 == 0) && (kp.frame_bytes % 16 == 0) && (kp.header_bytes % 16 == 0);
+    bool aligned = true;
+    const int nif = pl ? pl->prm.nif : 1;
+    for (int i = 0; i < nif; ++i) aligned = aligned && ((reinterpret_cast<uintptr_t>(kp.frames[i]) & 15) == 0);
+    const int stage_bytes = (kp.frame_bytes + 127) & ~127;
+    int sms = pl ? pl->num_sms : 148;
+    int gx = (int)std::max<int64_t>(1, std::min<int64_t>(kp.nframes, (4 * sms + nif - 1) / nif));
+    dim3 grid(gx, nif);
+    auto body = [&] {
+        if (vec && aligned) {
+            size_t smem = 128 + (size_t)kK0Stages * stage_bytes;
+            cudaFuncSetAttribute(k0_validate_compact<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            k0_validate_compact<true><<<grid, kK0Threads, smem, st>>>(kp);
+        } else {
+            size_t smem = 128 + (size_t)stage_bytes;
+            cudaFuncSetAttribute(k0_validate_compact<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            k0_validate_compact<false><<<grid, kK0Threads, smem, st>>>(kp);
+        }
+    };
+    if (pl && profile_ok) return timed(pl, B2F_K_VALIDATE, body);
+    body();
+    CU(cudaGetLastError());
+    return 0;
+}
+
+void free_plan(b2f_plan* pl) {
+    if (!pl) return;
+    cudaSetDevice(pl->prm.device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < 2; ++i) {
+        if (pl->d_stage[i]) cudaFree(pl->d_stage[i]);
+        if (pl->ev_stage_free[i]) cudaEventDestroy(pl->ev_stage_free[i]);
+        if (pl->ev_h2d_done[i]) cudaEventDestroy(pl->ev_h2d_done[i]);
+    }
+    void* bufs[] = {pl->d_compact, pl->d_wmask, pl->d_fstat, pl->d_blkdirty, pl->d_inter, pl->d_colsum,
+                    pl->d_eps, pl->d_F, pl->d_mean, pl->d_scale, pl->d_partial, pl->d_tab_g, pl->d_tab_h,
+                    pl->d_tab_w, pl->d_tab_r, pl->d_counters, pl->d_out_stage};
+    for (void* b : bufs)
+        if (b) cudaFree(b);
+    for (auto& t : pl->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+    for (auto& e : pl->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    if (pl->copy_stream) cudaStreamDestroy(pl->copy_stream);
+    if (pl->own_stream && pl->stream) cudaStreamDestroy(pl->stream);
+    delete pl;
+}
+
+int init_state(b2f_plan* pl) {
+    pl->rows_base = pl->rows_off = pl->rows_held = pl->rows_produced = pl->rows_emitted = 0;
+    pl->stats_ready = pl->prm.keep_bandpass != 0;
+    pl->flushed = false;
+    pl->have_base = false;
+    pl->frames_pushed = 0;
+    pl->blocks_dirty = 0;
+    pl->last_nblk = pl->last_nframes = 0;
+    const int ncol = pl->nprod * pl->N;
+    CU(cudaMemsetAsync(pl->d_counters, 0, C_COUNT * sizeof(unsigned long long), pl->stream));
+    CU(cudaMemsetAsync(pl->d_mean, 0, (size_t)pl->prm.nif * ncol * sizeof(float), pl->stream));
+    std::vector<float> ones((size_t)pl->prm.nif * ncol, 1.0f);
+    CU(cudaMemcpyAsync(pl->d_scale, ones.data(), ones.size() * sizeof(float), cudaMemcpyHostToDevice, pl->stream));
+    CU(cudaStreamSynchronize(pl->stream));
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b2f_version(void) { return B2F_VERSION; }
+const char* b2f_last_error(void) { return g_err.c_str(); }
+
+int b2f_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
+    if (!prm || !out) return fail(B2F_EINVAL, "null argument");
+    if (prm->struct_size != sizeof(b2f_params)) return fail(B2F_EINVAL, "b2f_params.struct_size mismatch");
+    *out = nullptr;
+    if (prm->nif < 1 || prm->nif > B2F_MAX_IF) return fail(B2F_EINVAL, "nif out of range");
+    const int nprod = nprod_of(prm->pol_mode);
+    if (!nprod) return fail(B2F_EINVAL, "pol_mode not in 0..6 (process_vdif --pol choices map to 0,1,2,3,4)");
+    if (!(prm->out_nbit == 2 || prm->out_nbit == 8 || prm->out_nbit == 16 || prm->out_nbit == -32))
+        return fail(B2F_EINVAL, "nbit not in supported values of [2, 8, 16, -32]");
+    if (!(prm->in_nbit == 2 || prm->in_nbit == 8)) return fail(B2F_EUNSUPPORTED, "VDIF bits/sample must be 2 or 8");
+    if (prm->nchan < 1) return fail(B2F_EINVAL, "nchan");
+    const int L = prm->freq_res > 0 ? prm->freq_res : (prm->nchan <= 128 ? 512 : 2 * prm->nchan);
+    if (L != kL) return fail(B2F_EUNSUPPORTED, "freq_res must be 512 (nchan <= 256) in this build");
+    const int R = 2 * prm->nchan;
+    if (!is_pow2(R) || R < 16 || R > 512) return fail(B2F_EUNSUPPORTED, "nchan must be a power of two in 8..256");
+    const int D = prm->tscrunch < 1 ? 1 : prm->tscrunch;
+    if (!is_pow2(D) || D > kL) return fail(B2F_EUNSUPPORTED, "tscrunch must be a power of two <= 512");
+    if (prm->header_bytes != 32 && prm->header_bytes != 16) return fail(B2F_EINVAL, "header_bytes must be 32 or 16");
+    const int payload = prm->frame_bytes - prm->header_bytes;
+    if (payload <= 0 || payload % 8) return fail(B2F_EINVAL, "frame_bytes");
+    if (prm->coherent || prm->dm != 0.0) return fail(B2F_EUNSUPPORTED, "coherent dedispersion not built yet");
+    const double abw = std::fabs(prm->bw_mhz[0]);
+    if (abw <= 0) return fail(B2F_EINVAL, "bw_mhz");
+    for (int i = 0; i < prm->nif; ++i) {
+        if (std::fabs(std::fabs(prm->bw_mhz[i]) - abw) > 1e-9) return fail(B2F_EINVAL, "all IFs must share |bw|");
+        if (prm->if_order[i] < 0 || prm->if_order[i] >= prm->nif) return fail(B2F_EINVAL, "if_order");
+    }
+    const int64_t spf = (int64_t)payload * 8 / (prm->in_nbit * 2);
+    const double fps_d = 2.0 * abw * 1e6 / (double)spf;
+    const int64_t fps = (int64_t)llround(fps_d);
+    if (std::fabs(fps_d - (double)fps) > 1e-6) return fail(B2F_EINVAL, "frames per second is not an integer");
+    if (nprod * prm->nchan % 4 || (prm->out_nbit == 2 && (int64_t)prm->nif * nprod * prm->nchan % 4))
+        return fail(B2F_EINVAL, "row size");
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(B2F_ECUDA, "no CUDA device: libb2f has no CPU fallback");
+    }
+    if (prm->device < 0 || prm->device >= ndev) return fail(B2F_EINVAL, "device ordinal");
+    CU(cudaSetDevice(prm->device));
+
+    b2f_plan* pl = new b2f_plan();
+    pl->prm = *prm;
+    pl->prm.freq_res = L;
+    pl->prm.tscrunch = D;
+    pl->R = R; pl->N = prm->nchan; pl->L = L; pl->D = D; pl->nprod = nprod;
+    pl->nstrips = R / kStripCols;
+    pl->M = (int64_t)R * L;
+    pl->spf = spf; pl->fps = fps; pl->payload = payload;
+    pl->groups_per_slot = (payload + 31) / 32;
+    const int64_t g = std::gcd(pl->spf, pl->M);
+    pl->unit_frames = pl->M / g;
+    pl->unit_blocks = pl->spf / g;
+    const int cu = prm->chunk_units > 0 ? prm->chunk_units : 1;
+    pl->chunk_frames = pl->unit_frames * cu;
+    pl->chunk_blocks = pl->unit_blocks * cu;
+    pl->chunk_rows = pl->chunk_blocks * L / D;
+    const double tsamp = (double)D * prm->nchan / (abw * 1e6);
+    const double interval = prm->rescale_interval_s > 0 ? prm->rescale_interval_s : 10.0;
+    pl->interval_rows = prm->keep_bandpass ? 0 : (int64_t)llround(interval / tsamp);
+    pl->F_cap_rows = pl->interval_rows + 2 * pl->chunk_rows;
+    pl->out_elem_bits = prm->out_nbit == -32 ? 32 : prm->out_nbit;
+    pl->row_elems = (int64_t)prm->nif * nprod * prm->nchan;
+    pl->row_bytes = pl->row_elems * pl->out_elem_bits / 8;
+
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, prm->device) != cudaSuccess) { free_plan(pl); return fail(B2F_ECUDA, "device properties"); }
+    pl->num_sms = prop.multiProcessorCount;
+
+    auto bail = [&](int rc) { free_plan(pl); return rc; };
+#define CUB(x)                                                                                      \
+    do {                                                                                            \
+        cudaError_t e__ = (x);                                                                      \
+        if (e__ != cudaSuccess) {                                                                   \
+            g_err = std::string(#x) + ": " + cudaGetErrorString(e__);                              \
+            return bail(e__ == cudaErrorMemoryAllocation ? B2F_ENOMEM : B2F_ECUDA);                \
+        }                                                                                           \
+    } while (0)
+
+    if (prm->stream) {
+        pl->stream = (cudaStream_t)prm->stream;
+    } else {
+        CUB(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
+        pl->own_stream = true;
+    }
+    CUB(cudaStreamCreateWithFlags(&pl->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CUB(cudaEventCreateWithFlags(&pl->ev_stage_free[i], cudaEventDisableTiming));
+        CUB(cudaEventCreateWithFlags(&pl->ev_h2d_done[i], cudaEventDisableTiming));
+    }
+    const int nif = prm->nif;
+    const int64_t nbt = (int64_t)nif * pl->chunk_blocks;
+    pl->compact_stride = (size_t)((pl->chunk_frames * payload + 255) / 256 * 256);
+    pl->wmask_stride = (size_t)((pl->chunk_frames * pl->groups_per_slot + 255) / 256 * 256);
+    pl->fstat_stride = (size_t)((pl->chunk_frames + 255) / 256 * 256);
+    CUB(cudaMalloc(&pl->d_compact, pl->compact_stride * nif));
+    CUB(cudaMalloc(&pl->d_wmask, pl->wmask_stride * nif));
+    CUB(cudaMalloc(&pl->d_fstat, pl->fstat_stride * nif));
+    CUB(cudaMalloc(&pl->d_blkdirty, (size_t)nbt));
+    CUB(cudaMalloc(&pl->d_inter, (size_t)nbt * L * R * sizeof(float2)));
+    CUB(cudaMalloc(&pl->d_colsum, (size_t)nbt * R * sizeof(float2)));
+    CUB(cudaMalloc(&pl->d_eps, (size_t)nbt * pl->N * sizeof(float2)));
+    pl->F_if_stride = pl->F_cap_rows * nprod * pl->N;
+    CUB(cudaMalloc(&pl->d_F, (size_t)pl->F_if_stride * nif * sizeof(float)));
+    CUB(cudaMalloc(&pl->d_mean, (size_t)nif * nprod * pl->N * sizeof(float)));
+    CUB(cudaMalloc(&pl->d_scale, (size_t)nif * nprod * pl->N * sizeof(float)));
+    CUB(cudaMalloc(&pl->d_partial, (size_t)nif * kStatSplit * nprod * pl->N * sizeof(double2)));
+    CUB(cudaMalloc(&pl->d_counters, C_COUNT * sizeof(unsigned long long)));
+    CUB(cudaFuncSetAttribute(ka_column_pass<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KASmem<2>::kBytes));
+    CUB(cudaFuncSetAttribute(ka_column_pass<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KASmem<8>::kBytes));
+#undef CUB
+    int rc = upload_tables(pl);
+    if (rc) return bail(rc);
+    rc = init_state(pl);
+    if (rc) return bail(rc);
+    *out = pl;
+    return 0;
+}
+
+int b2f_plan_destroy(b2f_plan* pl) {
+    free_plan(pl);
+    return 0;
+}
+
+int b2f_get_geometry(const b2f_plan* pl, b2f_geometry* g) {
+    if (!pl || !g) return fail(B2F_EINVAL, "null argument");
+    g->unit_frames = pl->unit_frames;
+    g->unit_blocks = pl->unit_blocks;
+    g->chunk_frames = pl->chunk_frames;
+    g->chunk_rows = pl->chunk_rows;
+    g->block_samples = pl->M;
+    g->samples_per_frame = pl->spf;
+    g->row_bytes = pl->row_bytes;
+    g->nprod = pl->nprod;
+    g->freq_res = pl->L;
+    g->tsamp_s = (double)pl->D * pl->N / (std::fabs(pl->prm.bw_mhz[0]) * 1e6);
+    g->interval_rows = pl->interval_rows;
+    return 0;
+}
+
+int b2f_reset(b2f_plan* pl) {
+    if (!pl) return fail(B2F_EINVAL, "null plan");
+    CU(cudaSetDevice(pl->prm.device));
+    CU(cudaStreamSynchronize(pl->stream));
+    CU(cudaStreamSynchronize(pl->copy_stream));
+    return init_state(pl);
+}
+
+int b2f_push(b2f_plan* pl, const void* const* frames, int64_t nframes, int on_device) {
+    if (!pl || !frames) return fail(B2F_EINVAL, "null argument");
+    if (nframes < 0 || nframes > pl->chunk_frames) return fail(B2F_EINVAL, "nframes exceeds chunk_frames");
+    if (pl->flushed) return fail(B2F_ESTATE, "push after flush; call b2f_reset for a new scan");
+    CU(cudaSetDevice(pl->prm.device));
+    const int nif = pl->prm.nif;
+    const int64_t nblk = nframes * pl->spf / pl->M;
+    const int64_t rows = nblk * pl->L / pl->D;
+    if (nblk == 0) return 0;
+    if (pl->rows_off + pl->rows_held + rows > pl->F_cap_rows)
+        return fail(B2F_ESTATE, "row buffer full: call b2f_pull before pushing more");
+    const size_t fbytes = (size_t)nframes * pl->prm.frame_bytes;
+
+    if (!pl->have_base) {
+        for (int i = 0; i < nif; ++i) {
+            uint32_t w[2];
+            if (on_device) CU(cudaMemcpy(w, frames[i], 8, cudaMemcpyDeviceToHost));
+            else memcpy(w, frames[i], 8);
+            pl->base_sec0[i] = w[0] & 0x3FFFFFFFu;
+            pl->base_fnum0[i] = w[1] & 0xFFFFFFu;
+        }
+        pl->have_base = true;
+    }
+
+    K0Params k0{};
+    if (on_device) {
+        for (int i = 0; i < nif; ++i) k0.frames[i] = static_cast<const uint8_t*>(frames[i]);
+    } else {
+        const int idx = pl->stage_idx;
+        if (!pl->d_stage[idx]) {
+            pl->stage_if_stride = (size_t)((pl->chunk_frames * pl->prm.frame_bytes + 255) / 256 * 256);
+            CU(cudaMalloc(&pl->d_stage[idx], pl->stage_if_stride * nif));
+        }
+        CU(cudaStreamWaitEvent(pl->copy_stream, pl->ev_stage_free[idx], 0));
+        for (int i = 0; i < nif; ++i) {
+            CU(cudaMemcpyAsync(pl->d_stage[idx] + i * pl->stage_if_stride, frames[i], fbytes, cudaMemcpyHostToDevice,
+                               pl->copy_stream));
+            k0.frames[i] = pl->d_stage[idx] + i * pl->stage_if_stride;
+        }
+        CU(cudaEventRecord(pl->ev_h2d_done[idx], pl->copy_stream));
+        CU(cudaStreamWaitEvent(pl->stream, pl->ev_h2d_done[idx], 0));
+    }
+
+    // ---- kernel 1: validate + de-frame
+    k0.compact = pl->d_compact; k0.compact_stride = pl->compact_stride;
+    k0.wmask = pl->d_wmask; k0.wmask_stride = pl->wmask_stride;
+    k0.fstat = pl->d_fstat; k0.fstat_stride = pl->fstat_stride;
+    k0.counters = pl->d_counters;
+    k0.nframes = nframes; k0.nslots = nframes;
+    k0.frame_bytes = pl->prm.frame_bytes; k0.header_bytes = pl->prm.header_bytes;
+    k0.payload_bytes = (int)pl->payload; k0.groups_per_slot = (int)pl->groups_per_slot;
+    k0.in_nbit = pl->prm.in_nbit; k0.time_mode = pl->prm.frame_time_mode; k0.mask_faults = pl->prm.mask_faults;
+    k0.fps = (int)pl->fps;
+    for (int i = 0; i < nif; ++i) {
+        const int64_t tot = (int64_t)pl->base_fnum0[i] + pl->frames_pushed;
+        k0.base_sec[i] = pl->base_sec0[i] + (uint32_t)(tot / pl->fps);
+        k0.base_fnum[i] = (uint32_t)(tot % pl->fps);
+    }
+    CU(cudaMemsetAsync(pl->d_fstat, 0, pl->fstat_stride * nif, pl->stream));
+    CU(cudaMemsetAsync(pl->d_blkdirty, 0, (size_t)nif * nblk, pl->stream));
+    int rc = launch_k0(pl, k0, pl->stream, true);
+    if (rc) return rc;
+    if (!on_device) {
+        CU(cudaEventRecord(pl->ev_stage_free[pl->stage_idx], pl->stream));
+        pl->stage_idx ^= 1;
+    }
+    {
+        K0bParams kb{};
+        kb.wmask = pl->d_wmask; kb.wmask_stride = pl->wmask_stride;
+        kb.fstat = pl->d_fstat; kb.fstat_stride = pl->fstat_stride;
+        kb.blkdirty = pl->d_blkdirty; kb.counters = pl->d_counters;
+        kb.nslots = nframes; kb.nif = nif; kb.nblk = (int)nblk;
+        kb.groups_per_slot = (int)pl->groups_per_slot; kb.samples_per_frame = (int)pl->spf;
+        kb.block_samples = pl->M;
+        const int64_t n = nframes * nif;
+        k0b_finish_slots<<<(unsigned)((n + 255) / 256), 256, 0, pl->stream>>>(kb);
+        CU(cudaGetLastError());
+    }
+    // ---- kernel 3a: column pass (decode fused)
+    {
+        KAParams ka{};
+        ka.compact = pl->d_compact; ka.compact_stride = pl->compact_stride;
+        ka.wmask = pl->d_wmask; ka.wmask_stride = pl->wmask_stride;
+        ka.blkdirty = pl->d_blkdirty;
+        ka.inter = pl->d_inter; ka.colsum = pl->d_colsum;
+        ka.tab_g = pl->d_tab_g; ka.tab_h = pl->d_tab_h; ka.tab_w = pl->d_tab_w;
+        ka.R = pl->R; ka.nstrips = pl->nstrips; ka.nblk = (int)nblk; ka.nif = nif;
+        ka.payload_bytes = (int)pl->payload; ka.groups_per_slot = (int)pl->groups_per_slot;
+        const int64_t work = (int64_t)nif * nblk * pl->nstrips;
+        int64_t grid = std::max<int64_t>(1, (2 * pl->num_sms) / pl->nstrips) * pl->nstrips;
+        grid = std::min<int64_t>(grid, work);
+        if (pl->prm.in_nbit == 2)
+            rc = timed(pl, B2F_K_COLUMN, [&] { ka_column_pass<2><<<(unsigned)grid, kKAThreads, KASmem<2>::kBytes, pl->stream>>>(ka); });
+        else
+            rc = timed(pl, B2F_K_COLUMN, [&] { ka_column_pass<8><<<(unsigned)grid, kKAThreads, KASmem<8>::kBytes, pl->stream>>>(ka); });
+        if (rc) return rc;
+    }
+    // ---- kernel 3b: eps
+    rc = timed(pl, B2F_K_EPS, [&] {
+        ke_eps<<<(unsigned)(nif * nblk), pl->R / 2, pl->R * sizeof(float2), pl->stream>>>(pl->d_colsum, pl->d_eps, pl->R);
+    });
+    if (rc) return rc;
+    // ---- kernel 3c+4: row pass + detect + tscrunch
+    {
+        KBParams kb{};
+        kb.inter = pl->d_inter; kb.eps = pl->d_eps; kb.tab_r = pl->d_tab_r;
+        kb.F = pl->d_F; kb.F_if_stride = pl->F_if_stride;
+        kb.row0 = pl->rows_off + pl->rows_held;
+        kb.nblk = (int)nblk; kb.nif = nif; kb.D = pl->D; kb.mode = pl->prm.pol_mode;
+        int TR, PT;
+        kb_shape(pl->R, &TR, &PT);
+        const int NRS = kKBThreads / TR;
+        const int G = std::max(pl->D, NRS);
+        const int64_t ngroups = (int64_t)nif * nblk * (kL / G);
+        const int grid = (int)std::min<int64_t>(ngroups, (int64_t)pl->num_sms * 2 * 4);
+        rc = launch_kb(pl, kb, grid);
+        if (rc) return rc;
+    }
+    pl->rows_held += rows;
+    pl->rows_produced += rows;
+    pl->frames_pushed += nframes;
+    pl->last_nblk = nblk;
+    pl->last_nframes = nframes;
+    return 0;
+}
+
+int b2f_flush(b2f_plan* pl) {
+    if (!pl) return fail(B2F_EINVAL, "null plan");
+    pl->flushed = true;
+    return 0;
+}
+
+int b2f_pull(b2f_plan* pl, void* out, int64_t max_rows, int out_on_device, int64_t* nrows) {
+    if (!pl || !nrows) return fail(B2F_EINVAL, "null argument");
+    *nrows = 0;
+    CU(cudaSetDevice(pl->prm.device));
+    const int nif = pl->prm.nif;
+    const int ncol = pl->nprod * pl->N;
+    if (!pl->stats_ready) {
+        if (pl->rows_held >= pl->interval_rows || (pl->flushed && pl->rows_held > 0)) {
+            const int64_t nstat = std::min(pl->rows_held, pl->interval_rows);
+            int rc = timed(pl, B2F_K_STATS, [&] {
+                dim3 g1((ncol + 127) / 128, nif, kStatSplit);
+                ks_partial<<<g1, 128, 0, pl->stream>>>(pl->d_F + pl->rows_off * ncol, pl->F_if_stride, nstat, ncol, pl->d_partial);
+                dim3 g2((ncol + 127) / 128, nif);
+                ks_final<<<g2, 128, 0, pl->stream>>>(pl->d_partial, kStatSplit, nstat, ncol, pl->d_mean, pl->d_scale);
+            });
+            if (rc) return rc;
+            pl->stats_ready = true;
+        } else {
+            return 0;
+        }
+    }
+    const int64_t n = std::min(pl->rows_held, max_rows);
+    if (n <= 0) return 0;
+    if (!out) return fail(B2F_EINVAL, "null output buffer");
+    void* dst = out;
+    const size_t bytes = (size_t)n * pl->row_bytes;
+    if (!out_on_device) {
+        if (pl->out_stage_bytes < bytes) {
+            if (pl->d_out_stage) CU(cudaFree(pl->d_out_stage));
+            pl->d_out_stage = nullptr;
+            CU(cudaMalloc(&pl->d_out_stage, bytes));
+            pl->out_stage_bytes = bytes;
+        }
+        dst = pl->d_out_stage;
+    }
+    KQParams kq{};
+    kq.F = pl->d_F + pl->rows_off * ncol; kq.F_if_stride = pl->F_if_stride;
+    kq.mean = pl->d_mean; kq.scale = pl->d_scale; kq.out = dst;
+    kq.rows = n; kq.out_row_elems = pl->row_elems;
+    kq.nif = nif; kq.nprod = pl->nprod; kq.nchan = pl->N; kq.out_nbit = pl->prm.out_nbit;
+    kq.pol_major = pl->prm.splice_pol_major;
+    for (int i = 0; i < nif; ++i) {
+        kq.if_order[i] = pl->prm.if_order[i];
+        kq.flip[i] = pl->prm.bw_mhz[i] > 0 ? 1 : 0;
+    }
+    const int64_t quads = n * (pl->row_elems / 4);
+    int rc = timed(pl, B2F_K_QUANT, [&] { kq_quantise<<<(unsigned)((quads + 255) / 256), 256, 0, pl->stream>>>(kq); });
+    if (rc) return rc;
+    if (!out_on_device) {
+        CU(cudaMemcpyAsync(out, dst, bytes, cudaMemcpyDeviceToHost, pl->stream));
+        CU(cudaStreamSynchronize(pl->stream));
+    }
+    pl->rows_held -= n;
+    pl->rows_emitted += n;
+    pl->rows_off = pl->rows_held ? pl->rows_off + n : 0;
+    *nrows = n;
+    return 0;
+}
+
+int b2f_sync(b2f_plan* pl) {
+    if (!pl) return fail(B2F_EINVAL, "null plan");
+    CU(cudaSetDevice(pl->prm.device));
+    CU(cudaStreamSynchronize(pl->copy_stream));
+    CU(cudaStreamSynchronize(pl->stream));
+    return 0;
+}
+
+int b2f_get_counters(b2f_plan* pl, b2f_counters* c) {
+    if (!pl || !c) return fail(B2F_EINVAL, "null argument");
+    CU(cudaSetDevice(pl->prm.device));
+    unsigned long long h[C_COUNT];
+    CU(cudaStreamSynchronize(pl->stream));
+    CU(cudaMemcpy(h, pl->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
+    c->frames_ok = h[C_OK]; c->frames_invalid = h[C_INVALID]; c->frames_with_fill = h[C_FILLFRAMES];
+    c->fill_words = h[C_FILLWORDS]; c->frames_dropped = h[C_DROPPED]; c->frames_misplaced = h[C_MISPLACED];
+    c->frames_badhdr = h[C_BADHDR]; c->slots_missing = h[C_MISSING];
+    c->rows_produced = pl->rows_produced; c->rows_emitted = pl->rows_emitted; c->blocks_dirty = h[C_DIRTY];
+    return 0;
+}
+
+int b2f_get_rescale(b2f_plan* pl, float* mean, float* scale) {
+    if (!pl || !mean || !scale) return fail(B2F_EINVAL, "null argument");
+    CU(cudaSetDevice(pl->prm.device));
+    CU(cudaStreamSynchronize(pl->stream));
+    const size_t n = (size_t)pl->prm.nif * pl->nprod * pl->N * sizeof(float);
+    CU(cudaMemcpy(mean, pl->d_mean, n, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(scale, pl->d_scale, n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int b2f_kernel_time(b2f_plan* pl, int kid, double* ms, int64_t* launches) {
+    if (!pl || kid < 0 || kid >= B2F_K_COUNT) return fail(B2F_EINVAL, "kernel id");
+    CU(cudaSetDevice(pl->prm.device));
+    int rc = collect_times(pl);
+    if (rc) return rc;
+    if (ms) *ms = pl->k_ms[kid];
+    if (launches) *launches = pl->k_n[kid];
+    return 0;
+}
+
+int b2f_reset_timers(b2f_plan* pl) {
+    if (!pl) return fail(B2F_EINVAL, "null plan");
+    CU(cudaSetDevice(pl->prm.device));
+    int rc = collect_times(pl);
+    if (rc) return rc;
+    for (int i = 0; i < B2F_K_COUNT; ++i) { pl->k_ms[i] = 0; pl->k_n[i] = 0; }
+    return 0;
+}
+
+int b2f_decode(const void* frames, int64_t nframes, int frame_bytes, int header_bytes, int in_nbit, int mask_faults,
+               int in_on_device, float* out, int out_on_device, int device, b2f_counters* counters) {
+    if (!frames || !out || nframes <= 0) return fail(B2F_EINVAL, "null argument");
+    if (!(in_nbit == 2 || in_nbit == 8)) return fail(B2F_EUNSUPPORTED, "VDIF bits/sample must be 2 or 8");
+    const int payload = frame_bytes - header_bytes;
+    if (payload <= 0 || payload % 8 || (header_bytes != 32 && header_bytes != 16)) return fail(B2F_EINVAL, "frame geometry");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(B2F_ECUDA, "no CUDA device: libb2f has no CPU fallback");
+    }
+    CU(cudaSetDevice(device));
+    const int64_t spf = (int64_t)payload * 8 / (in_nbit * 2);
+    const int64_t nsamp = nframes * spf;
+    const int gps = (payload + 31) / 32;
+    uint8_t *d_in = nullptr, *d_compact = nullptr, *d_wmask = nullptr, *d_fstat = nullptr, *d_dirty = nullptr;
+    unsigned long long* d_cnt = nullptr;
+    float* d_out = nullptr;
+    int rc = 0;
+    auto cleanup = [&] {
+        if (d_in) cudaFree(d_in);
+        if (d_compact) cudaFree(d_compact);
+        if (d_wmask) cudaFree(d_wmask);
+        if (d_fstat) cudaFree(d_fstat);
+        if (d_dirty) cudaFree(d_dirty);
+        if (d_cnt) cudaFree(d_cnt);
+        if (d_out && !out_on_device) cudaFree(d_out);
+    };
+#define CUD(x)                                                                     \
+    do {                                                                           \
+        cudaError_t e__ = (x);                                                     \
+        if (e__ != cudaSuccess) {                                                  \
+            cleanup();                                                             \
+            return fail(B2F_ECUDA, std::string(#x) + ": " + cudaGetErrorString(e__)); \
+        }                                                                          \
+    } while (0)
+    const uint8_t* src = static_cast<const uint8_t*>(frames);
+    if (!in_on_device) {
+        CUD(cudaMalloc(&d_in, (size_t)nframes * frame_bytes));
+        CUD(cudaMemcpy(d_in, frames, (size_t)nframes * frame_bytes, cudaMemcpyHostToDevice));
+        src = d_in;
+    }
+    CUD(cudaMalloc(&d_compact, (size_t)nframes * payload));
+    CUD(cudaMalloc(&d_wmask, (size_t)nframes * gps));
+    CUD(cudaMalloc(&d_fstat, (size_t)nframes));
+    CUD(cudaMalloc(&d_dirty, 1));
+    CUD(cudaMalloc(&d_cnt, C_COUNT * sizeof(unsigned long long)));
+    CUD(cudaMemset(d_cnt, 0, C_COUNT * sizeof(unsigned long long)));
+    CUD(cudaMemset(d_fstat, 0, (size_t)nframes));
+    if (out_on_device) d_out = out;
+    else CUD(cudaMalloc(&d_out, (size_t)2 * nsamp * sizeof(float)));
+    K0Params k0{};
+    k0.frames[0] = src;
+    k0.compact = d_compact; k0.wmask = d_wmask; k0.fstat = d_fstat; k0.counters = d_cnt;
+    k0.nframes = nframes; k0.nslots = nframes;
+    k0.frame_bytes = frame_bytes; k0.header_bytes = header_bytes; k0.payload_bytes = payload; k0.groups_per_slot = gps;
+    k0.in_nbit = in_nbit; k0.time_mode = 0; k0.mask_faults = mask_faults; k0.fps = 1;
+    rc = launch_k0(nullptr, k0, 0, false);
+    if (rc) { cleanup(); return rc; }
+    const int64_t nwords = nframes * (payload / 4);
+    if (in_nbit == 2)
+        k_decode<2><<<(unsigned)((nwords + 255) / 256), 256>>>(d_compact, d_wmask, payload, gps, nwords, d_out, nsamp);
+    else
+        k_decode<8><<<(unsigned)((nwords + 255) / 256), 256>>>(d_compact, d_wmask, payload, gps, nwords, d_out, nsamp);
+    CUD(cudaGetLastError());
+    CUD(cudaDeviceSynchronize());
+    if (!out_on_device) CUD(cudaMemcpy(out, d_out, (size_t)2 * nsamp * sizeof(float), cudaMemcpyDeviceToHost));
+    if (counters) {
+        unsigned long long h[C_COUNT];
+        CUD(cudaMemcpy(h, d_cnt, sizeof(h), cudaMemcpyDeviceToHost));
+        memset(counters, 0, sizeof(*counters));
+        counters->frames_ok = h[C_OK]; counters->frames_invalid = h[C_INVALID];
+        counters->frames_with_fill = h[C_FILLFRAMES]; counters->fill_words = h[C_FILLWORDS];
+        counters->frames_badhdr = h[C_BADHDR]; counters->frames_misplaced = h[C_MISPLACED];
+    }
+#undef CUD
+    cleanup();
+    return 0;
+}
+
+int b2f_debug_copy(b2f_plan* pl, int which, void* dst, size_t nbytes, size_t* needed) {
+    if (!pl) return fail(B2F_EINVAL, "null plan");
+    CU(cudaSetDevice(pl->prm.device));
+    CU(cudaStreamSynchronize(pl->stream));
+    const int nif = pl->prm.nif;
+    const int64_t nbt = (int64_t)nif * pl->last_nblk;
+    const void* src = nullptr;
+    size_t n = 0;
+    switch (which) {
+        case 0: src = pl->d_compact; n = pl->compact_stride * nif; break;
+        case 1: src = pl->d_wmask; n = pl->wmask_stride * nif; break;
+        case 2: src = pl->d_fstat; n = pl->fstat_stride * nif; break;
+        case 3: src = pl->d_blkdirty; n = (size_t)nbt; break;
+        case 4: src = pl->d_inter; n = (size_t)nbt * pl->L * pl->R * sizeof(float2); break;
+        case 5: src = pl->d_colsum; n = (size_t)nbt * pl->R * sizeof(float2); break;
+        case 6: src = pl->d_eps; n = (size_t)nbt * pl->N * sizeof(float2); break;
+        case 7: src = pl->d_F; n = (size_t)pl->F_if_stride * nif * sizeof(float); break;
+        default: return fail(B2F_EINVAL, "which");
+    }
+    if (needed) *needed = n;
+    if (!dst) return 0;
+    CU(cudaMemcpy(dst, src, std::min(n, nbytes), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,218 @@
+"""Python face of a libb2f plan: one object = one `digifil` invocation per IF plus the
+`splice` that joins them (/root/reference/process_vdif.py:142-199,
+/root/reference/base2fil.sh:404-448), running on one GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+from ._lib import B2FError  # noqa: F401  (re-export)
+
+
+def reference_freq_res(nchan: int) -> int:
+    """leakage factor digifil is given: /root/reference/process_vdif.py:162"""
+    return 512 if nchan <= 128 else 2 * nchan
+
+
+def pol_mode_from_reference(pol: int) -> int:
+    """--pol of process_vdif (/root/reference/process_vdif.py:58-64,163-176) -> b2f_pol_mode"""
+    try:
+        return {0: _lib.POL_P0, 1: _lib.POL_P1, 2: _lib.POL_I, 3: _lib.POL_I2, 4: _lib.POL_COHERENCE}[pol]
+    except KeyError:
+        raise ValueError(f"pol = {pol} not implemented. Choices are 0, 1, 2, 3, 4")
+
+
+@dataclass
+class PlanConfig:
+    nchan: int
+    bw_mhz: list[float]                     # signed per IF: negative = LSB
+    freq_mhz: list[float] | None = None
+    if_order: list[int] | None = None       # output tile s <- IF index; default: descending frequency
+    tscrunch: int = 1
+    pol_mode: int = _lib.POL_I
+    out_nbit: int = 8
+    in_nbit: int = 2
+    frame_bytes: int = 8032
+    header_bytes: int = 32
+    freq_res: int = 0
+    frame_time_mode: int = 0
+    mask_faults: bool = True
+    keep_bandpass: bool = False
+    splice_pol_major: bool = False
+    chunk_units: int = 1
+    rescale_interval_s: float = 10.0
+    device: int = 0
+    profile: bool = False
+    stream: int | None = None
+    extra: dict = field(default_factory=dict)
+
+
+class Plan:
+    def __init__(self, cfg: PlanConfig):
+        self.cfg = cfg
+        nif = len(cfg.bw_mhz)
+        p = _lib.Params()
+        p.struct_size = C.sizeof(_lib.Params)
+        p.device = cfg.device
+        p.nif = nif
+        p.nchan = cfg.nchan
+        p.freq_res = cfg.freq_res
+        p.tscrunch = cfg.tscrunch
+        p.pol_mode = cfg.pol_mode
+        p.out_nbit = cfg.out_nbit
+        p.in_nbit = cfg.in_nbit
+        p.frame_bytes = cfg.frame_bytes
+        p.header_bytes = cfg.header_bytes
+        p.frame_time_mode = cfg.frame_time_mode
+        p.mask_faults = int(cfg.mask_faults)
+        p.keep_bandpass = int(cfg.keep_bandpass)
+        p.splice_pol_major = int(cfg.splice_pol_major)
+        p.chunk_units = cfg.chunk_units
+        p.rescale_interval_s = cfg.rescale_interval_s
+        freq = cfg.freq_mhz if cfg.freq_mhz is not None else [1400.0 + abs(cfg.bw_mhz[0]) * i for i in range(nif)]
+        order = cfg.if_order
+        if order is None:  # highest sky frequency first, like base2fil's splice_list (base2fil.sh:350,367)
+            order = sorted(range(nif), key=lambda i: -freq[i])
+        if nif > _lib.B2F_MAX_IF:
+            raise B2FError(_lib.EINVAL, "nif out of range")
+        for i in range(nif):
+            p.bw_mhz[i] = cfg.bw_mhz[i]
+            p.freq_mhz[i] = freq[i]
+            p.if_order[i] = order[i]
+        p.dm = 0.0
+        p.coherent = 0
+        p.profile = int(cfg.profile)
+        p.stream = cfg.stream
+        self.if_order = list(order)
+        self.freq_mhz = list(freq)
+        self._h = C.c_void_p()
+        self.nif = nif
+        _lib.check(_lib.lib().b2f_plan_create(C.byref(p), C.byref(self._h)))
+        g = _lib.Geometry()
+        _lib.check(_lib.lib().b2f_get_geometry(self._h, C.byref(g)))
+        self.geometry = g
+        self.nprod = g.nprod
+        self.row_bytes = g.row_bytes
+        self.chunk_frames = g.chunk_frames
+        self.chunk_rows = g.chunk_rows
+        self.tsamp_s = g.tsamp_s
+
+    # ------------------------------------------------------------------ lifecycle
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().b2f_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ------------------------------------------------------------------ streaming
+    def push(self, frames, nframes: int | None = None, on_device: bool = False):
+        """frames: list (one per IF) of numpy uint8 arrays (host) or integer device pointers."""
+        ptrs = (C.c_void_p * self.nif)()
+        if on_device:
+            assert nframes is not None
+            for i, f in enumerate(frames):
+                ptrs[i] = int(f)
+        else:
+            keep = []
+            for i, f in enumerate(frames):
+                a = np.ascontiguousarray(f, dtype=np.uint8)
+                keep.append(a)
+                ptrs[i] = a.ctypes.data
+                n = a.size // self.cfg.frame_bytes
+                nframes = n if nframes is None else min(nframes, n)
+            self._keep = keep   # host buffers must outlive the asynchronous copy
+        _lib.check(_lib.lib().b2f_push(self._h, ptrs, int(nframes), int(on_device)))
+
+    def flush(self):
+        _lib.check(_lib.lib().b2f_flush(self._h))
+
+    def pull(self, max_rows: int | None = None) -> np.ndarray:
+        """Finished rows as a host array [rows, row_bytes] uint8 (view as needed)."""
+        if max_rows is None:
+            max_rows = int(self.geometry.interval_rows + 2 * self.chunk_rows)
+        out = np.empty((max_rows, self.row_bytes), dtype=np.uint8)
+        n = C.c_int64(0)
+        _lib.check(_lib.lib().b2f_pull(self._h, out.ctypes.data, max_rows, 0, C.byref(n)))
+        return out[: n.value]
+
+    def pull_device(self, dev_ptr: int, max_rows: int) -> int:
+        n = C.c_int64(0)
+        _lib.check(_lib.lib().b2f_pull(self._h, C.c_void_p(dev_ptr), max_rows, 1, C.byref(n)))
+        return n.value
+
+    def sync(self):
+        _lib.check(_lib.lib().b2f_sync(self._h))
+
+    def reset(self):
+        _lib.check(_lib.lib().b2f_reset(self._h))
+
+    # ------------------------------------------------------------------ introspection
+    def counters(self) -> dict:
+        c = _lib.Counters()
+        _lib.check(_lib.lib().b2f_get_counters(self._h, C.byref(c)))
+        return c.as_dict()
+
+    def rescale(self):
+        n = self.nif * self.nprod * self.cfg.nchan
+        mean = np.empty(n, np.float32)
+        scale = np.empty(n, np.float32)
+        _lib.check(_lib.lib().b2f_get_rescale(self._h, mean.ctypes.data, scale.ctypes.data))
+        shp = (self.nif, self.nprod, self.cfg.nchan)
+        return mean.reshape(shp), scale.reshape(shp)
+
+    def kernel_times(self) -> dict:
+        out = {}
+        for k, name in enumerate(_lib.KERNEL_NAMES):
+            ms = C.c_double(0)
+            n = C.c_int64(0)
+            _lib.check(_lib.lib().b2f_kernel_time(self._h, k, C.byref(ms), C.byref(n)))
+            out[name] = (ms.value, n.value)
+        return out
+
+    def reset_timers(self):
+        _lib.check(_lib.lib().b2f_reset_timers(self._h))
+
+    def debug(self, which: int, dtype, count: int | None = None) -> np.ndarray:
+        need = C.c_size_t(0)
+        _lib.check(_lib.lib().b2f_debug_copy(self._h, which, None, 0, C.byref(need)))
+        nbytes = need.value if count is None else min(need.value, count * np.dtype(dtype).itemsize)
+        buf = np.empty(nbytes, np.uint8)
+        _lib.check(_lib.lib().b2f_debug_copy(self._h, which, buf.ctypes.data, nbytes, None))
+        return buf.view(dtype)
+
+    def view_rows(self, raw: np.ndarray) -> np.ndarray:
+        """[rows, row_bytes] uint8 -> [rows, elems] in the output sample type."""
+        nb = self.cfg.out_nbit
+        if nb == 8 or nb == 2:
+            return raw
+        if nb == 16:
+            return raw.view(np.uint16)
+        return raw.view(np.float32)
+
+
+def decode(frames: np.ndarray, *, frame_bytes: int = 8032, header_bytes: int = 32, in_nbit: int = 2,
+           mask_faults: bool = True, device: int = 0):
+    """Stand-alone GPU decode: VDIF bytes -> x[2, nsamp] float32 and the fault counters."""
+    a = np.ascontiguousarray(frames, dtype=np.uint8)
+    nframes = a.size // frame_bytes
+    spf = (frame_bytes - header_bytes) * 8 // (in_nbit * 2)
+    out = np.empty((2, nframes * spf), np.float32)
+    c = _lib.Counters()
+    _lib.check(_lib.lib().b2f_decode(a.ctypes.data, nframes, frame_bytes, header_bytes, in_nbit, int(mask_faults), 0,
+                                     out.ctypes.data, 0, device, C.byref(c)))
+    return out, c.as_dict()

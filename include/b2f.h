@@ -1,0 +1,167 @@
+/* b2f.h -- C ABI of libb2f.so: B200-native baseband(VDIF) -> SIGPROC filterbank.
+ *
+ * This is the drop-in boundary for the one stage of pharaofranz/frb-baseband that
+ * process_vdif.py hands to DSPSR `digifil` (per subband) and base2fil.sh hands to SIGPROC
+ * `splice`.  The reference has no FFI for this path -- it shells out to two executables --
+ * so every entry point below cites the reference call site whose work it replaces:
+ *
+ *   digifil argv built at      process_vdif.py:156-182   -> b2f_params fields
+ *   digifil process run at     process_vdif.py:191        -> b2f_push / b2f_pull (per chunk)
+ *   .hdr semantics             process_vdif.py:115-139   -> freq_mhz / bw_mhz (sign = sideband)
+ *   one digifil per IF         base2fil.sh:60-66          -> nif > 1 batches the IFs in one plan
+ *   splice ${splice_list}      base2fil.sh:422-446        -> spliced row layout written by b2f_pull
+ *   splice order               base2fil.sh:350,367        -> IF slot s of the output row holds
+ *                                                            plan IF index if_order[s]
+ *
+ * Plain pointers and sizes only; no torch / C++ types.  All functions return 0 on success
+ * or a negative B2F_E* code; b2f_last_error() gives a thread-local message.  A plan owns
+ * its device memory and streams and may be used from one host thread at a time.  There is
+ * no CPU fallback: without a CUDA device every compute entry point fails with B2F_ECUDA.
+ */
+#ifndef B2F_H
+#define B2F_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2F_VERSION 100            /* 0.1.0 */
+#define B2F_MAX_IF 32
+
+enum b2f_error {
+    B2F_OK = 0,
+    B2F_EINVAL = -1,               /* bad parameter (InputError in process_vdif.py:236) */
+    B2F_ECUDA = -2,                /* CUDA runtime failure or no device (RunError, :247) */
+    B2F_ENOMEM = -3,
+    B2F_ESTATE = -4,               /* call sequence error */
+    B2F_EUNSUPPORTED = -5          /* valid request outside what the kernels implement */
+};
+
+/* detection products: process_vdif.py:163-176 maps --pol {0,1,2,3,4} to -P0,-P1,-d1,-d3,-d4 */
+enum b2f_pol_mode {
+    B2F_POL_P0 = 0,                /* -P0 : |pol0|^2                       */
+    B2F_POL_P1 = 1,                /* -P1 : |pol1|^2                       */
+    B2F_POL_I = 2,                 /* -d1 : PP+QQ                          */
+    B2F_POL_I2 = 3,                /* -d3 : (PP+QQ)^2                      */
+    B2F_POL_COHERENCE = 4,         /* -d4 : PP, QQ, Re PQ*, Im PQ*         */
+    B2F_POL_IQUV = 5,              /* Stokes, circular basis: I, Q=2Re RL*, U=2Im RL*, V=RR-LL */
+    B2F_POL_PPQQ = 6               /* -d2 : PP, QQ                         */
+};
+
+enum b2f_frame_time_mode {
+    B2F_FRAMES_POSITIONAL = 0,     /* frame k of a push is time slot k (digifil's reader) */
+    B2F_FRAMES_BY_HEADER = 1       /* slot from header seconds/frame#; gaps zero-filled    */
+};
+
+typedef struct b2f_params {
+    uint32_t struct_size;          /* = sizeof(b2f_params) */
+    int32_t device;                /* CUDA device ordinal */
+    int32_t nif;                   /* dual-pol IFs (subbands) processed together, 1..B2F_MAX_IF */
+    int32_t nchan;                 /* channels per IF        (--nchan, digifil -F<nchan>:..)  */
+    int32_t freq_res;              /* digifil -F ..:<freq_res>; 0 = reference rule
+                                      512 if nchan<=128 else 2*nchan (process_vdif.py:162) */
+    int32_t tscrunch;              /* digifil -t             (--tscrunch)                     */
+    int32_t pol_mode;              /* enum b2f_pol_mode                                       */
+    int32_t out_nbit;              /* digifil -b: 2, 8, 16, -32 (process_vdif.py:153)         */
+    int32_t in_nbit;               /* VDIF bits/sample: 2 or 8 (frb.conf nbits)               */
+    int32_t frame_bytes;           /* VDIF frame size incl. header (base2fil.sh:130-136)      */
+    int32_t header_bytes;          /* 32, or 16 for legacy (base2fil.sh:137-147)              */
+    int32_t frame_time_mode;       /* enum b2f_frame_time_mode                                */
+    int32_t mask_faults;           /* 1: invalid-bit frames and 0x11223344 words -> 0.0       */
+    int32_t keep_bandpass;         /* digifil -I0            (--keepBP)                       */
+    int32_t splice_pol_major;      /* 0: row = per-IF [pol][chan] tiles back to back (splice);
+                                      1: row = [pol][all channels]                            */
+    int32_t chunk_units;           /* frames per push = chunk_units * unit (see b2f_geometry)  */
+    double rescale_interval_s;     /* digifil -I (default 10 s), stats frozen after (-c)      */
+    double bw_mhz[B2F_MAX_IF];     /* signed: <0 = LSB (process_vdif.py:117-118)              */
+    double freq_mhz[B2F_MAX_IF];   /* centre frequency of each IF (-f)                        */
+    int32_t if_order[B2F_MAX_IF];  /* output tile s <- IF index if_order[s]; descending sky
+                                      frequency for base2fil's plan                           */
+    double dm;                     /* reserved: coherent in-channel dedispersion (-D, -F n:D) */
+    int32_t coherent;
+    int32_t profile;               /* 1: time every kernel launch with CUDA events            */
+    void* stream;                  /* cudaStream_t to launch on; NULL = plan-owned stream     */
+} b2f_params;
+
+typedef struct b2f_geometry {
+    int64_t unit_frames;           /* frames per IF that hold a whole number of FFT blocks    */
+    int64_t unit_blocks;           /* FFT blocks per unit                                     */
+    int64_t chunk_frames;          /* frames per IF expected by b2f_push                      */
+    int64_t chunk_rows;            /* output time samples produced per full push              */
+    int64_t block_samples;         /* M = 2*nchan*freq_res time samples                       */
+    int64_t samples_per_frame;
+    int64_t row_bytes;             /* bytes of one output time sample (all IFs, all products) */
+    int32_t nprod;                 /* detected streams (SIGPROC nifs)                         */
+    int32_t freq_res;
+    double tsamp_s;
+    int64_t interval_rows;         /* rows held before the first rescale is frozen            */
+} b2f_geometry;
+
+typedef struct b2f_counters {
+    uint64_t frames_ok, frames_invalid, frames_with_fill, fill_words;
+    uint64_t frames_dropped, frames_misplaced, frames_badhdr, slots_missing;
+    uint64_t rows_produced, rows_emitted, blocks_dirty;
+} b2f_counters;
+
+/* kernel ids for b2f_kernel_time */
+enum b2f_kernel_id {
+    B2F_K_VALIDATE = 0,            /* frame header validation + fill masking + de-framing     */
+    B2F_K_COLUMN = 1,              /* decode + column pass of the channeliser                 */
+    B2F_K_EPS = 2,                 /* block-constant correction                               */
+    B2F_K_ROW = 3,                 /* row pass + detection + time integration                 */
+    B2F_K_STATS = 4,               /* per-channel mean / sigma                                */
+    B2F_K_QUANT = 5,               /* rescale + requantise + sideband flip + splice           */
+    B2F_K_DECODE = 6,              /* stand-alone decode (tests / roofline)                   */
+    B2F_K_COUNT = 7
+};
+
+int b2f_version(void);
+const char* b2f_last_error(void);
+int b2f_device_count(void);
+
+int b2f_plan_create(const b2f_params* params, struct b2f_plan** plan);
+int b2f_plan_destroy(struct b2f_plan* plan);
+int b2f_get_geometry(const struct b2f_plan* plan, b2f_geometry* out);
+
+/* Feed one chunk: frames[i] -> nframes VDIF frames of IF i, on the host (pinned memory makes
+ * the copy asynchronous) or already on the device.  Asynchronous: returns once the work is
+ * queued.  nframes must be chunk_frames except for the final push of a scan. */
+int b2f_push(struct b2f_plan* plan, const void* const* frames, int64_t nframes, int on_device);
+
+/* End of scan: freeze the rescale even if fewer than interval_rows rows were seen. */
+int b2f_flush(struct b2f_plan* plan);
+
+/* Write finished, requantised, band-ordered rows to out (host or device).  Returns through
+ * *nrows how many rows were written (0 while the first rescale interval is still filling). */
+int b2f_pull(struct b2f_plan* plan, void* out, int64_t max_rows, int out_on_device, int64_t* nrows);
+
+int b2f_sync(struct b2f_plan* plan);
+int b2f_reset(struct b2f_plan* plan);        /* new scan, same parameters */
+int b2f_get_counters(struct b2f_plan* plan, b2f_counters* out);
+/* mean/scale the digitiser applies: arrays of nif*nprod*nchan floats, natural channel order */
+int b2f_get_rescale(struct b2f_plan* plan, float* mean, float* scale);
+/* accumulated device time (ms) and launch count of one kernel kind since the last reset of
+ * the timers; requires params.profile = 1 */
+int b2f_kernel_time(struct b2f_plan* plan, int kernel_id, double* ms, int64_t* launches);
+int b2f_reset_timers(struct b2f_plan* plan);
+
+/* Stand-alone decode of VDIF frames (host or device) -> planar float samples
+ * out[2][nframes*samples_per_frame] on the device or host (kernel 1 of the path without the
+ * channeliser; bit-exact contract).  counters may be NULL. */
+int b2f_decode(const void* frames, int64_t nframes, int frame_bytes, int header_bytes, int in_nbit,
+               int mask_faults, int in_on_device, float* out, int out_on_device, int device,
+               b2f_counters* counters);
+
+/* Test hooks: copy an internal device buffer of the most recent push to the host.
+ * which: 0 compact payload, 1 word mask, 2 frame status, 3 block dirty flags,
+ *        4 column-pass output [blk][L][R] float2, 5 column sums [blk][R] float2,
+ *        6 eps [blk][nchan] float2, 7 detected floats of held rows [if][row][prod][chan]. */
+int b2f_debug_copy(struct b2f_plan* plan, int which, void* dst, size_t nbytes, size_t* needed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2F_H */

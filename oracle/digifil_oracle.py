@@ -1,0 +1,333 @@
+"""CPU oracle: NumPy restatement of `digifil` (DSPSR) + `splice` (SIGPROC) semantics.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``frb-baseband_b200/`` may import this module;
+only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs do, and there only as the checker / the timed CPU arm.
+
+PARITY UNPINNED.  The arithmetic of the reference's baseband->filterbank path lives in two
+external executables that are neither vendored under /root/reference nor installable
+offline: ``digifil`` (DSPSR, fork pharaofranz/dspsr, advised commit b68528e15e8 with PSRCHIVE
+79ed5c0821 -- /root/reference/INSTALL.md:37-39) and ``splice`` (SIGPROC, fork
+pharaofranz/sigproc, unpinned -- /root/reference/README.md:8).  The reference holds no tests,
+fixtures or golden vectors, so this oracle restates the published
+algorithm of those tools and anchors on the reference's own call sites:
+
+* digifil argv                  /root/reference/process_vdif.py:156-182
+* leakage factor (freq_res)     /root/reference/process_vdif.py:162
+* pol -> -d/-P mapping          /root/reference/process_vdif.py:163-176
+* .hdr semantics (BW sign etc.) /root/reference/process_vdif.py:115-139
+* frequency plan per IF         /root/reference/base2fil.sh:54,65,254,407-414
+* splice order (highest first)  /root/reference/base2fil.sh:350,367,422
+* input bit layout              /root/reference/spif2file.sh:31-98,181
+
+It is pinned instead by analytic known-answer tests (tests/test_oracle_kat.py): exhaustive
+2-bit LUT, tone -> predicted channel with LSB/USB mirror, Parseval, Gaussian -> 8-bit
+mean 127.5 / sigma 21.25, splice == concatenate, header round trip.
+
+All arithmetic is float64 unless ``dtype=np.float32`` is requested (used by the timed CPU
+baseline, which mirrors digifil's single-precision FFTW path).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+try:  # scipy's pocketfft is ~2x faster than numpy's for float32 and keeps float32
+    import scipy.fft as _fft
+except Exception:  # pragma: no cover
+    _fft = np.fft
+
+# ----------------------------------------------------------------------------------------
+# VDIF format (VDIF 1.1 spec).  The reference only ever reads these
+# fields through `vdif_print_headers` (/root/reference/base2fil.sh:130-147,
+# /root/reference/extract_baseband_chunk.py:36-70).
+# ----------------------------------------------------------------------------------------
+VDIF_FILL_WORD = 0x11223344
+OPT2BIT_LO = 1.0
+OPT2BIT_HI = 3.3359          # standard VLBI optimal 4-level reconstruction ratio
+LEVELS_2BIT = np.array([-OPT2BIT_HI, -OPT2BIT_LO, OPT2BIT_LO, OPT2BIT_HI])
+
+
+def parse_vdif_header(words: np.ndarray) -> dict:
+    """Decode the first 4 little-endian 32-bit words of a VDIF frame header."""
+    w0, w1, w2, w3 = (int(w) for w in words[:4])
+    return {
+        "seconds": w0 & 0x3FFFFFFF,
+        "legacy": (w0 >> 30) & 1,
+        "invalid": (w0 >> 31) & 1,
+        "frame_nr": w1 & 0xFFFFFF,
+        "ref_epoch": (w1 >> 24) & 0x3F,
+        "frame_bytes": (w2 & 0xFFFFFF) * 8,
+        "log2_nchan": (w2 >> 24) & 0x1F,
+        "version": (w2 >> 29) & 0x7,
+        "station": w3 & 0xFFFF,
+        "thread": (w3 >> 16) & 0x3FF,
+        "nbit": ((w3 >> 26) & 0x1F) + 1,
+        "complex": (w3 >> 31) & 1,
+    }
+
+
+def vdif_epoch_mjd(ref_epoch: int) -> int:
+    """MJD of 00:00 UTC at the start of a VDIF reference epoch (half-years since 2000)."""
+    year = 2000 + ref_epoch // 2
+    month = 1 if ref_epoch % 2 == 0 else 7
+    # Fliegel & Van Flandern
+    a = (14 - month) // 12
+    y = year + 4800 - a
+    m = month + 12 * a - 3
+    jdn = 1 + (153 * m + 2) // 5 + 365 * y + y // 4 - y // 100 + y // 400 - 32045
+    return jdn - 2400001  # JDN at noon -> MJD at preceding midnight
+
+
+def decode_vdif(buf: np.ndarray, *, nbit: int = 2, header_bytes: int = 32,
+                frame_bytes: int | None = None, mask_invalid: bool = True,
+                offset8: float = 127.5, return_flags: bool = False):
+    """VDIF byte stream (2 channels, real) -> x[2, nsamp] float64.
+
+    Follows digifil's VDIF reader + unpacker as restated in SURVEY.md Appendix A1/A2:
+    positional frames, 32 B header stripped, ch0 -> pol 0, ch1 -> pol 1, 2-bit offset
+    binary 0..3 -> (-hi,-lo,+lo,+hi) with the static optimal levels, 8-bit offset binary
+    -> code-127.5.  Fault handling (Appendix D1 default): samples of frames with the invalid
+    bit set are 0.0; every 32-bit payload word equal to the fill pattern 0x11223344 yields
+    0.0 for the time samples it holds.
+    """
+    buf = np.ascontiguousarray(buf, dtype=np.uint8)
+    if frame_bytes is None:
+        frame_bytes = parse_vdif_header(buf[:16].view("<u4"))["frame_bytes"]
+    nframes = buf.size // frame_bytes
+    fr = buf[: nframes * frame_bytes].reshape(nframes, frame_bytes)
+    w0 = fr[:, 0:4].copy().view("<u4")[:, 0]
+    invalid = (w0 >> 31).astype(bool)
+    payload = fr[:, header_bytes:]
+    pbytes = payload.shape[1]
+    words = np.ascontiguousarray(payload).view("<u4")            # [nframes, pbytes/4]
+    fill = words == VDIF_FILL_WORD
+    if nbit == 2:
+        # byte: bits[1:0]=ch0 t, [3:2]=ch1 t, [5:4]=ch0 t+1, [7:6]=ch1 t+1
+        p = payload
+        c = np.empty((nframes, pbytes, 2, 2), dtype=np.uint8)    # [.., t-in-byte, ch]
+        c[..., 0, 0] = p & 3
+        c[..., 0, 1] = (p >> 2) & 3
+        c[..., 1, 0] = (p >> 4) & 3
+        c[..., 1, 1] = (p >> 6) & 3
+        x = LEVELS_2BIT[c]                                        # float64
+        x = x.reshape(nframes, pbytes * 2, 2)
+        samp_per_word = 8
+    elif nbit == 8:
+        x = payload.astype(np.float64).reshape(nframes, pbytes // 2, 2) - offset8
+        samp_per_word = 2
+    else:
+        raise ValueError(f"unsupported VDIF nbit={nbit}")
+    if mask_invalid:
+        x[invalid] = 0.0
+        fm = np.repeat(fill, samp_per_word, axis=1)               # [nframes, t]
+        x[fm] = 0.0
+    out = np.ascontiguousarray(x.reshape(-1, 2).T)
+    if return_flags:
+        return out, {"invalid_frames": int(invalid.sum()), "fill_words": int(fill.sum())}
+    return out
+
+
+# ----------------------------------------------------------------------------------------
+# digifil stages
+# ----------------------------------------------------------------------------------------
+def filterbank(x: np.ndarray, nchan: int, freq_res: int, dtype=np.float64) -> np.ndarray:
+    """DSPSR convolving filterbank `-F nchan:freq_res` on one real polarisation.
+
+    Per non-overlapping block of M = 2*nchan*freq_res samples: unnormalised forward real FFT,
+    Nyquist bin discarded, the M/2 bins cut into nchan segments of freq_res bins, each
+    segment sent through an unnormalised backward complex FFT (Appendix A3).  Returns
+    y[t, chan] complex with t = block*freq_res + m.  Trailing samples that do not fill a
+    block are dropped.
+    """
+    M = 2 * nchan * freq_res
+    nblk = x.size // M
+    cdt = np.complex64 if dtype == np.float32 else np.complex128
+    xb = np.asarray(x[: nblk * M], dtype=dtype).reshape(nblk, M)
+    X = _fft.rfft(xb, axis=1)[:, : M // 2]
+    seg = X.reshape(nblk, nchan, freq_res)
+    if freq_res > 1:
+        y = _fft.ifft(seg, axis=2, norm="forward")               # unnormalised backward
+    else:
+        y = seg
+    return np.ascontiguousarray(np.transpose(y, (0, 2, 1))).reshape(nblk * freq_res, nchan).astype(cdt, copy=False)
+
+
+#: output products per pol mode.  'I' = -d1, 'PPQQ' = -d2, 'I2' = -d3, 'coherence' = -d4
+#: (PP,QQ,Re PQ*,Im PQ*; /root/reference/process_vdif.py:169-171), 'P0'/'P1' = -P0/-P1,
+#: 'IQUV' = north-star Stokes in a circular basis (I=RR+LL, Q=2Re RL*, U=2Im RL*, V=RR-LL).
+POL_MODES = ("P0", "P1", "I", "I2", "coherence", "IQUV", "PPQQ")
+
+
+def pol_mode_from_reference(pol: int) -> str:
+    """--pol value of process_vdif (/root/reference/process_vdif.py:58-64,163-176)."""
+    return {0: "P0", 1: "P1", 2: "I", 3: "I2", 4: "coherence"}[pol]
+
+
+def detect(yP: np.ndarray, yQ: np.ndarray, mode: str) -> np.ndarray:
+    """Detection (Appendix A5).  Returns d[t, npol_out, chan] real."""
+    pp = yP.real ** 2 + yP.imag ** 2
+    qq = yQ.real ** 2 + yQ.imag ** 2
+    if mode == "P0":
+        out = [pp]
+    elif mode == "P1":
+        out = [qq]
+    elif mode == "I":
+        out = [pp + qq]
+    elif mode == "I2":
+        out = [(pp + qq) ** 2]
+    elif mode == "PPQQ":
+        out = [pp, qq]
+    elif mode in ("coherence", "IQUV"):
+        x = yP * np.conj(yQ)
+        if mode == "coherence":
+            out = [pp, qq, x.real, x.imag]
+        else:
+            out = [pp + qq, 2 * x.real, 2 * x.imag, pp - qq]
+    else:
+        raise ValueError(mode)
+    return np.stack(out, axis=1)
+
+
+def tscrunch(d: np.ndarray, D: int) -> np.ndarray:
+    """Sum D consecutive time samples (Appendix A6); incomplete tail dropped."""
+    if D <= 1:
+        return d
+    n = d.shape[0] // D
+    return d[: n * D].reshape(n, D, *d.shape[1:]).sum(axis=1)
+
+
+def rescale_stats(d: np.ndarray, nsamp_interval: int):
+    """mean / sigma per (pol, chan) over the first interval (Appendix A7, `-c`)."""
+    n = min(nsamp_interval, d.shape[0]) if nsamp_interval > 0 else d.shape[0]
+    seg = d[:n].astype(np.float64)
+    mean = seg.mean(axis=0)
+    var = (seg * seg).mean(axis=0) - mean * mean
+    scale = np.where(var > 0, 1.0 / np.sqrt(np.where(var > 0, var, 1.0)), 1.0)
+    return mean, scale
+
+
+def digitise(y: np.ndarray, nbit: int) -> np.ndarray:
+    """SigProcDigitizer (Appendix A8)."""
+    if nbit == -32:
+        return y.astype(np.float32)
+    if nbit == 8:
+        return np.clip(np.floor(y * (127.5 / 6.0) + 127.5 + 0.5), 0, 255).astype(np.uint8)
+    if nbit == 16:
+        return np.clip(np.floor(y * (32768.0 / 6.0) + 32768.0 + 0.5), 0, 65535).astype(np.uint16)
+    if nbit == 2:
+        q = np.clip(np.floor(y + 1.5 + 0.5), 0, 3).astype(np.uint8)
+        flat = q.reshape(q.shape[0], -1)
+        assert flat.shape[1] % 4 == 0
+        f4 = flat.reshape(flat.shape[0], -1, 4)
+        return (f4[..., 0] | (f4[..., 1] << 2) | (f4[..., 2] << 4) | (f4[..., 3] << 6)).astype(np.uint8)
+    raise ValueError(f"nbit={nbit}")
+
+
+def chirp(nchan: int, freq_res: int, freq_mhz: float, bw_mhz: float, dm: float) -> np.ndarray:
+    """In-channel coherent dedispersion response H[chan, bin] (Appendix A4).
+
+    Channel c has sky centre f_c = FREQ - BW/2 + (c+0.5)*BW/N (BW signed) and the bin j of
+    its segment sits at baseband offset (j+0.5... ) -- bins are taken at their lower edge
+    like DSPSR: f = (j/freq_res - 0.5)*|BW|/N, mirrored in sign for LSB.
+    H = exp(+i*2pi*D*DM*f^2 / (f_c^2 (f_c+f))), D = 1e6/2.41e-4 (us MHz^2).
+    """
+    N, L = nchan, freq_res
+    chbw = bw_mhz / N                                     # signed
+    fc = freq_mhz - bw_mhz / 2 + (np.arange(N) + 0.5) * chbw
+    j = np.arange(L)
+    f = (j / L - 0.5) * chbw                              # sky offset from channel centre
+    disp = 1.0 / 2.41e-4                                  # s MHz^2 pc^-1 cm^3
+    phase = 2 * np.pi * disp * 1e6 * dm * f[None, :] ** 2 / (fc[:, None] ** 2 * (fc[:, None] + f[None, :]))
+    if bw_mhz < 0:
+        phase = -phase
+    return np.exp(1j * phase)
+
+
+def digifil(vdif: np.ndarray, *, freq_mhz: float, bw_mhz: float, nchan: int,
+            freq_res: int | None = None, tscrunch_factor: int = 1, pol_mode: str = "I",
+            out_nbit: int = 8, in_nbit: int = 2, start_s: float = 0.0, nsec: float | None = None,
+            rescale_interval_s: float = 10.0, keep_bandpass: bool = False,
+            frame_bytes: int | None = None, header_bytes: int = 32,
+            dtype=np.float64, return_float: bool = False) -> dict:
+    """One IF: VDIF bytes -> SIGPROC samples, as `digifil -cont -c -b<nbit> -S<start> -T<nsec>
+    -2 -D 0.0 [-t D] -d<..> -F<nchan>:<freq_res> [-I0]` (/root/reference/process_vdif.py:157-182).
+
+    bw_mhz is signed like the .hdr BW keyword: negative = LSB
+    (/root/reference/process_vdif.py:117-118).  Returns dict with 'data' [t, npol, chan] in
+    file order (descending frequency), 'float' (pre-digitiser, natural channel order) when
+    requested, and the header quantities tsamp_s / fch1 / foff / nchans / nifs / tstart.
+    """
+    if freq_res is None:
+        freq_res = 512 if nchan <= 128 else 2 * nchan     # /root/reference/process_vdif.py:162
+    vdif = np.ascontiguousarray(vdif, dtype=np.uint8)
+    h0 = parse_vdif_header(vdif[:16].view("<u4"))
+    if frame_bytes is None:
+        frame_bytes = h0["frame_bytes"]
+    fs = 2.0 * abs(bw_mhz) * 1e6                            # real Nyquist sampling
+    spf = (frame_bytes - header_bytes) * 8 // (in_nbit * 2)  # time samples per frame
+    fps = fs / spf
+    f0 = int(round(start_s * fps))
+    nfr = vdif.size // frame_bytes - f0
+    if nsec is not None:
+        nfr = min(nfr, int(round(nsec * fps)))
+    x = decode_vdif(vdif[f0 * frame_bytes: (f0 + nfr) * frame_bytes], nbit=in_nbit,
+                    header_bytes=header_bytes, frame_bytes=frame_bytes)
+    yP = filterbank(x[0], nchan, freq_res, dtype)
+    yQ = filterbank(x[1], nchan, freq_res, dtype)
+    d = tscrunch(detect(yP, yQ, pol_mode), tscrunch_factor)
+    tsamp = tscrunch_factor * nchan / (abs(bw_mhz) * 1e6)
+    if keep_bandpass:
+        y = d.astype(np.float64)
+        mean = np.zeros(d.shape[1:]); scale = np.ones(d.shape[1:])
+    else:
+        mean, scale = rescale_stats(d, int(np.floor(rescale_interval_s / tsamp + 0.5)))
+        y = (d - mean) * scale
+    if bw_mhz > 0:                                           # USB: flip so that foff < 0
+        yo = y[:, :, ::-1]
+    else:
+        yo = y
+    data = digitise(yo, out_nbit)
+    h_first = parse_vdif_header(vdif[f0 * frame_bytes: f0 * frame_bytes + 16].view("<u4"))
+    tstart = (vdif_epoch_mjd(h_first["ref_epoch"]) + (h_first["seconds"] + h_first["frame_nr"] / fps) / 86400.0)
+    out = {
+        "data": data, "tsamp_s": tsamp, "nchans": nchan, "nifs": d.shape[1],
+        "nbits": 32 if out_nbit == -32 else out_nbit,
+        "fch1": freq_mhz + abs(bw_mhz) / 2 - abs(bw_mhz) / (2 * nchan),
+        "foff": -abs(bw_mhz) / nchan, "tstart": tstart, "mean": mean, "scale": scale,
+    }
+    if return_float:
+        out["float"] = d
+    return out
+
+
+def splice(parts: list[dict]) -> dict:
+    """SIGPROC `splice` (Appendix A10): inputs highest-frequency first
+    (/root/reference/base2fil.sh:350,367); per time sample concatenate each file's row;
+    header = first file's with nchans summed; shortest input ends the output."""
+    n = min(p["data"].shape[0] for p in parts)
+    for p in parts[1:]:
+        assert p["nbits"] == parts[0]["nbits"] and abs(p["tsamp_s"] - parts[0]["tsamp_s"]) < 1e-15
+    rows = [p["data"][:n].reshape(n, -1) for p in parts]
+    out = dict(parts[0])
+    out["data"] = np.concatenate(rows, axis=1)
+    out["nchans"] = sum(p["nchans"] for p in parts)
+    return out
+
+
+def if_plan(nif: int, freq_lsb0: float, bw: float):
+    """Frequency plan of base2fil (/root/reference/base2fil.sh:54,65,254,407-414):
+    IF i (1-based) centred at freqLSB_0 + (i-1)*bw; odd = LSB, even = USB.  Returns
+    [(if_number, centre_mhz, signed_bw)] in splice order (highest frequency first)."""
+    plan = []
+    for i in range(1, nif + 1):
+        usb = (i % 2 == 0)
+        plan.append((i, freq_lsb0 + (i - 1) * bw, bw if usb else -bw))
+    return plan[::-1]
+
+
+def base2fil(vdifs: dict[int, np.ndarray], *, nif: int, freq_lsb0: float, bw: float, **kw) -> dict:
+    """All IFs of a scan -> spliced filterbank (digifil per IF, then splice)."""
+    parts = []
+    for i, fc, sbw in if_plan(nif, freq_lsb0, bw):
+        parts.append(digifil(vdifs[i], freq_mhz=fc, bw_mhz=sbw, **kw))
+    return splice(parts)

@@ -1,0 +1,171 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle.  Runs on the B200 box."""
+import numpy as np
+import pytest
+
+from oracle import digifil_oracle as o
+from frb_baseband_b200 import _lib, synth
+from frb_baseband_b200.plan import Plan, PlanConfig, decode
+import algo_prototype as ap
+from helpers import REL_TOL, assert_rel, run_plan
+
+pytestmark = pytest.mark.gpu
+
+
+def test_decode_bit_exact(gpu):
+    v = synth.make_vdif(257, seed=7, invalid_frac=0.05, fill_frac=0.05)
+    x, cnt = decode(v)
+    ref, fl = o.decode_vdif(v, return_flags=True)
+    assert np.array_equal(x, ref.astype(np.float32))                      # bit-exact
+    assert cnt["frames_invalid"] == fl["invalid_frames"]
+    assert cnt["frames_ok"] + cnt["frames_invalid"] + cnt["frames_with_fill"] == 257
+
+
+def test_decode_8bit_bit_exact(gpu):
+    v = synth.make_vdif(33, seed=8, nbit=8, bw_mhz=32.0, invalid_frac=0.1)
+    x, _ = decode(v, in_nbit=8)
+    assert np.array_equal(x, o.decode_vdif(v, nbit=8).astype(np.float32))
+
+
+def test_column_pass_stages(gpu):
+    """Intermediates of one push against the NumPy model of the same decomposition."""
+    nchan, bw = 32, 16.0
+    cfg = PlanConfig(nchan=nchan, bw_mhz=[-bw], keep_bandpass=True, out_nbit=-32)
+    with Plan(cfg) as pl:
+        v = synth.make_vdif(int(pl.chunk_frames), seed=11, bw_mhz=bw)
+        pl.push([v])
+        R, L = 2 * nchan, 512
+        nblk = int(pl.geometry.unit_blocks)
+        inter = pl.debug(4, np.complex64).reshape(nblk, L, R)
+        colsum = pl.debug(5, np.complex64).reshape(nblk, R)
+        eps = pl.debug(6, np.complex64).reshape(nblk, nchan)
+        x = o.decode_vdif(v)
+        z = x[0] + 1j * x[1]
+        M = R * L
+        for b in (0, 1, nblk - 1):
+            B, S = ap.column_pass(z[b * M:(b + 1) * M], R, L)
+            sc = np.abs(B).max()
+            assert np.abs(inter[b] - B).max() <= 2e-6 * sc, f"column pass block {b}"
+            assert np.abs(colsum[b] - S).max() <= 1e-6 * np.abs(S).max() + 1e-3
+            e = ap.eps_from_colsum(S, R)
+            assert np.abs(eps[b] - e).max() <= 1e-5 * np.abs(e).max()
+
+
+@pytest.mark.parametrize("nchan,bw,D", [(128, 32.0, 16), (32, 16.0, 32), (64, 32.0, 1), (128, 32.0, 512), (8, 16.0, 4)])
+@pytest.mark.parametrize("usb", [False, True])
+def test_float_spectra(gpu, nchan, bw, D, usb):
+    """Detected, time-integrated floats (digifil -b-32 -I0) within 1e-5 relative."""
+    cfg = PlanConfig(nchan=nchan, bw_mhz=[bw if usb else -bw])
+    with Plan(cfg) as pl:
+        nfr = int(pl.chunk_frames)
+    v = synth.make_vdif(nfr, seed=21 + nchan, bw_mhz=bw, tone_frac=0.3, rho=0.3)
+    rows, info = run_plan([v], nchan=nchan, bw=[bw if usb else -bw], tscrunch=D, out_nbit=-32, keep_bandpass=True)
+    ref = o.digifil(v, freq_mhz=1400.0, bw_mhz=bw if usb else -bw, nchan=nchan, tscrunch_factor=D, out_nbit=-32,
+                    keep_bandpass=True)
+    assert rows.shape == (ref["data"].shape[0], nchan)
+    assert_rel(rows.reshape(-1, 1, nchan), ref["data"].astype(np.float64), REL_TOL, "float spectra")
+
+
+@pytest.mark.parametrize("mode,name", [(_lib.POL_P0, "P0"), (_lib.POL_P1, "P1"), (_lib.POL_I2, "I2"),
+                                       (_lib.POL_COHERENCE, "coherence"), (_lib.POL_IQUV, "IQUV"), (_lib.POL_PPQQ, "PPQQ")])
+def test_pol_modes(gpu, mode, name):
+    nchan, bw, D = 128, 32.0, 16
+    v = synth.make_vdif(1024, seed=31, bw_mhz=bw, rho=0.4, tone_frac=0.6)
+    rows, info = run_plan([v], nchan=nchan, bw=[-bw], tscrunch=D, pol_mode=mode, out_nbit=-32, keep_bandpass=True)
+    ref = o.digifil(v, freq_mhz=1400.0, bw_mhz=-bw, nchan=nchan, tscrunch_factor=D, pol_mode=name, out_nbit=-32,
+                    keep_bandpass=True)["data"]
+    assert_rel(rows.reshape(ref.shape), ref.astype(np.float64), REL_TOL, name)
+
+
+@pytest.mark.parametrize("out_nbit", [8, 16, 2, -32])
+def test_requantised_output(gpu, out_nbit):
+    """8-bit output within +-1 LSB of the oracle (BASELINE.json), rescale stats included."""
+    nchan, bw, D = 128, 32.0, 16
+    v = synth.make_vdif(2048, seed=41, bw_mhz=bw)
+    rows, info = run_plan([v], nchan=nchan, bw=[bw], tscrunch=D, out_nbit=out_nbit, interval=0.3)
+    ref = o.digifil(v, freq_mhz=1400.0, bw_mhz=bw, nchan=nchan, tscrunch_factor=D, out_nbit=out_nbit,
+                    rescale_interval_s=0.3)
+    rd = ref["data"].reshape(ref["data"].shape[0], -1)
+    assert rows.shape == rd.shape
+    if out_nbit == -32:
+        assert np.abs(rows - rd).max() <= 1e-3        # y = (x-mean)/sigma, sigma-units
+    elif out_nbit == 2:
+        a = np.stack([(rows >> s) & 3 for s in (0, 2, 4, 6)], -1).astype(int)
+        b = np.stack([(rd >> s) & 3 for s in (0, 2, 4, 6)], -1).astype(int)
+        assert np.abs(a - b).max() <= 1 and (a != b).mean() < 1e-3
+    else:
+        d = np.abs(rows.astype(np.int64) - rd.astype(np.int64))
+        assert d.max() <= 1, f"max LSB diff {d.max()}"
+        assert (d != 0).mean() < 1e-3
+    mean, scale = info["rescale"]
+    assert np.allclose(mean[0, 0], ref["mean"][0], rtol=1e-5) and np.allclose(scale[0, 0], ref["scale"][0], rtol=1e-4)
+
+
+def test_multi_if_splice_and_flip(gpu):
+    """8 IFs in base2fil's frequency plan: odd LSB / even USB, spliced highest frequency first."""
+    nif, bw, nchan, D = 8, 32.0, 128, 16
+    plan = o.if_plan(nif, 1254.0, bw)
+    vd = {i: synth.make_vdif(1024, seed=synth.config_seed(2, i), bw_mhz=bw, tone_frac=0.1 * i) for i in range(1, nif + 1)}
+    bws = [0.0] * nif
+    freqs = [0.0] * nif
+    for i, fc, sbw in plan:
+        bws[i - 1], freqs[i - 1] = sbw, fc
+    rows, info = run_plan([vd[i] for i in range(1, nif + 1)], nchan=nchan, bw=bws, freq=freqs, tscrunch=D, interval=0.1)
+    assert info["if_order"] == [7, 6, 5, 4, 3, 2, 1, 0]
+    ref = o.base2fil(vd, nif=nif, freq_lsb0=1254.0, bw=bw, nchan=nchan, tscrunch_factor=D, rescale_interval_s=0.1)
+    assert rows.shape == ref["data"].shape == (4000, nif * nchan)
+    d = np.abs(rows.astype(int) - ref["data"].astype(int))
+    assert d.max() <= 1 and (d != 0).mean() < 1e-3
+
+
+def test_faulty_frames_masked(gpu):
+    nchan, bw, D = 128, 32.0, 16
+    v = synth.make_vdif(1024, seed=51, bw_mhz=bw, invalid_frac=0.01, fill_frac=0.01)
+    rows, info = run_plan([v], nchan=nchan, bw=[-bw], tscrunch=D, out_nbit=-32, keep_bandpass=True)
+    ref = o.digifil(v, freq_mhz=1400.0, bw_mhz=-bw, nchan=nchan, tscrunch_factor=D, out_nbit=-32, keep_bandpass=True)
+    assert info["counters"]["frames_invalid"] > 0 and info["counters"]["frames_with_fill"] > 0
+    assert_rel(rows.reshape(-1, 1, nchan), ref["data"].astype(np.float64), REL_TOL, "masked frames")
+
+
+def test_chunked_equals_single_and_ragged_tail(gpu):
+    """Two pushes + a ragged final push give the same rows as the oracle on the whole file
+    (trailing samples that do not fill an FFT block are dropped)."""
+    nchan, bw, D = 128, 32.0, 16
+    v = synth.make_vdif(2048 + 300, seed=61, bw_mhz=bw)
+    rows, _ = run_plan([v], nchan=nchan, bw=[-bw], tscrunch=D, interval=0.2)
+    ref = o.digifil(v, freq_mhz=1400.0, bw_mhz=-bw, nchan=nchan, tscrunch_factor=D, rescale_interval_s=0.2)
+    assert rows.shape[0] == ref["data"].shape[0]
+    d = np.abs(rows.astype(int) - ref["data"].reshape(rows.shape).astype(int))
+    assert d.max() <= 1
+
+
+def test_8bit_input(gpu):
+    nchan, bw, D = 128, 32.0, 16
+    cfg = PlanConfig(nchan=nchan, bw_mhz=[-bw], in_nbit=8)
+    with Plan(cfg) as pl:
+        nfr = int(pl.chunk_frames)
+    v = synth.make_vdif(nfr, seed=71, bw_mhz=bw, nbit=8)
+    rows, _ = run_plan([v], nchan=nchan, bw=[-bw], tscrunch=D, in_nbit=8, out_nbit=-32, keep_bandpass=True)
+    ref = o.digifil(v, freq_mhz=1400.0, bw_mhz=-bw, nchan=nchan, tscrunch_factor=D, in_nbit=8, out_nbit=-32,
+                    keep_bandpass=True)
+    assert_rel(rows.reshape(-1, 1, nchan), ref["data"].astype(np.float64), REL_TOL, "8-bit input")
+
+
+def test_linearity_full_size_property(gpu):
+    """Size-independent property at the full C2 block geometry: an all-zero payload (every word
+    the fill pattern) yields exactly zero power, and Parseval holds per block."""
+    nchan, bw = 128, 32.0
+    v = synth.make_vdif(1024, seed=81, bw_mhz=bw)
+    rows, _ = run_plan([v], nchan=nchan, bw=[-bw], tscrunch=512, out_nbit=-32, keep_bandpass=True)
+    x = o.decode_vdif(v)
+    M = 2 * nchan * 512
+    for b in range(0, 125, 31):
+        tot = rows[b].sum()
+        # sum_c sum_m |y|^2 = L * sum_{k<M/2} |X_k|^2 ~= L*M/2 * sum x^2
+        X0 = np.fft.rfft(x[0, b * M:(b + 1) * M])[: M // 2]
+        X1 = np.fft.rfft(x[1, b * M:(b + 1) * M])[: M // 2]
+        expect = 512 * ((np.abs(X0) ** 2).sum() + (np.abs(X1) ** 2).sum())
+        assert abs(tot - expect) <= 1e-5 * expect
+    v2 = v.copy().reshape(1024, 8032)
+    v2[:, 32:].view("<u4")[:] = 0x11223344
+    rows2, info2 = run_plan([v2.reshape(-1)], nchan=nchan, bw=[-bw], tscrunch=16, out_nbit=-32, keep_bandpass=True)
+    assert np.all(rows2 == 0) and info2["counters"]["fill_words"] == 1024 * 2000

@@ -1,0 +1,121 @@
+"""Analytic known-answer tests that pin the oracle (the reference ships no golden vectors;
+SURVEY.md section 4 / 8c)."""
+import numpy as np
+import pytest
+
+from oracle import digifil_oracle as o
+from frb_baseband_b200 import synth, vdif
+import algo_prototype as ap
+
+
+def test_decode_lut_exhaustive():
+    # every byte value, both nibbles: VDIF 2-bit offset binary -> (-hi,-lo,+lo,+hi)
+    pay = np.resize(np.arange(256, dtype=np.uint8), 8000)
+    fr = np.zeros(8032, np.uint8)
+    fr[:32] = vdif.make_headers(1, frames_per_sec=4000).view(np.uint8)
+    fr[32:] = pay
+    x = o.decode_vdif(fr)
+    lev = np.array([-3.3359, -1.0, 1.0, 3.3359])
+    for k in range(8000):
+        b = int(pay[k])
+        assert x[0, 2 * k] == lev[b & 3] and x[1, 2 * k] == lev[(b >> 2) & 3]
+        assert x[0, 2 * k + 1] == lev[(b >> 4) & 3] and x[1, 2 * k + 1] == lev[(b >> 6) & 3]
+
+
+def test_decode_faults_zeroed():
+    v = synth.make_vdif(64, seed=3, invalid_frac=0.2, fill_frac=0.2)
+    x, fl = o.decode_vdif(v, return_flags=True)
+    assert fl["invalid_frames"] > 0 and fl["fill_words"] > 0
+    fr = v.reshape(64, 8032)
+    inv = (fr[:, 0:4].copy().view("<u4")[:, 0] >> 31).astype(bool)
+    xs = x.reshape(2, 64, 16000)
+    assert np.all(xs[:, inv] == 0)
+    words = np.ascontiguousarray(fr[:, 32:]).view("<u4")
+    clean = ~inv & ~(words == vdif.FILL_WORD).any(axis=1)
+    assert clean.any() and np.all(np.abs(xs[:, clean]) > 0)
+    part = ~inv & (words == vdif.FILL_WORD).any(axis=1) & ~(words == vdif.FILL_WORD).all(axis=1)
+    assert part.any()
+    for f in np.nonzero(part)[0]:
+        zero = np.repeat(words[f] == vdif.FILL_WORD, 8)
+        assert np.all(xs[:, f, zero] == 0) and np.all(xs[:, f, ~zero] != 0)
+
+
+@pytest.mark.parametrize("usb", [True, False])
+def test_tone_lands_in_predicted_channel(usb):
+    nchan, L = 32, 64
+    M = 2 * nchan * L
+    n = 4 * M
+    c_true = 11
+    # baseband frequency (c+0.5)/nchan of Nyquist
+    t = np.arange(n)
+    x = np.cos(np.pi * (c_true + 0.5) / nchan * t)
+    y = o.filterbank(x, nchan, L)
+    p = (np.abs(y) ** 2).sum(axis=0)
+    assert p.argmax() == c_true
+    assert p[c_true] > 100 * np.delete(p, c_true).max()
+    # through digifil(): USB files are flipped so that the first channel is the highest frequency
+    xs = np.stack([x, x]) * 2.0
+    v = synth.make_vdif(n // 16000 + 1, seed=0, x=np.pad(xs, ((0, 0), (0, (n // 16000 + 1) * 16000 - n))))
+    r = o.digifil(v, freq_mhz=1400.0, bw_mhz=32.0 if usb else -32.0, nchan=nchan, freq_res=L, out_nbit=-32,
+                  keep_bandpass=True)
+    prof = r["data"][:, 0, :].sum(axis=0)
+    assert prof.argmax() == (nchan - 1 - c_true if usb else c_true)
+    assert r["foff"] < 0 and abs(r["fch1"] - (1400.0 + 16.0 - 0.5)) < 1e-12
+
+
+def test_parseval():
+    rng = np.random.default_rng(1)
+    nchan, L = 16, 32
+    M = 2 * nchan * L
+    x = rng.standard_normal(3 * M)
+    y = o.filterbank(x, nchan, L)
+    # unnormalised rFFT then unnormalised backward FFT of length L: sum|y|^2 = L * sum_k |X_k|^2
+    # and sum over the kept half of the spectrum ~ M/2 * sum x^2 (DC/Nyquist edge terms aside)
+    for b in range(3):
+        X = np.fft.rfft(x[b * M:(b + 1) * M])[: M // 2]
+        assert np.allclose((np.abs(y[b * L:(b + 1) * L]) ** 2).sum(), L * (np.abs(X) ** 2).sum(), rtol=1e-12)
+
+
+def test_gaussian_requantise_moments():
+    v = synth.make_vdif(256, seed=5, bw_mhz=16.0)
+    r = o.digifil(v, freq_mhz=1400.0, bw_mhz=-16.0, nchan=32, tscrunch_factor=32, out_nbit=8)
+    d = r["data"].astype(np.float64)
+    assert abs(d.mean() - 127.5) < 0.6
+    assert abs(d.std() - 127.5 / 6.0) < 0.6
+
+
+def test_splice_is_concatenate_highest_first():
+    nif = 4
+    vd = {i: synth.make_vdif(256, seed=10 + i, bw_mhz=16.0) for i in range(1, nif + 1)}
+    r = o.base2fil(vd, nif=nif, freq_lsb0=1300.0, bw=16.0, nchan=32, tscrunch_factor=32)
+    assert r["nchans"] == nif * 32 and r["data"].shape[1] == nif * 32
+    top = o.digifil(vd[4], freq_mhz=1300.0 + 3 * 16.0, bw_mhz=16.0, nchan=32, tscrunch_factor=32)
+    assert np.array_equal(r["data"][:, :32], top["data"].reshape(-1, 32))
+    assert abs(r["fch1"] - (1300.0 + 3.5 * 16.0 - 0.25)) < 1e-12
+
+
+def test_if_plan_matches_reference_stepping():
+    # base2fil.sh:54,65,254,407-414: odd IFs LSB from freqLSB_0 in steps of 2*bw, even IFs USB from +bw
+    plan = o.if_plan(8, 1254.0, 32.0)
+    assert [p[0] for p in plan] == [8, 7, 6, 5, 4, 3, 2, 1]
+    assert plan[-1] == (1, 1254.0, -32.0) and plan[-2] == (2, 1286.0, 32.0)
+    assert plan[0] == (8, 1254.0 + 7 * 32.0, 32.0)
+
+
+@pytest.mark.parametrize("nchan,L", [(128, 512), (32, 512), (8, 16)])
+def test_gpu_decomposition_equals_oracle(nchan, L):
+    """The column-pass / row-pass / eps algebra the CUDA kernels implement is exactly the
+    oracle's filterbank."""
+    rng = np.random.default_rng(0)
+    M = 2 * nchan * L
+    x = rng.standard_normal((2, 2 * M + 7))
+    yP, yQ = o.filterbank(x[0], nchan, L), o.filterbank(x[1], nchan, L)
+    pP, pQ = ap.filterbank_dualpol(x, nchan, L)
+    s = np.abs(yP).max()
+    assert np.abs(pP - yP).max() < 1e-12 * s and np.abs(pQ - yQ).max() < 1e-12 * s
+
+
+def test_epoch_mjd():
+    assert o.vdif_epoch_mjd(0) == 51544            # 2000-01-01
+    assert o.vdif_epoch_mjd(40) == 58849           # 2020-01-01
+    assert vdif.epoch_mjd(41) == 59031             # 2020-07-01
