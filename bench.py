@@ -1,0 +1,378 @@
+#!/usr/bin/env python3
+"""bench.py -- baseband -> filterbank throughput on B200 (BASELINE.json metric).
+
+Workload (config C2): Effelsberg-style 8 dual-pol IFs x 32 MHz (16 BBC channels, 2 Gbps),
+2-bit VDIF, 60 s, Stokes I, 128 channels per IF, freq_res 512 (digifil -F128:512), tscrunch 16
+(64 us), 8-bit spliced filterbank.  One step = one pass of the whole hot path (validate ->
+decode -> channelise -> detect -> integrate -> rescale -> requantise -> splice) over the full
+60 s scan.  `value` is measured with the VDIF already in HBM; `e2e` pushes the same scan from
+pinned host memory through the C ABI and reads the finished rows back to the host.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--seconds S] [--impl reference]
+
+N > 1: launched under torch.distributed.run, one rank per GPU; every rank processes its own
+8-IF band (weak scaling: N x 8 subbands) and the finished 8-bit tiles are gathered over NCCL
+into rank 0's band-ordered rows -- the one exchange the path has (base2fil.sh:422).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+NIF, BW, NCHAN, FREQ_RES, TSCRUNCH = 8, 32.0, 128, 512, 16
+FRAME_BYTES, PAYLOAD = 8032, 8000
+FPS = 4000                                  # frames per second per IF
+BYTES_PER_DATA_SEC = NIF * FPS * FRAME_BYTES   # 257.024 MB of VDIF per second of sky
+FREQ_LSB0 = 1254.0
+METRIC = "input baseband GB/s (VDIF bytes, headers included) per B200, 2 Gbps 16x32 MHz 2-bit -> 8-bit Stokes I"
+
+
+def if_plan():
+    """base2fil.sh:54,65,254,407-414: IF i centred at freqLSB_0+(i-1)*bw, odd LSB / even USB"""
+    bws, freqs = [], []
+    for i in range(1, NIF + 1):
+        freqs.append(FREQ_LSB0 + (i - 1) * BW)
+        bws.append(BW if i % 2 == 0 else -BW)
+    return bws, freqs
+
+
+# --------------------------------------------------------------------------------------------
+# synthetic input on the device (BASELINE.md section 5 recipe, torch Philox instead of PCG64:
+# 15.4 GB cannot be generated with NumPy in bench time)
+# --------------------------------------------------------------------------------------------
+def make_device_vdif(torch, dev, nframes: int, seed: int):
+    """uint8 tensor [nframes, 8032]: Gaussian sigma=1 per pol, thresholds +-0.9674, offset binary."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    out = torch.empty((nframes, FRAME_BYTES), dtype=torch.uint8, device=dev)
+    step = 2048
+    for f0 in range(0, nframes, step):
+        n = min(step, nframes - f0)
+        x = torch.randn((n, PAYLOAD, 2, 2), generator=g, device=dev)        # [frame, byte, t-in-byte, pol]
+        c = ((x >= -0.9674).to(torch.uint8) + (x >= 0).to(torch.uint8) + (x >= 0.9674).to(torch.uint8))
+        b = c[..., 0, 0] | (c[..., 0, 1] << 2) | (c[..., 1, 0] << 4) | (c[..., 1, 1] << 6)
+        out[f0:f0 + n, 32:] = b
+        idx = torch.arange(f0, f0 + n, device=dev, dtype=torch.int64)
+        hdr = torch.zeros((n, 8), dtype=torch.int32, device=dev)
+        hdr[:, 0] = (idx // FPS).to(torch.int32)
+        hdr[:, 1] = ((idx % FPS) | (40 << 24)).to(torch.int32)
+        hdr[:, 2] = (FRAME_BYTES // 8) | (1 << 24)
+        hdr[:, 3] = 0x4566 | (1 << 26)
+        out[f0:f0 + n, :32] = hdr.view(torch.uint8).reshape(n, 32)
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.rows = []
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        sm, mx, reasons = [], None, set()
+        for ts, line in self.rows:
+            if ts < t0 - 0.05 or ts > t1 + 0.15:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: the oracle port, one single-threaded worker process per IF (base2fil.sh:60-66,219)
+# --------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    seed, nframes, fc, sbw = args
+    os.environ["OMP_NUM_THREADS"] = "1"
+    from frb_baseband_b200 import synth
+    from oracle import digifil_oracle as o
+    v = synth.make_vdif(nframes, seed=seed, bw_mhz=BW)
+    t0 = time.perf_counter()
+    r = o.digifil(v, freq_mhz=fc, bw_mhz=sbw, nchan=NCHAN, freq_res=FREQ_RES, tscrunch_factor=TSCRUNCH,
+                  out_nbit=8, dtype=np.float32)
+    return time.perf_counter() - t0, r["data"].shape[0]
+
+
+def cpu_arm(sample_seconds: float, steps: int = 1):
+    """Time the oracle (CPU restatement of digifil+splice) on this box's host cores."""
+    import multiprocessing as mp
+    from frb_baseband_b200 import synth
+    cores = len(os.sched_getaffinity(0))
+    workers = min(NIF, cores)
+    nframes = int(round(sample_seconds * FPS / 1024)) * 1024 or 1024
+    bws, freqs = if_plan()
+    jobs = [(synth.config_seed(2, i + 1), nframes, freqs[i], bws[i]) for i in range(NIF)]
+    ctx = mp.get_context("spawn")      # the parent may hold a CUDA context: never fork it
+    times = []
+    with ctx.Pool(workers) as pool:
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            res = pool.map(_cpu_worker, jobs)
+            # splice: concatenate per-IF rows, highest frequency first (trivial next to digifil)
+            wall = max(r[0] for r in res) if workers >= NIF else sum(r[0] for r in res) / workers
+            times.append(max(wall, 1e-9))
+            _ = time.perf_counter() - t0
+    t = float(np.median(times))
+    data_sec = nframes / FPS
+    return {"value": NIF * nframes * FRAME_BYTES / t / 1e9, "unit": "GB/s", "cores": workers, "kind": "port",
+            "sample": f"{data_sec:.3f} s of all {NIF} IFs of the C2 workload, one single-threaded oracle process per IF "
+                      f"(NumPy/SciPy-pocketfft float32 restatement of digifil+splice, not DSPSR itself)",
+            "rt_factor": data_sec / t, "seconds_per_step": t}
+
+
+# --------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--seconds", type=float, default=60.0, help="seconds of sky data per step (C2: 60)")
+    ap.add_argument("--impl", default="b2f", choices=["b2f", "reference"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-sample", type=float, default=1.024, help="seconds of data for the cpu_baseline leg")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        W = max(args.warmup, 0)
+        r = cpu_arm(args.cpu_sample, steps=max(1, args.steps + min(W, 1)))
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "GB/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["seconds_per_step"] * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "rt_factor": r["rt_factor"],
+                "config": {"workload": "C2: 8 IF x 32 MHz dual-pol 2-bit VDIF (2 Gbps), nchan 128, freq_res 512, "
+                                       "tscrunch 16, 8-bit Stokes I; bounded sample per step: " + r["sample"]},
+                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": r["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from frb_baseband_b200 import _lib
+    from frb_baseband_b200.plan import Plan, PlanConfig, fp32_peak_tflops
+    from frb_baseband_b200.dist import gather_splice, rank_if_plan
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the b2f path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    nframes = int(round(args.seconds * FPS))
+    _, bws, freqs = rank_if_plan(NIF * world, world, rank, FREQ_LSB0, BW)   # rank r owns the next 8 subbands up
+    stream = torch.cuda.current_stream(dev)
+    cfg = PlanConfig(nchan=NCHAN, bw_mhz=bws, freq_mhz=freqs, tscrunch=TSCRUNCH, out_nbit=8, freq_res=FREQ_RES,
+                     device=local_rank, profile=True, stream=stream.cuda_stream)
+    pl = Plan(cfg)
+    cf = int(pl.chunk_frames)
+    rows_total = (nframes * 16000 // (2 * NCHAN * FREQ_RES)) * FREQ_RES // TSCRUNCH   # only an upper bound
+    vd = [make_device_vdif(torch, dev, nframes, 20121102 + 2000 + 100 * rank + i) for i in range(NIF)]
+    out_dev = torch.empty((rows_total + cf, NIF * NCHAN), dtype=torch.uint8, device=dev)
+    gathered = torch.empty((world, rows_total + cf, NIF * NCHAN), dtype=torch.uint8, device=dev) if (world > 1 and rank == 0) else None
+    chunks = [(f0, min(cf, nframes - f0)) for f0 in range(0, nframes, cf)]
+
+    def step_device():
+        pl.reset()
+        got = 0
+        for f0, n in chunks:
+            pl.push([v[f0].data_ptr() for v in vd], nframes=n, on_device=True)
+            got += pl.pull_device(out_dev[got].data_ptr(), rows_total + cf - got)
+        pl.flush()
+        got += pl.pull_device(out_dev[got].data_ptr(), rows_total + cf - got)
+        if world > 1:       # the splice gather: every rank's 8-bit tile into rank 0's band-ordered rows
+            gather_splice(out_dev, world, rank, dst=0, out=gathered)
+        return got
+
+    def timed(fn, steps, warmup, sampler=None):
+        for _ in range(warmup):
+            fn()
+        pl.sync(); torch.cuda.synchronize(dev)
+        pl.reset_timers()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        l0 = pl.counters()["kernel_launches"]
+        e0.record(stream)
+        for _ in range(steps):
+            rows = fn()
+        pl.sync()
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        t1 = time.time()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        launches = pl.counters()["kernel_launches"] - l0
+        return ms / steps, rows, launches, (t0, t1)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    ms_step, rows, launches, (t0, t1) = timed(step_device, args.steps, max(args.warmup, 3))
+    clocks = sampler.stop(t0, t1)
+    ktimes = pl.kernel_times()
+    data_sec = nframes / FPS
+    in_bytes = NIF * nframes * FRAME_BYTES
+    value = world * in_bytes / (ms_step * 1e-3) / 1e9
+
+    # ---- e2e: pinned host VDIF -> C ABI -> rows back in pinned host memory
+    e2e = None
+    if not args.no_e2e:
+        hold_frames = min(nframes, 12 * FPS)            # pinned host copy of 12 s, cycled through the scan
+        hold_frames -= hold_frames % cf
+        host = [torch.empty((hold_frames, FRAME_BYTES), dtype=torch.uint8, pin_memory=True) for _ in range(NIF)]
+        for i in range(NIF):
+            host[i].copy_(vd[i][:hold_frames])
+        torch.cuda.synchronize(dev)
+        out_host = torch.empty((rows_total + cf, NIF * NCHAN), dtype=torch.uint8, pin_memory=True)
+        hptr = [h.data_ptr() for h in host]
+        import ctypes as C
+
+        def step_host():
+            pl.reset()
+            got = 0
+            for f0, n in chunks:
+                h0 = f0 % hold_frames
+                if h0 + n > hold_frames:
+                    n = hold_frames - h0
+                ptrs = (C.c_void_p * NIF)(*[p + h0 * FRAME_BYTES for p in hptr])
+                _lib.check(_lib.lib().b2f_push(pl._h, ptrs, n, 0))
+                got += pl.pull_async(out_host[got].data_ptr(), rows_total + cf - got)
+            pl.flush()
+            got += pl.pull_async(out_host[got].data_ptr(), rows_total + cf - got)
+            pl.sync()
+            return got
+
+        cfg_pos = pl.cfg   # positional frames: the cycled 12 s hold repeats header seconds, samples are what is timed
+        ms_e2e, rows_e, _, _ = timed(step_host, max(1, min(args.steps, 3)), 1)
+        h2d = sum(n for _, n in chunks) * NIF * FRAME_BYTES
+        e2e = {"value": world * in_bytes / (ms_e2e * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(rows_e * NIF * NCHAN), "ms_per_step": ms_e2e,
+               "rt_factor": data_sec / (ms_e2e * 1e-3),
+               "note": "pinned host VDIF pushed chunk by chunk through b2f_push, rows pulled to pinned host memory; "
+                       "12 s of host-resident VDIF cycled to cover the 60 s scan"}
+
+    # ---- roofline of the dominant kernel (column pass) + the FP32 view that actually binds
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    col_ms, col_n = ktimes["column"]
+    row_ms, row_n = ktimes["row"]
+    blocks_per_step = NIF * (nframes * 16000 // (2 * NCHAN * FREQ_RES))
+    R, L = 2 * NCHAN, FREQ_RES
+    # algorithmic bytes of the column pass per launch: 2-bit payload in + (the path's output share is
+    # written by later kernels) -> SURVEY 8(d): input 32.128 MB + output 2 MB per IF-second
+    alg_bytes_step = in_bytes + rows * NIF * NCHAN
+    col_launch_ms = col_ms / max(col_n, 1)
+    launches_per_step = col_n / args.steps
+    alg_bytes_launch = alg_bytes_step / launches_per_step
+    achieved = alg_bytes_launch / (col_launch_ms * 1e-3) / 1e9
+    roofline = {"kernel": "ka_column_pass<2>", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "avg_launch_ms": col_launch_ms, "share_of_step": col_ms / args.steps / ms_step,
+                "note": "path is FP32-FFT bound (AI ~245 FLOP/B, SURVEY 8d); see roofline_fp32"}
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        roofline["traffic"] = prof.get("ka_column_pass_dram_bytes_per_launch")
+    except Exception:
+        pass
+    fp32_peak = fp32_peak_tflops(local_rank)
+    col_flops = blocks_per_step * 2.0 * R * 5 * L * 9            # FFT_512 + IFFT_512 per column, 5 N log2 N
+    row_flops = blocks_per_step * L * 5.0 * R * 8
+    roofline_fp32 = {
+        "bound": "fp32", "unit": "TFLOP/s", "peak": fp32_peak, "peak_source": "measured live: FMA loop (b2f_fp32_peak)",
+        "column": {"achieved": col_flops / (col_ms / args.steps * 1e-3) / 1e12},
+        "row": {"achieved": row_flops / (row_ms / args.steps * 1e-3) / 1e12},
+        "step": {"achieved": (col_flops + row_flops) / (ms_step * 1e-3) / 1e12},
+        "convention": "5 N log2 N per complex FFT (SURVEY 8d): 17.04 MFLOP per 131072-sample dual-pol block",
+    }
+    for k in ("column", "row", "step"):
+        roofline_fp32[k]["frac"] = roofline_fp32[k]["achieved"] / fp32_peak
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "rt_factor": world * data_sec / (ms_step * 1e-3),
+        "config": {"workload": "C2: 8 IF x 32 MHz dual-pol 2-bit VDIF (2 Gbps), %.0f s, nchan 128, freq_res 512 "
+                               "(digifil -F128:512), tscrunch 16, 8-bit Stokes I spliced to 1024 channels" % data_sec,
+                   "nif_per_gpu": NIF, "chunk_frames": cf, "l2": "inputs (15.4 GB/step) and intermediates larger than L2",
+                   "parallelism": f"subband groups x{world}, NCCL gather of 8-bit tiles" if world > 1 else "1 GPU"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": roofline, "roofline_fp32": roofline_fp32,
+        "kernel_ms_per_step": {k: v[0] / args.steps for k, v in ktimes.items() if v[1]},
+        "rows_per_step": int(rows),
+    }
+    if rank == 0 and world == 1:
+        try:
+            line["cpu_baseline"] = {k: v for k, v in cpu_arm(args.cpu_sample).items() if k != "seconds_per_step"}
+        except Exception as ex:      # never lose the GPU number to a host-side hiccup
+            line["cpu_baseline"] = {"error": repr(ex)}
+    if rank == 0:
+        print(json.dumps(line))
+    pl.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -42,7 +42,7 @@ class Counters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "frames_ok", "frames_invalid", "frames_with_fill", "fill_words", "frames_dropped",
         "frames_misplaced", "frames_badhdr", "slots_missing", "rows_produced", "rows_emitted",
-        "blocks_dirty")]
+        "blocks_dirty", "kernel_launches")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
@@ -67,6 +67,7 @@ SYMBOLS = {
     "b2f_reset_timers": (C.c_int, [C.c_void_p]),
     "b2f_decode": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                              C.c_void_p, C.c_int, C.c_int, C.POINTER(Counters)]),
+    "b2f_fp32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     "b2f_debug_copy": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
 }
 

@@ -50,10 +50,11 @@ struct b2f_plan {
     int out_elem_bits = 8;
     int64_t row_elems = 0, row_bytes = 0;
 
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr, d2h_stream = nullptr;
     bool own_stream = false;
-    cudaEvent_t ev_stage_free[2]{}, ev_h2d_done[2]{};
-    int stage_idx = 0;
+    cudaEvent_t ev_stage_free[2]{}, ev_h2d_done[2]{}, ev_out_free[2]{}, ev_kq_done[2]{};
+    int stage_idx = 0, out_idx = 0;
+    int64_t launches = 0;
 
     uint8_t* d_stage[2]{};
     size_t stage_if_stride = 0;
@@ -66,8 +67,8 @@ struct b2f_plan {
     double2* d_partial = nullptr;
     float2 *d_tab_g = nullptr, *d_tab_h = nullptr, *d_tab_w = nullptr, *d_tab_r = nullptr;
     unsigned long long* d_counters = nullptr;
-    uint8_t* d_out_stage = nullptr;
-    size_t out_stage_bytes = 0;
+    uint8_t* d_out_stage[2]{};
+    size_t out_stage_bytes[2]{};
 
     // state
     int64_t rows_base = 0;         // rows already emitted and dropped from the front of F
@@ -92,6 +93,7 @@ static const int kStatSplit = 64;
 
 template <class Fn>
 int timed(b2f_plan* pl, int kid, Fn&& fn) {
+    pl->launches++;
     if (!pl->prm.profile) {
         fn();
         pl->k_n[kid]++;
@@ -245,15 +247,19 @@ void free_plan(b2f_plan* pl) {
         if (pl->d_stage[i]) cudaFree(pl->d_stage[i]);
         if (pl->ev_stage_free[i]) cudaEventDestroy(pl->ev_stage_free[i]);
         if (pl->ev_h2d_done[i]) cudaEventDestroy(pl->ev_h2d_done[i]);
+        if (pl->ev_out_free[i]) cudaEventDestroy(pl->ev_out_free[i]);
+        if (pl->ev_kq_done[i]) cudaEventDestroy(pl->ev_kq_done[i]);
+        if (pl->d_out_stage[i]) cudaFree(pl->d_out_stage[i]);
     }
     void* bufs[] = {pl->d_compact, pl->d_wmask, pl->d_fstat, pl->d_blkdirty, pl->d_inter, pl->d_colsum,
                     pl->d_eps, pl->d_F, pl->d_mean, pl->d_scale, pl->d_partial, pl->d_tab_g, pl->d_tab_h,
-                    pl->d_tab_w, pl->d_tab_r, pl->d_counters, pl->d_out_stage};
+                    pl->d_tab_w, pl->d_tab_r, pl->d_counters};
     for (void* b : bufs)
         if (b) cudaFree(b);
     for (auto& t : pl->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     for (auto& e : pl->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     if (pl->copy_stream) cudaStreamDestroy(pl->copy_stream);
+    if (pl->d2h_stream) cudaStreamDestroy(pl->d2h_stream);
     if (pl->own_stream && pl->stream) cudaStreamDestroy(pl->stream);
     delete pl;
 }
@@ -378,9 +384,12 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
         pl->own_stream = true;
     }
     CUB(cudaStreamCreateWithFlags(&pl->copy_stream, cudaStreamNonBlocking));
+    CUB(cudaStreamCreateWithFlags(&pl->d2h_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
         CUB(cudaEventCreateWithFlags(&pl->ev_stage_free[i], cudaEventDisableTiming));
         CUB(cudaEventCreateWithFlags(&pl->ev_h2d_done[i], cudaEventDisableTiming));
+        CUB(cudaEventCreateWithFlags(&pl->ev_out_free[i], cudaEventDisableTiming));
+        CUB(cudaEventCreateWithFlags(&pl->ev_kq_done[i], cudaEventDisableTiming));
     }
     const int nif = prm->nif;
     const int64_t nbt = (int64_t)nif * pl->chunk_blocks;
@@ -437,6 +446,7 @@ int b2f_reset(b2f_plan* pl) {
     CU(cudaSetDevice(pl->prm.device));
     CU(cudaStreamSynchronize(pl->stream));
     CU(cudaStreamSynchronize(pl->copy_stream));
+    CU(cudaStreamSynchronize(pl->d2h_stream));
     return init_state(pl);
 }
 
@@ -516,6 +526,7 @@ int b2f_push(b2f_plan* pl, const void* const* frames, int64_t nframes, int on_de
         kb.block_samples = pl->M;
         const int64_t n = nframes * nif;
         k0b_finish_slots<<<(unsigned)((n + 255) / 256), 256, 0, pl->stream>>>(kb);
+        pl->launches++;
         CU(cudaGetLastError());
     }
     // ---- kernel 3a: column pass (decode fused)
@@ -598,14 +609,18 @@ int b2f_pull(b2f_plan* pl, void* out, int64_t max_rows, int out_on_device, int64
     if (!out) return fail(B2F_EINVAL, "null output buffer");
     void* dst = out;
     const size_t bytes = (size_t)n * pl->row_bytes;
-    if (!out_on_device) {
-        if (pl->out_stage_bytes < bytes) {
-            if (pl->d_out_stage) CU(cudaFree(pl->d_out_stage));
-            pl->d_out_stage = nullptr;
-            CU(cudaMalloc(&pl->d_out_stage, bytes));
-            pl->out_stage_bytes = bytes;
+    const int oi = pl->out_idx;
+    if (out_on_device != 1) {
+        if (pl->out_stage_bytes[oi] < bytes) {
+            CU(cudaStreamSynchronize(pl->d2h_stream));
+            if (pl->d_out_stage[oi]) CU(cudaFree(pl->d_out_stage[oi]));
+            pl->d_out_stage[oi] = nullptr;
+            pl->out_stage_bytes[oi] = 0;
+            CU(cudaMalloc(&pl->d_out_stage[oi], bytes));
+            pl->out_stage_bytes[oi] = bytes;
         }
-        dst = pl->d_out_stage;
+        dst = pl->d_out_stage[oi];
+        CU(cudaStreamWaitEvent(pl->stream, pl->ev_out_free[oi], 0));
     }
     KQParams kq{};
     kq.F = pl->d_F + pl->rows_off * ncol; kq.F_if_stride = pl->F_if_stride;
@@ -620,9 +635,14 @@ int b2f_pull(b2f_plan* pl, void* out, int64_t max_rows, int out_on_device, int64
     const int64_t quads = n * (pl->row_elems / 4);
     int rc = timed(pl, B2F_K_QUANT, [&] { kq_quantise<<<(unsigned)((quads + 255) / 256), 256, 0, pl->stream>>>(kq); });
     if (rc) return rc;
-    if (!out_on_device) {
-        CU(cudaMemcpyAsync(out, dst, bytes, cudaMemcpyDeviceToHost, pl->stream));
-        CU(cudaStreamSynchronize(pl->stream));
+    if (out_on_device != 1) {
+        // device -> host on its own stream so the next chunk's kernels are not held up
+        CU(cudaEventRecord(pl->ev_kq_done[oi], pl->stream));
+        CU(cudaStreamWaitEvent(pl->d2h_stream, pl->ev_kq_done[oi], 0));
+        CU(cudaMemcpyAsync(out, dst, bytes, cudaMemcpyDeviceToHost, pl->d2h_stream));
+        CU(cudaEventRecord(pl->ev_out_free[oi], pl->d2h_stream));
+        pl->out_idx ^= 1;
+        if (out_on_device == 0) CU(cudaStreamSynchronize(pl->d2h_stream));
     }
     pl->rows_held -= n;
     pl->rows_emitted += n;
@@ -636,6 +656,7 @@ int b2f_sync(b2f_plan* pl) {
     CU(cudaSetDevice(pl->prm.device));
     CU(cudaStreamSynchronize(pl->copy_stream));
     CU(cudaStreamSynchronize(pl->stream));
+    CU(cudaStreamSynchronize(pl->d2h_stream));
     return 0;
 }
 
@@ -649,6 +670,7 @@ int b2f_get_counters(b2f_plan* pl, b2f_counters* c) {
     c->fill_words = h[C_FILLWORDS]; c->frames_dropped = h[C_DROPPED]; c->frames_misplaced = h[C_MISPLACED];
     c->frames_badhdr = h[C_BADHDR]; c->slots_missing = h[C_MISSING];
     c->rows_produced = pl->rows_produced; c->rows_emitted = pl->rows_emitted; c->blocks_dirty = h[C_DIRTY];
+    c->kernel_launches = (uint64_t)pl->launches;
     return 0;
 }
 
@@ -758,6 +780,55 @@ int b2f_decode(const void* frames, int64_t nframes, int frame_bytes, int header_
     }
 #undef CUD
     cleanup();
+    return 0;
+}
+
+// FP32 FMA-loop peak of this device (the denominator of the FFT roofline: MEASURED_PEAKS.json
+// only holds the HBM copy and bf16 GEMM figures).  8 independent FMA chains per thread.
+__global__ void k_fma_peak(float* out, int iters) {
+    float a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const float b = 1.0000001f, c = 1e-7f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            a0 = fmaf(a0, b, c); a1 = fmaf(a1, b, c); a2 = fmaf(a2, b, c); a3 = fmaf(a3, b, c);
+            a4 = fmaf(a4, b, c); a5 = fmaf(a5, b, c); a6 = fmaf(a6, b, c); a7 = fmaf(a7, b, c);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+int b2f_fp32_peak(int device, double* tflops) {
+    if (!tflops) return fail(B2F_EINVAL, "null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(B2F_ECUDA, "no CUDA device");
+    }
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    float* d = nullptr;
+    CU(cudaMalloc(&d, (size_t)blocks * threads * sizeof(float)));
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a));
+    CU(cudaEventCreate(&b));
+    double best = 0;
+    for (int rep = 0; rep < 6; ++rep) {
+        CU(cudaEventRecord(a));
+        k_fma_peak<<<blocks, threads>>>(d, iters);
+        CU(cudaEventRecord(b));
+        CU(cudaEventSynchronize(b));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, a, b));
+        const double fl = 2.0 * 64.0 * iters * (double)blocks * threads;
+        if (rep >= 2) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(d);
+    *tflops = best;
     return 0;
 }
 

@@ -1,0 +1,47 @@
+"""Multi-GPU sharding of the path: subbands (IFs) are independent from VDIF bytes to
+requantised bytes -- the reference already runs one process per IF
+(/root/reference/base2fil.sh:60-66) -- so ranks take disjoint groups of IFs with no data-path
+collective.  The single exchange is the frequency splice (/root/reference/base2fil.sh:422):
+each rank's finished [rows, tile] bytes are gathered into the owner's band-ordered rows.
+torch.distributed is plumbing only (NCCL on GPUs, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+
+def shard_ifs(nif_total: int, world: int, rank: int) -> list[int]:
+    """1-based IF numbers owned by `rank`: contiguous groups, rank 0 lowest in frequency."""
+    per = (nif_total + world - 1) // world
+    lo = rank * per + 1
+    return list(range(lo, min(nif_total, lo + per - 1) + 1))
+
+
+def rank_if_plan(nif_total: int, world: int, rank: int, freq_lsb0: float, bw: float):
+    """(if numbers, signed bandwidths, centre frequencies) of one rank, following base2fil's plan
+    (/root/reference/base2fil.sh:54,65,254,407-414): IF i at freqLSB_0+(i-1)*bw, odd LSB, even USB."""
+    ifs = shard_ifs(nif_total, world, rank)
+    bws = [bw if i % 2 == 0 else -bw for i in ifs]
+    freqs = [freq_lsb0 + (i - 1) * bw for i in ifs]
+    return ifs, bws, freqs
+
+
+def gather_splice(local_rows, world: int, rank: int, dst: int = 0, group=None, out=None):
+    """Gather every rank's [rows, tile_bytes] uint8 tensor to `dst` and lay the tiles out in
+    splice order: highest sky frequency first, i.e. rank world-1's tile leftmost
+    (/root/reference/base2fil.sh:350,367).  Returns [rows, world*tile_bytes] on dst, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+
+    if world == 1:
+        return local_rows
+    rows, tile = local_rows.shape
+    if rank == dst:
+        if out is None:
+            out = torch.empty((world, rows, tile), dtype=local_rows.dtype, device=local_rows.device)
+        parts = [out[r] for r in range(world)]
+    else:
+        parts = None
+    dist.gather(local_rows.contiguous(), parts, dst=dst, group=group)
+    if rank != dst:
+        return None
+    # [world, rows, tile] -> [rows, world(descending), tile]
+    return out.flip(0).permute(1, 0, 2).reshape(rows, world * tile)

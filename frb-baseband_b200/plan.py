@@ -150,6 +150,12 @@ class Plan:
         _lib.check(_lib.lib().b2f_pull(self._h, out.ctypes.data, max_rows, 0, C.byref(n)))
         return out[: n.value]
 
+    def pull_async(self, host_ptr: int, max_rows: int) -> int:
+        """Queue finished rows into pinned host memory; call sync() before reading them."""
+        n = C.c_int64(0)
+        _lib.check(_lib.lib().b2f_pull(self._h, C.c_void_p(host_ptr), max_rows, 2, C.byref(n)))
+        return n.value
+
     def pull_device(self, dev_ptr: int, max_rows: int) -> int:
         n = C.c_int64(0)
         _lib.check(_lib.lib().b2f_pull(self._h, C.c_void_p(dev_ptr), max_rows, 1, C.byref(n)))
@@ -203,6 +209,12 @@ class Plan:
         if nb == 16:
             return raw.view(np.uint16)
         return raw.view(np.float32)
+
+
+def fp32_peak_tflops(device: int = 0) -> float:
+    v = C.c_double(0)
+    _lib.check(_lib.lib().b2f_fp32_peak(device, C.byref(v)))
+    return v.value
 
 
 def decode(frames: np.ndarray, *, frame_bytes: int = 8032, header_bytes: int = 32, in_nbit: int = 2,

@@ -104,6 +104,7 @@ typedef struct b2f_counters {
     uint64_t frames_ok, frames_invalid, frames_with_fill, fill_words;
     uint64_t frames_dropped, frames_misplaced, frames_badhdr, slots_missing;
     uint64_t rows_produced, rows_emitted, blocks_dirty;
+    uint64_t kernel_launches;     /* kernels this plan has launched since it was created */
 } b2f_counters;
 
 /* kernel ids for b2f_kernel_time */
@@ -134,8 +135,11 @@ int b2f_push(struct b2f_plan* plan, const void* const* frames, int64_t nframes, 
 /* End of scan: freeze the rescale even if fewer than interval_rows rows were seen. */
 int b2f_flush(struct b2f_plan* plan);
 
-/* Write finished, requantised, band-ordered rows to out (host or device).  Returns through
- * *nrows how many rows were written (0 while the first rescale interval is still filling). */
+/* Write finished, requantised, band-ordered rows to out.  out_on_device: 0 = host memory,
+ * returns when the rows are there; 1 = device memory, queued on the plan's stream; 2 = pinned
+ * host memory, queued on the plan's copy-out stream -- call b2f_sync before reading.  Returns
+ * through *nrows how many rows were (or will be) written: 0 while the first rescale interval
+ * is still filling. */
 int b2f_pull(struct b2f_plan* plan, void* out, int64_t max_rows, int out_on_device, int64_t* nrows);
 
 int b2f_sync(struct b2f_plan* plan);
@@ -154,6 +158,10 @@ int b2f_reset_timers(struct b2f_plan* plan);
 int b2f_decode(const void* frames, int64_t nframes, int frame_bytes, int header_bytes, int in_nbit,
                int mask_faults, int in_on_device, float* out, int out_on_device, int device,
                b2f_counters* counters);
+
+/* Measured FP32 FMA throughput of the device in TFLOP/s (roofline denominator for the
+ * channeliser; the reference path is FP32 FFTW inside digifil, process_vdif.py:157-161). */
+int b2f_fp32_peak(int device, double* tflops);
 
 /* Test hooks: copy an internal device buffer of the most recent push to the host.
  * which: 0 compact payload, 1 word mask, 2 frame status, 3 block dirty flags,

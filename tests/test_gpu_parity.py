@@ -95,7 +95,8 @@ def test_requantised_output(gpu, out_nbit):
     else:
         d = np.abs(rows.astype(np.int64) - rd.astype(np.int64))
         assert d.max() <= 1, f"max LSB diff {d.max()}"
-        assert (d != 0).mean() < 1e-3
+        # a 16-bit LSB is 1/256 of an 8-bit one, so fp32-vs-fp64 rounding flips proportionally more samples
+        assert (d != 0).mean() < (1e-3 if out_nbit == 8 else 2e-2)
     mean, scale = info["rescale"]
     assert np.allclose(mean[0, 0], ref["mean"][0], rtol=1e-5) and np.allclose(scale[0, 0], ref["scale"][0], rtol=1e-4)
 
