@@ -60,6 +60,7 @@ struct b2f_plan {
     size_t stage_if_stride = 0;
     uint8_t *d_compact = nullptr, *d_wmask = nullptr, *d_fstat = nullptr, *d_blkdirty = nullptr;
     size_t compact_stride = 0, wmask_stride = 0, fstat_stride = 0;
+    int slot_bytes = 0;
     float2 *d_inter = nullptr, *d_colsum = nullptr, *d_eps = nullptr;
     float* d_F = nullptr;
     int64_t F_if_stride = 0;
@@ -162,6 +163,27 @@ int launch_kb(b2f_plan* pl, const KBParams& kp, int grid) {
         case 512: return launch_kb_np<16, 32>(pl, kp, grid);
     }
     return fail(B2F_EUNSUPPORTED, "row length");
+}
+
+template <int NBIT>
+int launch_ka_r(b2f_plan* pl, const KAParams& ka, unsigned grid) {
+    auto go = [&](auto kern) -> int {
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KASmem<NBIT>::kBytes));
+        return timed(pl, B2F_K_COLUMN, [&] { kern<<<grid, kKAThreads, KASmem<NBIT>::kBytes, pl->stream>>>(ka); });
+    };
+    switch (pl->R) {
+        case 16: return go(ka_column_pass<NBIT, 16>);
+        case 32: return go(ka_column_pass<NBIT, 32>);
+        case 64: return go(ka_column_pass<NBIT, 64>);
+        case 128: return go(ka_column_pass<NBIT, 128>);
+        case 256: return go(ka_column_pass<NBIT, 256>);
+        case 512: return go(ka_column_pass<NBIT, 512>);
+    }
+    return fail(B2F_EUNSUPPORTED, "row length");
+}
+
+int launch_ka(b2f_plan* pl, const KAParams& ka, unsigned grid) {
+    return pl->prm.in_nbit == 2 ? launch_ka_r<2>(pl, ka, grid) : launch_ka_r<8>(pl, ka, grid);
 }
 
 void kb_shape(int R, int* TR, int* PT) {
@@ -393,7 +415,8 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
     }
     const int nif = prm->nif;
     const int64_t nbt = (int64_t)nif * pl->chunk_blocks;
-    pl->compact_stride = (size_t)((pl->chunk_frames * payload + 255) / 256 * 256);
+    pl->slot_bytes = prm->in_nbit == 2 ? 2 * payload : payload;      // 2-bit: one index byte per time sample
+    pl->compact_stride = (size_t)((pl->chunk_frames * (int64_t)pl->slot_bytes + 255) / 256 * 256);
     pl->wmask_stride = (size_t)((pl->chunk_frames * pl->groups_per_slot + 255) / 256 * 256);
     pl->fstat_stride = (size_t)((pl->chunk_frames + 255) / 256 * 256);
     CUB(cudaMalloc(&pl->d_compact, pl->compact_stride * nif));
@@ -409,8 +432,6 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
     CUB(cudaMalloc(&pl->d_scale, (size_t)nif * nprod * pl->N * sizeof(float)));
     CUB(cudaMalloc(&pl->d_partial, (size_t)nif * kStatSplit * nprod * pl->N * sizeof(double2)));
     CUB(cudaMalloc(&pl->d_counters, C_COUNT * sizeof(unsigned long long)));
-    CUB(cudaFuncSetAttribute(ka_column_pass<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KASmem<2>::kBytes));
-    CUB(cudaFuncSetAttribute(ka_column_pass<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KASmem<8>::kBytes));
 #undef CUB
     int rc = upload_tables(pl);
     if (rc) return bail(rc);
@@ -501,6 +522,7 @@ int b2f_push(b2f_plan* pl, const void* const* frames, int64_t nframes, int on_de
     k0.nframes = nframes; k0.nslots = nframes;
     k0.frame_bytes = pl->prm.frame_bytes; k0.header_bytes = pl->prm.header_bytes;
     k0.payload_bytes = (int)pl->payload; k0.groups_per_slot = (int)pl->groups_per_slot;
+    k0.slot_bytes = pl->slot_bytes;
     k0.in_nbit = pl->prm.in_nbit; k0.time_mode = pl->prm.frame_time_mode; k0.mask_faults = pl->prm.mask_faults;
     k0.fps = (int)pl->fps;
     for (int i = 0; i < nif; ++i) {
@@ -542,10 +564,7 @@ int b2f_push(b2f_plan* pl, const void* const* frames, int64_t nframes, int on_de
         const int64_t work = (int64_t)nif * nblk * pl->nstrips;
         int64_t grid = std::max<int64_t>(1, (2 * pl->num_sms) / pl->nstrips) * pl->nstrips;
         grid = std::min<int64_t>(grid, work);
-        if (pl->prm.in_nbit == 2)
-            rc = timed(pl, B2F_K_COLUMN, [&] { ka_column_pass<2><<<(unsigned)grid, kKAThreads, KASmem<2>::kBytes, pl->stream>>>(ka); });
-        else
-            rc = timed(pl, B2F_K_COLUMN, [&] { ka_column_pass<8><<<(unsigned)grid, kKAThreads, KASmem<8>::kBytes, pl->stream>>>(ka); });
+        rc = launch_ka(pl, ka, (unsigned)grid);
         if (rc) return rc;
     }
     // ---- kernel 3b: eps
@@ -562,10 +581,11 @@ int b2f_push(b2f_plan* pl, const void* const* frames, int64_t nframes, int on_de
         kb.nblk = (int)nblk; kb.nif = nif; kb.D = pl->D; kb.mode = pl->prm.pol_mode;
         int TR, PT;
         kb_shape(pl->R, &TR, &PT);
-        const int NRS = kKBThreads / TR;
-        const int G = std::max(pl->D, NRS);
-        const int64_t ngroups = (int64_t)nif * nblk * (kL / G);
-        const int grid = (int)std::min<int64_t>(ngroups, (int64_t)pl->num_sms * 2 * 4);
+        const int RW = 32 / TR;                                   // rows per warp pass
+        const int GW = std::max(pl->D, RW);
+        const int64_t ngroups = (int64_t)nif * nblk * (kL / GW);
+        const int64_t ctas = (ngroups + kKBThreads / 32 - 1) / (kKBThreads / 32);
+        const int grid = (int)std::min<int64_t>(ctas, (int64_t)pl->num_sms * 2);     // persistent
         rc = launch_kb(pl, kb, grid);
         if (rc) return rc;
     }
@@ -745,7 +765,8 @@ int b2f_decode(const void* frames, int64_t nframes, int frame_bytes, int header_
         CUD(cudaMemcpy(d_in, frames, (size_t)nframes * frame_bytes, cudaMemcpyHostToDevice));
         src = d_in;
     }
-    CUD(cudaMalloc(&d_compact, (size_t)nframes * payload));
+    const int slot_bytes = in_nbit == 2 ? 2 * payload : payload;
+    CUD(cudaMalloc(&d_compact, (size_t)nframes * slot_bytes));
     CUD(cudaMalloc(&d_wmask, (size_t)nframes * gps));
     CUD(cudaMalloc(&d_fstat, (size_t)nframes));
     CUD(cudaMalloc(&d_dirty, 1));
@@ -759,10 +780,11 @@ int b2f_decode(const void* frames, int64_t nframes, int frame_bytes, int header_
     k0.compact = d_compact; k0.wmask = d_wmask; k0.fstat = d_fstat; k0.counters = d_cnt;
     k0.nframes = nframes; k0.nslots = nframes;
     k0.frame_bytes = frame_bytes; k0.header_bytes = header_bytes; k0.payload_bytes = payload; k0.groups_per_slot = gps;
+    k0.slot_bytes = slot_bytes;
     k0.in_nbit = in_nbit; k0.time_mode = 0; k0.mask_faults = mask_faults; k0.fps = 1;
     rc = launch_k0(nullptr, k0, 0, false);
     if (rc) { cleanup(); return rc; }
-    const int64_t nwords = nframes * (payload / 4);
+    const int64_t nwords = nframes * (int64_t)(slot_bytes / 4);      // 2-bit: index words of 4 time samples
     if (in_nbit == 2)
         k_decode<2><<<(unsigned)((nwords + 255) / 256), 256>>>(d_compact, d_wmask, payload, gps, nwords, d_out, nsamp);
     else

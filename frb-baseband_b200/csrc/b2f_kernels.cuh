@@ -88,8 +88,19 @@ struct K0Params {
     int64_t nframes, nslots;
     int frame_bytes, header_bytes, payload_bytes, groups_per_slot;
     int in_nbit, time_mode, mask_faults, fps;
+    int slot_bytes;            // bytes one frame occupies in the de-framed stream
     uint32_t base_sec[B2F_MAX_IF], base_fnum[B2F_MAX_IF];
 };
+
+// 2-bit payload word (8 time samples x 2 pols) -> 8 index bytes, one per time sample:
+// (ch1 code << 2 | ch0 code) << 3, i.e. the byte offset of that sample's (pol0, pol1) float2 in
+// the 17-entry decode table; index 16 selects the (0, 0) entry for masked samples.
+__device__ __forceinline__ uint2 expand_word_2bit(uint32_t w, bool masked) {
+    if (masked) return make_uint2(0x80808080u, 0x80808080u);
+    const uint32_t x = w & 0x0F0F0F0Fu, y = (w >> 4) & 0x0F0F0F0Fu;      // even / odd nibbles
+    const uint32_t lo = __byte_perm(x, y, 0x5140), hi = __byte_perm(x, y, 0x7362);
+    return make_uint2(lo << 3, hi << 3);
+}
 
 constexpr int kK0Threads = 128;
 constexpr int kK0Stages = 4;
@@ -151,31 +162,46 @@ __global__ void __launch_bounds__(kK0Threads) k0_validate_compact(const K0Params
         if (in_range) {
             const bool dead = invalid || bad;
             const int ngroups = p.groups_per_slot;
-            uint8_t* dst = compact + slot * (int64_t)p.payload_bytes;
+            uint8_t* dst = compact + slot * (int64_t)p.slot_bytes;
             const uint8_t* pay = buf + p.header_bytes;
+            const bool two = p.in_nbit == 2;
             for (int g = tid; g < ngroups; g += kK0Threads) {
                 uint32_t m = 0;
+                uint32_t w[8];
+                const int nw = VEC ? 8 : min(8, (p.payload_bytes - 32 * g) / 4);
                 if (VEC) {
                     const uint4 a = *reinterpret_cast<const uint4*>(pay + 32 * g);
                     const uint4 b = *reinterpret_cast<const uint4*>(pay + 32 * g + 16);
-                    m = (a.x == kFillWord) | ((a.y == kFillWord) << 1) | ((a.z == kFillWord) << 2) |
-                        ((a.w == kFillWord) << 3) | ((b.x == kFillWord) << 4) | ((b.y == kFillWord) << 5) |
-                        ((b.z == kFillWord) << 6) | ((b.w == kFillWord) << 7);
-                    *reinterpret_cast<uint4*>(dst + 32 * g) = a;
-                    *reinterpret_cast<uint4*>(dst + 32 * g + 16) = b;
+                    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
                 } else {
-                    const int nw = min(8, (p.payload_bytes - 32 * g) / 4);
-                    for (int k = 0; k < nw; ++k) {
-                        const uint32_t w = *reinterpret_cast<const uint32_t*>(pay + 32 * g + 4 * k);
-                        m |= (w == kFillWord) << k;
-                        *reinterpret_cast<uint32_t*>(dst + 32 * g + 4 * k) = w;
-                    }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        w[k] = k < nw ? *reinterpret_cast<const uint32_t*>(pay + 32 * g + 4 * k) : 0u;
                 }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) m |= (uint32_t)(k < nw && w[k] == kFillWord) << k;
                 if (!dead) nfill += __popc(m);
                 if (!p.mask_faults) m = 0;
                 else if (dead) m = 0xFF;
                 wmask[slot * (int64_t)ngroups + g] = (uint8_t)m;
                 any_fill |= (m != 0);
+                if (two) {               // 8 words -> 64 index bytes
+                    uint2 e[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) e[k] = expand_word_2bit(w[k], (m >> k) & 1);
+                    if (VEC) {
+                        uint4* d4 = reinterpret_cast<uint4*>(dst + 64 * g);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) d4[k] = make_uint4(e[2 * k].x, e[2 * k].y, e[2 * k + 1].x, e[2 * k + 1].y);
+                    } else {
+                        for (int k = 0; k < nw; ++k) reinterpret_cast<uint2*>(dst + 64 * g)[k] = e[k];
+                    }
+                } else if (VEC) {
+                    *reinterpret_cast<uint4*>(dst + 32 * g) = make_uint4(w[0], w[1], w[2], w[3]);
+                    *reinterpret_cast<uint4*>(dst + 32 * g + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+                } else {
+                    for (int k = 0; k < nw; ++k) *reinterpret_cast<uint32_t*>(dst + 32 * g + 4 * k) = w[k];
+                }
             }
         }
         // barrier: everybody is done with buf; also reduces the fill flag
@@ -249,27 +275,25 @@ __global__ void k_decode(const uint8_t* __restrict__ compact, const uint8_t* __r
     const int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (w >= nwords) return;
     const uint32_t v = reinterpret_cast<const uint32_t*>(compact)[w];
-    const int words_per_slot = payload_bytes / 4;
-    const int64_t slot = w / words_per_slot;
-    const int ws = (int)(w % words_per_slot);
-    const bool bad = (wmask[slot * groups_per_slot + (ws >> 3)] >> (ws & 7)) & 1;
     if (NBIT == 2) {
-        float a[8], b[8];
+        // w counts index words: 4 time samples each, masking already folded into the index
+        float a[4], b[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const uint32_t c0 = (v >> (4 * k)) & 3u, c1 = (v >> (4 * k + 2)) & 3u;
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t idx = ((v >> (8 * k)) & 255u) >> 3;
+            const uint32_t c0 = idx & 3u, c1 = (idx >> 2) & 3u;
             const float m0 = (c0 == 0 || c0 == 3) ? kLevHi : kLevLo;
             const float m1 = (c1 == 0 || c1 == 3) ? kLevHi : kLevLo;
-            a[k] = bad ? 0.f : ((c0 & 2) ? m0 : -m0);
-            b[k] = bad ? 0.f : ((c1 & 2) ? m1 : -m1);
+            a[k] = idx >= 16 ? 0.f : ((c0 & 2) ? m0 : -m0);
+            b[k] = idx >= 16 ? 0.f : ((c1 & 2) ? m1 : -m1);
         }
-        float4* o0 = reinterpret_cast<float4*>(out + w * 8);
-        float4* o1 = reinterpret_cast<float4*>(out + nsamp + w * 8);
-        o0[0] = make_float4(a[0], a[1], a[2], a[3]);
-        o0[1] = make_float4(a[4], a[5], a[6], a[7]);
-        o1[0] = make_float4(b[0], b[1], b[2], b[3]);
-        o1[1] = make_float4(b[4], b[5], b[6], b[7]);
+        reinterpret_cast<float4*>(out)[w] = make_float4(a[0], a[1], a[2], a[3]);
+        reinterpret_cast<float4*>(out + nsamp)[w] = make_float4(b[0], b[1], b[2], b[3]);
     } else {
+        const int words_per_slot = payload_bytes / 4;
+        const int64_t slot = w / words_per_slot;
+        const int ws = (int)(w % words_per_slot);
+        const bool bad = (wmask[slot * groups_per_slot + (ws >> 3)] >> (ws & 7)) & 1;
         float2* o0 = reinterpret_cast<float2*>(out + w * 2);
         float2* o1 = reinterpret_cast<float2*>(out + nsamp + w * 2);
         const float x0 = bad ? 0.f : (float)(v & 255u) - 127.5f, y0 = bad ? 0.f : (float)((v >> 8) & 255u) - 127.5f;
@@ -301,12 +325,16 @@ struct KAParams {
 
 template <int NBIT>
 struct KASmem {
-    static constexpr int kPiece = NBIT == 2 ? 8 : 32;          // raw bytes per (row, strip)
+    static constexpr int kPiece = NBIT == 2 ? 16 : 32;         // staged bytes per (row, strip)
     static constexpr int kRawBytes = kL * kPiece;
-    static constexpr size_t kBytes = (size_t)(kL * 16 + 512 + 512 + 512 + 256 + 16) * sizeof(float2) + 2 * kRawBytes;
+    static constexpr int kLutEntries = NBIT == 2 ? 32 : 0;      // index byte >> 3 -> (pol0, pol1); 16 = zero
+    static constexpr size_t kBytes =
+        (size_t)(kL * 16 + 512 + 512 + 512 + 256 + kLutEntries) * sizeof(float2) + 2 * kRawBytes;
 };
 
-template <int NBIT>
+// R (row length = 2*nchan) is a template parameter so that every global and shared address
+// in the loop body is base + immediate.
+template <int NBIT, int R>
 __global__ void __launch_bounds__(kKAThreads, 2) ka_column_pass(const KAParams p) {
     using S = KASmem<NBIT>;
     extern __shared__ __align__(16) uint8_t ka_smem[];
@@ -315,13 +343,12 @@ __global__ void __launch_bounds__(kKAThreads, 2) ka_column_pass(const KAParams p
     float2* s_wT = s_w + 512;                                // [16][32]
     float2* s_h = s_wT + 512;                                // [32][16 lanes]
     float2* s_g = s_h + 512;                                 // [16][16 lanes]
-    float2* s_lut = s_g + 256;                               // [16] nibble -> (pol0, pol1)
-    uint8_t* s_raw = reinterpret_cast<uint8_t*>(s_lut + 16); // [2][512][kPiece]
+    float2* s_lut = s_g + 256;                               // 17 used: sample index -> (pol0, pol1)
+    uint8_t* s_raw = reinterpret_cast<uint8_t*>(s_lut + S::kLutEntries);   // [2][512][kPiece]
 
     const int tid = threadIdx.x;
     const int lane16 = tid & 15;
     const int item = tid >> 4;
-    const int R = p.R;
     const int strip = blockIdx.x % p.nstrips;
     const int n1 = strip * kStripCols + lane16;
 
@@ -332,18 +359,19 @@ __global__ void __launch_bounds__(kKAThreads, 2) ka_column_pass(const KAParams p
         s_h[i] = p.tab_h[(i >> 4) * R + strip * kStripCols + (i & 15)];
     }
     s_g[tid] = p.tab_g[(tid >> 4) * R + strip * kStripCols + (tid & 15)];
-    if (tid < 16) {
-        const int c0 = tid & 3, c1 = tid >> 2;
+    if (NBIT == 2 && tid < 32) {
+        // 16 entries span exactly the 32 banks once (conflict-free for any index pattern);
+        // entry 16 = (0, 0) is what masked samples point at
+        const int c0 = tid & 3, c1 = (tid >> 2) & 3;
         const float m0 = (c0 == 0 || c0 == 3) ? kLevHi : kLevLo;
         const float m1 = (c1 == 0 || c1 == 3) ? kLevHi : kLevLo;
-        s_lut[tid] = make_float2((c0 & 2) ? m0 : -m0, (c1 & 2) ? m1 : -m1);
+        s_lut[tid] = tid < 16 ? make_float2((c0 & 2) ? m0 : -m0, (c1 & 2) ? m1 : -m1) : make_float2(0.f, 0.f);
     }
 
     const int64_t nbt = (int64_t)p.nif * p.nblk;
     const int64_t first = blockIdx.x / p.nstrips;
     const int64_t step = gridDim.x / p.nstrips;
-    const int bytes_per_samp4 = NBIT == 2 ? 1 : 4;            // bytes per 2 time samples (both pols)
-    const int64_t row_bytes = (int64_t)R * bytes_per_samp4 / 2;
+    const int64_t row_bytes = (int64_t)R * (NBIT == 2 ? 1 : 2);   // stream bytes per time sample: 1 index / 2 raw
     const int64_t blk_bytes = row_bytes * kL;
 
     auto issue_raw = [&](int64_t gb, int buf) {
@@ -355,7 +383,7 @@ __global__ void __launch_bounds__(kKAThreads, 2) ka_column_pass(const KAParams p
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const int row = tid + k * kKAThreads;
-                cp_async8(dst + row * 8, src + row * row_bytes);
+                cp_async16(dst + row * 16, src + row * row_bytes);
             }
         } else {
 #pragma unroll
@@ -369,16 +397,20 @@ __global__ void __launch_bounds__(kKAThreads, 2) ka_column_pass(const KAParams p
 
     if (first < nbt) issue_raw(first, 0);
     cp_async_commit();
+    uint8_t dirty_next = first < nbt ? p.blkdirty[first] : 0;
 
     int it = 0;
     for (int64_t gb = first; gb < nbt; gb += step, ++it) {
         const int buf = it & 1;
-        if (gb + step < nbt) issue_raw(gb + step, buf ^ 1);
+        const bool dirty = dirty_next != 0;
+        if (gb + step < nbt) {
+            issue_raw(gb + step, buf ^ 1);
+            dirty_next = p.blkdirty[gb + step];           // consumed one work item later
+        }
         cp_async_commit();
         cp_async_wait<1>();
         __syncthreads();
 
-        const bool dirty = p.blkdirty[gb] != 0;
         const uint8_t* raw = s_raw + buf * S::kRawBytes;
         const int ifi = (int)(gb / p.nblk);
         const int64_t blk = gb % p.nblk;
@@ -392,20 +424,18 @@ __global__ void __launch_bounds__(kKAThreads, 2) ka_column_pass(const KAParams p
             for (int r = 0; r < 16; ++r) {
                 const int row = 32 * r + l;
                 if (NBIT == 2) {
-                    const uint32_t b = raw[row * 8 + (lane16 >> 1)];
-                    v[r] = s_lut[(b >> ((lane16 & 1) * 4)) & 15u];
+                    v[r] = *reinterpret_cast<const float2*>(reinterpret_cast<const uint8_t*>(s_lut) + raw[row * 16 + lane16]);
                 } else {
                     const uint32_t b = *reinterpret_cast<const uint16_t*>(raw + row * 32 + lane16 * 2);
                     v[r] = make_float2((float)(b & 255u) - 127.5f, (float)(b >> 8) - 127.5f);
                 }
             }
-            if (dirty) {
+            if (NBIT == 8 && dirty) {
                 const uint8_t* wm = p.wmask + ifi * p.wmask_stride;
 #pragma unroll 1
                 for (int r = 0; r < 16; ++r) {
                     const int row = 32 * r + l;
-                    const int64_t off = blk * blk_bytes + row * row_bytes + (int64_t)strip * S::kPiece +
-                                        (NBIT == 2 ? (lane16 >> 1) : lane16 * 2);
+                    const int64_t off = blk * blk_bytes + row * row_bytes + (int64_t)strip * S::kPiece + lane16 * 2;
                     const int64_t slot = off / p.payload_bytes;
                     const int w = (int)(off % p.payload_bytes) >> 2;
                     if ((wm[slot * p.groups_per_slot + (w >> 3)] >> (w & 7)) & 1) {
@@ -464,7 +494,9 @@ __global__ void __launch_bounds__(kKAThreads, 2) ka_column_pass(const KAParams p
             for (int q = 1; q < 16; ++q) y[q] = cmul(y[q], s_g[q * 16 + lane16]);
             fft_inreg<16, true>(y);
 #pragma unroll
-            for (int m2 = 0; m2 < 16; ++m2) dst[(int64_t)(m1 + 32 * m2) * R] = y[m2];
+            float2* d1 = dst + m1 * R;
+#pragma unroll
+            for (int m2 = 0; m2 < 16; ++m2) d1[32 * m2 * R] = y[m2];
         }
         __syncthreads();
     }
@@ -539,108 +571,162 @@ __device__ __forceinline__ void detect_acc(float (&acc)[NPROD], float2 P, float2
 
 template <int TR, int PT, int NPROD>
 struct KBSmem {
-    static constexpr int NRS = kKBThreads / TR;
-    static constexpr int N = TR * PT / 2;
-    static constexpr size_t kXch = (size_t)NRS * TR * (PT + 1) * sizeof(float2);
-    static constexpr size_t kRed = (size_t)NRS * NPROD * N * sizeof(float);
-    static constexpr size_t kTw = (size_t)PT * TR * sizeof(float2);
-    static constexpr size_t kBytes = kXch + kRed + kTw;
+    static constexpr int R = TR * PT;
+    static constexpr int N = R / 2;
+    static constexpr int RW = 32 / TR;                          // rows one warp transforms per pass
+    static constexpr int kWarps = kKBThreads / 32;
+    // rows of different row slots that share a half-warp must not share banks: short rows are padded
+    static constexpr int kPitch = R * (int)sizeof(float2) + (TR < 16 ? TR * (int)sizeof(float2) : 0);
+    static constexpr int kRows = RW * kPitch;
+    static constexpr int kXch = RW * TR * (PT + 1) * (int)sizeof(float2);   // aliases the rows just consumed
+    static constexpr int kBody = kRows > kXch ? kRows : kXch;
+    static constexpr int kEps = N * (int)sizeof(float2);
+    static constexpr int kStage = (kBody + kEps + 127) / 128 * 128;
+    static constexpr int kWarpBytes = 2 * kStage;
+    static constexpr int kTw = PT * TR * (int)sizeof(float2);
+    static constexpr size_t kBytes = 128 + (size_t)kWarps * kWarpBytes + kTw;
 };
 
+// Every warp is its own pipeline: it owns whole time-integration groups (D consecutive rows
+// of one FFT block), walks them RW rows per pass, and keeps a private two-stage TMA ring
+// (cp.async.bulk + mbarrier) so the next pass's rows land in shared memory while this pass is
+// transformed.  Nothing in the loop synchronises the block.
 template <int TR, int PT, int NPROD>
 __global__ void __launch_bounds__(kKBThreads, 2) kb_row_pass(const KBParams p) {
-    constexpr int R = TR * PT, N = R / 2, NRS = kKBThreads / TR, QPT = PT / TR, HP = TR / 2;
     using S = KBSmem<TR, PT, NPROD>;
-    extern __shared__ __align__(16) uint8_t kb_smem[];
-    float2* xch = reinterpret_cast<float2*>(kb_smem);
-    float* red = reinterpret_cast<float*>(kb_smem + S::kXch);
-    float2* s_tw = reinterpret_cast<float2*>(kb_smem + S::kXch + S::kRed);
+    constexpr int R = TR * PT, N = R / 2, RW = S::RW, QPT = PT / TR, HP = TR / 2;
+    extern __shared__ __align__(128) uint8_t kb_smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int s = lane % TR, rsw = lane / TR;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(kb_smem) + 2 * warp;
+    uint8_t* stage0 = kb_smem + 128 + (size_t)warp * S::kWarpBytes;
+    float2* s_tw = reinterpret_cast<float2*>(kb_smem + 128 + (size_t)S::kWarps * S::kWarpBytes);
 
-    const int tid = threadIdx.x;
-    const int s = tid % TR, rs = tid / TR;
     for (int i = tid; i < PT * TR; i += kKBThreads) s_tw[i] = p.tab_r[i];
+    if (lane == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        mbar_fence_init();
+    }
     __syncthreads();
 
     const int D = p.D;
-    const int G = D > NRS ? D : NRS;                // rows per group
-    const int passes = G / NRS;
-    const int nout = G / D;
-    const int rs_per_out = NRS / nout;
-    const int groups_per_blk = kL / G;
+    const int GW = D > RW ? D : RW;                 // rows per group
+    const int passes = GW / RW;
+    const int nout = GW / D;                        // output samples per group (1 unless D < RW)
+    const int slots_per_out = RW / nout;
+    const int groups_per_blk = kL / GW;
     const int64_t ngroups = (int64_t)p.nif * p.nblk * groups_per_blk;
-    float2* myx = xch + (size_t)rs * TR * (PT + 1);
+    const int64_t wstride = (int64_t)gridDim.x * S::kWarps;
 
-    for (int64_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+    auto issue = [&](int64_t grp, int pass, int buf) {
         const int64_t gb = grp / groups_per_blk;
-        const int g0 = (int)(grp % groups_per_blk) * G;
-        float2 e[QPT][HP];
-#pragma unroll
-        for (int j = 0; j < QPT; ++j)
-#pragma unroll
-            for (int pp = 0; pp < HP; ++pp) e[j][pp] = p.eps[gb * N + (s + TR * j) + PT * pp];
-        float acc[QPT][HP][NPROD];
-#pragma unroll
-        for (int j = 0; j < QPT; ++j)
-#pragma unroll
-            for (int pp = 0; pp < HP; ++pp)
-#pragma unroll
-                for (int k = 0; k < NPROD; ++k) acc[j][pp][k] = 0.f;
+        const int row0 = (int)(grp % groups_per_blk) * GW + pass * RW;
+        uint8_t* dst = stage0 + buf * S::kStage;
+        const float2* src = p.inter + (gb * (int64_t)kL + row0) * R;
+        fence_proxy_async();
+        if (lane == 0)
+            mbar_expect_tx(&mbar[buf], (uint32_t)(RW * R * sizeof(float2) + (pass == 0 ? S::kEps : 0)));
+        __syncwarp();
+        if (S::kPitch == R * (int)sizeof(float2)) {
+            if (lane == 0) bulk_g2s(dst, src, (uint32_t)(RW * R * sizeof(float2)), &mbar[buf]);
+        } else if (lane < RW) {
+            bulk_g2s(dst + lane * S::kPitch, src + (int64_t)lane * R, (uint32_t)(R * sizeof(float2)), &mbar[buf]);
+        }
+        if (lane == 0 && pass == 0) bulk_g2s(dst + S::kBody, p.eps + gb * N, (uint32_t)S::kEps, &mbar[buf]);
+    };
 
-#pragma unroll 1
-        for (int pass = 0; pass < passes; ++pass) {
-            const int row = g0 + pass * NRS + rs;
-            const float2* src = p.inter + (gb * (int64_t)kL + row) * R;
-            float2 v[PT];
-#pragma unroll
-            for (int a = 0; a < PT; ++a) v[a] = src[s + TR * a];
-            fft_inreg<PT, false>(v);
-#pragma unroll
-            for (int q = 1; q < PT; ++q) v[q] = cmul(v[q], s_tw[q * TR + s]);
-            __syncwarp();
-#pragma unroll
-            for (int q = 0; q < PT; ++q) myx[s * (PT + 1) + q] = v[q];
-            __syncwarp();
-            float2 z[QPT][TR];
-#pragma unroll
-            for (int j = 0; j < QPT; ++j)
-#pragma unroll
-                for (int t = 0; t < TR; ++t) z[j][t] = myx[t * (PT + 1) + s + TR * j];
-#pragma unroll
-            for (int j = 0; j < QPT; ++j) fft_inreg<TR, false>(z[j]);
-            // z[j][pp] = Z_c at c = (s + TR j) + PT pp.  Mirror R-1-c lives in lane s^(TR-1),
-            // register [QPT-1-j][TR-1-pp].
+    int64_t grp_cur = (int64_t)blockIdx.x * S::kWarps + warp;
+    int pass_cur = 0;
+    if (grp_cur < ngroups) issue(grp_cur, 0, 0);
+
+    float acc[QPT][HP][NPROD];
+    float2 e[QPT][HP];
+    int it = 0;
+    while (grp_cur < ngroups) {
+        const int buf = it & 1;
+        int64_t grp_nxt = grp_cur;
+        int pass_nxt = pass_cur + 1;
+        if (pass_nxt == passes) { pass_nxt = 0; grp_nxt += wstride; }
+        // stage buf^1 was last touched by this warp one iteration ago (program order): refill it
+        if (grp_nxt < ngroups) issue(grp_nxt, pass_nxt, buf ^ 1);
+
+        mbar_wait(&mbar[buf], (it >> 1) & 1);
+        uint8_t* st = stage0 + buf * S::kStage;
+        const float2* tile = reinterpret_cast<const float2*>(st + rsw * S::kPitch);
+        if (pass_cur == 0) {
+            const float2* s_eps = reinterpret_cast<const float2*>(st + S::kBody);
 #pragma unroll
             for (int j = 0; j < QPT; ++j)
 #pragma unroll
                 for (int pp = 0; pp < HP; ++pp) {
-                    const float2 a = z[j][pp];
-                    const float2 bs = z[QPT - 1 - j][TR - 1 - pp];
-                    const float bx = __shfl_xor_sync(0xffffffffu, bs.x, TR - 1);
-                    const float by = __shfl_xor_sync(0xffffffffu, bs.y, TR - 1);
-                    const float2 bp = make_float2(bx - e[j][pp].x, -by - e[j][pp].y);
-                    detect_acc<NPROD>(acc[j][pp], make_float2(a.x + bp.x, a.y + bp.y),
-                                      make_float2(a.x - bp.x, a.y - bp.y), p.mode);
+                    e[j][pp] = s_eps[(s + TR * j) + PT * pp];
+#pragma unroll
+                    for (int k = 0; k < NPROD; ++k) acc[j][pp][k] = 0.f;
                 }
         }
-        // reduce the row slots that integrate into the same output sample
+        float2 v[PT];
+#pragma unroll
+        for (int a = 0; a < PT; ++a) v[a] = tile[s + TR * a];
+        fft_inreg<PT, false>(v);
+#pragma unroll
+        for (int q = 1; q < PT; ++q) v[q] = cmul(v[q], s_tw[q * TR + s]);
+        // transpose PT x TR through the (now consumed) row area of this stage
+        float2* myx = reinterpret_cast<float2*>(st) + (size_t)rsw * TR * (PT + 1);
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < PT; ++q) myx[s * (PT + 1) + q] = v[q];
+        __syncwarp();
+        float2 z[QPT][TR];
 #pragma unroll
         for (int j = 0; j < QPT; ++j)
 #pragma unroll
-            for (int pp = 0; pp < HP; ++pp)
+            for (int t = 0; t < TR; ++t) z[j][t] = myx[t * (PT + 1) + s + TR * j];
+#pragma unroll
+        for (int j = 0; j < QPT; ++j) fft_inreg<TR, false>(z[j]);
+        // z[j][pp] = Z_c at c = (s + TR j) + PT pp.  Mirror R-1-c lives in lane s^(TR-1),
+        // register [QPT-1-j][TR-1-pp].
+#pragma unroll
+        for (int j = 0; j < QPT; ++j)
+#pragma unroll
+            for (int pp = 0; pp < HP; ++pp) {
+                const float2 a = z[j][pp];
+                const float2 bs = z[QPT - 1 - j][TR - 1 - pp];
+                const float bx = __shfl_xor_sync(0xffffffffu, bs.x, TR - 1);
+                const float by = __shfl_xor_sync(0xffffffffu, bs.y, TR - 1);
+                const float2 bp = make_float2(bx - e[j][pp].x, -by - e[j][pp].y);
+                detect_acc<NPROD>(acc[j][pp], make_float2(a.x + bp.x, a.y + bp.y),
+                                  make_float2(a.x - bp.x, a.y - bp.y), p.mode);
+            }
+        if (pass_cur == passes - 1) {
+            // add up the row slots that integrate into the same output sample
+            for (int m = TR; m < TR * slots_per_out; m <<= 1) {
+#pragma unroll
+                for (int j = 0; j < QPT; ++j)
+#pragma unroll
+                    for (int pp = 0; pp < HP; ++pp)
+#pragma unroll
+                        for (int k = 0; k < NPROD; ++k)
+                            acc[j][pp][k] += __shfl_xor_sync(0xffffffffu, acc[j][pp][k], m);
+            }
+            if (rsw % slots_per_out == 0) {
+                const int64_t gb = grp_cur / groups_per_blk;
+                const int ifi = (int)(gb / p.nblk);
+                const int64_t blk = gb % p.nblk;
+                const int g0 = (int)(grp_cur % groups_per_blk) * GW;
+                const int64_t t = p.row0 + (blk * kL + g0) / D + rsw / slots_per_out;
+                float* dst = p.F + ifi * p.F_if_stride + t * (int64_t)(NPROD * N);
 #pragma unroll
                 for (int k = 0; k < NPROD; ++k)
-                    red[(rs * NPROD + k) * N + (s + TR * j) + PT * pp] = acc[j][pp][k];
-        __syncthreads();
-        const int ifi = (int)(gb / p.nblk);
-        const int64_t blk = gb % p.nblk;
-        const int64_t t0 = p.row0 + (blk * kL + g0) / D;
-        for (int idx = tid; idx < nout * NPROD * N; idx += kKBThreads) {
-            const int o = idx / (NPROD * N), rem = idx % (NPROD * N);
-            float sum = 0.f;
-            for (int r = 0; r < rs_per_out; ++r) sum += red[(o * rs_per_out + r) * NPROD * N + rem];
-            p.F[ifi * p.F_if_stride + (t0 + o) * (int64_t)(NPROD * N) + rem] = sum;
+#pragma unroll
+                    for (int j = 0; j < QPT; ++j)
+#pragma unroll
+                        for (int pp = 0; pp < HP; ++pp) dst[k * N + (s + TR * j) + PT * pp] = acc[j][pp][k];
+            }
         }
-        __syncthreads();
+        grp_cur = grp_nxt;
+        pass_cur = pass_nxt;
+        ++it;
     }
 }
 
