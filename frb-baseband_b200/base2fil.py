@@ -1,0 +1,162 @@
+"""Scan-level driver: every subband of a scan through one GPU plan, spliced in device memory.
+
+This replaces lines 387-448 of /root/reference/base2fil.sh -- the fan-out of one background
+`process_vdif`/`digifil` per IF into FIFOs plus the `splice` that joins them -- with a single
+call that writes the final file base2fil names
+    ${outdir}/${experiment}_${st}_no0${scanname}_IFall_vdif_pol${pol}.fil        (base2fil.sh:389)
+from the split files
+    ${workdir_odd|even}/${experiment}_${st}_no0${scanname}_IF${i}.vdif          (base2fil.sh:336,353)
+Everything around it in base2fil.sh (jive5ab split, FETCH submission, folding) is untouched;
+INTEGRATION.md shows the ten-line change that calls this instead of run_process_vdif+splice.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+from . import sigproc, vdif
+from .conf import FrbConf, read_conf
+from .plan import Plan, PlanConfig, pol_mode_from_reference
+
+#: /root/reference/base2fil.sh:149-169
+STATION_CODES = dict(zip(
+    "onsala85 onsala60 srt wsrt effelsberg torun tianma irbene irbene16 medicina noto urumqi badary svetloe".split(),
+    "o8 o6 sr wb ef tr t6 ir ib mc nt ur bd sv".split()))
+
+
+def station_code(station: str) -> str:
+    try:
+        return STATION_CODES[station.lower()]
+    except KeyError:
+        raise ValueError(f"Station {station.lower()} not known. Options are: ({' '.join(STATION_CODES)})")
+
+
+def scan_files(cfg: FrbConf, scanname: str, workdir_odd: str | None = None, workdir_even: str | None = None):
+    """{IF number: split VDIF path}; odd IFs live under workdir_odd, even under workdir_even."""
+    st = station_code(cfg.station)
+    odd = workdir_odd or os.path.join(os.path.expandvars(cfg.workdir_odd_base), cfg.experiment)
+    even = workdir_even or os.path.join(os.path.expandvars(cfg.workdir_even_base), cfg.experiment)
+    name = "%03d" % int(scanname)
+    return {i: os.path.join(odd if i % 2 else even, f"{cfg.experiment}_{st}_no0{name}_IF{i}.vdif")
+            for i in range(1, int(cfg.nif) + 1)}
+
+
+def spliced_name(cfg: FrbConf, scanname: str) -> str:
+    return f"{cfg.experiment}_{station_code(cfg.station)}_no0{'%03d' % int(scanname)}_IFall_vdif_pol{cfg.pol}.fil"
+
+
+def seconds_in_file(path: str, info: vdif.FrameInfo, datarate_mbps: int, nif: int) -> int:
+    """nsec exactly as base2fil.sh:395-402 derives it with integer `bc` arithmetic"""
+    fps_all = datarate_mbps * 1000000 // 8 // info.payload_bytes
+    return vdif.nsec_in_file(os.path.getsize(path), info.frame_bytes, fps_all // nif)
+
+
+def run_scan(files: dict[int, str], out_path: str, *, bw: float, freq_lsb0: float, nchan: int, tscrunch: int = 1,
+             pol: int = 2, nbit: int = 8, start: float = 0.0, nsec: float | None = None, keep_bandpass: bool = False,
+             source: str = "unknown", ra: str | None = None, dec: str | None = None, telescope: str = "",
+             device: int = 0, chunk_units: int = 1, verbose: bool = True) -> dict:
+    """All IFs of one scan -> one band-ordered SIGPROC filterbank.  Returns counters + geometry."""
+    ifs = sorted(files)
+    nif = len(ifs)
+    freqs = [freq_lsb0 + (i - 1) * bw for i in ifs]                    # base2fil.sh:54,65,254
+    bws = [bw if i % 2 == 0 else -bw for i in ifs]                     # odd = LSB (-l), even = USB (-u)
+    fh = [open(files[i], "rb") for i in ifs]
+    try:
+        infos = [vdif.parse_header(f.read(32)) for f in fh]
+        info = infos[0]
+        for k, other in enumerate(infos):
+            if (other.frame_bytes, other.nbit, other.header_bytes) != (info.frame_bytes, info.nbit, info.header_bytes):
+                raise ValueError(f"{files[ifs[k]]}: frame geometry differs from {files[ifs[0]]}")
+        fps = int(round(vdif.frames_per_second(bw, info)))
+        f0 = int(round(start * fps))
+        nfr = min(os.path.getsize(files[i]) // info.frame_bytes for i in ifs) - f0
+        if nsec is not None:
+            nfr = min(nfr, int(round(nsec * fps)))
+        nfr = max(nfr, 0)
+        cfg = PlanConfig(nchan=nchan, bw_mhz=bws, freq_mhz=freqs, tscrunch=max(1, tscrunch),
+                         pol_mode=pol_mode_from_reference(pol), out_nbit=nbit, in_nbit=info.nbit,
+                         frame_bytes=info.frame_bytes, header_bytes=info.header_bytes, keep_bandpass=keep_bandpass,
+                         device=device, chunk_units=chunk_units)
+        for f in fh:
+            f.seek(f0 * info.frame_bytes)
+        head = fh[0].read(32)
+        fh[0].seek(f0 * info.frame_bytes)
+        with Plan(cfg) as pl, open(out_path, "wb") as out:
+            top = max(freqs)
+            out.write(sigproc.FilHeader(
+                source_name=source, rawdatafile=os.path.basename(files[ifs[-1]]),
+                telescope_id=sigproc.TELESCOPE_IDS.get(telescope.lower(), 0),
+                src_raj=sigproc.sexagesimal_to_sigproc(ra), src_dej=sigproc.sexagesimal_to_sigproc(dec),
+                tstart=vdif.frame_mjd(vdif.parse_header(head), fps) if len(head) == 32 else 0.0, tsamp=pl.tsamp_s,
+                nbits=32 if nbit == -32 else nbit, fch1=top + bw / 2 - bw / (2 * nchan), foff=-bw / nchan,
+                nchans=nif * nchan, nifs=pl.nprod).pack())
+            cf = int(pl.chunk_frames)
+            bufs = [np.empty(cf * info.frame_bytes, np.uint8) for _ in ifs]
+            left, rows_out = nfr, 0
+            while left > 0:
+                want = min(cf, left)
+                got = min(f.readinto(memoryview(b)[: want * info.frame_bytes]) for f, b in zip(fh, bufs)) // info.frame_bytes
+                if got == 0:
+                    break
+                pl.push([b[: got * info.frame_bytes] for b in bufs])
+                pl.sync()
+                rows = pl.pull()
+                out.write(rows.tobytes())
+                rows_out += len(rows)
+                left -= got
+            pl.flush()
+            rows = pl.pull()
+            out.write(rows.tobytes())
+            rows_out += len(rows)
+            c = pl.counters()
+        if verbose:
+            print(f"b2f: {nif} IFs x {nfr / fps:.3f} s -> {out_path}: {rows_out} samples x {nif * nchan} channels; "
+                  f"frames ok/invalid/fill/bad = {c['frames_ok']}/{c['frames_invalid']}/{c['frames_with_fill']}/"
+                  f"{c['frames_badhdr']}", file=sys.stderr)
+        return {"rows": rows_out, "counters": c, "nchans": nif * nchan, "tsamp_s": pl.tsamp_s}
+    finally:
+        for f in fh:
+            f.close()
+
+
+def base2fil(conf_path: str, *, device: int = 0, workdir_odd: str | None = None, workdir_even: str | None = None,
+             outdir: str | None = None) -> list[str]:
+    """Filterbank stage of `base2fil <conf>` for scans whose split VDIF files already exist."""
+    cfg = read_conf(conf_path)
+    outdir = outdir or os.path.join(os.path.expandvars(cfg.outdir_base), cfg.experiment)
+    os.makedirs(outdir, exist_ok=True)
+    targ = cfg.target_args()
+    source = targ[0] if targ else "unknown"
+    ra = dec = None
+    for k, tok in enumerate(targ):
+        if tok == "--ra" and k + 1 < len(targ):
+            ra = targ[k + 1]
+        elif tok.startswith("--ra="):
+            ra = tok[5:]
+        elif tok == "--dec" and k + 1 < len(targ):
+            dec = targ[k + 1]
+        elif tok.startswith("--dec="):
+            dec = tok[6:]
+    done = []
+    for scanname in cfg.scannames:
+        files = scan_files(cfg, scanname, workdir_odd, workdir_even)
+        out_path = os.path.join(outdir, spliced_name(cfg, scanname))
+        last = files[int(cfg.nif)]
+        if os.path.getsize(last) == 0:                      # base2fil.sh:391-394
+            open(out_path, "wb").close()
+            continue
+        with open(last, "rb") as f:
+            info = vdif.parse_header(f.read(32))
+        nsec = seconds_in_file(last, info, cfg.datarate, int(cfg.nif))
+        run_scan(files, out_path, bw=float(cfg.bw), freq_lsb0=float(cfg.freqLSB_0), nchan=int(cfg.nchan),
+                 tscrunch=int(cfg.tscrunch), pol=int(cfg.pol), nbit=int(cfg.nbit), start=float(cfg.start), nsec=nsec,
+                 keep_bandpass=int(cfg.keepBP) > 0, source=source, ra=ra, dec=dec, telescope=cfg.station, device=device)
+        done.append(out_path)
+    return done
+
+
+if __name__ == "__main__":
+    for p in base2fil(sys.argv[1]):
+        print(p)

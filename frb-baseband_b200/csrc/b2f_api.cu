@@ -6,12 +6,13 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
 #include <vector>
 
-#include "b2f_kernels.cuh"
+#include "b2f_launch.h"
 
 using namespace b2f;
 
@@ -68,6 +69,8 @@ struct b2f_plan {
     double2* d_partial = nullptr;
     float2 *d_tab_g = nullptr, *d_tab_h = nullptr, *d_tab_w = nullptr, *d_tab_r = nullptr;
     unsigned long long* d_counters = nullptr;
+    int* d_sm_slots = nullptr;
+    int stagger_cycles = 0;
     uint8_t* d_out_stage[2]{};
     size_t out_stage_bytes[2]{};
 
@@ -140,50 +143,20 @@ int nprod_of(int mode) {
     }
 }
 
-template <int TR, int PT>
-int launch_kb_np(b2f_plan* pl, const KBParams& kp, int grid) {
-    auto go = [&](auto kern, size_t smem) -> int {
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        return timed(pl, B2F_K_ROW, [&] { kern<<<grid, kKBThreads, smem, pl->stream>>>(kp); });
-    };
-    switch (pl->nprod) {
-        case 1: return go(kb_row_pass<TR, PT, 1>, KBSmem<TR, PT, 1>::kBytes);
-        case 2: return go(kb_row_pass<TR, PT, 2>, KBSmem<TR, PT, 2>::kBytes);
-        default: return go(kb_row_pass<TR, PT, 4>, KBSmem<TR, PT, 4>::kBytes);
-    }
-}
-
 int launch_kb(b2f_plan* pl, const KBParams& kp, int grid) {
-    switch (pl->R) {
-        case 16: return launch_kb_np<4, 4>(pl, kp, grid);
-        case 32: return launch_kb_np<4, 8>(pl, kp, grid);
-        case 64: return launch_kb_np<8, 8>(pl, kp, grid);
-        case 128: return launch_kb_np<8, 16>(pl, kp, grid);
-        case 256: return launch_kb_np<16, 16>(pl, kp, grid);
-        case 512: return launch_kb_np<16, 32>(pl, kp, grid);
-    }
-    return fail(B2F_EUNSUPPORTED, "row length");
-}
-
-template <int NBIT>
-int launch_ka_r(b2f_plan* pl, const KAParams& ka, unsigned grid) {
-    auto go = [&](auto kern) -> int {
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KASmem<NBIT>::kBytes));
-        return timed(pl, B2F_K_COLUMN, [&] { kern<<<grid, kKAThreads, KASmem<NBIT>::kBytes, pl->stream>>>(ka); });
-    };
-    switch (pl->R) {
-        case 16: return go(ka_column_pass<NBIT, 16>);
-        case 32: return go(ka_column_pass<NBIT, 32>);
-        case 64: return go(ka_column_pass<NBIT, 64>);
-        case 128: return go(ka_column_pass<NBIT, 128>);
-        case 256: return go(ka_column_pass<NBIT, 256>);
-        case 512: return go(ka_column_pass<NBIT, 512>);
-    }
-    return fail(B2F_EUNSUPPORTED, "row length");
+    cudaError_t e = cudaSuccess;
+    int rc = timed(pl, B2F_K_ROW, [&] { e = b2f_launch_kb(pl->R, pl->prm.pol_mode, kp, grid, pl->stream); });
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(B2F_ECUDA, std::string("row pass launch: ") + cudaGetErrorString(e));
+    return 0;
 }
 
 int launch_ka(b2f_plan* pl, const KAParams& ka, unsigned grid) {
-    return pl->prm.in_nbit == 2 ? launch_ka_r<2>(pl, ka, grid) : launch_ka_r<8>(pl, ka, grid);
+    cudaError_t e = cudaSuccess;
+    int rc = timed(pl, B2F_K_COLUMN, [&] { e = b2f_launch_ka(pl->prm.in_nbit, pl->R, ka, grid, pl->stream); });
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(B2F_ECUDA, std::string("column pass launch: ") + cudaGetErrorString(e));
+    return 0;
 }
 
 void kb_shape(int R, int* TR, int* PT) {
@@ -275,7 +248,7 @@ void free_plan(b2f_plan* pl) {
     }
     void* bufs[] = {pl->d_compact, pl->d_wmask, pl->d_fstat, pl->d_blkdirty, pl->d_inter, pl->d_colsum,
                     pl->d_eps, pl->d_F, pl->d_mean, pl->d_scale, pl->d_partial, pl->d_tab_g, pl->d_tab_h,
-                    pl->d_tab_w, pl->d_tab_r, pl->d_counters};
+                    pl->d_tab_w, pl->d_tab_r, pl->d_counters, pl->d_sm_slots};
     for (void* b : bufs)
         if (b) cudaFree(b);
     for (auto& t : pl->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
@@ -304,6 +277,15 @@ int init_state(b2f_plan* pl) {
 }
 
 }  // namespace
+
+cudaError_t b2f_launch_ka(int in_nbit, int R, const KAParams& p, unsigned grid, cudaStream_t st) {
+    return in_nbit == 2 ? b2f_launch_ka_2(R, p, grid, st) : b2f_launch_ka_8(R, p, grid, st);
+}
+cudaError_t b2f_launch_kb(int R, int mode, const KBParams& p, int grid, cudaStream_t st) {
+    if (R <= 64) return b2f_launch_kb_part0(R, mode, p, grid, st);
+    if (R == 256) return b2f_launch_kb_part2(R, mode, p, grid, st);
+    return b2f_launch_kb_part1(R, mode, p, grid, st);
+}
 
 extern "C" {
 
@@ -432,6 +414,12 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
     CUB(cudaMalloc(&pl->d_scale, (size_t)nif * nprod * pl->N * sizeof(float)));
     CUB(cudaMalloc(&pl->d_partial, (size_t)nif * kStatSplit * nprod * pl->N * sizeof(double2)));
     CUB(cudaMalloc(&pl->d_counters, C_COUNT * sizeof(unsigned long long)));
+    CUB(cudaMalloc(&pl->d_sm_slots, 1024 * sizeof(int)));
+    CUB(cudaMemset(pl->d_sm_slots, 0, 1024 * sizeof(int)));
+    {
+        const char* e = getenv("B2F_STAGGER");
+        pl->stagger_cycles = e ? atoi(e) : 0;
+    }
 #undef CUB
     int rc = upload_tables(pl);
     if (rc) return bail(rc);
@@ -561,6 +549,7 @@ int b2f_push(b2f_plan* pl, const void* const* frames, int64_t nframes, int on_de
         ka.tab_g = pl->d_tab_g; ka.tab_h = pl->d_tab_h; ka.tab_w = pl->d_tab_w;
         ka.R = pl->R; ka.nstrips = pl->nstrips; ka.nblk = (int)nblk; ka.nif = nif;
         ka.payload_bytes = (int)pl->payload; ka.groups_per_slot = (int)pl->groups_per_slot;
+        ka.sm_slots = pl->d_sm_slots; ka.stagger_cycles = pl->stagger_cycles;
         const int64_t work = (int64_t)nif * nblk * pl->nstrips;
         int64_t grid = std::max<int64_t>(1, (2 * pl->num_sms) / pl->nstrips) * pl->nstrips;
         grid = std::min<int64_t>(grid, work);
@@ -578,7 +567,7 @@ int b2f_push(b2f_plan* pl, const void* const* frames, int64_t nframes, int on_de
         kb.inter = pl->d_inter; kb.eps = pl->d_eps; kb.tab_r = pl->d_tab_r;
         kb.F = pl->d_F; kb.F_if_stride = pl->F_if_stride;
         kb.row0 = pl->rows_off + pl->rows_held;
-        kb.nblk = (int)nblk; kb.nif = nif; kb.D = pl->D; kb.mode = pl->prm.pol_mode;
+        kb.nblk = (int)nblk; kb.nif = nif; kb.D = pl->D;
         int TR, PT;
         kb_shape(pl->R, &TR, &PT);
         const int RW = 32 / TR;                                   // rows per warp pass

@@ -248,7 +248,7 @@ struct K0bParams {
     unsigned long long* counters;
     int64_t nslots; int nif, nblk, groups_per_slot, samples_per_frame; int64_t block_samples;
 };
-__global__ void k0b_finish_slots(const K0bParams p) {
+static __global__ void k0b_finish_slots(const K0bParams p) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= p.nslots * p.nif) return;
     const int ifi = (int)(i / p.nslots);
@@ -321,6 +321,8 @@ struct KAParams {
     const float2* tab_h;     // [32][R]  W_M^(16 p n1)
     const float2* tab_w;     // [32][16] W_512^(l q)
     int R, nstrips, nblk, nif, payload_bytes, groups_per_slot;
+    int* sm_slots;           // [>= #SMs] arrival counters used to stagger co-resident CTAs
+    int stagger_cycles;
 };
 
 template <int NBIT>
@@ -366,6 +368,23 @@ __global__ void __launch_bounds__(kKAThreads, 2) ka_column_pass(const KAParams p
         const float m0 = (c0 == 0 || c0 == 3) ? kLevHi : kLevLo;
         const float m1 = (c1 == 0 || c1 == 3) ? kLevHi : kLevLo;
         s_lut[tid] = tid < 16 ? make_float2((c0 & 2) ? m0 : -m0, (c1 & 2) ? m1 : -m1) : make_float2(0.f, 0.f);
+    }
+
+    // Co-resident CTAs do identical work; started together they stay in lockstep and their
+    // shared-memory bursts collide.  Every second CTA to arrive on an SM waits half a work item
+    // once, so that one CTA's exchanges hide under the other's butterflies.
+    if (p.stagger_cycles > 0) {
+        __shared__ int s_slot;
+        if (tid == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            s_slot = atomicAdd(&p.sm_slots[smid], 1) & 1;
+        }
+        __syncthreads();
+        if (s_slot) {
+            const long long t0 = clock64();
+            while (clock64() - t0 < p.stagger_cycles) {}
+        }
     }
 
     const int64_t nbt = (int64_t)p.nif * p.nblk;
@@ -416,7 +435,7 @@ __global__ void __launch_bounds__(kKAThreads, 2) ka_column_pass(const KAParams p
         const int64_t blk = gb % p.nblk;
 
         // ---- P1: decode + 16-point FFT over r (n2 = 32 r + l), twiddle W_512^(l q)
-#pragma unroll 1
+#pragma unroll
         for (int rnd = 0; rnd < 2; ++rnd) {
             const int l = item + 16 * rnd;
             float2 v[16];
@@ -484,7 +503,7 @@ __global__ void __launch_bounds__(kKAThreads, 2) ka_column_pass(const KAParams p
 
         // ---- P3: * W_M^(q n1) ; IFFT_16 over q -> m2 ; m = m1 + 32 m2
         float2* dst = p.inter + (gb * (int64_t)kL) * R + n1;
-#pragma unroll 1
+#pragma unroll
         for (int rnd = 0; rnd < 2; ++rnd) {
             const int m1 = item + 16 * rnd;
             float2 y[16];
@@ -506,7 +525,7 @@ __global__ void __launch_bounds__(kKAThreads, 2) ka_column_pass(const KAParams p
 // ================================================================== kernel 3b: eps
 // eps_c = conj(G[R-1-c] - G[(R-c) mod R]),  G = FFT_R(column sums): the one block-constant
 // term that separating the two real polarisations after the row pass needs.
-__global__ void ke_eps(const float2* __restrict__ colsum, float2* __restrict__ eps, int R) {
+static __global__ void ke_eps(const float2* __restrict__ colsum, float2* __restrict__ eps, int R) {
     extern __shared__ float2 ke_s[];
     const int t = threadIdx.x;                      // R/2 threads
     const int lg = 31 - __clz(R);
@@ -542,34 +561,44 @@ struct KBParams {
     float* F;                   // [nif][cap_rows][nprod][R/2]
     int64_t F_if_stride;        // floats between IFs
     int64_t row0;               // first output row of this push inside F
-    int nblk, nif, D, mode;
+    int nblk, nif, D;
 };
 
-template <int NPROD>
-__device__ __forceinline__ void detect_acc(float (&acc)[NPROD], float2 P, float2 Q, int mode) {
+__host__ __device__ constexpr int nprod_of_mode(int mode) {
+    return (mode == B2F_POL_COHERENCE || mode == B2F_POL_IQUV) ? 4 : (mode == B2F_POL_PPQQ ? 2 : 1);
+}
+
+// P = 2 yP, Q = 2i yQ (the un-mixed polarisations up to constant factors); MODE is compile-time
+template <int MODE>
+__device__ __forceinline__ void detect_acc(float (&acc)[nprod_of_mode(MODE)], float2 P, float2 Q) {
     const float pp = 0.25f * (P.x * P.x + P.y * P.y);
     const float qq = 0.25f * (Q.x * Q.x + Q.y * Q.y);
-    if (NPROD == 1) {
-        if (mode == B2F_POL_I) acc[0] += pp + qq;
-        else if (mode == B2F_POL_P0) acc[0] += pp;
-        else if (mode == B2F_POL_P1) acc[0] += qq;
-        else { const float s = pp + qq; acc[0] = fmaf(s, s, acc[0]); }
-    } else if (NPROD == 2) {
+    if (MODE == B2F_POL_I) {
+        acc[0] += pp + qq;
+    } else if (MODE == B2F_POL_P0) {
         acc[0] += pp;
-        acc[1 % NPROD] += qq;
+    } else if (MODE == B2F_POL_P1) {
+        acc[0] += qq;
+    } else if (MODE == B2F_POL_I2) {
+        const float s = pp + qq;
+        acc[0] = fmaf(s, s, acc[0]);
+    } else if (MODE == B2F_POL_PPQQ) {
+        acc[0] += pp;
+        acc[nprod_of_mode(MODE) > 1 ? 1 : 0] += qq;
     } else {
         // yP yQ* = (i/4) P conj(Q):  Re = -Im(P conj Q)/4,  Im = Re(P conj Q)/4
+        constexpr int n = nprod_of_mode(MODE);
         const float xr = P.x * Q.x + P.y * Q.y, xi = P.y * Q.x - P.x * Q.y;
         const float re = -0.25f * xi, im = 0.25f * xr;
-        if (mode == B2F_POL_COHERENCE) {
-            acc[0] += pp; acc[1 % NPROD] += qq; acc[2 % NPROD] += re; acc[3 % NPROD] += im;
+        if (MODE == B2F_POL_COHERENCE) {
+            acc[0] += pp; acc[1 % n] += qq; acc[2 % n] += re; acc[3 % n] += im;
         } else {
-            acc[0] += pp + qq; acc[1 % NPROD] += 2.f * re; acc[2 % NPROD] += 2.f * im; acc[3 % NPROD] += pp - qq;
+            acc[0] += pp + qq; acc[1 % n] += 2.f * re; acc[2 % n] += 2.f * im; acc[3 % n] += pp - qq;
         }
     }
 }
 
-template <int TR, int PT, int NPROD>
+template <int TR, int PT>
 struct KBSmem {
     static constexpr int R = TR * PT;
     static constexpr int N = R / 2;
@@ -591,9 +620,10 @@ struct KBSmem {
 // of one FFT block), walks them RW rows per pass, and keeps a private two-stage TMA ring
 // (cp.async.bulk + mbarrier) so the next pass's rows land in shared memory while this pass is
 // transformed.  Nothing in the loop synchronises the block.
-template <int TR, int PT, int NPROD>
+template <int TR, int PT, int MODE>
 __global__ void __launch_bounds__(kKBThreads, 2) kb_row_pass(const KBParams p) {
-    using S = KBSmem<TR, PT, NPROD>;
+    using S = KBSmem<TR, PT>;
+    constexpr int NPROD = nprod_of_mode(MODE);
     constexpr int R = TR * PT, N = R / 2, RW = S::RW, QPT = PT / TR, HP = TR / 2;
     extern __shared__ __align__(128) uint8_t kb_smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -695,8 +725,7 @@ __global__ void __launch_bounds__(kKBThreads, 2) kb_row_pass(const KBParams p) {
                 const float bx = __shfl_xor_sync(0xffffffffu, bs.x, TR - 1);
                 const float by = __shfl_xor_sync(0xffffffffu, bs.y, TR - 1);
                 const float2 bp = make_float2(bx - e[j][pp].x, -by - e[j][pp].y);
-                detect_acc<NPROD>(acc[j][pp], make_float2(a.x + bp.x, a.y + bp.y),
-                                  make_float2(a.x - bp.x, a.y - bp.y), p.mode);
+                detect_acc<MODE>(acc[j][pp], make_float2(a.x + bp.x, a.y + bp.y), make_float2(a.x - bp.x, a.y - bp.y));
             }
         if (pass_cur == passes - 1) {
             // add up the row slots that integrate into the same output sample
@@ -733,7 +762,7 @@ __global__ void __launch_bounds__(kKBThreads, 2) kb_row_pass(const KBParams p) {
 // ================================================================== kernel 5a: statistics
 // mean / sigma per (IF, product, channel) over the first rescale interval, fp64 accumulators,
 // deterministic two-level reduction.
-__global__ void ks_partial(const float* __restrict__ F, int64_t F_if_stride, int64_t rows, int ncol,
+static __global__ void ks_partial(const float* __restrict__ F, int64_t F_if_stride, int64_t rows, int ncol,
                            double2* __restrict__ partial) {
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= ncol) return;
@@ -748,7 +777,7 @@ __global__ void ks_partial(const float* __restrict__ F, int64_t F_if_stride, int
     }
     partial[((int64_t)ifi * nsplit + split) * ncol + col] = make_double2(s, ss);
 }
-__global__ void ks_final(const double2* __restrict__ partial, int nsplit, int64_t rows, int ncol,
+static __global__ void ks_final(const double2* __restrict__ partial, int nsplit, int64_t rows, int ncol,
                          float* __restrict__ mean, float* __restrict__ scale) {
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= ncol) return;
@@ -782,7 +811,7 @@ __device__ __forceinline__ float quant(float y, float dscale, float dmean, float
     return fminf(fmaxf(floorf(fmaf(y, dscale, dmean + 0.5f)), 0.f), dmax);
 }
 
-__global__ void kq_quantise(const KQParams p) {
+static __global__ void kq_quantise(const KQParams p) {
     const int64_t quads_per_row = p.out_row_elems / 4;
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= p.rows * quads_per_row) return;

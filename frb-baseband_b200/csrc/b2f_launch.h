@@ -1,0 +1,12 @@
+// Launchers of the two heavily templated kernels, compiled in separate translation units
+// (b2f_ka.cu, b2f_kb.cu with -DB2F_PART=n) so that `make -j` builds them in parallel.
+#pragma once
+#include "b2f_kernels.cuh"
+
+cudaError_t b2f_launch_ka(int in_nbit, int R, const b2f::KAParams& p, unsigned grid, cudaStream_t st);
+cudaError_t b2f_launch_kb(int R, int mode, const b2f::KBParams& p, int grid, cudaStream_t st);
+cudaError_t b2f_launch_ka_2(int R, const b2f::KAParams& p, unsigned grid, cudaStream_t st);
+cudaError_t b2f_launch_ka_8(int R, const b2f::KAParams& p, unsigned grid, cudaStream_t st);
+cudaError_t b2f_launch_kb_part0(int R, int mode, const b2f::KBParams& p, int grid, cudaStream_t st);   // R = 16, 32, 64
+cudaError_t b2f_launch_kb_part1(int R, int mode, const b2f::KBParams& p, int grid, cudaStream_t st);   // R = 128, 512
+cudaError_t b2f_launch_kb_part2(int R, int mode, const b2f::KBParams& p, int grid, cudaStream_t st);   // R = 256

@@ -1,0 +1,85 @@
+"""The reference-facing entry points on a GPU: process_vdif CLI (regular file and FIFO) and the
+scan driver, against the oracle."""
+import os
+import threading
+
+import numpy as np
+import pytest
+
+from oracle import digifil_oracle as o
+from frb_baseband_b200 import base2fil, process_vdif, sigproc, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _write_vdif(path, nframes, seed, bw, **kw):
+    v = synth.make_vdif(nframes, seed=seed, bw_mhz=bw, **kw)
+    v.tofile(path)
+    return v
+
+
+def test_process_vdif_cli_regular_file(gpu, tmp_path):
+    vd = tmp_path / "ek_ef_no0001_IF3.vdif"
+    v = _write_vdif(str(vd), 4000 + 1024, 5, 32.0, tone_frac=0.4)
+    out = tmp_path / "fil"
+    out.mkdir()
+    rc = process_vdif.main(["R3", "--ra", "01:58:00.75", "--dec=65:43:00.31", str(vd), "-f", "1318.0", "-b", "32", "-l",
+                            "--nchan", "128", "--nsec", "1", "--start", "0.256", "--force", "-t", "effelsberg", "--pol", "2",
+                            "--nthreads", "1", "--tscrunch", "16", "--fil_out_dir", str(out), "--nbit=8"])
+    assert rc == 0
+    fil = out / "ek_ef_no0001_IF3.vdif_pol2.fil"
+    assert fil.exists() and (tmp_path / "ek_ef_no0001_IF3.vdif_pol2.hdr").exists()
+    h, d = sigproc.read_fil(str(fil))
+    ref = o.digifil(v, freq_mhz=1318.0, bw_mhz=-32.0, nchan=128, tscrunch_factor=16, start_s=0.256, nsec=1.0)
+    assert (h.nchans, h.nifs, h.nbits, h.source_name, h.telescope_id) == (128, 1, 8, "R3", 8)
+    assert h.tsamp == pytest.approx(64e-6) and h.foff == pytest.approx(-0.25) and h.fch1 == pytest.approx(ref["fch1"])
+    assert h.tstart == pytest.approx(ref["tstart"], abs=1e-9)
+    assert d.shape == ref["data"].shape
+    assert np.abs(d.astype(int) - ref["data"].astype(int)).max() <= 1
+
+
+def test_process_vdif_writes_into_existing_fifo(gpu, tmp_path):
+    """base2fil.sh:348-349 makes the FIFO first; splice reads it (here: a reader thread)."""
+    vd = tmp_path / "ek_ef_no0001_IF2.vdif"
+    v = _write_vdif(str(vd), 1024, 6, 16.0)
+    fifo = tmp_path / "ek_ef_no0001_IF2.vdif_pol2.fil"
+    os.mkfifo(fifo)
+    got = {}
+
+    def reader():
+        with open(fifo, "rb") as f:
+            got["raw"] = f.read()
+
+    t = threading.Thread(target=reader)
+    t.start()
+    process_vdif.main(["SRC", "--ra", "00:00:00", "--dec", "00:00:00", str(vd), "-f", "1400", "-b", "16", "-u", "--nchan", "32",
+                       "--nsec", "10", "--start", "0", "--force", "--tscrunch", "32", "--fil_out_dir", str(tmp_path)])
+    t.join(60)
+    assert not t.is_alive() and os.path.exists(fifo)
+    h, off = sigproc.read_header(got["raw"])
+    d = np.frombuffer(got["raw"], np.uint8, offset=off).reshape(-1, 32)
+    ref = o.digifil(v, freq_mhz=1400.0, bw_mhz=16.0, nchan=32, tscrunch_factor=32)
+    assert np.abs(d.astype(int) - ref["data"].reshape(d.shape).astype(int)).max() <= 1
+
+
+def test_base2fil_conf_to_spliced_file(gpu, tmp_path):
+    """frb.conf -> final IFall file, 4 IFs x 16 MHz (BASELINE config 1, 512 Mbps reading)."""
+    odd, even, outd = tmp_path / "s0" / "c1test", tmp_path / "s1" / "c1test", tmp_path / "out"
+    for d in (odd, even):
+        d.mkdir(parents=True)
+    nif, bw = 4, 16.0
+    vd = {}
+    for i in range(1, nif + 1):
+        p = (odd if i % 2 else even) / f"c1test_o8_no0007_IF{i}.vdif"
+        vd[i] = _write_vdif(str(p), 2000, synth.config_seed(1, i), bw, tone_frac=0.15 * i)
+    c = tmp_path / "frb.conf"
+    c.write_text(f"experiment=c1test\ntarget=\"B0329+54 --ra 03:32:59.4 --dec +54:34:43.3\"\nscans=( 7 )\nskips=( 0 )\n"
+                 f"lengths=( 1 )\nscannames=( 007 )\nbw=16\nnif={nif}\nfreqLSB_0=1300.0\nstation=onsala85\nnchan=32\n"
+                 f"tscrunch=32\nworkdir_odd_base={tmp_path}/s0\nworkdir_even_base={tmp_path}/s1\noutdir_base={tmp_path}/out\n")
+    done = base2fil.base2fil(str(c))
+    assert done == [str(tmp_path / "out" / "c1test" / "c1test_o8_no0007_IFall_vdif_pol2.fil")]
+    h, d = sigproc.read_fil(done[0])
+    ref = o.base2fil(vd, nif=nif, freq_lsb0=1300.0, bw=bw, nchan=32, tscrunch_factor=32, nsec=1.0)
+    assert h.nchans == 128 and h.fch1 == pytest.approx(ref["fch1"]) and h.source_name == "B0329+54"
+    assert d.shape[0] == ref["data"].shape[0] and d.shape[2] == 128
+    assert np.abs(d[:, 0, :].astype(int) - ref["data"].astype(int)).max() <= 1
