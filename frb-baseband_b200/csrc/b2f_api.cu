@@ -71,6 +71,7 @@ struct b2f_plan {
     unsigned long long* d_counters = nullptr;
     int* d_sm_slots = nullptr;
     int stagger_cycles = 0;
+    int64_t batch_blocks = 0;      // FFT blocks per column/row launch pair (0 = whole chunk)
     uint8_t* d_out_stage[2]{};
     size_t out_stage_bytes[2]{};
 
@@ -366,6 +367,13 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
     pl->out_elem_bits = prm->out_nbit == -32 ? 32 : prm->out_nbit;
     pl->row_elems = (int64_t)prm->nif * nprod * prm->nchan;
     pl->row_bytes = pl->row_elems * pl->out_elem_bits / 8;
+    {
+        // FFT blocks per column/row launch pair.  0 = the whole push.  L2-sized sub-batches (e.g. 72
+        // blocks = 72 MiB) were measured SLOWER on B200: the per-block kernel cost is the same whether
+        // or not the intermediate stays in L2, and every extra launch costs ~7 us.
+        const char* b = getenv("B2F_BATCH_BLOCKS");
+        pl->batch_blocks = b ? atoll(b) : 0;
+    }
 
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, prm->device) != cudaSuccess) { free_plan(pl); return fail(B2F_ECUDA, "device properties"); }
@@ -405,7 +413,8 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
     CUB(cudaMalloc(&pl->d_wmask, pl->wmask_stride * nif));
     CUB(cudaMalloc(&pl->d_fstat, pl->fstat_stride * nif));
     CUB(cudaMalloc(&pl->d_blkdirty, (size_t)nbt));
-    CUB(cudaMalloc(&pl->d_inter, (size_t)nbt * L * R * sizeof(float2)));
+    const int64_t inter_blocks = pl->batch_blocks > 0 ? std::min<int64_t>(pl->batch_blocks, nbt) : nbt;
+    CUB(cudaMalloc(&pl->d_inter, (size_t)inter_blocks * L * R * sizeof(float2)));
     CUB(cudaMalloc(&pl->d_colsum, (size_t)nbt * R * sizeof(float2)));
     CUB(cudaMalloc(&pl->d_eps, (size_t)nbt * pl->N * sizeof(float2)));
     pl->F_if_stride = pl->F_cap_rows * nprod * pl->N;
@@ -539,8 +548,15 @@ int b2f_push(b2f_plan* pl, const void* const* frames, int64_t nframes, int on_de
         pl->launches++;
         CU(cudaGetLastError());
     }
-    // ---- kernel 3a: column pass (decode fused)
+    // ---- channeliser in L2-sized sub-batches: the column pass writes [nb][512][R] float2 and the
+    // row pass reads it straight back, so the intermediate never has to reach HBM.
     {
+        const int64_t nbt = (int64_t)nif * nblk;
+        const int64_t NB = pl->batch_blocks > 0 ? std::min<int64_t>(pl->batch_blocks, nbt) : nbt;
+        int TR, PT;
+        kb_shape(pl->R, &TR, &PT);
+        const int RW = 32 / TR;                                   // rows per warp pass
+        const int GW = std::max(pl->D, RW);
         KAParams ka{};
         ka.compact = pl->d_compact; ka.compact_stride = pl->compact_stride;
         ka.wmask = pl->d_wmask; ka.wmask_stride = pl->wmask_stride;
@@ -550,33 +566,34 @@ int b2f_push(b2f_plan* pl, const void* const* frames, int64_t nframes, int on_de
         ka.R = pl->R; ka.nstrips = pl->nstrips; ka.nblk = (int)nblk; ka.nif = nif;
         ka.payload_bytes = (int)pl->payload; ka.groups_per_slot = (int)pl->groups_per_slot;
         ka.sm_slots = pl->d_sm_slots; ka.stagger_cycles = pl->stagger_cycles;
-        const int64_t work = (int64_t)nif * nblk * pl->nstrips;
-        int64_t grid = std::max<int64_t>(1, (2 * pl->num_sms) / pl->nstrips) * pl->nstrips;
-        grid = std::min<int64_t>(grid, work);
-        rc = launch_ka(pl, ka, (unsigned)grid);
-        if (rc) return rc;
-    }
-    // ---- kernel 3b: eps
-    rc = timed(pl, B2F_K_EPS, [&] {
-        ke_eps<<<(unsigned)(nif * nblk), pl->R / 2, pl->R * sizeof(float2), pl->stream>>>(pl->d_colsum, pl->d_eps, pl->R);
-    });
-    if (rc) return rc;
-    // ---- kernel 3c+4: row pass + detect + tscrunch
-    {
+        {
+            const char* e = getenv("B2F_KA_VARIANT");      // timing ablations only (tools/ablate.py)
+            ka.variant = e ? atoi(e) : 0;
+        }
         KBParams kb{};
         kb.inter = pl->d_inter; kb.eps = pl->d_eps; kb.tab_r = pl->d_tab_r;
         kb.F = pl->d_F; kb.F_if_stride = pl->F_if_stride;
         kb.row0 = pl->rows_off + pl->rows_held;
         kb.nblk = (int)nblk; kb.nif = nif; kb.D = pl->D;
-        int TR, PT;
-        kb_shape(pl->R, &TR, &PT);
-        const int RW = 32 / TR;                                   // rows per warp pass
-        const int GW = std::max(pl->D, RW);
-        const int64_t ngroups = (int64_t)nif * nblk * (kL / GW);
-        const int64_t ctas = (ngroups + kKBThreads / 32 - 1) / (kKBThreads / 32);
-        const int grid = (int)std::min<int64_t>(ctas, (int64_t)pl->num_sms * 2);     // persistent
-        rc = launch_kb(pl, kb, grid);
-        if (rc) return rc;
+        for (int64_t b0 = 0; b0 < nbt; b0 += NB) {
+            const int64_t nb = std::min(NB, nbt - b0);
+            ka.gb_begin = b0; ka.gb_end = b0 + nb;
+            const int64_t work = nb * pl->nstrips;
+            int64_t grid = std::max<int64_t>(1, (kKACtasPerSM * pl->num_sms) / pl->nstrips) * pl->nstrips;
+            grid = std::min<int64_t>(grid, work);
+            rc = launch_ka(pl, ka, (unsigned)grid);
+            if (rc) return rc;
+            rc = timed(pl, B2F_K_EPS, [&] {
+                ke_eps<<<(unsigned)nb, pl->R / 2, pl->R * sizeof(float2), pl->stream>>>(pl->d_colsum + b0 * pl->R,
+                                                                                       pl->d_eps + b0 * pl->N, pl->R);
+            });
+            if (rc) return rc;
+            kb.gb_begin = b0; kb.gb_end = b0 + nb;
+            const int64_t ngroups = nb * (kL / GW);
+            const int64_t ctas = (ngroups + kKBThreads / 32 - 1) / (kKBThreads / 32);
+            rc = launch_kb(pl, kb, (int)std::min<int64_t>(ctas, (int64_t)pl->num_sms * 2));
+            if (rc) return rc;
+        }
     }
     pl->rows_held += rows;
     pl->rows_produced += rows;
@@ -856,7 +873,10 @@ int b2f_debug_copy(b2f_plan* pl, int which, void* dst, size_t nbytes, size_t* ne
         case 1: src = pl->d_wmask; n = pl->wmask_stride * nif; break;
         case 2: src = pl->d_fstat; n = pl->fstat_stride * nif; break;
         case 3: src = pl->d_blkdirty; n = (size_t)nbt; break;
-        case 4: src = pl->d_inter; n = (size_t)nbt * pl->L * pl->R * sizeof(float2); break;
+        case 4: {       // intermediate of the last sub-batch only (whole push when batching is off)
+            const int64_t nbk = pl->batch_blocks > 0 ? std::min<int64_t>(pl->batch_blocks, nbt) : nbt;
+            src = pl->d_inter; n = (size_t)nbk * pl->L * pl->R * sizeof(float2); break;
+        }
         case 5: src = pl->d_colsum; n = (size_t)nbt * pl->R * sizeof(float2); break;
         case 6: src = pl->d_eps; n = (size_t)nbt * pl->N * sizeof(float2); break;
         case 7: src = pl->d_F; n = (size_t)pl->F_if_stride * nif * sizeof(float); break;

@@ -12,8 +12,12 @@
 namespace b2f {
 
 constexpr int kL = 512;                 // column FFT length (= digifil freq_res) of the fused path
-constexpr int kStripCols = 16;          // columns per column-pass CTA
-constexpr int kKAThreads = 256;
+#ifndef B2F_STRIP_COLS
+#define B2F_STRIP_COLS 16
+#endif
+constexpr int kStripCols = B2F_STRIP_COLS;   // columns per column-pass CTA (8 or 16)
+constexpr int kKAThreads = 16 * kStripCols;  // 16 work items x columns
+constexpr int kKACtasPerSM = 32 / kStripCols;  // 4 x 128 threads or 2 x 256 threads: 16 warps per SM either way
 constexpr int kKBThreads = 256;
 constexpr uint32_t kFillWord = 0x11223344u;
 constexpr float kLevLo = 1.0f;          // standard VLBI optimal 2-bit reconstruction levels
@@ -321,36 +325,46 @@ struct KAParams {
     const float2* tab_h;     // [32][R]  W_M^(16 p n1)
     const float2* tab_w;     // [32][16] W_512^(l q)
     int R, nstrips, nblk, nif, payload_bytes, groups_per_slot;
+    int64_t gb_begin, gb_end;   // this launch covers FFT blocks [gb_begin, gb_end); inter is indexed gb - gb_begin
     int* sm_slots;           // [>= #SMs] arrival counters used to stagger co-resident CTAs
     int stagger_cycles;
+    int variant;             // 0 = product kernel; else a timing ablation
 };
 
 template <int NBIT>
 struct KASmem {
-    static constexpr int kPiece = NBIT == 2 ? 16 : 32;         // staged bytes per (row, strip)
+    static constexpr int kPiece = (NBIT == 2 ? 1 : 2) * kStripCols;   // staged bytes per (row, strip)
     static constexpr int kRawBytes = kL * kPiece;
     static constexpr int kLutEntries = NBIT == 2 ? 32 : 0;      // index byte >> 3 -> (pol0, pol1); 16 = zero
     static constexpr size_t kBytes =
-        (size_t)(kL * 16 + 512 + 512 + 512 + 256 + kLutEntries) * sizeof(float2) + 2 * kRawBytes;
+        (size_t)(kL * kStripCols + 512 + 512 + 32 * kStripCols + 16 * kStripCols + kLutEntries) * sizeof(float2) + 2 * kRawBytes;
 };
 
 // R (row length = 2*nchan) is a template parameter so that every global and shared address
 // in the loop body is base + immediate.
-template <int NBIT, int R>
-__global__ void __launch_bounds__(kKAThreads, 2) ka_column_pass(const KAParams p) {
+// VAR != 0 are timing ablations (wrong results, used by tools/ablate.py only): bit 0 drops the
+// butterflies, bit 1 the table twiddles, bit 2 the shared-memory exchanges.
+template <int NBIT, int R, int VAR = 0>
+__global__ void __launch_bounds__(kKAThreads, kKACtasPerSM) ka_column_pass(const KAParams p) {
+    constexpr bool kFFT = !(VAR & 1), kTW = !(VAR & 2), kXCH = !(VAR & 4);
+    constexpr bool kOneBlock = (VAR & 8) != 0, kNoStore = (VAR & 16) != 0;   // bit 3: all stores hit block 0; bit 4: none
     using S = KASmem<NBIT>;
     extern __shared__ __align__(16) uint8_t ka_smem[];
-    float2* data = reinterpret_cast<float2*>(ka_smem);      // [512][16]
-    float2* s_w = data + kL * 16;                            // [32][16]  W_512^(l q)
+    float2* data = reinterpret_cast<float2*>(ka_smem);      // 512 points x 16 lanes, as [256 pairs][16] float4
+    float4* data4 = reinterpret_cast<float4*>(ka_smem);
+    constexpr int C = kStripCols;
+    float2* s_w = data + kL * C;                             // [32][16]  W_512^(l q)
     float2* s_wT = s_w + 512;                                // [16][32]
-    float2* s_h = s_wT + 512;                                // [32][16 lanes]
-    float2* s_g = s_h + 512;                                 // [16][16 lanes]
-    float2* s_lut = s_g + 256;                               // 17 used: sample index -> (pol0, pol1)
+    float2* s_h = s_wT + 512;                                // [16][16 lanes] float4 = (h^p, h^(p+16))
+    float2* s_g = s_h + 32 * C;                              // [8][C lanes]  float4 = (g^q, g^(q+8))
+    float4* s_h4 = reinterpret_cast<float4*>(s_h);
+    float4* s_g4 = reinterpret_cast<float4*>(s_g);
+    float2* s_lut = s_g + 16 * C;                               // 17 used: sample index -> (pol0, pol1)
     uint8_t* s_raw = reinterpret_cast<uint8_t*>(s_lut + S::kLutEntries);   // [2][512][kPiece]
 
     const int tid = threadIdx.x;
-    const int lane16 = tid & 15;
-    const int item = tid >> 4;
+    const int lane16 = tid % C;          // column within the strip
+    const int item = tid / C;            // 0..15
     const int strip = blockIdx.x % p.nstrips;
     const int n1 = strip * kStripCols + lane16;
 
@@ -358,9 +372,15 @@ __global__ void __launch_bounds__(kKAThreads, 2) ka_column_pass(const KAParams p
         const float2 w = p.tab_w[i];
         s_w[i] = w;
         s_wT[(i & 15) * 32 + (i >> 4)] = w;
-        s_h[i] = p.tab_h[(i >> 4) * R + strip * kStripCols + (i & 15)];
     }
-    s_g[tid] = p.tab_g[(tid >> 4) * R + strip * kStripCols + (tid & 15)];
+    for (int i = tid; i < 32 * C; i += kKAThreads) {       // entry (p, lane) -> pair slot ((p & 15) * C + lane) * 2 + (p >> 4)
+        const int pp = i / C, ln = i % C;
+        s_h[((pp & 15) * C + ln) * 2 + (pp >> 4)] = p.tab_h[pp * R + strip * C + ln];
+    }
+    for (int i = tid; i < 16 * C; i += kKAThreads) {
+        const int q = i / C, ln = i % C;
+        s_g[((q & 7) * C + ln) * 2 + (q >> 3)] = p.tab_g[q * R + strip * C + ln];
+    }
     if (NBIT == 2 && tid < 32) {
         // 16 entries span exactly the 32 banks once (conflict-free for any index pattern);
         // entry 16 = (0, 0) is what masked samples point at
@@ -387,8 +407,8 @@ __global__ void __launch_bounds__(kKAThreads, 2) ka_column_pass(const KAParams p
         }
     }
 
-    const int64_t nbt = (int64_t)p.nif * p.nblk;
-    const int64_t first = blockIdx.x / p.nstrips;
+    const int64_t nbt = p.gb_end;
+    const int64_t first = p.gb_begin + blockIdx.x / p.nstrips;
     const int64_t step = gridDim.x / p.nstrips;
     const int64_t row_bytes = (int64_t)R * (NBIT == 2 ? 1 : 2);   // stream bytes per time sample: 1 index / 2 raw
     const int64_t blk_bytes = row_bytes * kL;
@@ -398,18 +418,19 @@ __global__ void __launch_bounds__(kKAThreads, 2) ka_column_pass(const KAParams p
         const int64_t blk = gb % p.nblk;
         const uint8_t* src = p.compact + ifi * p.compact_stride + blk * blk_bytes + (int64_t)strip * S::kPiece;
         uint8_t* dst = s_raw + buf * S::kRawBytes;
-        if (NBIT == 2) {
+        if (S::kPiece == 8) {
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
+            for (int k = 0; k < kL / kKAThreads; ++k) {
                 const int row = tid + k * kKAThreads;
-                cp_async16(dst + row * 16, src + row * row_bytes);
+                cp_async8(dst + row * 8, src + row * row_bytes);
             }
         } else {
+            constexpr int PPR = S::kPiece / 16;                 // 16-byte pieces per row
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int j = tid + k * kKAThreads;             // 1024 pieces of 16 B
-                const int row = j >> 1, h = j & 1;
-                cp_async16(dst + row * 32 + h * 16, src + row * row_bytes + h * 16);
+            for (int k = 0; k < kL * PPR / kKAThreads; ++k) {
+                const int j = tid + k * kKAThreads;
+                const int row = j / PPR, h = j % PPR;
+                cp_async16(dst + row * S::kPiece + h * 16, src + row * row_bytes + h * 16);
             }
         }
     };
@@ -434,47 +455,63 @@ __global__ void __launch_bounds__(kKAThreads, 2) ka_column_pass(const KAParams p
         const int ifi = (int)(gb / p.nblk);
         const int64_t blk = gb % p.nblk;
 
-        // ---- P1: decode + 16-point FFT over r (n2 = 32 r + l), twiddle W_512^(l q)
-#pragma unroll
-        for (int rnd = 0; rnd < 2; ++rnd) {
-            const int l = item + 16 * rnd;
-            float2 v[16];
+        // Shared-memory exchanges move float4 = the same element of rounds `item` and `item+16`,
+        // so every exchange is one 128-bit access per two points (the LSU instruction queue, not
+        // bandwidth, was the limiter with 64-bit accesses).
+        // ---- P1: decode + 16-point FFT over r (n2 = 32 r + l) for l = item and item+16, twiddle W_512^(l q)
+        float2 keepA[16], keepB[16];     // only live in the no-exchange ablation
+        {
+            float2 vA[16], vB[16];
 #pragma unroll
             for (int r = 0; r < 16; ++r) {
-                const int row = 32 * r + l;
+                const int rowA = 32 * r + item, rowB = rowA + 16;
                 if (NBIT == 2) {
-                    v[r] = *reinterpret_cast<const float2*>(reinterpret_cast<const uint8_t*>(s_lut) + raw[row * 16 + lane16]);
+                    vA[r] = *reinterpret_cast<const float2*>(reinterpret_cast<const uint8_t*>(s_lut) + raw[rowA * C + lane16]);
+                    vB[r] = *reinterpret_cast<const float2*>(reinterpret_cast<const uint8_t*>(s_lut) + raw[rowB * C + lane16]);
                 } else {
-                    const uint32_t b = *reinterpret_cast<const uint16_t*>(raw + row * 32 + lane16 * 2);
-                    v[r] = make_float2((float)(b & 255u) - 127.5f, (float)(b >> 8) - 127.5f);
+                    const uint32_t a = *reinterpret_cast<const uint16_t*>(raw + rowA * 2 * C + lane16 * 2);
+                    const uint32_t b = *reinterpret_cast<const uint16_t*>(raw + rowB * 2 * C + lane16 * 2);
+                    vA[r] = make_float2((float)(a & 255u) - 127.5f, (float)(a >> 8) - 127.5f);
+                    vB[r] = make_float2((float)(b & 255u) - 127.5f, (float)(b >> 8) - 127.5f);
                 }
             }
             if (NBIT == 8 && dirty) {
                 const uint8_t* wm = p.wmask + ifi * p.wmask_stride;
 #pragma unroll 1
-                for (int r = 0; r < 16; ++r) {
-                    const int row = 32 * r + l;
+                for (int rr = 0; rr < 32; ++rr) {
+                    const int r = rr & 15;
+                    const int row = 32 * r + item + (rr >> 4) * 16;
                     const int64_t off = blk * blk_bytes + row * row_bytes + (int64_t)strip * S::kPiece + lane16 * 2;
                     const int64_t slot = off / p.payload_bytes;
                     const int w = (int)(off % p.payload_bytes) >> 2;
                     if ((wm[slot * p.groups_per_slot + (w >> 3)] >> (w & 7)) & 1) {
-                        // cannot index v[] dynamically without spilling: select per r
 #pragma unroll
-                        for (int rr = 0; rr < 16; ++rr)
-                            if (rr == r) v[rr] = make_float2(0.f, 0.f);
+                        for (int k = 0; k < 16; ++k) {       // static indexing keeps v[] in registers
+                            if (k == r && rr < 16) vA[k] = make_float2(0.f, 0.f);
+                            if (k == r && rr >= 16) vB[k] = make_float2(0.f, 0.f);
+                        }
                     }
                 }
             }
-            fft_inreg<16, false>(v);
-            const float4* tw = reinterpret_cast<const float4*>(s_w + l * 16);
+            if (kFFT) { fft_inreg<16, false>(vA); fft_inreg<16, false>(vB); }
+            const float4* twA = reinterpret_cast<const float4*>(s_w + item * 16);
+            const float4* twB = reinterpret_cast<const float4*>(s_w + (item + 16) * 16);
 #pragma unroll
-            for (int q = 0; q < 16; q += 2) {
-                const float4 t = tw[q >> 1];
-                if (q) v[q] = cmul(v[q], make_float2(t.x, t.y));
-                v[q + 1] = cmul(v[q + 1], make_float2(t.z, t.w));
+            for (int q = 0; q < (kTW ? 16 : 0); q += 2) {
+                const float4 ta = twA[q >> 1], tb = twB[q >> 1];
+                if (q) vA[q] = cmul(vA[q], make_float2(ta.x, ta.y));
+                vA[q + 1] = cmul(vA[q + 1], make_float2(ta.z, ta.w));
+                if (q) vB[q] = cmul(vB[q], make_float2(tb.x, tb.y));
+                vB[q + 1] = cmul(vB[q + 1], make_float2(tb.z, tb.w));
             }
+            if (kXCH) {
 #pragma unroll
-            for (int q = 0; q < 16; ++q) data[(q * 32 + l) * 16 + lane16] = v[q];
+                for (int q = 0; q < 16; ++q)
+                    data4[(q * 16 + item) * C + lane16] = make_float4(vA[q].x, vA[q].y, vB[q].x, vB[q].y);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) { keepA[q] = vA[q]; keepB[q] = vB[q]; }
+            }
         }
         __syncthreads();
 
@@ -483,39 +520,75 @@ __global__ void __launch_bounds__(kKAThreads, 2) ka_column_pass(const KAParams p
             const int q = item;
             float2 u[32];
 #pragma unroll
-            for (int l = 0; l < 32; ++l) u[l] = data[(q * 32 + l) * 16 + lane16];
-            fft_inreg<32, false>(u);
+            for (int l = 0; l < 16; ++l) {
+                if (kXCH) {
+                    const float4 t = data4[(q * 16 + l) * C + lane16];
+                    u[l] = make_float2(t.x, t.y);
+                    u[l + 16] = make_float2(t.z, t.w);
+                } else {
+                    u[l] = keepA[l];
+                    u[l + 16] = keepB[l];
+                }
+            }
+            if (kFFT) fft_inreg<32, false>(u);
             if (q == 0) p.colsum[gb * R + n1] = u[0];          // A[k2 = 0]: column sum
 #pragma unroll
-            for (int pp = 1; pp < 32; ++pp) u[pp] = cmul(u[pp], s_h[pp * 16 + lane16]);
-            fft_inreg<32, true>(u);
+            for (int pp = 0; pp < (kTW ? 16 : 0); ++pp) {
+                const float4 h = s_h4[pp * C + lane16];
+                if (pp) u[pp] = cmul(u[pp], make_float2(h.x, h.y));
+                u[pp + 16] = cmul(u[pp + 16], make_float2(h.z, h.w));
+            }
+            if (kFFT) fft_inreg<32, true>(u);
             const float4* tw = reinterpret_cast<const float4*>(s_wT + q * 32);
 #pragma unroll
-            for (int m1 = 0; m1 < 32; m1 += 2) {
+            for (int m1 = 0; m1 < (kTW ? 32 : 0); m1 += 2) {
                 const float4 t = tw[m1 >> 1];
                 if (m1) u[m1] = cmul_conj(u[m1], make_float2(t.x, t.y));
                 u[m1 + 1] = cmul_conj(u[m1 + 1], make_float2(t.z, t.w));
             }
+            if (kXCH) {
 #pragma unroll
-            for (int m1 = 0; m1 < 32; ++m1) data[(q * 32 + m1) * 16 + lane16] = u[m1];
+                for (int m = 0; m < 16; ++m)
+                    data4[(q * 16 + m) * C + lane16] = make_float4(u[m].x, u[m].y, u[m + 16].x, u[m + 16].y);
+            } else {
+#pragma unroll
+                for (int m = 0; m < 16; ++m) { keepA[m] = u[m]; keepB[m] = u[m + 16]; }
+            }
         }
         __syncthreads();
 
-        // ---- P3: * W_M^(q n1) ; IFFT_16 over q -> m2 ; m = m1 + 32 m2
-        float2* dst = p.inter + (gb * (int64_t)kL) * R + n1;
+        // ---- P3: * W_M^(q n1) ; IFFT_16 over q -> m2 ; m = m1 + 32 m2 for m1 = item and item+16
+        {
+            float2 yA[16], yB[16];
 #pragma unroll
-        for (int rnd = 0; rnd < 2; ++rnd) {
-            const int m1 = item + 16 * rnd;
-            float2 y[16];
+            for (int q = 0; q < 16; ++q) {
+                if (kXCH) {
+                    const float4 t = data4[(q * 16 + item) * C + lane16];
+                    yA[q] = make_float2(t.x, t.y);
+                    yB[q] = make_float2(t.z, t.w);
+                } else {
+                    yA[q] = keepA[q];
+                    yB[q] = keepB[q];
+                }
+            }
 #pragma unroll
-            for (int q = 0; q < 16; ++q) y[q] = data[(q * 32 + m1) * 16 + lane16];
+            for (int q = 0; q < (kTW ? 8 : 0); ++q) {
+                const float4 g = s_g4[q * C + lane16];
+                if (q) {
+                    yA[q] = cmul(yA[q], make_float2(g.x, g.y));
+                    yB[q] = cmul(yB[q], make_float2(g.x, g.y));
+                }
+                yA[q + 8] = cmul(yA[q + 8], make_float2(g.z, g.w));
+                yB[q + 8] = cmul(yB[q + 8], make_float2(g.z, g.w));
+            }
+            if (kFFT) { fft_inreg<16, true>(yA); fft_inreg<16, true>(yB); }
+            float2* dA = p.inter + ((kOneBlock ? 0 : (gb - p.gb_begin)) * (int64_t)kL + item) * R + n1;
+            float2* dB = dA + 16 * R;
 #pragma unroll
-            for (int q = 1; q < 16; ++q) y[q] = cmul(y[q], s_g[q * 16 + lane16]);
-            fft_inreg<16, true>(y);
-#pragma unroll
-            float2* d1 = dst + m1 * R;
-#pragma unroll
-            for (int m2 = 0; m2 < 16; ++m2) d1[32 * m2 * R] = y[m2];
+            for (int m2 = 0; m2 < 16; ++m2) {
+                if (!kNoStore || yA[m2].x == 123456.789f) dA[32 * m2 * R] = yA[m2];
+                if (!kNoStore || yB[m2].x == 123456.789f) dB[32 * m2 * R] = yB[m2];
+            }
         }
         __syncthreads();
     }
@@ -562,6 +635,7 @@ struct KBParams {
     int64_t F_if_stride;        // floats between IFs
     int64_t row0;               // first output row of this push inside F
     int nblk, nif, D;
+    int64_t gb_begin, gb_end;   // FFT blocks of this launch; inter is indexed gb - gb_begin
 };
 
 __host__ __device__ constexpr int nprod_of_mode(int mode) {
@@ -646,14 +720,15 @@ __global__ void __launch_bounds__(kKBThreads, 2) kb_row_pass(const KBParams p) {
     const int nout = GW / D;                        // output samples per group (1 unless D < RW)
     const int slots_per_out = RW / nout;
     const int groups_per_blk = kL / GW;
-    const int64_t ngroups = (int64_t)p.nif * p.nblk * groups_per_blk;
+    const int64_t ngroups = (p.gb_end - p.gb_begin) * groups_per_blk;      // groups of this launch
     const int64_t wstride = (int64_t)gridDim.x * S::kWarps;
 
     auto issue = [&](int64_t grp, int pass, int buf) {
-        const int64_t gb = grp / groups_per_blk;
+        const int64_t lb = grp / groups_per_blk;                // block index inside this launch
+        const int64_t gb = p.gb_begin + lb;
         const int row0 = (int)(grp % groups_per_blk) * GW + pass * RW;
         uint8_t* dst = stage0 + buf * S::kStage;
-        const float2* src = p.inter + (gb * (int64_t)kL + row0) * R;
+        const float2* src = p.inter + (lb * (int64_t)kL + row0) * R;
         fence_proxy_async();
         if (lane == 0)
             mbar_expect_tx(&mbar[buf], (uint32_t)(RW * R * sizeof(float2) + (pass == 0 ? S::kEps : 0)));
@@ -739,7 +814,7 @@ __global__ void __launch_bounds__(kKBThreads, 2) kb_row_pass(const KBParams p) {
                             acc[j][pp][k] += __shfl_xor_sync(0xffffffffu, acc[j][pp][k], m);
             }
             if (rsw % slots_per_out == 0) {
-                const int64_t gb = grp_cur / groups_per_blk;
+                const int64_t gb = p.gb_begin + grp_cur / groups_per_blk;
                 const int ifi = (int)(gb / p.nblk);
                 const int64_t blk = gb % p.nblk;
                 const int g0 = (int)(grp_cur % groups_per_blk) * GW;
