@@ -10,8 +10,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb2f.so")
 
 POL_P0, POL_P1, POL_I, POL_I2, POL_COHERENCE, POL_IQUV, POL_PPQQ = range(7)
-K_VALIDATE, K_COLUMN, K_EPS, K_ROW, K_STATS, K_QUANT, K_DECODE = range(7)
-KERNEL_NAMES = ["validate", "column", "eps", "row", "stats", "quant", "decode"]
+K_VALIDATE, K_COLUMN, K_EPS, K_ROW, K_STATS, K_QUANT, K_DECODE, K_DEDISP = range(8)
+KERNEL_NAMES = ["validate", "column", "eps", "row", "stats", "quant", "decode", "dedisp"]
 
 EINVAL, ECUDA, ENOMEM, ESTATE, EUNSUPPORTED = -1, -2, -3, -4, -5
 
@@ -34,7 +34,7 @@ class Geometry(C.Structure):
         ("unit_frames", C.c_int64), ("unit_blocks", C.c_int64), ("chunk_frames", C.c_int64),
         ("chunk_rows", C.c_int64), ("block_samples", C.c_int64), ("samples_per_frame", C.c_int64),
         ("row_bytes", C.c_int64), ("nprod", C.c_int32), ("freq_res", C.c_int32), ("tsamp_s", C.c_double),
-        ("interval_rows", C.c_int64),
+        ("interval_rows", C.c_int64), ("nfilt_pos", C.c_int32), ("nfilt_neg", C.c_int32),
     ]
 
 

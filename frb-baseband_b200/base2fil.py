@@ -56,7 +56,7 @@ def seconds_in_file(path: str, info: vdif.FrameInfo, datarate_mbps: int, nif: in
 def run_scan(files: dict[int, str], out_path: str, *, bw: float, freq_lsb0: float, nchan: int, tscrunch: int = 1,
              pol: int = 2, nbit: int = 8, start: float = 0.0, nsec: float | None = None, keep_bandpass: bool = False,
              source: str = "unknown", ra: str | None = None, dec: str | None = None, telescope: str = "",
-             device: int = 0, chunk_units: int = 1, verbose: bool = True) -> dict:
+             device: int = 0, chunk_units: int = 0, verbose: bool = True, dm: float = 0.0, coherent: bool = False) -> dict:
     """All IFs of one scan -> one band-ordered SIGPROC filterbank.  Returns counters + geometry."""
     ifs = sorted(files)
     nif = len(ifs)
@@ -78,7 +78,7 @@ def run_scan(files: dict[int, str], out_path: str, *, bw: float, freq_lsb0: floa
         cfg = PlanConfig(nchan=nchan, bw_mhz=bws, freq_mhz=freqs, tscrunch=max(1, tscrunch),
                          pol_mode=pol_mode_from_reference(pol), out_nbit=nbit, in_nbit=info.nbit,
                          frame_bytes=info.frame_bytes, header_bytes=info.header_bytes, keep_bandpass=keep_bandpass,
-                         device=device, chunk_units=chunk_units)
+                         device=device, chunk_units=chunk_units, dm=dm, coherent=coherent and dm > 0)
         for f in fh:
             f.seek(f0 * info.frame_bytes)
         head = fh[0].read(32)

@@ -72,6 +72,14 @@ struct b2f_plan {
     int* d_sm_slots = nullptr;
     int stagger_cycles = 0;
     int64_t batch_blocks = 0;      // FFT blocks per column/row launch pair (0 = whole chunk)
+    // coherent dedispersion (digifil -D dm -F nchan:D): overlap-save geometry and halo carry
+    bool dedisp = false;
+    int nfilt_pos = 0, nfilt_neg = 0, keep = 0;
+    int64_t step = 0;              // samples between block starts = keep * R
+    int64_t carry_len = 0;         // samples of the previous push still needed (per IF)
+    uint8_t* d_carry = nullptr;
+    float2* d_spec = nullptr;
+    float2* d_chirp = nullptr;
     uint8_t* d_out_stage[2]{};
     size_t out_stage_bytes[2]{};
 
@@ -249,7 +257,7 @@ void free_plan(b2f_plan* pl) {
     }
     void* bufs[] = {pl->d_compact, pl->d_wmask, pl->d_fstat, pl->d_blkdirty, pl->d_inter, pl->d_colsum,
                     pl->d_eps, pl->d_F, pl->d_mean, pl->d_scale, pl->d_partial, pl->d_tab_g, pl->d_tab_h,
-                    pl->d_tab_w, pl->d_tab_r, pl->d_counters, pl->d_sm_slots};
+                    pl->d_tab_w, pl->d_tab_r, pl->d_counters, pl->d_sm_slots, pl->d_carry, pl->d_spec, pl->d_chirp};
     for (void* b : bufs)
         if (b) cudaFree(b);
     for (auto& t : pl->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
@@ -266,6 +274,7 @@ int init_state(b2f_plan* pl) {
     pl->flushed = false;
     pl->have_base = false;
     pl->frames_pushed = 0;
+    pl->carry_len = 0;
     pl->blocks_dirty = 0;
     pl->last_nblk = pl->last_nframes = 0;
     const int ncol = pl->nprod * pl->N;
@@ -278,6 +287,68 @@ int init_state(b2f_plan* pl) {
 }
 
 }  // namespace
+
+// Dedispersion path of one push: forward column pass -> row FFT (spectrum) -> un-mix, chirp, backward
+// column FFT, overlap discard, detect, integrate.  Leaves the unconsumed tail of the sample stream in
+// d_carry for the next push ("time-chunked coherent dedispersion carries its overlap halo").
+int push_dedisp(b2f_plan* pl, int64_t nblk, int64_t T) {
+    const int nif = pl->prm.nif;
+    const int64_t nbt = (int64_t)nif * nblk;
+    int rc = 0;
+    if (nblk > 0) {
+        const int64_t cap = pl->batch_blocks > 0 ? pl->batch_blocks : (int64_t)nif * pl->chunk_blocks;
+        const int64_t NB = std::min<int64_t>(cap, nbt);
+        KAParams ka{};
+        ka.compact = pl->d_compact; ka.compact_stride = pl->compact_stride;
+        ka.wmask = pl->d_wmask; ka.wmask_stride = pl->wmask_stride; ka.blkdirty = pl->d_blkdirty;
+        ka.inter = pl->d_inter; ka.colsum = pl->d_colsum;
+        ka.tab_g = pl->d_tab_g; ka.tab_h = pl->d_tab_h; ka.tab_w = pl->d_tab_w;
+        ka.R = pl->R; ka.nstrips = pl->nstrips; ka.nblk = (int)nblk; ka.nif = nif;
+        ka.payload_bytes = (int)pl->payload; ka.groups_per_slot = (int)pl->groups_per_slot;
+        ka.blk_step_bytes = pl->step;                             // 1 index byte per sample
+        ka.sm_slots = pl->d_sm_slots; ka.stagger_cycles = 0; ka.variant = 32;      // forward only
+        KBParams kb{};
+        kb.inter = pl->d_inter; kb.eps = nullptr; kb.tab_r = pl->d_tab_r; kb.spec = pl->d_spec;
+        kb.F = nullptr; kb.nblk = (int)nblk; kb.nif = nif; kb.D = 1;
+        KCParams kc{};
+        kc.spec = pl->d_spec; kc.chirp = pl->d_chirp; kc.tab_w = pl->d_tab_w;
+        kc.F = pl->d_F; kc.F_if_stride = pl->F_if_stride; kc.row0 = pl->rows_off + pl->rows_held;
+        kc.nblk = (int)nblk; kc.nif = nif; kc.D = pl->D; kc.mode = pl->prm.pol_mode;
+        kc.nfilt_pos = pl->nfilt_pos; kc.keep = pl->keep;
+        int TR, PT;
+        kb_shape(pl->R, &TR, &PT);
+        const int RW = 32 / TR;
+        for (int64_t b0 = 0; b0 < nbt; b0 += NB) {
+            const int64_t nb = std::min(NB, nbt - b0);
+            ka.gb_begin = b0; ka.gb_end = b0 + nb;
+            int64_t grid = std::max<int64_t>(1, (kKACtasPerSM * pl->num_sms) / pl->nstrips) * pl->nstrips;
+            grid = std::min<int64_t>(grid, nb * pl->nstrips);
+            rc = launch_ka(pl, ka, (unsigned)grid);
+            if (rc) return rc;
+            kb.gb_begin = b0; kb.gb_end = b0 + nb;
+            const int64_t ngroups = nb * (kL / RW);
+            const int64_t ctas = (ngroups + kKBThreads / 32 - 1) / (kKBThreads / 32);
+            cudaError_t e = cudaSuccess;
+            rc = timed(pl, B2F_K_ROW, [&] { e = b2f_launch_kb(pl->R, kModeSpectrum, kb, (int)std::min<int64_t>(ctas, (int64_t)pl->num_sms * 2), pl->stream); });
+            if (rc) return rc;
+            if (e != cudaSuccess) return fail(B2F_ECUDA, std::string("row pass launch: ") + cudaGetErrorString(e));
+            kc.gb_begin = b0; kc.gb_end = b0 + nb;
+            const int64_t work = nb * (pl->N / 8);
+            rc = timed(pl, B2F_K_DEDISP, [&] { e = b2f_launch_kc(pl->R, kc, (int)std::min<int64_t>(work, (int64_t)pl->num_sms * 2), pl->stream); });
+            if (rc) return rc;
+            if (e != cudaSuccess) return fail(B2F_ECUDA, std::string("dedispersion back end launch: ") + cudaGetErrorString(e));
+        }
+    }
+    // keep what the next push still needs
+    const int64_t used = nblk * pl->step;
+    const int64_t tail = T - used;
+    if (tail > pl->M) return fail(B2F_ESTATE, "internal: dedispersion carry larger than one block");
+    for (int i = 0; i < nif; ++i)
+        CU(cudaMemcpyAsync(pl->d_carry + (size_t)i * pl->M, pl->d_compact + i * pl->compact_stride + used, (size_t)tail,
+                           cudaMemcpyDeviceToDevice, pl->stream));
+    pl->carry_len = tail;
+    return 0;
+}
 
 cudaError_t b2f_launch_ka(int in_nbit, int R, const KAParams& p, unsigned grid, cudaStream_t st) {
     return in_nbit == 2 ? b2f_launch_ka_2(R, p, grid, st) : b2f_launch_ka_8(R, p, grid, st);
@@ -322,7 +393,9 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
     if (prm->header_bytes != 32 && prm->header_bytes != 16) return fail(B2F_EINVAL, "header_bytes must be 32 or 16");
     const int payload = prm->frame_bytes - prm->header_bytes;
     if (payload <= 0 || payload % 8) return fail(B2F_EINVAL, "frame_bytes");
-    if (prm->coherent || prm->dm != 0.0) return fail(B2F_EUNSUPPORTED, "coherent dedispersion not built yet");
+    const bool dedisp = prm->coherent && prm->dm > 0.0;
+    if (dedisp && prm->in_nbit != 2) return fail(B2F_EUNSUPPORTED, "coherent dedispersion needs 2-bit input in this build");
+    if (dedisp && D > 128) return fail(B2F_EUNSUPPORTED, "coherent dedispersion needs tscrunch <= 128");
     const double abw = std::fabs(prm->bw_mhz[0]);
     if (abw <= 0) return fail(B2F_EINVAL, "bw_mhz");
     for (int i = 0; i < prm->nif; ++i) {
@@ -353,13 +426,34 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
     pl->M = (int64_t)R * L;
     pl->spf = spf; pl->fps = fps; pl->payload = payload;
     pl->groups_per_slot = (payload + 31) / 32;
-    const int64_t g = std::gcd(pl->spf, pl->M);
-    pl->unit_frames = pl->M / g;
+    pl->dedisp = dedisp;
+    pl->step = pl->M;
+    pl->keep = L;
+    if (dedisp) {
+        // smearing across the lowest channel of the lowest subband (8.3 us DM dnu/nu_GHz^3, the rule of
+        // submit_job.py:62), half of it on each side plus 10 %, rounded up to a multiple of tscrunch so
+        // that every block yields whole output samples
+        double fmin = 1e30;
+        for (int i = 0; i < prm->nif; ++i) fmin = std::min(fmin, prm->freq_mhz[i] - abw / 2 + abw / prm->nchan / 2);
+        const double chbw = abw / prm->nchan;
+        const double ns = 8.3 * prm->dm * chbw / std::pow(fmin / 1000.0, 3) / ((double)prm->nchan / abw);
+        int nf = (int)std::ceil(0.55 * ns);
+        nf = (nf + D - 1) / D * D;
+        if (nf < D) nf = D;
+        if (2 * nf >= L) { delete pl; return fail(B2F_EUNSUPPORTED, "dispersion smearing exceeds half of freq_res = 512 channel samples"); }
+        pl->nfilt_pos = pl->nfilt_neg = nf;
+        pl->keep = L - 2 * nf;
+        pl->step = (int64_t)pl->keep * R;
+    }
+    const int64_t g = std::gcd(pl->spf, pl->step);
+    pl->unit_frames = pl->step / g;
     pl->unit_blocks = pl->spf / g;
-    const int cu = prm->chunk_units > 0 ? prm->chunk_units : 1;
+    int cu = prm->chunk_units > 0 ? prm->chunk_units : 1;
+    if (dedisp && prm->chunk_units <= 0) cu = (int)std::max<int64_t>(1, 1024 / pl->unit_frames);
     pl->chunk_frames = pl->unit_frames * cu;
     pl->chunk_blocks = pl->unit_blocks * cu;
-    pl->chunk_rows = pl->chunk_blocks * L / D;
+    if (dedisp) pl->chunk_blocks += 1;                         // carried samples can complete one more block
+    pl->chunk_rows = pl->chunk_blocks * pl->keep / D;
     const double tsamp = (double)D * prm->nchan / (abw * 1e6);
     const double interval = prm->rescale_interval_s > 0 ? prm->rescale_interval_s : 10.0;
     pl->interval_rows = prm->keep_bandpass ? 0 : (int64_t)llround(interval / tsamp);
@@ -406,7 +500,7 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
     const int nif = prm->nif;
     const int64_t nbt = (int64_t)nif * pl->chunk_blocks;
     pl->slot_bytes = prm->in_nbit == 2 ? 2 * payload : payload;      // 2-bit: one index byte per time sample
-    pl->compact_stride = (size_t)((pl->chunk_frames * (int64_t)pl->slot_bytes + 255) / 256 * 256);
+    pl->compact_stride = (size_t)((pl->chunk_frames * (int64_t)pl->slot_bytes + (dedisp ? pl->M : 0) + 255) / 256 * 256);
     pl->wmask_stride = (size_t)((pl->chunk_frames * pl->groups_per_slot + 255) / 256 * 256);
     pl->fstat_stride = (size_t)((pl->chunk_frames + 255) / 256 * 256);
     CUB(cudaMalloc(&pl->d_compact, pl->compact_stride * nif));
@@ -424,6 +518,26 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
     CUB(cudaMalloc(&pl->d_partial, (size_t)nif * kStatSplit * nprod * pl->N * sizeof(double2)));
     CUB(cudaMalloc(&pl->d_counters, C_COUNT * sizeof(unsigned long long)));
     CUB(cudaMalloc(&pl->d_sm_slots, 1024 * sizeof(int)));
+    if (dedisp) {
+        CUB(cudaMalloc(&pl->d_carry, (size_t)pl->M * nif));
+        CUB(cudaMalloc(&pl->d_spec, (size_t)inter_blocks * L * R * sizeof(float2)));
+        // chirp H[if][k2][c] = exp(-i 2 pi D DM 1e6 f^2 / (fc^2 (fc + f))), conjugated for LSB, in double
+        std::vector<float2> h((size_t)nif * L * prm->nchan);
+        for (int i = 0; i < nif; ++i) {
+            const double bw = prm->bw_mhz[i], chbw = bw / prm->nchan;
+            for (int c = 0; c < prm->nchan; ++c) {
+                const double fc = prm->freq_mhz[i] - bw / 2 + (c + 0.5) * chbw;
+                for (int k2 = 0; k2 < L; ++k2) {
+                    const double f = ((double)k2 / L - 0.5) * chbw;
+                    double ph = 2.0 * M_PI * (1.0 / 2.41e-4) * 1e6 * prm->dm * f * f / (fc * fc * (fc + f));
+                    if (bw < 0) ph = -ph;
+                    h[((size_t)i * L + k2) * prm->nchan + c] = make_float2((float)cos(ph), (float)-sin(ph));
+                }
+            }
+        }
+        CUB(cudaMalloc(&pl->d_chirp, h.size() * sizeof(float2)));
+        CUB(cudaMemcpy(pl->d_chirp, h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    }
     CUB(cudaMemset(pl->d_sm_slots, 0, 1024 * sizeof(int)));
     {
         const char* e = getenv("B2F_STAGGER");
@@ -455,7 +569,10 @@ int b2f_get_geometry(const b2f_plan* pl, b2f_geometry* g) {
     g->nprod = pl->nprod;
     g->freq_res = pl->L;
     g->tsamp_s = (double)pl->D * pl->N / (std::fabs(pl->prm.bw_mhz[0]) * 1e6);
+    g->unit_blocks = pl->unit_blocks;
     g->interval_rows = pl->interval_rows;
+    g->nfilt_pos = pl->nfilt_pos;
+    g->nfilt_neg = pl->nfilt_neg;
     return 0;
 }
 
@@ -474,9 +591,10 @@ int b2f_push(b2f_plan* pl, const void* const* frames, int64_t nframes, int on_de
     if (pl->flushed) return fail(B2F_ESTATE, "push after flush; call b2f_reset for a new scan");
     CU(cudaSetDevice(pl->prm.device));
     const int nif = pl->prm.nif;
-    const int64_t nblk = nframes * pl->spf / pl->M;
-    const int64_t rows = nblk * pl->L / pl->D;
-    if (nblk == 0) return 0;
+    const int64_t T = pl->carry_len + nframes * pl->spf;          // samples available per IF (carry + new)
+    const int64_t nblk = pl->dedisp ? (T >= pl->M ? (T - pl->M) / pl->step + 1 : 0) : nframes * pl->spf / pl->M;
+    const int64_t rows = nblk * pl->keep / pl->D;
+    if (nblk == 0 && !pl->dedisp) return 0;
     if (pl->rows_off + pl->rows_held + rows > pl->F_cap_rows)
         return fail(B2F_ESTATE, "row buffer full: call b2f_pull before pushing more");
     const size_t fbytes = (size_t)nframes * pl->prm.frame_bytes;
@@ -512,7 +630,7 @@ int b2f_push(b2f_plan* pl, const void* const* frames, int64_t nframes, int on_de
     }
 
     // ---- kernel 1: validate + de-frame
-    k0.compact = pl->d_compact; k0.compact_stride = pl->compact_stride;
+    k0.compact = pl->d_compact + pl->carry_len; k0.compact_stride = pl->compact_stride;   // carried halo sits in front
     k0.wmask = pl->d_wmask; k0.wmask_stride = pl->wmask_stride;
     k0.fstat = pl->d_fstat; k0.fstat_stride = pl->fstat_stride;
     k0.counters = pl->d_counters;
@@ -527,8 +645,13 @@ int b2f_push(b2f_plan* pl, const void* const* frames, int64_t nframes, int on_de
         k0.base_sec[i] = pl->base_sec0[i] + (uint32_t)(tot / pl->fps);
         k0.base_fnum[i] = (uint32_t)(tot % pl->fps);
     }
+    if (pl->dedisp && pl->carry_len) {
+        for (int i = 0; i < nif; ++i)
+            CU(cudaMemcpyAsync(pl->d_compact + i * pl->compact_stride, pl->d_carry + (size_t)i * pl->M, (size_t)pl->carry_len,
+                               cudaMemcpyDeviceToDevice, pl->stream));
+    }
     CU(cudaMemsetAsync(pl->d_fstat, 0, pl->fstat_stride * nif, pl->stream));
-    CU(cudaMemsetAsync(pl->d_blkdirty, 0, (size_t)nif * nblk, pl->stream));
+    if (nblk > 0) CU(cudaMemsetAsync(pl->d_blkdirty, 0, (size_t)nif * nblk, pl->stream));
     int rc = launch_k0(pl, k0, pl->stream, true);
     if (rc) return rc;
     if (!on_device) {
@@ -540,7 +663,7 @@ int b2f_push(b2f_plan* pl, const void* const* frames, int64_t nframes, int on_de
         kb.wmask = pl->d_wmask; kb.wmask_stride = pl->wmask_stride;
         kb.fstat = pl->d_fstat; kb.fstat_stride = pl->fstat_stride;
         kb.blkdirty = pl->d_blkdirty; kb.counters = pl->d_counters;
-        kb.nslots = nframes; kb.nif = nif; kb.nblk = (int)nblk;
+        kb.nslots = nframes; kb.nif = nif; kb.nblk = pl->dedisp ? 0 : (int)nblk;
         kb.groups_per_slot = (int)pl->groups_per_slot; kb.samples_per_frame = (int)pl->spf;
         kb.block_samples = pl->M;
         const int64_t n = nframes * nif;
@@ -548,6 +671,10 @@ int b2f_push(b2f_plan* pl, const void* const* frames, int64_t nframes, int on_de
         pl->launches++;
         CU(cudaGetLastError());
     }
+    if (pl->dedisp) {
+        rc = push_dedisp(pl, nblk, T);
+        if (rc) return rc;
+    } else
     // ---- channeliser in L2-sized sub-batches: the column pass writes [nb][512][R] float2 and the
     // row pass reads it straight back, so the intermediate never has to reach HBM.
     {
@@ -565,6 +692,7 @@ int b2f_push(b2f_plan* pl, const void* const* frames, int64_t nframes, int on_de
         ka.tab_g = pl->d_tab_g; ka.tab_h = pl->d_tab_h; ka.tab_w = pl->d_tab_w;
         ka.R = pl->R; ka.nstrips = pl->nstrips; ka.nblk = (int)nblk; ka.nif = nif;
         ka.payload_bytes = (int)pl->payload; ka.groups_per_slot = (int)pl->groups_per_slot;
+        ka.blk_step_bytes = pl->M * (pl->prm.in_nbit == 2 ? 1 : 2);
         ka.sm_slots = pl->d_sm_slots; ka.stagger_cycles = pl->stagger_cycles;
         {
             const char* e = getenv("B2F_KA_VARIANT");      // timing ablations only (tools/ablate.py)

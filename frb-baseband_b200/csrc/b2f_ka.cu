@@ -31,6 +31,19 @@ cudaError_t B2F_CAT(b2f_launch_ka_, B2F_NBIT)(int R, const KAParams& p, unsigned
         }
     }
 #endif
+#if B2F_NBIT == 2
+    if (p.variant == 32) {                     // forward-only product mode of the dedispersion path
+        switch (R) {
+            case 16: return go<16, 32>(p, grid, st);
+            case 32: return go<32, 32>(p, grid, st);
+            case 64: return go<64, 32>(p, grid, st);
+            case 128: return go<128, 32>(p, grid, st);
+            case 256: return go<256, 32>(p, grid, st);
+            case 512: return go<512, 32>(p, grid, st);
+        }
+        return cudaErrorInvalidValue;
+    }
+#endif
     switch (R) {
         case 16: return go<16>(p, grid, st);
         case 32: return go<32>(p, grid, st);

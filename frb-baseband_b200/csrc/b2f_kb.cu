@@ -25,6 +25,7 @@ static cudaError_t by_mode(int mode, const KBParams& p, int grid, cudaStream_t s
         case B2F_POL_COHERENCE: return go<TR, PT, B2F_POL_COHERENCE>(p, grid, st);
         case B2F_POL_IQUV: return go<TR, PT, B2F_POL_IQUV>(p, grid, st);
         case B2F_POL_PPQQ: return go<TR, PT, B2F_POL_PPQQ>(p, grid, st);
+        case kModeSpectrum: return go<TR, PT, kModeSpectrum>(p, grid, st);
     }
     return cudaErrorInvalidValue;
 }

@@ -326,6 +326,7 @@ struct KAParams {
     const float2* tab_w;     // [32][16] W_512^(l q)
     int R, nstrips, nblk, nif, payload_bytes, groups_per_slot;
     int64_t gb_begin, gb_end;   // this launch covers FFT blocks [gb_begin, gb_end); inter is indexed gb - gb_begin
+    int64_t blk_step_bytes;     // stream bytes between the starts of consecutive blocks (= block size unless overlap-save)
     int* sm_slots;           // [>= #SMs] arrival counters used to stagger co-resident CTAs
     int stagger_cycles;
     int variant;             // 0 = product kernel; else a timing ablation
@@ -348,6 +349,10 @@ template <int NBIT, int R, int VAR = 0>
 __global__ void __launch_bounds__(kKAThreads, kKACtasPerSM) ka_column_pass(const KAParams p) {
     constexpr bool kFFT = !(VAR & 1), kTW = !(VAR & 2), kXCH = !(VAR & 4);
     constexpr bool kOneBlock = (VAR & 8) != 0, kNoStore = (VAR & 16) != 0;   // bit 3: all stores hit block 0; bit 4: none
+    // bit 5 is a product mode, not an ablation: forward transform only.  The kernel stops after
+    // A'[k2][n1] = FFT_512(column) * W_M^(k2 n1) and stores it; used by the dedispersion path, where
+    // the chirp has to be applied between the row FFT and the backward FFT.
+    constexpr bool kFwdOnly = (VAR & 32) != 0;
     using S = KASmem<NBIT>;
     extern __shared__ __align__(16) uint8_t ka_smem[];
     float2* data = reinterpret_cast<float2*>(ka_smem);      // 512 points x 16 lanes, as [256 pairs][16] float4
@@ -416,7 +421,7 @@ __global__ void __launch_bounds__(kKAThreads, kKACtasPerSM) ka_column_pass(const
     auto issue_raw = [&](int64_t gb, int buf) {
         const int ifi = (int)(gb / p.nblk);
         const int64_t blk = gb % p.nblk;
-        const uint8_t* src = p.compact + ifi * p.compact_stride + blk * blk_bytes + (int64_t)strip * S::kPiece;
+        const uint8_t* src = p.compact + ifi * p.compact_stride + blk * p.blk_step_bytes + (int64_t)strip * S::kPiece;
         uint8_t* dst = s_raw + buf * S::kRawBytes;
         if (S::kPiece == 8) {
 #pragma unroll
@@ -481,7 +486,7 @@ __global__ void __launch_bounds__(kKAThreads, kKACtasPerSM) ka_column_pass(const
                 for (int rr = 0; rr < 32; ++rr) {
                     const int r = rr & 15;
                     const int row = 32 * r + item + (rr >> 4) * 16;
-                    const int64_t off = blk * blk_bytes + row * row_bytes + (int64_t)strip * S::kPiece + lane16 * 2;
+                    const int64_t off = blk * p.blk_step_bytes + row * row_bytes + (int64_t)strip * S::kPiece + lane16 * 2;
                     const int64_t slot = off / p.payload_bytes;
                     const int w = (int)(off % p.payload_bytes) >> 2;
                     if ((wm[slot * p.groups_per_slot + (w >> 3)] >> (w & 7)) & 1) {
@@ -531,6 +536,18 @@ __global__ void __launch_bounds__(kKAThreads, kKACtasPerSM) ka_column_pass(const
                 }
             }
             if (kFFT) fft_inreg<32, false>(u);
+            if (kFwdOnly) {
+                // u[pp] = A[k2 = q + 16 pp]; full twiddle W_M^(k2 n1) = h^pp g^q, then straight to global
+                const float4 g4 = s_g4[(q & 7) * C + lane16];
+                const float2 gq = (q & 8) ? make_float2(g4.z, g4.w) : make_float2(g4.x, g4.y);
+                float2* dst = p.inter + ((gb - p.gb_begin) * (int64_t)kL + q) * R + n1;
+#pragma unroll
+                for (int pp = 0; pp < 16; ++pp) {
+                    const float4 h = s_h4[pp * C + lane16];
+                    dst[(int64_t)(16 * pp) * R] = cmul(cmul(u[pp], make_float2(h.x, h.y)), gq);
+                    dst[(int64_t)(16 * (pp + 16)) * R] = cmul(cmul(u[pp + 16], make_float2(h.z, h.w)), gq);
+                }
+            } else {
             if (q == 0) p.colsum[gb * R + n1] = u[0];          // A[k2 = 0]: column sum
 #pragma unroll
             for (int pp = 0; pp < (kTW ? 16 : 0); ++pp) {
@@ -554,8 +571,10 @@ __global__ void __launch_bounds__(kKAThreads, kKACtasPerSM) ka_column_pass(const
 #pragma unroll
                 for (int m = 0; m < 16; ++m) { keepA[m] = u[m]; keepB[m] = u[m + 16]; }
             }
+            }   // !kFwdOnly
         }
         __syncthreads();
+        if (kFwdOnly) continue;
 
         // ---- P3: * W_M^(q n1) ; IFFT_16 over q -> m2 ; m = m1 + 32 m2 for m1 = item and item+16
         {
@@ -636,7 +655,11 @@ struct KBParams {
     int64_t row0;               // first output row of this push inside F
     int nblk, nif, D;
     int64_t gb_begin, gb_end;   // FFT blocks of this launch; inter is indexed gb - gb_begin
+    float2* spec;               // kModeSpectrum: [gb - gb_begin][512][R] output
 };
+
+// row-pass mode of the dedispersion path: no un-mixing or detection, store Z[k2][c] for all R channels
+constexpr int kModeSpectrum = 100;
 
 __host__ __device__ constexpr int nprod_of_mode(int mode) {
     return (mode == B2F_POL_COHERENCE || mode == B2F_POL_IQUV) ? 4 : (mode == B2F_POL_PPQQ ? 2 : 1);
@@ -714,7 +737,7 @@ __global__ void __launch_bounds__(kKBThreads, 2) kb_row_pass(const KBParams p) {
     }
     __syncthreads();
 
-    const int D = p.D;
+    const int D = MODE == kModeSpectrum ? 1 : p.D;
     const int GW = D > RW ? D : RW;                 // rows per group
     const int passes = GW / RW;
     const int nout = GW / D;                        // output samples per group (1 unless D < RW)
@@ -731,14 +754,14 @@ __global__ void __launch_bounds__(kKBThreads, 2) kb_row_pass(const KBParams p) {
         const float2* src = p.inter + (lb * (int64_t)kL + row0) * R;
         fence_proxy_async();
         if (lane == 0)
-            mbar_expect_tx(&mbar[buf], (uint32_t)(RW * R * sizeof(float2) + (pass == 0 ? S::kEps : 0)));
+            mbar_expect_tx(&mbar[buf], (uint32_t)(RW * R * sizeof(float2) + ((pass == 0 && MODE != kModeSpectrum) ? S::kEps : 0)));
         __syncwarp();
         if (S::kPitch == R * (int)sizeof(float2)) {
             if (lane == 0) bulk_g2s(dst, src, (uint32_t)(RW * R * sizeof(float2)), &mbar[buf]);
         } else if (lane < RW) {
             bulk_g2s(dst + lane * S::kPitch, src + (int64_t)lane * R, (uint32_t)(R * sizeof(float2)), &mbar[buf]);
         }
-        if (lane == 0 && pass == 0) bulk_g2s(dst + S::kBody, p.eps + gb * N, (uint32_t)S::kEps, &mbar[buf]);
+        if (lane == 0 && pass == 0 && MODE != kModeSpectrum) bulk_g2s(dst + S::kBody, p.eps + gb * N, (uint32_t)S::kEps, &mbar[buf]);
     };
 
     int64_t grp_cur = (int64_t)blockIdx.x * S::kWarps + warp;
@@ -759,7 +782,7 @@ __global__ void __launch_bounds__(kKBThreads, 2) kb_row_pass(const KBParams p) {
         mbar_wait(&mbar[buf], (it >> 1) & 1);
         uint8_t* st = stage0 + buf * S::kStage;
         const float2* tile = reinterpret_cast<const float2*>(st + rsw * S::kPitch);
-        if (pass_cur == 0) {
+        if (pass_cur == 0 && MODE != kModeSpectrum) {
             const float2* s_eps = reinterpret_cast<const float2*>(st + S::kBody);
 #pragma unroll
             for (int j = 0; j < QPT; ++j)
@@ -789,6 +812,20 @@ __global__ void __launch_bounds__(kKBThreads, 2) kb_row_pass(const KBParams p) {
             for (int t = 0; t < TR; ++t) z[j][t] = myx[t * (PT + 1) + s + TR * j];
 #pragma unroll
         for (int j = 0; j < QPT; ++j) fft_inreg<TR, false>(z[j]);
+        if (MODE == kModeSpectrum) {
+            // z[j][pp] = Z[k2 = this row][c = (s + TR j) + PT pp]: store the whole row
+            const int64_t lb = grp_cur / groups_per_blk;
+            const int row = (int)(grp_cur % groups_per_blk) * GW + pass_cur * RW + rsw;
+            float2* dst = p.spec + (lb * (int64_t)kL + row) * R;
+#pragma unroll
+            for (int j = 0; j < QPT; ++j)
+#pragma unroll
+                for (int pp = 0; pp < TR; ++pp) dst[(s + TR * j) + PT * pp] = z[j][pp];
+            grp_cur = grp_nxt;
+            pass_cur = pass_nxt;
+            ++it;
+            continue;
+        }
         // z[j][pp] = Z_c at c = (s + TR j) + PT pp.  Mirror R-1-c lives in lane s^(TR-1),
         // register [QPT-1-j][TR-1-pp].
 #pragma unroll
@@ -800,7 +837,7 @@ __global__ void __launch_bounds__(kKBThreads, 2) kb_row_pass(const KBParams p) {
                 const float bx = __shfl_xor_sync(0xffffffffu, bs.x, TR - 1);
                 const float by = __shfl_xor_sync(0xffffffffu, bs.y, TR - 1);
                 const float2 bp = make_float2(bx - e[j][pp].x, -by - e[j][pp].y);
-                detect_acc<MODE>(acc[j][pp], make_float2(a.x + bp.x, a.y + bp.y), make_float2(a.x - bp.x, a.y - bp.y));
+                detect_acc<MODE == kModeSpectrum ? B2F_POL_I : MODE>(acc[j][pp], make_float2(a.x + bp.x, a.y + bp.y), make_float2(a.x - bp.x, a.y - bp.y));
             }
         if (pass_cur == passes - 1) {
             // add up the row slots that integrate into the same output sample
@@ -831,6 +868,129 @@ __global__ void __launch_bounds__(kKBThreads, 2) kb_row_pass(const KBParams p) {
         grp_cur = grp_nxt;
         pass_cur = pass_nxt;
         ++it;
+    }
+}
+
+// ================================================================== kernel 2: dedispersion back end
+// Dedispersion path only (digifil -D dm -F nchan:D).  Input: the full spectrum Z[k2][k1] of one
+// overlap-save block (forward column pass + row FFT).  One CTA owns 8 channels x 2 polarisations =
+// 16 lanes and, per lane, un-mixes the polarisation (Z[k] with conj Z[M-k]), multiplies by the
+// chirp H[c][k2], runs the 512-point backward FFT (16 x 32, one exchange), keeps samples
+// [nfilt_pos, 512 - nfilt_neg), detects (partner polarisation by shuffle) and integrates D samples.
+struct KCParams {
+    const float2* spec;         // [gb - gb_begin][512][R]
+    const float2* chirp;        // [nif][512][N]  H[c][k2] stored k2-major
+    const float2* tab_w;        // [32][16] W_512^(l q)
+    float* F; int64_t F_if_stride; int64_t row0;
+    int nblk, nif, D, mode, nfilt_pos, keep;      // keep = 512 - nfilt_pos - nfilt_neg (multiple of D)
+    int64_t gb_begin, gb_end;
+};
+
+constexpr size_t kKCSmemBytes = (size_t)(kL * 16 + 512) * sizeof(float2);
+
+template <int R>
+__global__ void __launch_bounds__(256, 2) kc_dedisp_back(const KCParams p) {
+    constexpr int N = R / 2;
+    extern __shared__ __align__(16) uint8_t kc_smem[];
+    float4* data4 = reinterpret_cast<float4*>(kc_smem);             // [256 pairs][16 lanes]
+    float* pw = reinterpret_cast<float*>(kc_smem);                  // aliases data: [prod][512][8 ch]
+    float2* s_w = reinterpret_cast<float2*>(kc_smem) + kL * 16;     // [32][16] W_512^(l q)
+    const int tid = threadIdx.x, lane16 = tid & 15, item = tid >> 4;
+    const int ch8 = lane16 >> 1, pol = lane16 & 1;
+    for (int i = tid; i < 512; i += 256) s_w[i] = p.tab_w[i];
+    __syncthreads();
+
+    const int nstrips = N / 8;
+    const int nprod = nprod_of_mode(p.mode);
+    const int64_t nwork = (p.gb_end - p.gb_begin) * nstrips;
+    for (int64_t w = blockIdx.x; w < nwork; w += gridDim.x) {
+        const int64_t lb = w / nstrips;
+        const int64_t gb = p.gb_begin + lb;
+        const int ifi = (int)(gb / p.nblk);
+        const int64_t blk = gb % p.nblk;
+        const int c = (int)(w % nstrips) * 8 + ch8;
+        const float2* Z = p.spec + lb * (int64_t)kL * R;
+        const float2* H = p.chirp + (int64_t)ifi * kL * N;
+
+        // ---- P1: un-mix + chirp on load, IFFT_16 over a (k2 = 32 a + l) for l = item, item + 16
+        {
+            float2 vA[16], vB[16];
+#pragma unroll
+            for (int a = 0; a < 16; ++a) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int k2 = 32 * a + item + 16 * h;
+                    const float2 z1 = Z[(int64_t)k2 * R + c];
+                    // mirror bin M - (c L + k2): row L - k2, channel R-1-c (k2 > 0) or row 0, channel (R-c) mod R
+                    const float2 z2 = k2 ? Z[(int64_t)(kL - k2) * R + (R - 1 - c)] : Z[(R - c) & (R - 1)];
+                    float2 x;
+                    if (pol == 0) x = make_float2(0.5f * (z1.x + z2.x), 0.5f * (z1.y - z2.y));          // (z1 + conj z2)/2
+                    else          x = make_float2(0.5f * (z1.y + z2.y), -0.5f * (z1.x - z2.x));         // (z1 - conj z2)/(2i)
+                    x = cmul(x, H[(int64_t)k2 * N + c]);
+                    if (h == 0) vA[a] = x; else vB[a] = x;
+                }
+            }
+            fft_inreg<16, true>(vA);
+            fft_inreg<16, true>(vB);
+            const float4* twA = reinterpret_cast<const float4*>(s_w + item * 16);
+            const float4* twB = reinterpret_cast<const float4*>(s_w + (item + 16) * 16);
+#pragma unroll
+            for (int q = 0; q < 16; q += 2) {            // * conj W_512^(l m_lo)
+                const float4 ta = twA[q >> 1], tb = twB[q >> 1];
+                if (q) vA[q] = cmul_conj(vA[q], make_float2(ta.x, ta.y));
+                vA[q + 1] = cmul_conj(vA[q + 1], make_float2(ta.z, ta.w));
+                if (q) vB[q] = cmul_conj(vB[q], make_float2(tb.x, tb.y));
+                vB[q + 1] = cmul_conj(vB[q + 1], make_float2(tb.z, tb.w));
+            }
+#pragma unroll
+            for (int q = 0; q < 16; ++q)
+                data4[(q * 16 + item) * 16 + lane16] = make_float4(vA[q].x, vA[q].y, vB[q].x, vB[q].y);
+        }
+        __syncthreads();
+        // ---- P2: IFFT_32 over l for m_lo = item -> y[m = m_lo + 16 m_hi]; detect into smem
+        {
+            float2 u[32];
+#pragma unroll
+            for (int l = 0; l < 16; ++l) {
+                const float4 t = data4[(item * 16 + l) * 16 + lane16];
+                u[l] = make_float2(t.x, t.y);
+                u[l + 16] = make_float2(t.z, t.w);
+            }
+            fft_inreg<32, true>(u);
+            __syncthreads();                   // everyone has its u[]: the exchange buffer becomes the power buffer
+#pragma unroll
+            for (int mh = 0; mh < 32; ++mh) {
+                const float ox = __shfl_xor_sync(0xffffffffu, u[mh].x, 1), oy = __shfl_xor_sync(0xffffffffu, u[mh].y, 1);
+                if (pol == 0) {                 // this lane holds yP, its neighbour yQ
+                    const float2 yP = u[mh], yQ = make_float2(ox, oy);
+                    const float pp = yP.x * yP.x + yP.y * yP.y, qq = yQ.x * yQ.x + yQ.y * yQ.y;
+                    const float re = yP.x * yQ.x + yP.y * yQ.y, im = yP.y * yQ.x - yP.x * yQ.y;   // yP conj(yQ)
+                    float* dst = pw + (size_t)(item + 16 * mh) * 8 + ch8;
+                    constexpr size_t PS = (size_t)kL * 8;        // product stride
+                    switch (p.mode) {
+                        case B2F_POL_P0: dst[0] = pp; break;
+                        case B2F_POL_P1: dst[0] = qq; break;
+                        case B2F_POL_I: dst[0] = pp + qq; break;
+                        case B2F_POL_I2: dst[0] = (pp + qq) * (pp + qq); break;
+                        case B2F_POL_PPQQ: dst[0] = pp; dst[PS] = qq; break;
+                        case B2F_POL_COHERENCE: dst[0] = pp; dst[PS] = qq; dst[2 * PS] = re; dst[3 * PS] = im; break;
+                        default: dst[0] = pp + qq; dst[PS] = 2.f * re; dst[2 * PS] = 2.f * im; dst[3 * PS] = pp - qq; break;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- integrate D kept samples per output row
+        const int nrow = p.keep / p.D;
+        const int64_t t0 = p.row0 + blk * nrow;
+        for (int o = tid; o < nprod * nrow * 8; o += 256) {
+            const int ch = o & 7, r = (o >> 3) % nrow, k = (o >> 3) / nrow;
+            const float* src = pw + ((size_t)k * kL + p.nfilt_pos + r * p.D) * 8 + ch;
+            float sum = 0.f;
+            for (int i = 0; i < p.D; ++i) sum += src[i * 8];
+            p.F[ifi * p.F_if_stride + (t0 + r) * (int64_t)(nprod * N) + k * N + (int)(w % nstrips) * 8 + ch] = sum;
+        }
+        __syncthreads();
     }
 }
 

@@ -48,6 +48,8 @@ class PlanConfig:
     device: int = 0
     profile: bool = False
     stream: int | None = None
+    dm: float = 0.0                          # digifil -D
+    coherent: bool = False                   # digifil -F nchan:D
     extra: dict = field(default_factory=dict)
 
 
@@ -83,8 +85,8 @@ class Plan:
             p.bw_mhz[i] = cfg.bw_mhz[i]
             p.freq_mhz[i] = freq[i]
             p.if_order[i] = order[i]
-        p.dm = 0.0
-        p.coherent = 0
+        p.dm = cfg.dm
+        p.coherent = int(cfg.coherent)
         p.profile = int(cfg.profile)
         p.stream = cfg.stream
         self.if_order = list(order)

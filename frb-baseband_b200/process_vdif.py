@@ -46,6 +46,9 @@ _CLI = [
     (("--tscrunch",), dict(type=int, default=1, help="time integration factor, digifil -t (%(default)s)"), _D),
     (("--nthreads",), dict(type=int, default=1, help="accepted for compatibility, unused on the GPU"), _D),
     (("--device",), dict(type=int, default=int(os.environ.get("B2F_DEVICE", "0")), help="CUDA ordinal (extension)"), _D),
+    (("--coherent_dm",), dict(type=float, default=0.0,
+                              help="extension: coherently dedisperse inside each channel at this DM "
+                                   "(run_digifil's dm/coherent arguments, which the reference CLI never sets)"), _D),
     (("--do_prepdata",), dict(action="store_true", help="run PRESTO prepdata/prepsubband afterwards"), _P),
     (("--ncpus",), dict(type=int, default=1, help="1: prepdata, >1: prepsubband"), _P),
     (("--dm",), dict(type=float, default=None, help="DM for prepdata (default: psrcat)"), _P),
@@ -142,15 +145,14 @@ def run_digifil(hdr, fil_out_dir=None, start=1, nsecs=120, nchan=128, overwrite=
         raise InputError(f"nbit={nbit} not in supported values of [2, 8, 16, -32]. ")
     if pol not in (0, 1, 2, 3, 4):
         raise InputError(f"pol = {pol} not implemented. Choices are 0, 1, 2, 3, 4")
-    if dm > 0.0 and coherent:
-        raise RunError("coherent dedispersion (-F nchan:D) is not available in this build of libb2f")
     from . import _lib, sigproc, vdif
     from .plan import Plan, PlanConfig, pol_mode_from_reference, reference_freq_res
 
     kv = read_hdr(hdr)
     datafile, freq, bw = kv["DATAFILE"], float(kv["FREQ"]), float(kv["BW"])
     print("running b2f -b{0} -S{1} -T{2} -t {3} -o {4} {5} pol={6} -F{7}:{8}{9} (libb2f.so, cuda:{10})".format(
-        nbit, start, nsecs, tscrunch, fil, hdr, pol, nchan, reference_freq_res(nchan), " -I0" if keepBP else "", device))
+        nbit, start, nsecs, tscrunch, fil, hdr, pol, nchan, "D -D {0}".format(dm) if (coherent and dm > 0) else reference_freq_res(nchan),
+        " -I0" if keepBP else "", device))
     try:
         with open(datafile, "rb") as src:
             info = vdif.parse_header(src.read(32))
@@ -164,7 +166,7 @@ def run_digifil(hdr, fil_out_dir=None, start=1, nsecs=120, nchan=128, overwrite=
             cfg = PlanConfig(nchan=nchan, bw_mhz=[bw], freq_mhz=[freq], tscrunch=max(1, tscrunch),
                              pol_mode=pol_mode_from_reference(pol), out_nbit=nbit, in_nbit=info.nbit,
                              frame_bytes=info.frame_bytes, header_bytes=info.header_bytes, keep_bandpass=keepBP,
-                             device=device)
+                             device=device, dm=float(dm), coherent=bool(coherent and dm > 0.0))
             src.seek(first_frame * info.frame_bytes)
             head = src.read(32)
             src.seek(first_frame * info.frame_bytes)
@@ -237,7 +239,8 @@ def main(argv=None):
         print("Not creating filterbanks. Hdr files done.")
         return 0
     fil = run_digifil(hdr, a.fil_out_dir, a.start, a.nsec, a.nchan, overwrite=a.force, pol=a.pol, nbit=a.nbit,
-                      tscrunch=a.tscrunch, nthreads=a.nthreads, keepBP=a.keepBP, device=a.device)
+                      tscrunch=a.tscrunch, nthreads=a.nthreads, keepBP=a.keepBP, device=a.device,
+                      dm=a.coherent_dm, coherent=a.coherent_dm > 0.0)
     if a.do_prepdata:
         prepdata(fil, a.dm if a.dm is not None else psr_info(a.psrname)[2], zerodm=a.nozerodm, clip=a.clip,
                  dm2=a.dm2, dmstep=a.dmstep, ncpus=a.ncpus)

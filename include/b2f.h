@@ -80,8 +80,8 @@ typedef struct b2f_params {
     double freq_mhz[B2F_MAX_IF];   /* centre frequency of each IF (-f)                        */
     int32_t if_order[B2F_MAX_IF];  /* output tile s <- IF index if_order[s]; descending sky
                                       frequency for base2fil's plan                           */
-    double dm;                     /* reserved: coherent in-channel dedispersion (-D, -F n:D) */
-    int32_t coherent;
+    double dm;                     /* digifil -D dm (process_vdif.py:177-178)                 */
+    int32_t coherent;              /* digifil -F nchan:D: in-channel coherent dedispersion by overlap-save (:179-180) */
     int32_t profile;               /* 1: time every kernel launch with CUDA events            */
     void* stream;                  /* cudaStream_t to launch on; NULL = plan-owned stream     */
 } b2f_params;
@@ -98,6 +98,7 @@ typedef struct b2f_geometry {
     int32_t freq_res;
     double tsamp_s;
     int64_t interval_rows;         /* rows held before the first rescale is frozen            */
+    int32_t nfilt_pos, nfilt_neg;  /* overlap-save samples discarded per block and channel (dedispersion) */
 } b2f_geometry;
 
 typedef struct b2f_counters {
@@ -116,7 +117,8 @@ enum b2f_kernel_id {
     B2F_K_STATS = 4,               /* per-channel mean / sigma                                */
     B2F_K_QUANT = 5,               /* rescale + requantise + sideband flip + splice           */
     B2F_K_DECODE = 6,              /* stand-alone decode (tests / roofline)                   */
-    B2F_K_COUNT = 7
+    B2F_K_DEDISP = 7,              /* un-mix + chirp + backward FFT + overlap discard + detect */
+    B2F_K_COUNT = 8
 };
 
 int b2f_version(void);

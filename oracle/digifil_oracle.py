@@ -223,24 +223,58 @@ def digitise(y: np.ndarray, nbit: int) -> np.ndarray:
     raise ValueError(f"nbit={nbit}")
 
 
-def chirp(nchan: int, freq_res: int, freq_mhz: float, bw_mhz: float, dm: float) -> np.ndarray:
-    """In-channel coherent dedispersion response H[chan, bin] (Appendix A4).
+DISPERSION_CONSTANT = 1.0 / 2.41e-4        # s MHz^2 pc^-1 cm^3 (DSPSR's 2.41e-4; same constant family as
+                                           # the 8.3 us smearing rule of /root/reference/submit_job.py:62)
 
-    Channel c has sky centre f_c = FREQ - BW/2 + (c+0.5)*BW/N (BW signed) and the bin j of
-    its segment sits at baseband offset (j+0.5... ) -- bins are taken at their lower edge
-    like DSPSR: f = (j/freq_res - 0.5)*|BW|/N, mirrored in sign for LSB.
-    H = exp(+i*2pi*D*DM*f^2 / (f_c^2 (f_c+f))), D = 1e6/2.41e-4 (us MHz^2).
+
+def chirp(nchan: int, freq_res: int, freq_mhz: float, bw_mhz: float, dm: float) -> np.ndarray:
+    """In-channel coherent dedispersion response H[chan, bin].
+
+    Channel c has sky centre f_c = FREQ - BW/2 + (c+0.5)*BW/N (BW signed); bin j of its segment
+    sits at sky offset f = (j/freq_res - 0.5)*BW/N from that centre.
+        H = exp(-i * 2pi * D * DM * 1e6 * f^2 / (f_c^2 (f_c + f))),  conjugated for LSB.
+    The sign is the physical one for a forward FFT with exp(-i w t): a pulse dispersed by the
+    cold-plasma delay D*DM/f^2 is compressed to ~1 sample (tests/test_oracle_kat.py::
+    test_chirp_compresses_dispersed_pulse).  SURVEY A4 recalls the opposite sign for DSPSR;
+    with it the same pulse is smeared to twice its dispersed width, so it is not used.
     """
     N, L = nchan, freq_res
     chbw = bw_mhz / N                                     # signed
     fc = freq_mhz - bw_mhz / 2 + (np.arange(N) + 0.5) * chbw
     j = np.arange(L)
     f = (j / L - 0.5) * chbw                              # sky offset from channel centre
-    disp = 1.0 / 2.41e-4                                  # s MHz^2 pc^-1 cm^3
-    phase = 2 * np.pi * disp * 1e6 * dm * f[None, :] ** 2 / (fc[:, None] ** 2 * (fc[:, None] + f[None, :]))
+    phase = 2 * np.pi * DISPERSION_CONSTANT * 1e6 * dm * f[None, :] ** 2 / (fc[:, None] ** 2 * (fc[:, None] + f[None, :]))
     if bw_mhz < 0:
         phase = -phase
-    return np.exp(1j * phase)
+    return np.exp(-1j * phase)
+
+
+def smearing_samples(freq_mhz: float, bw_mhz: float, nchan: int, dm: float) -> float:
+    """Dispersion smearing across the lowest channel of a subband, in channel samples
+    (t = 8.3 us * DM * dnu_MHz / nu_GHz^3, the rule the reference uses in submit_job.py:62)."""
+    chbw = abs(bw_mhz) / nchan
+    f_low = freq_mhz - abs(bw_mhz) / 2 + chbw / 2
+    t_us = 8.3 * dm * chbw / (f_low / 1000.0) ** 3
+    return t_us / (nchan / abs(bw_mhz))                   # channel sample = nchan/|BW| us
+
+
+def filterbank_dedisp(x: np.ndarray, nchan: int, freq_res: int, H: np.ndarray, nfilt_pos: int, nfilt_neg: int,
+                      dtype=np.float64) -> np.ndarray:
+    """Convolving filterbank with an in-channel response, overlap-save (Appendix A4): blocks of
+    M = 2*nchan*freq_res samples advance by (freq_res - nfilt_pos - nfilt_neg)*2*nchan samples; each
+    channel's segment is multiplied by H[c] before the backward FFT and the first nfilt_pos / last
+    nfilt_neg samples of every block are discarded.  Returns y[t, chan]."""
+    N, L = nchan, freq_res
+    M = 2 * N * L
+    keep = L - nfilt_pos - nfilt_neg
+    step = keep * 2 * N
+    nblk = 0 if x.size < M else (x.size - M) // step + 1
+    out = np.empty((nblk * keep, N), dtype=np.complex128)
+    for b in range(nblk):
+        X = _fft.rfft(np.asarray(x[b * step: b * step + M], dtype=dtype))[: M // 2].reshape(N, L)
+        y = _fft.ifft(X * H, axis=1, norm="forward")      # unnormalised backward
+        out[b * keep:(b + 1) * keep] = y[:, nfilt_pos: L - nfilt_neg].T
+    return out
 
 
 def digifil(vdif: np.ndarray, *, freq_mhz: float, bw_mhz: float, nchan: int,
@@ -248,7 +282,8 @@ def digifil(vdif: np.ndarray, *, freq_mhz: float, bw_mhz: float, nchan: int,
             out_nbit: int = 8, in_nbit: int = 2, start_s: float = 0.0, nsec: float | None = None,
             rescale_interval_s: float = 10.0, keep_bandpass: bool = False,
             frame_bytes: int | None = None, header_bytes: int = 32,
-            dtype=np.float64, return_float: bool = False) -> dict:
+            dtype=np.float64, return_float: bool = False, dm: float = 0.0, coherent: bool = False,
+            nfilt: tuple[int, int] | None = None) -> dict:
     """One IF: VDIF bytes -> SIGPROC samples, as `digifil -cont -c -b<nbit> -S<start> -T<nsec>
     -2 -D 0.0 [-t D] -d<..> -F<nchan>:<freq_res> [-I0]` (/root/reference/process_vdif.py:157-182).
 
@@ -272,8 +307,13 @@ def digifil(vdif: np.ndarray, *, freq_mhz: float, bw_mhz: float, nchan: int,
         nfr = min(nfr, int(round(nsec * fps)))
     x = decode_vdif(vdif[f0 * frame_bytes: (f0 + nfr) * frame_bytes], nbit=in_nbit,
                     header_bytes=header_bytes, frame_bytes=frame_bytes)
-    yP = filterbank(x[0], nchan, freq_res, dtype)
-    yQ = filterbank(x[1], nchan, freq_res, dtype)
+    if coherent and dm > 0:                                  # digifil -D dm -F nchan:D (process_vdif.py:177-180)
+        H = chirp(nchan, freq_res, freq_mhz, bw_mhz, dm)
+        yP = filterbank_dedisp(x[0], nchan, freq_res, H, nfilt[0], nfilt[1], dtype)
+        yQ = filterbank_dedisp(x[1], nchan, freq_res, H, nfilt[0], nfilt[1], dtype)
+    else:
+        yP = filterbank(x[0], nchan, freq_res, dtype)
+        yQ = filterbank(x[1], nchan, freq_res, dtype)
     d = tscrunch(detect(yP, yQ, pol_mode), tscrunch_factor)
     tsamp = tscrunch_factor * nchan / (abs(bw_mhz) * 1e6)
     if keep_bandpass:

@@ -170,3 +170,30 @@ def test_linearity_full_size_property(gpu):
     v2[:, 32:].view("<u4")[:] = 0x11223344
     rows2, info2 = run_plan([v2.reshape(-1)], nchan=nchan, bw=[-bw], tscrunch=16, out_nbit=-32, keep_bandpass=True)
     assert np.all(rows2 == 0) and info2["counters"]["fill_words"] == 1024 * 2000
+
+
+@pytest.mark.parametrize("usb,mode,name", [(False, _lib.POL_I, "I"), (True, _lib.POL_I, "I"), (False, _lib.POL_COHERENCE, "coherence")])
+def test_coherent_dedispersion(gpu, usb, mode, name):
+    """digifil -D 560 -F128:D: overlap-save chirp, halo carried across pushes, ragged last push."""
+    nchan, bw, D, dm, fc = 128, 32.0, 16, 560.0, 1254.0
+    sbw = bw if usb else -bw
+    cfg = PlanConfig(nchan=nchan, bw_mhz=[sbw], freq_mhz=[fc], tscrunch=D, pol_mode=mode, out_nbit=-32, keep_bandpass=True,
+                     dm=dm, coherent=True)
+    v = synth.make_vdif(2048 + 300, seed=91, bw_mhz=bw, rho=0.3, tone_frac=0.37)
+    out = []
+    with Plan(cfg) as pl:
+        g = pl.geometry
+        nf = (int(g.nfilt_pos), int(g.nfilt_neg))
+        assert nf[0] == nf[1] and nf[0] % D == 0 and 64 <= nf[0] < 256
+        cf, fb = int(pl.chunk_frames), cfg.frame_bytes
+        for f0 in range(0, 2348, cf):
+            n = min(cf, 2348 - f0)
+            pl.push([v[f0 * fb:(f0 + n) * fb]])
+            out.append(pl.pull().copy())
+        pl.flush()
+        out.append(pl.pull().copy())
+        rows = pl.view_rows(np.concatenate(out))
+    ref = o.digifil(v, freq_mhz=fc, bw_mhz=sbw, nchan=nchan, tscrunch_factor=D, pol_mode=name, out_nbit=-32,
+                    keep_bandpass=True, dm=dm, coherent=True, nfilt=nf)["data"]
+    assert rows.shape[0] == ref.shape[0] and rows.shape[0] > 0
+    assert_rel(rows.reshape(ref.shape), ref.astype(np.float64), REL_TOL, "dedispersed " + name)

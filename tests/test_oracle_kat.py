@@ -119,3 +119,52 @@ def test_epoch_mjd():
     assert o.vdif_epoch_mjd(0) == 51544            # 2000-01-01
     assert o.vdif_epoch_mjd(40) == 58849           # 2020-01-01
     assert vdif.epoch_mjd(41) == 59031             # 2020-07-01
+
+
+@pytest.mark.parametrize("usb", [True, False])
+def test_chirp_compresses_dispersed_pulse(usb):
+    """Physical KAT for the dedispersion sign: an impulse dispersed by the cold-plasma law
+    (delay = D*DM/f^2, DM 560) over a 32 MHz subband is compressed by the oracle's chirp to
+    1-2 channel samples; with the opposite sign it stays smeared over hundreds."""
+    BW, f_lo, DM, nchan, L = 32.0, 1238.0, 560.0, 128, 512
+    M = 2 * nchan * L
+    nblk = 6
+    n = nblk * M
+    k = np.arange(n // 2 + 1)
+    fsky = f_lo + k * (2 * BW) / n
+    phi = 2 * np.pi * o.DISPERSION_CONSTANT * DM * 1e6 * (1.0 / fsky - 1.0 / fsky[-1])
+    x = np.fft.irfft(np.exp(1j * phi) * np.exp(-2j * np.pi * k * (n // 2) / n), n)
+    if not usb:
+        x = x * (-1.0) ** np.arange(n)                       # spectral inversion = the LSB-sampled view
+    H = o.chirp(nchan, L, f_lo + BW / 2, BW if usb else -BW, DM)
+
+    def width(c, Hc):
+        best = None
+        for b in range(nblk):
+            Xb = np.fft.rfft(x[b * M:(b + 1) * M])[: M // 2].reshape(nchan, L)
+            p = np.abs(np.fft.ifft(Xb[c] * Hc)) ** 2
+            if best is None or p.max() > best.max():
+                best = p
+        return int((best > 0.5 * best.max()).sum())
+
+    for c in (5, 64, 120):
+        assert width(c, H[c]) <= 2
+        assert width(c, np.conj(H[c])) > 50
+    assert 100 < o.smearing_samples(f_lo + BW / 2, BW, nchan, DM) < 200      # ~152 samples at 1.238 GHz
+
+
+def test_overlap_save_equals_long_convolution():
+    """filterbank_dedisp keeps exactly the samples of each block that the response cannot wrap
+    into: on the kept region it equals the same filter applied to a block shifted by half a step."""
+    rng = np.random.default_rng(3)
+    nchan, L = 8, 64
+    M = 2 * nchan * L
+    H = o.chirp(nchan, L, 1400.0, 16.0, 30.0)
+    npos = nneg = 8
+    x = rng.standard_normal(4 * M)
+    y = o.filterbank_dedisp(x, nchan, L, H, npos, nneg)
+    keep = L - npos - nneg
+    assert y.shape == (((x.size - M) // (keep * 2 * nchan) + 1) * keep, nchan)
+    # block 1 starts keep*2N samples in; its first kept sample follows block 0's last kept one
+    y_shift = o.filterbank_dedisp(x[keep * 2 * nchan:], nchan, L, H, npos, nneg)
+    assert np.allclose(y[keep:2 * keep], y_shift[:keep], rtol=0, atol=1e-9 * np.abs(y).max())
