@@ -302,7 +302,7 @@ def main():
         h2d = sum(n for _, n in chunks) * NIF * FRAME_BYTES
         e2e = {"value": world * in_bytes / (ms_e2e * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(rows_e * NIF * NCHAN), "ms_per_step": ms_e2e,
-               "rt_factor": data_sec / (ms_e2e * 1e-3),
+               "rt_factor": world * data_sec / (ms_e2e * 1e-3),
                "note": "pinned host VDIF pushed chunk by chunk through b2f_push, rows pulled to pinned host memory; "
                        "12 s of host-resident VDIF cycled to cover the 60 s scan"}
 

@@ -1,8 +1,8 @@
 // In-register radix-2 DIT FFTs of length 2..32 with compile-time twiddles.
 //
-// Every loop is fully unrolled, so indices and twiddles are literals in SASS: trivial
-// twiddles (1, -i) cost 4 FADD per butterfly, every other butterfly is the 6-FMA form
-//     a' = a + w b  (4 FFMA),   b' = 2a - a'  (2 FFMA).
+// Every loop is fully unrolled, so indices and twiddles are literals in SASS.  All arithmetic is
+// on packed (re, im) pairs: trivial twiddles (1, -i) cost 2 FADD2 per butterfly, every other
+// butterfly is 3 FFMA2:  a' = a + w b (2),  b' = 2a - a' (1).
 // Input and output are both in natural order; the bit reversal DIT needs is a compile-time
 // register renaming.
 #pragma once
@@ -49,34 +49,72 @@ __host__ __device__ constexpr int bitrev(int x, int bits) {
 }
 __host__ __device__ constexpr int ilog2(int n) { return n <= 1 ? 0 : 1 + ilog2(n >> 1); }
 
-__host__ __device__ __forceinline__ float2 cmul(float2 a, float2 w) {
-    return make_float2(fmaf(a.x, w.x, -a.y * w.y), fmaf(a.x, w.y, a.y * w.x));
+// ---- packed FP32 pairs.  Blackwell executes add/mul/fma .f32x2 as one instruction per lane
+// (SASS FADD2 / FMUL2 / FFMA2) whose operands can be half-swapped and negated per half for free
+// (R.F32x2.LO_HI.NP) and whose multiplier can be a broadcast scalar or immediate.  A complex number
+// is one (re, im) pair, so a general butterfly costs 3 issue slots instead of 6 and a twiddle
+// multiply 2 instead of 4.  Every formula keeps the twiddle as a pure broadcast (s, s) and puts the
+// swap / sign pattern on the data operand, which ptxas folds into the operand modifiers.
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ unsigned long long f2pack(float2 a) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+    return r;
 }
-__host__ __device__ __forceinline__ float2 cmul_conj(float2 a, float2 w) {   // a * conj(w)
-    return make_float2(fmaf(a.x, w.x, a.y * w.y), fmaf(a.y, w.x, -a.x * w.y));
+__device__ __forceinline__ float2 f2unpack(unsigned long long r) {
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(r));
+    return d;
+}
+__device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c) {      // a*b + c per component
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2pack(a)), "l"(f2pack(b)), "l"(f2pack(c)));
+    return f2unpack(r);
+}
+__device__ __forceinline__ float2 f2mul(float2 a, float2 b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2pack(a)), "l"(f2pack(b)));
+    return f2unpack(r);
+}
+__device__ __forceinline__ float2 f2add(float2 a, float2 b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2pack(a)), "l"(f2pack(b)));
+    return f2unpack(r);
+}
+#else
+inline float2 f2fma(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+inline float2 f2mul(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+inline float2 f2add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+#endif
+
+// a * w = w.x (a.x, a.y) + w.y (-a.y, a.x)
+__host__ __device__ __forceinline__ float2 cmul(float2 a, float2 w) {
+    return f2fma(make_float2(-a.y, a.x), make_float2(w.y, w.y), f2mul(a, make_float2(w.x, w.x)));
+}
+// a * conj(w) = w.x (a.x, a.y) + w.y (a.y, -a.x)
+__host__ __device__ __forceinline__ float2 cmul_conj(float2 a, float2 w) {
+    return f2fma(make_float2(a.y, -a.x), make_float2(w.y, w.y), f2mul(a, make_float2(w.x, w.x)));
 }
 
-// One DIT butterfly with twiddle W = exp(-+2 pi i k64/64) (INV: conjugate).
+// One DIT butterfly  a' = a + w b,  b' = a - w b  with W = exp(-+2 pi i k64/64) (INV: conjugate).
 template <bool INV>
 __host__ __device__ __forceinline__ void bfly(float2& a, float2& b, int k64) {
     k64 &= 63;
     if (k64 == 0) {
-        float2 t = b;
-        b = make_float2(a.x - t.x, a.y - t.y);
-        a = make_float2(a.x + t.x, a.y + t.y);
-    } else if (k64 == 16) {                 // w = -i (fwd) / +i (inv):  w*b = (b.y, -b.x) / (-b.y, b.x)
-        float2 t = INV ? make_float2(-b.y, b.x) : make_float2(b.y, -b.x);
-        b = make_float2(a.x - t.x, a.y - t.y);
-        a = make_float2(a.x + t.x, a.y + t.y);
+        const float2 t = b;
+        b = f2add(a, make_float2(-t.x, -t.y));
+        a = f2add(a, t);
+    } else if (k64 == 16) {                 // w = -i (fwd): w b = (b.y, -b.x);  +i (inv): (-b.y, b.x)
+        const float2 t = INV ? make_float2(-b.y, b.x) : make_float2(b.y, -b.x);
+        b = f2add(a, make_float2(-t.x, -t.y));
+        a = f2add(a, t);
     } else {
         const float wr = cos64(k64);
-        const float wi = INV ? sin64(k64) : -sin64(k64);
-        float tr = fmaf(wr, b.x, a.x);
-        tr = fmaf(-wi, b.y, tr);
-        float ti = fmaf(wr, b.y, a.y);
-        ti = fmaf(wi, b.x, ti);
-        b = make_float2(fmaf(2.0f, a.x, -tr), fmaf(2.0f, a.y, -ti));
-        a = make_float2(tr, ti);
+        const float wi = INV ? sin64(k64) : -sin64(k64);                       // w = wr + i wi
+        float2 t = f2fma(b, make_float2(wr, wr), a);                            // a + wr b
+        t = f2fma(make_float2(-b.y, b.x), make_float2(wi, wi), t);              //   + wi (i b)
+        b = f2fma(a, make_float2(2.0f, 2.0f), make_float2(-t.x, -t.y));         // 2a - a'
+        a = t;
     }
 }
 
