@@ -666,6 +666,8 @@ int b2f_push(b2f_plan* pl, const void* const* frames, int64_t nframes, int on_de
         kb.nslots = nframes; kb.nif = nif; kb.nblk = pl->dedisp ? 0 : (int)nblk;
         kb.groups_per_slot = (int)pl->groups_per_slot; kb.samples_per_frame = (int)pl->spf;
         kb.block_samples = pl->M;
+        kb.compact = pl->d_compact + pl->carry_len; kb.compact_stride = pl->compact_stride;
+        kb.slot_bytes = pl->slot_bytes; kb.in_nbit = pl->prm.in_nbit;
         const int64_t n = nframes * nif;
         k0b_finish_slots<<<(unsigned)((n + 255) / 256), 256, 0, pl->stream>>>(kb);
         pl->launches++;

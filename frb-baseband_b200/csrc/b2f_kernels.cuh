@@ -251,6 +251,7 @@ struct K0bParams {
     uint8_t* blkdirty;                         // [nif][nblk]
     unsigned long long* counters;
     int64_t nslots; int nif, nblk, groups_per_slot, samples_per_frame; int64_t block_samples;
+    uint8_t* compact; size_t compact_stride; int slot_bytes, in_nbit;   // 2-bit: missing slots get the zero-entry index
 };
 static __global__ void k0b_finish_slots(const K0bParams p) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -262,6 +263,10 @@ static __global__ void k0b_finish_slots(const K0bParams p) {
     if (st == 0) {
         uint8_t* m = p.wmask + ifi * p.wmask_stride + slot * (int64_t)p.groups_per_slot;
         for (int g = 0; g < p.groups_per_slot; ++g) m[g] = 0xFF;
+        if (p.in_nbit == 2) {                                   // masking lives in the index stream for 2-bit input
+            uint4* d = reinterpret_cast<uint4*>(p.compact + ifi * p.compact_stride + slot * (int64_t)p.slot_bytes);
+            for (int k = 0; k < p.slot_bytes / 16; ++k) d[k] = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
+        }
         atomicAdd(&p.counters[C_MISSING], 1ull);
     }
     const int64_t s0 = slot * p.samples_per_frame;

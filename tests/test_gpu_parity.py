@@ -197,3 +197,49 @@ def test_coherent_dedispersion(gpu, usb, mode, name):
                     keep_bandpass=True, dm=dm, coherent=True, nfilt=nf)["data"]
     assert rows.shape[0] == ref.shape[0] and rows.shape[0] > 0
     assert_rel(rows.reshape(ref.shape), ref.astype(np.float64), REL_TOL, "dedispersed " + name)
+
+
+def test_frames_placed_by_header_time_with_gap(gpu):
+    """B2F_FRAMES_BY_HEADER: a run of frames missing from the file is zero-filled in place, the
+    frames after it keep their time slots (positional mode would shift them)."""
+    nchan, bw, D = 128, 32.0, 16
+    v = synth.make_vdif(1024, seed=101, bw_mhz=bw).reshape(1024, 8032)
+    lost = np.arange(300, 317)
+    keep = np.setdiff1d(np.arange(1024), lost)
+    vg = v[keep].reshape(-1)                                   # file with a 17-frame gap
+    cfg = PlanConfig(nchan=nchan, bw_mhz=[-bw], tscrunch=D, out_nbit=-32, keep_bandpass=True, frame_time_mode=1)
+    with Plan(cfg) as pl:
+        # the caller still hands over one chunk of file data; slots come from the headers
+        pad = np.zeros((1024 - keep.size) * 8032, np.uint8)
+        # filler frames carry a time stamp far outside the chunk: they must be dropped, not placed
+        pad.reshape(-1, 8032)[:, 0:4] = np.frombuffer(np.uint32((1 << 31) | 100000).tobytes(), np.uint8)
+        pad.reshape(-1, 8032)[:, 8:12] = v[0, 8:12]
+        pad.reshape(-1, 8032)[:, 12:16] = v[0, 12:16]
+        pl.push([np.concatenate([vg, pad])])
+        rows = pl.view_rows(pl.pull())
+        c = pl.counters()
+    vz = v.copy()
+    vz[lost, 0:4] = np.frombuffer(np.uint32((1 << 31)).tobytes(), np.uint8)      # oracle: those frames invalid -> zeros
+    ref = o.digifil(vz.reshape(-1), freq_mhz=1400.0, bw_mhz=-bw, nchan=nchan, tscrunch_factor=D, out_nbit=-32,
+                    keep_bandpass=True)["data"]
+    assert c["slots_missing"] == lost.size and c["frames_ok"] == keep.size and c["frames_dropped"] == lost.size
+    assert_rel(rows.reshape(ref.shape), ref.astype(np.float64), REL_TOL, "gap by header time")
+
+
+@pytest.mark.parametrize("nchan,bw,D", [(256, 32.0, 8), (16, 16.0, 64)])
+def test_other_row_lengths(gpu, nchan, bw, D):
+    """R = 512 (nchan 256 -> freq_res 2*256 = 512, process_vdif.py:162) and R = 32."""
+    cfg = PlanConfig(nchan=nchan, bw_mhz=[bw])
+    with Plan(cfg) as pl:
+        nfr = int(pl.chunk_frames)
+    v = synth.make_vdif(nfr, seed=111 + nchan, bw_mhz=bw, tone_frac=0.71)
+    rows, _ = run_plan([v], nchan=nchan, bw=[bw], tscrunch=D, out_nbit=-32, keep_bandpass=True)
+    ref = o.digifil(v, freq_mhz=1400.0, bw_mhz=bw, nchan=nchan, tscrunch_factor=D, out_nbit=-32, keep_bandpass=True)["data"]
+    assert_rel(rows.reshape(ref.shape), ref.astype(np.float64), REL_TOL, f"nchan {nchan}")
+
+
+def test_unsupported_requests_fail_loudly(gpu):
+    for kw in (dict(nchan=512), dict(nchan=128, tscrunch=3), dict(nchan=128, tscrunch=1024), dict(nchan=4)):
+        with pytest.raises(_lib.B2FError) as e:
+            Plan(PlanConfig(bw_mhz=[-32.0], **kw))
+        assert e.value.code == _lib.EUNSUPPORTED
