@@ -74,6 +74,9 @@ struct b2f_plan {
     int64_t batch_blocks = 0;      // FFT blocks per column/row launch pair (0 = whole chunk)
     // coherent dedispersion (digifil -D dm -F nchan:D): overlap-save geometry and halo carry
     bool dedisp = false;
+    bool generic = false;          // freq_res / nchan outside the tuned 512-point kernels
+    bool carry_mode = false;       // pushes need not hold whole blocks: unconsumed samples are carried over
+    float2 *d_tw_col = nullptr, *d_tw_row = nullptr;
     int nfilt_pos = 0, nfilt_neg = 0, keep = 0;
     int64_t step = 0;              // samples between block starts = keep * R
     int64_t carry_len = 0;         // samples of the previous push still needed (per IF)
@@ -257,7 +260,7 @@ void free_plan(b2f_plan* pl) {
     }
     void* bufs[] = {pl->d_compact, pl->d_wmask, pl->d_fstat, pl->d_blkdirty, pl->d_inter, pl->d_colsum,
                     pl->d_eps, pl->d_F, pl->d_mean, pl->d_scale, pl->d_partial, pl->d_tab_g, pl->d_tab_h,
-                    pl->d_tab_w, pl->d_tab_r, pl->d_counters, pl->d_sm_slots, pl->d_carry, pl->d_spec, pl->d_chirp};
+                    pl->d_tab_w, pl->d_tab_r, pl->d_counters, pl->d_sm_slots, pl->d_carry, pl->d_spec, pl->d_chirp, pl->d_tw_col, pl->d_tw_row};
     for (void* b : bufs)
         if (b) cudaFree(b);
     for (auto& t : pl->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
@@ -295,7 +298,40 @@ int push_dedisp(b2f_plan* pl, int64_t nblk, int64_t T) {
     const int nif = pl->prm.nif;
     const int64_t nbt = (int64_t)nif * nblk;
     int rc = 0;
-    if (nblk > 0) {
+    if (nblk > 0 && pl->generic) {
+        const int64_t NB = pl->batch_blocks > 0 ? std::min<int64_t>(pl->batch_blocks, nbt) : nbt;
+        KGParams kg{};
+        kg.compact = pl->d_compact; kg.compact_stride = pl->compact_stride;
+        kg.inter = pl->d_inter; kg.colsum = pl->d_colsum; kg.eps = pl->d_eps;
+        kg.tw_col = pl->d_tw_col; kg.tw_row = pl->d_tw_row;
+        kg.F = pl->d_F; kg.F_if_stride = pl->F_if_stride; kg.row0 = pl->rows_off + pl->rows_held;
+        kg.L = pl->L; kg.lgL = 31 - __builtin_clz(pl->L); kg.R = pl->R; kg.lgR = 31 - __builtin_clz(pl->R);
+        kg.C = std::min(16, 16384 / pl->L);
+        kg.nblk = (int)nblk; kg.nif = nif; kg.D = pl->D; kg.mode = pl->prm.pol_mode; kg.M = pl->M;
+        const size_t smem_col = ((size_t)pl->L * kg.C + pl->L / 2 + 32) * sizeof(float2);
+        const size_t smem_row = ((size_t)pl->R + pl->R / 2) * sizeof(float2);
+        CU(cudaFuncSetAttribute(kg_column_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_col));
+        CU(cudaFuncSetAttribute(kg_row_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row));
+        for (int64_t b0 = 0; b0 < nbt; b0 += NB) {
+            const int64_t nb = std::min(NB, nbt - b0);
+            kg.gb_begin = b0; kg.gb_end = b0 + nb;
+            const int64_t work = nb * (pl->R / kg.C);
+            rc = timed(pl, B2F_K_COLUMN, [&] {
+                kg_column_pass<<<(unsigned)std::min<int64_t>(work, pl->num_sms), 256, smem_col, pl->stream>>>(kg);
+            });
+            if (rc) return rc;
+            rc = timed(pl, B2F_K_EPS, [&] {
+                ke_eps<<<(unsigned)nb, pl->R / 2, pl->R * sizeof(float2), pl->stream>>>(pl->d_colsum + b0 * pl->R,
+                                                                                       pl->d_eps + b0 * pl->N, pl->R);
+            });
+            if (rc) return rc;
+            const int64_t ngroups = nb * (pl->L / pl->D);
+            rc = timed(pl, B2F_K_ROW, [&] {
+                kg_row_pass<<<(unsigned)std::min<int64_t>(ngroups, (int64_t)pl->num_sms * 4), 256, smem_row, pl->stream>>>(kg);
+            });
+            if (rc) return rc;
+        }
+    } else if (nblk > 0) {
         const int64_t cap = pl->batch_blocks > 0 ? pl->batch_blocks : (int64_t)nif * pl->chunk_blocks;
         const int64_t NB = std::min<int64_t>(cap, nbt);
         KAParams ka{};
@@ -385,17 +421,20 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
     if (!(prm->in_nbit == 2 || prm->in_nbit == 8)) return fail(B2F_EUNSUPPORTED, "VDIF bits/sample must be 2 or 8");
     if (prm->nchan < 1) return fail(B2F_EINVAL, "nchan");
     const int L = prm->freq_res > 0 ? prm->freq_res : (prm->nchan <= 128 ? 512 : 2 * prm->nchan);
-    if (L != kL) return fail(B2F_EUNSUPPORTED, "freq_res must be 512 (nchan <= 256) in this build");
     const int R = 2 * prm->nchan;
-    if (!is_pow2(R) || R < 16 || R > 512) return fail(B2F_EUNSUPPORTED, "nchan must be a power of two in 8..256");
+    if (!is_pow2(R) || R < 16 || R > 2048) return fail(B2F_EUNSUPPORTED, "nchan must be a power of two in 8..1024");
+    if (!is_pow2(L) || L < 16 || L > 2048) return fail(B2F_EUNSUPPORTED, "freq_res must be a power of two in 16..2048");
+    const bool generic = !(L == kL && R <= 512);        // tuned kernels: 512-point columns, rows up to 512
+    if (generic && prm->in_nbit != 2) return fail(B2F_EUNSUPPORTED, "freq_res != 512 or nchan > 256 needs 2-bit input in this build");
     const int D = prm->tscrunch < 1 ? 1 : prm->tscrunch;
-    if (!is_pow2(D) || D > kL) return fail(B2F_EUNSUPPORTED, "tscrunch must be a power of two <= 512");
+    if (!is_pow2(D) || D > L) return fail(B2F_EUNSUPPORTED, "tscrunch must be a power of two <= freq_res");
     if (prm->header_bytes != 32 && prm->header_bytes != 16) return fail(B2F_EINVAL, "header_bytes must be 32 or 16");
     const int payload = prm->frame_bytes - prm->header_bytes;
     if (payload <= 0 || payload % 8) return fail(B2F_EINVAL, "frame_bytes");
     const bool dedisp = prm->coherent && prm->dm > 0.0;
     if (dedisp && prm->in_nbit != 2) return fail(B2F_EUNSUPPORTED, "coherent dedispersion needs 2-bit input in this build");
     if (dedisp && D > 128) return fail(B2F_EUNSUPPORTED, "coherent dedispersion needs tscrunch <= 128");
+    if (dedisp && generic) return fail(B2F_EUNSUPPORTED, "coherent dedispersion needs freq_res 512 and nchan <= 256 in this build");
     const double abw = std::fabs(prm->bw_mhz[0]);
     if (abw <= 0) return fail(B2F_EINVAL, "bw_mhz");
     for (int i = 0; i < prm->nif; ++i) {
@@ -427,6 +466,8 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
     pl->spf = spf; pl->fps = fps; pl->payload = payload;
     pl->groups_per_slot = (payload + 31) / 32;
     pl->dedisp = dedisp;
+    pl->generic = generic;
+    pl->carry_mode = dedisp || generic;
     pl->step = pl->M;
     pl->keep = L;
     if (dedisp) {
@@ -450,9 +491,15 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
     pl->unit_blocks = pl->spf / g;
     int cu = prm->chunk_units > 0 ? prm->chunk_units : 1;
     if (dedisp && prm->chunk_units <= 0) cu = (int)std::max<int64_t>(1, 1024 / pl->unit_frames);
+    if (generic) {                 // blocks span seconds: pushes are plain 1024-frame pieces, the carry does the rest
+        pl->unit_frames = 1;
+        pl->unit_blocks = 0;
+        cu = prm->chunk_units > 0 ? prm->chunk_units : 1024;
+    }
     pl->chunk_frames = pl->unit_frames * cu;
     pl->chunk_blocks = pl->unit_blocks * cu;
-    if (dedisp) pl->chunk_blocks += 1;                         // carried samples can complete one more block
+    if (generic) pl->chunk_blocks = pl->chunk_frames * pl->spf / pl->M;
+    if (pl->carry_mode) pl->chunk_blocks += 1;                 // carried samples can complete one more block
     pl->chunk_rows = pl->chunk_blocks * pl->keep / D;
     const double tsamp = (double)D * prm->nchan / (abw * 1e6);
     const double interval = prm->rescale_interval_s > 0 ? prm->rescale_interval_s : 10.0;
@@ -467,6 +514,7 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
         // or not the intermediate stays in L2, and every extra launch costs ~7 us.
         const char* b = getenv("B2F_BATCH_BLOCKS");
         pl->batch_blocks = b ? atoll(b) : 0;
+        if (!b && generic) pl->batch_blocks = std::max<int64_t>(1, (1ll << 30) / ((int64_t)L * R * (int64_t)sizeof(float2)));
     }
 
     cudaDeviceProp prop;
@@ -500,7 +548,7 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
     const int nif = prm->nif;
     const int64_t nbt = (int64_t)nif * pl->chunk_blocks;
     pl->slot_bytes = prm->in_nbit == 2 ? 2 * payload : payload;      // 2-bit: one index byte per time sample
-    pl->compact_stride = (size_t)((pl->chunk_frames * (int64_t)pl->slot_bytes + (dedisp ? pl->M : 0) + 255) / 256 * 256);
+    pl->compact_stride = (size_t)((pl->chunk_frames * (int64_t)pl->slot_bytes + (pl->carry_mode ? pl->M : 0) + 255) / 256 * 256);
     pl->wmask_stride = (size_t)((pl->chunk_frames * pl->groups_per_slot + 255) / 256 * 256);
     pl->fstat_stride = (size_t)((pl->chunk_frames + 255) / 256 * 256);
     CUB(cudaMalloc(&pl->d_compact, pl->compact_stride * nif));
@@ -518,8 +566,17 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
     CUB(cudaMalloc(&pl->d_partial, (size_t)nif * kStatSplit * nprod * pl->N * sizeof(double2)));
     CUB(cudaMalloc(&pl->d_counters, C_COUNT * sizeof(unsigned long long)));
     CUB(cudaMalloc(&pl->d_sm_slots, 1024 * sizeof(int)));
+    if (pl->carry_mode) CUB(cudaMalloc(&pl->d_carry, (size_t)pl->M * nif));
+    if (generic) {
+        std::vector<float2> tc(L / 2), tr(R / 2);
+        for (int k = 0; k < L / 2; ++k) tc[k] = make_float2((float)cos(-2.0 * M_PI * k / L), (float)sin(-2.0 * M_PI * k / L));
+        for (int k = 0; k < R / 2; ++k) tr[k] = make_float2((float)cos(-2.0 * M_PI * k / R), (float)sin(-2.0 * M_PI * k / R));
+        CUB(cudaMalloc(&pl->d_tw_col, tc.size() * sizeof(float2)));
+        CUB(cudaMalloc(&pl->d_tw_row, tr.size() * sizeof(float2)));
+        CUB(cudaMemcpy(pl->d_tw_col, tc.data(), tc.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        CUB(cudaMemcpy(pl->d_tw_row, tr.data(), tr.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    }
     if (dedisp) {
-        CUB(cudaMalloc(&pl->d_carry, (size_t)pl->M * nif));
         CUB(cudaMalloc(&pl->d_spec, (size_t)inter_blocks * L * R * sizeof(float2)));
         // chirp H[if][k2][c] = exp(-i 2 pi D DM 1e6 f^2 / (fc^2 (fc + f))), conjugated for LSB, in double
         std::vector<float2> h((size_t)nif * L * prm->nchan);
@@ -592,9 +649,9 @@ int b2f_push(b2f_plan* pl, const void* const* frames, int64_t nframes, int on_de
     CU(cudaSetDevice(pl->prm.device));
     const int nif = pl->prm.nif;
     const int64_t T = pl->carry_len + nframes * pl->spf;          // samples available per IF (carry + new)
-    const int64_t nblk = pl->dedisp ? (T >= pl->M ? (T - pl->M) / pl->step + 1 : 0) : nframes * pl->spf / pl->M;
+    const int64_t nblk = pl->carry_mode ? (T >= pl->M ? (T - pl->M) / pl->step + 1 : 0) : nframes * pl->spf / pl->M;
     const int64_t rows = nblk * pl->keep / pl->D;
-    if (nblk == 0 && !pl->dedisp) return 0;
+    if (nblk == 0 && !pl->carry_mode) return 0;
     if (pl->rows_off + pl->rows_held + rows > pl->F_cap_rows)
         return fail(B2F_ESTATE, "row buffer full: call b2f_pull before pushing more");
     const size_t fbytes = (size_t)nframes * pl->prm.frame_bytes;
@@ -645,7 +702,7 @@ int b2f_push(b2f_plan* pl, const void* const* frames, int64_t nframes, int on_de
         k0.base_sec[i] = pl->base_sec0[i] + (uint32_t)(tot / pl->fps);
         k0.base_fnum[i] = (uint32_t)(tot % pl->fps);
     }
-    if (pl->dedisp && pl->carry_len) {
+    if (pl->carry_mode && pl->carry_len) {
         for (int i = 0; i < nif; ++i)
             CU(cudaMemcpyAsync(pl->d_compact + i * pl->compact_stride, pl->d_carry + (size_t)i * pl->M, (size_t)pl->carry_len,
                                cudaMemcpyDeviceToDevice, pl->stream));
@@ -663,7 +720,7 @@ int b2f_push(b2f_plan* pl, const void* const* frames, int64_t nframes, int on_de
         kb.wmask = pl->d_wmask; kb.wmask_stride = pl->wmask_stride;
         kb.fstat = pl->d_fstat; kb.fstat_stride = pl->fstat_stride;
         kb.blkdirty = pl->d_blkdirty; kb.counters = pl->d_counters;
-        kb.nslots = nframes; kb.nif = nif; kb.nblk = pl->dedisp ? 0 : (int)nblk;
+        kb.nslots = nframes; kb.nif = nif; kb.nblk = pl->carry_mode ? 0 : (int)nblk;
         kb.groups_per_slot = (int)pl->groups_per_slot; kb.samples_per_frame = (int)pl->spf;
         kb.block_samples = pl->M;
         kb.compact = pl->d_compact + pl->carry_len; kb.compact_stride = pl->compact_stride;
@@ -673,7 +730,7 @@ int b2f_push(b2f_plan* pl, const void* const* frames, int64_t nframes, int on_de
         pl->launches++;
         CU(cudaGetLastError());
     }
-    if (pl->dedisp) {
+    if (pl->carry_mode) {
         rc = push_dedisp(pl, nblk, T);
         if (rc) return rc;
     } else

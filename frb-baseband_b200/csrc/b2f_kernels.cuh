@@ -999,6 +999,167 @@ __global__ void __launch_bounds__(256, 2) kc_dedisp_back(const KCParams p) {
     }
 }
 
+// ================================================================== generic channeliser
+// Any power-of-two freq_res (L) and row length (R = 2 nchan) outside the tuned 512-point kernels,
+// e.g. process_vdif's default --nchan 512 -> -F512:1024 (/root/reference/process_vdif.py:46,162).
+// Same algebra as the tuned path, iterative radix-2 FFTs in shared memory:
+// forward DIF leaves the spectrum bit-reversed, the diagonal is applied in that order and the
+// inverse DIT consumes it, so no reordering pass is needed.  2-bit input (index stream) only.
+struct KGParams {
+    const uint8_t* compact; size_t compact_stride;
+    float2* inter;               // [gb - gb_begin][L][R]
+    float2* colsum;              // [nif*nblk][R]
+    const float2* eps;           // [nif*nblk][R/2]
+    const float2* tw_col;        // [L/2]  exp(-2 pi i k / L)
+    const float2* tw_row;        // [R/2]  exp(-2 pi i k / R)
+    float* F; int64_t F_if_stride; int64_t row0;
+    int L, lgL, R, lgR, C, nblk, nif, D, mode;
+    int64_t M, gb_begin, gb_end;
+};
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+
+static __global__ void __launch_bounds__(256) kg_column_pass(const KGParams p) {
+    extern __shared__ __align__(16) uint8_t kg_smem[];
+    float2* data = reinterpret_cast<float2*>(kg_smem);                   // [L][C]
+    float2* tw = data + (size_t)p.L * p.C;                                // [L/2]
+    float2* lut = tw + p.L / 2;                                           // [32]
+    const int tid = threadIdx.x, L = p.L, C = p.C, R = p.R, lgL = p.lgL;
+    for (int i = tid; i < L / 2; i += 256) tw[i] = p.tw_col[i];
+    if (tid < 32) {
+        const int c0 = tid & 3, c1 = (tid >> 2) & 3;
+        const float m0 = (c0 == 0 || c0 == 3) ? kLevHi : kLevLo, m1 = (c1 == 0 || c1 == 3) ? kLevHi : kLevLo;
+        lut[tid] = tid < 16 ? make_float2((c0 & 2) ? m0 : -m0, (c1 & 2) ? m1 : -m1) : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    const int nstrips = R / C;
+    const int64_t nwork = (p.gb_end - p.gb_begin) * nstrips;
+    const int nel = L * C, nbf = (L / 2) * C;
+    for (int64_t w = blockIdx.x; w < nwork; w += gridDim.x) {
+        const int64_t lb = w / nstrips, gb = p.gb_begin + lb;
+        const int strip = (int)(w % nstrips);
+        const int ifi = (int)(gb / p.nblk);
+        const int64_t blk = gb % p.nblk;
+        const uint8_t* src = p.compact + ifi * p.compact_stride + blk * p.M + (int64_t)strip * C;
+        for (int i = tid; i < nel; i += 256) {
+            const int n2 = i / C, cl = i % C;
+            data[i] = *reinterpret_cast<const float2*>(reinterpret_cast<const uint8_t*>(lut) + src[(int64_t)n2 * R + cl]);
+        }
+        __syncthreads();
+        for (int s = lgL - 1; s >= 0; --s) {                 // forward DIF: natural in, bit-reversed out
+            const int half = 1 << s;
+            for (int i = tid; i < nbf; i += 256) {
+                const int cl = i % C, b = i / C;
+                const int j = b & (half - 1);
+                const int i0 = (((b >> s) << (s + 1)) + j) * C + cl, i1 = i0 + half * C;
+                const float2 x = data[i0], y = data[i1];
+                data[i0] = cadd(x, y);
+                data[i1] = cmul(csub(x, y), tw[j << (lgL - 1 - s)]);
+            }
+            __syncthreads();
+        }
+        if (tid < C) p.colsum[gb * R + strip * C + tid] = data[tid];            // A[k2 = 0] sits at position 0
+        for (int i = tid; i < nel; i += 256) {               // * W_M^(k2 n1), k2 = bitrev(position)
+            const int pos = i / C, cl = i % C;
+            const unsigned k2 = __brev((unsigned)pos) >> (32 - lgL);
+            const long long ph = ((long long)k2 * (strip * C + cl)) % p.M;
+            float sn, cs;
+            sincospif(-2.0f * (float)((double)ph / (double)p.M), &sn, &cs);
+            data[i] = cmul(data[i], make_float2(cs, sn));
+        }
+        __syncthreads();
+        for (int s = 0; s < lgL; ++s) {                      // inverse DIT: bit-reversed in, natural out
+            const int half = 1 << s;
+            for (int i = tid; i < nbf; i += 256) {
+                const int cl = i % C, b = i / C;
+                const int j = b & (half - 1);
+                const int i0 = (((b >> s) << (s + 1)) + j) * C + cl, i1 = i0 + half * C;
+                const float2 x = data[i0], t = cmul_conj(data[i1], tw[j << (lgL - 1 - s)]);
+                data[i0] = cadd(x, t);
+                data[i1] = csub(x, t);
+            }
+            __syncthreads();
+        }
+        float2* dst = p.inter + lb * (int64_t)L * R + strip * C;
+        for (int i = tid; i < nel; i += 256) dst[(int64_t)(i / C) * R + (i % C)] = data[i];
+        __syncthreads();
+    }
+}
+
+// generic row pass: one CTA walks the D rows of an output sample; row FFT in shared memory
+static __global__ void __launch_bounds__(256) kg_row_pass(const KGParams p) {
+    extern __shared__ __align__(16) uint8_t kg_smem[];
+    float2* row = reinterpret_cast<float2*>(kg_smem);                    // [R]
+    float2* tw = row + p.R;                                               // [R/2]
+    const int tid = threadIdx.x, R = p.R, N = R / 2, lgR = p.lgR, L = p.L, D = p.D;
+    for (int i = tid; i < R / 2; i += 256) tw[i] = p.tw_row[i];
+    __syncthreads();
+    const int nprod = nprod_of_mode(p.mode);
+    const int groups_per_blk = L / D;
+    const int64_t ngroups = (p.gb_end - p.gb_begin) * groups_per_blk;
+    constexpr int CPT = 4;                                               // channels per thread: nchan <= 1024
+    for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+        const int64_t lb = g / groups_per_blk, gb = p.gb_begin + lb;
+        const int g0 = (int)(g % groups_per_blk) * D;
+        float acc[CPT][4];
+#pragma unroll
+        for (int k = 0; k < CPT; ++k)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[k][q] = 0.f;
+        for (int r = 0; r < D; ++r) {
+            const float2* src = p.inter + (lb * (int64_t)L + g0 + r) * R;
+            for (int i = tid; i < R; i += 256) row[i] = src[i];
+            __syncthreads();
+            for (int s = lgR - 1; s >= 0; --s) {             // forward DIF, output bit-reversed
+                const int half = 1 << s;
+                for (int b = tid; b < R / 2; b += 256) {
+                    const int j = b & (half - 1);
+                    const int i0 = ((b >> s) << (s + 1)) + j, i1 = i0 + half;
+                    const float2 x = row[i0], y = row[i1];
+                    row[i0] = cadd(x, y);
+                    row[i1] = cmul(csub(x, y), tw[j << (lgR - 1 - s)]);
+                }
+                __syncthreads();
+            }
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) {
+                const int c = tid + 256 * k;
+                if (c < N) {
+                    const float2 a = row[__brev((unsigned)c) >> (32 - lgR)];
+                    const float2 b = row[__brev((unsigned)(R - 1 - c)) >> (32 - lgR)];
+                    const float2 e = p.eps[gb * N + c];
+                    const float2 bp = make_float2(b.x - e.x, -b.y - e.y);
+                    const float2 P = cadd(a, bp), Q = csub(a, bp);
+                    const float pp = 0.25f * (P.x * P.x + P.y * P.y), qq = 0.25f * (Q.x * Q.x + Q.y * Q.y);
+                    const float xr = P.x * Q.x + P.y * Q.y, xi = P.y * Q.x - P.x * Q.y;
+                    const float re = -0.25f * xi, im = 0.25f * xr;
+                    switch (p.mode) {
+                        case B2F_POL_P0: acc[k][0] += pp; break;
+                        case B2F_POL_P1: acc[k][0] += qq; break;
+                        case B2F_POL_I: acc[k][0] += pp + qq; break;
+                        case B2F_POL_I2: acc[k][0] += (pp + qq) * (pp + qq); break;
+                        case B2F_POL_PPQQ: acc[k][0] += pp; acc[k][1] += qq; break;
+                        case B2F_POL_COHERENCE: acc[k][0] += pp; acc[k][1] += qq; acc[k][2] += re; acc[k][3] += im; break;
+                        default: acc[k][0] += pp + qq; acc[k][1] += 2.f * re; acc[k][2] += 2.f * im; acc[k][3] += pp - qq; break;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        const int ifi = (int)(gb / p.nblk);
+        const int64_t blk = gb % p.nblk;
+        const int64_t t = p.row0 + (blk * L + g0) / D;
+        float* dst = p.F + ifi * p.F_if_stride + t * (int64_t)(nprod * N);
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) {
+            const int c = tid + 256 * k;
+            if (c < N)
+                for (int q = 0; q < nprod; ++q) dst[q * N + c] = acc[k][q];
+        }
+    }
+}
+
 // ================================================================== kernel 5a: statistics
 // mean / sigma per (IF, product, channel) over the first rescale interval, fp64 accumulators,
 // deterministic two-level reduction.

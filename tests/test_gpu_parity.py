@@ -239,7 +239,35 @@ def test_other_row_lengths(gpu, nchan, bw, D):
 
 
 def test_unsupported_requests_fail_loudly(gpu):
-    for kw in (dict(nchan=512), dict(nchan=128, tscrunch=3), dict(nchan=128, tscrunch=1024), dict(nchan=4)):
+    for kw in (dict(nchan=2048), dict(nchan=128, tscrunch=3), dict(nchan=128, tscrunch=1024), dict(nchan=4),
+               dict(nchan=512, in_nbit=8), dict(nchan=512, dm=100.0, coherent=True)):
         with pytest.raises(_lib.B2FError) as e:
             Plan(PlanConfig(bw_mhz=[-32.0], **kw))
         assert e.value.code == _lib.EUNSUPPORTED
+
+
+@pytest.mark.parametrize("nchan,freq_res,D,nframes", [(512, 0, 4, 1500), (1024, 0, 2, 1100), (128, 64, 16, 300), (32, 2048, 32, 700)])
+def test_generic_channeliser(gpu, nchan, freq_res, D, nframes):
+    """freq_res / nchan outside the tuned kernels, e.g. process_vdif's default --nchan 512 ->
+    digifil -F512:1024 (process_vdif.py:46,162).  Pushes are 1024-frame pieces that do not align
+    with the multi-second FFT blocks: the unconsumed samples are carried to the next push."""
+    bw = 32.0
+    L = freq_res or (512 if nchan <= 128 else 2 * nchan)
+    v = synth.make_vdif(nframes, seed=121 + nchan, bw_mhz=bw, tone_frac=0.43, rho=0.2)
+    cfg = PlanConfig(nchan=nchan, bw_mhz=[bw], freq_res=freq_res, tscrunch=D, out_nbit=-32, keep_bandpass=True, chunk_units=400)
+    out = []
+    with Plan(cfg) as pl:
+        assert int(pl.geometry.freq_res) == L
+        cf, fb = int(pl.chunk_frames), cfg.frame_bytes
+        assert cf == 400
+        for f0 in range(0, nframes, cf):
+            n = min(cf, nframes - f0)
+            pl.push([v[f0 * fb:(f0 + n) * fb]])
+            out.append(pl.pull().copy())
+        pl.flush()
+        out.append(pl.pull().copy())
+        rows = pl.view_rows(np.concatenate(out))
+    ref = o.digifil(v, freq_mhz=1400.0, bw_mhz=bw, nchan=nchan, freq_res=L, tscrunch_factor=D, out_nbit=-32,
+                    keep_bandpass=True)["data"]
+    assert rows.shape[0] == ref.shape[0] and ref.shape[0] > 0
+    assert_rel(rows.reshape(ref.shape), ref.astype(np.float64), REL_TOL, f"generic nchan {nchan} L {L}")
