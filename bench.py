@@ -169,6 +169,7 @@ def main():
     ap.add_argument("--seconds", type=float, default=60.0, help="seconds of sky data per step (C2: 60)")
     ap.add_argument("--impl", default="b2f", choices=["b2f", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--nccl-gather", action="store_true", help="splice with an NCCL gather instead of peer stores")
     ap.add_argument("--cpu-sample", type=float, default=1.024, help="seconds of data for the cpu_baseline leg")
     args = ap.parse_args()
 
@@ -197,7 +198,7 @@ def main():
     import torch.distributed as dist
     from frb_baseband_b200 import _lib
     from frb_baseband_b200.plan import Plan, PlanConfig, fp32_peak_tflops
-    from frb_baseband_b200.dist import gather_splice, rank_if_plan
+    from frb_baseband_b200.dist import PeerSplice, gather_splice, rank_if_plan
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the b2f path has no CPU fallback")
@@ -216,19 +217,35 @@ def main():
     rows_total = (nframes * 16000 // (2 * NCHAN * FREQ_RES)) * FREQ_RES // TSCRUNCH   # only an upper bound
     vd = [make_device_vdif(torch, dev, nframes, 20121102 + 2000 + 100 * rank + i) for i in range(NIF)]
     out_dev = torch.empty((rows_total + cf, NIF * NCHAN), dtype=torch.uint8, device=dev)
-    gathered = torch.empty((world, rows_total + cf, NIF * NCHAN), dtype=torch.uint8, device=dev) if (world > 1 and rank == 0) else None
+    gathered = None
+    peer = None
+    if world > 1 and not args.nccl_gather:
+        try:       # splice by peer stores over NVLink from the requantise kernel itself
+            peer = PeerSplice(rows_total + cf, NIF * NCHAN, world, rank, dev)
+        except Exception as ex:
+            if rank == 0:
+                print(f"peer splice unavailable ({ex!r}); falling back to an NCCL gather", file=sys.stderr)
+    if world > 1 and peer is None and rank == 0:
+        gathered = torch.empty((world, rows_total + cf, NIF * NCHAN), dtype=torch.uint8, device=dev)
     chunks = [(f0, min(cf, nframes - f0)) for f0 in range(0, nframes, cf)]
 
     def step_device():
         pl.reset()
         got = 0
+        cap = rows_total + cf
         for f0, n in chunks:
             pl.push([v[f0].data_ptr() for v in vd], nframes=n, on_device=True)
-            got += pl.pull_device(out_dev[got].data_ptr(), rows_total + cf - got)
+            if peer is not None:
+                got += pl.pull_strided(peer.dst(got), cap - got, peer.pitch)
+            else:
+                got += pl.pull_device(out_dev[got].data_ptr(), cap - got)
         pl.flush()
-        got += pl.pull_device(out_dev[got].data_ptr(), rows_total + cf - got)
-        if world > 1:       # the splice gather: every rank's 8-bit tile into rank 0's band-ordered rows
-            gather_splice(out_dev, world, rank, dst=0, out=gathered)
+        if peer is not None:
+            got += pl.pull_strided(peer.dst(got), cap - got, peer.pitch)
+        else:
+            got += pl.pull_device(out_dev[got].data_ptr(), cap - got)
+            if world > 1:   # fallback: gather every rank's 8-bit tile into rank 0's band-ordered rows
+                gather_splice(out_dev, world, rank, dst=0, out=gathered)
         return got
 
     def timed(fn, steps, warmup, sampler=None):
@@ -355,7 +372,7 @@ def main():
         "config": {"workload": "C2: 8 IF x 32 MHz dual-pol 2-bit VDIF (2 Gbps), %.0f s, nchan 128, freq_res 512 "
                                "(digifil -F128:512), tscrunch 16, 8-bit Stokes I spliced to 1024 channels" % data_sec,
                    "nif_per_gpu": NIF, "chunk_frames": cf, "l2": "inputs (15.4 GB/step) and intermediates larger than L2",
-                   "parallelism": f"subband groups x{world}, NCCL gather of 8-bit tiles" if world > 1 else "1 GPU"},
+                   "parallelism": (f"subband groups x{world}, " + ("splice by NVLink peer stores from the requantise kernel" if peer is not None else "NCCL gather of 8-bit tiles")) if world > 1 else "1 GPU"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roofline, "roofline_fp32": roofline_fp32,
         "kernel_ms_per_step": {k: v[0] / args.steps for k, v in ktimes.items() if v[1]},

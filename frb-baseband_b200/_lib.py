@@ -59,6 +59,7 @@ SYMBOLS = {
     "b2f_push": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int64, C.c_int]),
     "b2f_flush": (C.c_int, [C.c_void_p]),
     "b2f_pull": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_int64)]),
+    "b2f_pull_strided": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.c_int64)]),
     "b2f_sync": (C.c_int, [C.c_void_p]),
     "b2f_reset": (C.c_int, [C.c_void_p]),
     "b2f_get_counters": (C.c_int, [C.c_void_p, C.POINTER(Counters)]),

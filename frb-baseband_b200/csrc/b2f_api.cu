@@ -796,7 +796,19 @@ int b2f_flush(b2f_plan* pl) {
     return 0;
 }
 
+static int pull_impl(b2f_plan* pl, void* out, int64_t max_rows, int out_on_device, int64_t pitch_bytes, int64_t* nrows);
+
 int b2f_pull(b2f_plan* pl, void* out, int64_t max_rows, int out_on_device, int64_t* nrows) {
+    return pull_impl(pl, out, max_rows, out_on_device, 0, nrows);
+}
+
+int b2f_pull_strided(b2f_plan* pl, void* out, int64_t max_rows, int64_t row_pitch_bytes, int64_t* nrows) {
+    if (pl && row_pitch_bytes < pl->row_bytes) return fail(B2F_EINVAL, "row pitch smaller than one output row");
+    if (row_pitch_bytes % 4) return fail(B2F_EINVAL, "row pitch must be a multiple of 4 bytes");
+    return pull_impl(pl, out, max_rows, 1, row_pitch_bytes, nrows);
+}
+
+static int pull_impl(b2f_plan* pl, void* out, int64_t max_rows, int out_on_device, int64_t pitch_bytes, int64_t* nrows) {
     if (!pl || !nrows) return fail(B2F_EINVAL, "null argument");
     *nrows = 0;
     CU(cudaSetDevice(pl->prm.device));
@@ -839,6 +851,7 @@ int b2f_pull(b2f_plan* pl, void* out, int64_t max_rows, int out_on_device, int64
     kq.F = pl->d_F + pl->rows_off * ncol; kq.F_if_stride = pl->F_if_stride;
     kq.mean = pl->d_mean; kq.scale = pl->d_scale; kq.out = dst;
     kq.rows = n; kq.out_row_elems = pl->row_elems;
+    kq.out_pitch_bytes = pitch_bytes > 0 ? pitch_bytes : pl->row_bytes;
     kq.nif = nif; kq.nprod = pl->nprod; kq.nchan = pl->N; kq.out_nbit = pl->prm.out_nbit;
     kq.pol_major = pl->prm.splice_pol_major;
     for (int i = 0; i < nif; ++i) {

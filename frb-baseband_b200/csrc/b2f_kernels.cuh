@@ -1203,6 +1203,7 @@ struct KQParams {
     const float* mean; const float* scale;        // [nif][nprod*nchan]
     void* out;
     int64_t rows; int64_t out_row_elems;
+    int64_t out_pitch_bytes;                       // bytes between output rows (>= one row); rows may live on a peer GPU
     int nif, nprod, nchan, out_nbit, pol_major;
     int if_order[B2F_MAX_IF];
     int flip[B2F_MAX_IF];                          // 1: channel reversal (USB)
@@ -1239,26 +1240,28 @@ static __global__ void kq_quantise(const KQParams p) {
         const int c = p.flip[ifi] ? (p.nchan - 1 - (k + a)) : (k + a);
         y[a] = (f[c] - mu[c]) * sc[c];
     }
-    const int64_t o = row * p.out_row_elems + j;
+    // byte address of element j of this row: the row pitch lets a rank drop its tile into the
+    // owner's wider spliced rows (possibly peer memory over NVLink)
+    uint8_t* orow = reinterpret_cast<uint8_t*>(p.out) + row * p.out_pitch_bytes;
     if (p.out_nbit == 8) {
         uint32_t w = 0;
 #pragma unroll
         for (int a = 0; a < 4; ++a) w |= (uint32_t)quant(y[a], 127.5f / 6.0f, 127.5f, 255.f) << (8 * a);
-        reinterpret_cast<uint32_t*>(p.out)[o / 4] = w;
+        *reinterpret_cast<uint32_t*>(orow + j) = w;
     } else if (p.out_nbit == 16) {
         ushort4 w;
         w.x = (unsigned short)quant(y[0], 32768.0f / 6.0f, 32768.0f, 65535.f);
         w.y = (unsigned short)quant(y[1], 32768.0f / 6.0f, 32768.0f, 65535.f);
         w.z = (unsigned short)quant(y[2], 32768.0f / 6.0f, 32768.0f, 65535.f);
         w.w = (unsigned short)quant(y[3], 32768.0f / 6.0f, 32768.0f, 65535.f);
-        reinterpret_cast<ushort4*>(p.out)[o / 4] = w;
+        *reinterpret_cast<ushort4*>(orow + 2 * (int64_t)j) = w;
     } else if (p.out_nbit == 2) {
         uint32_t w = 0;
 #pragma unroll
         for (int a = 0; a < 4; ++a) w |= (uint32_t)quant(y[a], 1.0f, 1.5f, 3.f) << (2 * a);
-        reinterpret_cast<uint8_t*>(p.out)[o / 4] = (uint8_t)w;
+        orow[j / 4] = (uint8_t)w;
     } else {
-        reinterpret_cast<float4*>(p.out)[o / 4] = make_float4(y[0], y[1], y[2], y[3]);
+        *reinterpret_cast<float4*>(orow + 4 * (int64_t)j) = make_float4(y[0], y[1], y[2], y[3]);
     }
 }
 

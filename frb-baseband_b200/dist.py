@@ -45,3 +45,31 @@ def gather_splice(local_rows, world: int, rank: int, dst: int = 0, group=None, o
         return None
     # [world, rows, tile] -> [rows, world(descending), tile]
     return out.flip(0).permute(1, 0, 2).reshape(rows, world * tile)
+
+
+class PeerSplice:
+    """In-GPU splice across ranks without a collective on the data path: the owner's spliced rows
+    [rows, world*tile_bytes] live in symmetric memory, every rank gets the owner's device pointer
+    (NVLink-mapped) and its requantise kernel stores its tile there at column
+    (world-1-rank)*tile_bytes -- highest sky frequency first, like base2fil's splice_list
+    (/root/reference/base2fil.sh:350,367,422).  torch only provides the mapping."""
+
+    def __init__(self, rows: int, tile_bytes: int, world: int, rank: int, device, owner: int = 0, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+
+        self.rows, self.tile, self.world, self.rank, self.owner = rows, tile_bytes, world, rank, owner
+        self.pitch = world * tile_bytes
+        self.col = (world - 1 - rank) * tile_bytes
+        self.buf = symm.empty((rows, self.pitch), dtype=torch.uint8, device=device)
+        self.handle = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.owner_ptr = int(self.handle.buffer_ptrs[owner])
+
+    def dst(self, row: int) -> int:
+        """device pointer of this rank's tile in output row `row` of the owner's buffer"""
+        return self.owner_ptr + row * self.pitch + self.col
+
+    def result(self):
+        """the spliced rows (valid on the owner after every rank has synchronised)"""
+        return self.buf if self.rank == self.owner else None

@@ -163,6 +163,12 @@ class Plan:
         _lib.check(_lib.lib().b2f_pull(self._h, C.c_void_p(dev_ptr), max_rows, 1, C.byref(n)))
         return n.value
 
+    def pull_strided(self, dev_ptr: int, max_rows: int, row_pitch_bytes: int) -> int:
+        """Rows into device (or NVLink-mapped peer) memory with a row pitch: in-GPU splice across ranks."""
+        n = C.c_int64(0)
+        _lib.check(_lib.lib().b2f_pull_strided(self._h, C.c_void_p(dev_ptr), max_rows, row_pitch_bytes, C.byref(n)))
+        return n.value
+
     def sync(self):
         _lib.check(_lib.lib().b2f_sync(self._h))
 

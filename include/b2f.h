@@ -144,6 +144,11 @@ int b2f_flush(struct b2f_plan* plan);
  * is still filling. */
 int b2f_pull(struct b2f_plan* plan, void* out, int64_t max_rows, int out_on_device, int64_t* nrows);
 
+/* Like b2f_pull with out_on_device = 1, but consecutive rows are row_pitch_bytes apart: a rank that
+ * owns part of the band drops its tile into the wider spliced rows of the rank that owns the file --
+ * `out` may be that rank's memory mapped over NVLink (the in-GPU form of base2fil.sh:422's splice). */
+int b2f_pull_strided(struct b2f_plan* plan, void* out, int64_t max_rows, int64_t row_pitch_bytes, int64_t* nrows);
+
 int b2f_sync(struct b2f_plan* plan);
 int b2f_reset(struct b2f_plan* plan);        /* new scan, same parameters */
 int b2f_get_counters(struct b2f_plan* plan, b2f_counters* out);
