@@ -271,3 +271,29 @@ def test_generic_channeliser(gpu, nchan, freq_res, D, nframes):
                     keep_bandpass=True)["data"]
     assert rows.shape[0] == ref.shape[0] and ref.shape[0] > 0
     assert_rel(rows.reshape(ref.shape), ref.astype(np.float64), REL_TOL, f"generic nchan {nchan} L {L}")
+
+
+def test_property_random_configurations(gpu):
+    """GPU == oracle on random short scans over the configuration space."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    modes = [(_lib.POL_P0, "P0"), (_lib.POL_P1, "P1"), (_lib.POL_I, "I"), (_lib.POL_I2, "I2"),
+             (_lib.POL_COHERENCE, "coherence"), (_lib.POL_IQUV, "IQUV"), (_lib.POL_PPQQ, "PPQQ")]
+
+    @settings(max_examples=10, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+    @given(lg_nchan=st.integers(3, 8), lg_d=st.integers(0, 6), usb=st.booleans(), mode=st.sampled_from(modes),
+           bw=st.sampled_from([16.0, 32.0]), seed=st.integers(0, 2 ** 16), faults=st.booleans(), units=st.integers(1, 2))
+    def run(lg_nchan, lg_d, usb, mode, bw, seed, faults, units):
+        nchan, D = 1 << lg_nchan, 1 << lg_d
+        sbw = bw if usb else -bw
+        with Plan(PlanConfig(nchan=nchan, bw_mhz=[sbw])) as pl:
+            nfr = int(pl.chunk_frames) * units + 37             # ragged tail
+        v = synth.make_vdif(nfr, seed=seed, bw_mhz=bw, rho=0.25, tone_frac=0.31,
+                            invalid_frac=0.02 if faults else 0.0, fill_frac=0.02 if faults else 0.0)
+        rows, _ = run_plan([v], nchan=nchan, bw=[sbw], tscrunch=D, pol_mode=mode[0], out_nbit=-32, keep_bandpass=True)
+        ref = o.digifil(v, freq_mhz=1400.0, bw_mhz=sbw, nchan=nchan, tscrunch_factor=D, pol_mode=mode[1], out_nbit=-32,
+                        keep_bandpass=True)["data"]
+        assert rows.shape[0] == ref.shape[0]
+        assert_rel(rows.reshape(ref.shape), ref.astype(np.float64), REL_TOL, f"nchan {nchan} D {D} {mode[1]} usb={usb}")
+
+    run()

@@ -168,3 +168,33 @@ def test_overlap_save_equals_long_convolution():
     # block 1 starts keep*2N samples in; its first kept sample follows block 0's last kept one
     y_shift = o.filterbank_dedisp(x[keep * 2 * nchan:], nchan, L, H, npos, nneg)
     assert np.allclose(y[keep:2 * keep], y_shift[:keep], rtol=0, atol=1e-9 * np.abs(y).max())
+
+
+def test_filterbank_against_brute_force_dft():
+    """Pins sign and normalisation conventions without any FFT library: X[k] = sum_n x[n] e^{-2 pi i k n/M}
+    (unnormalised), channel c = bins [cL, (c+1)L), y_c[m] = sum_j X[cL+j] e^{+2 pi i j m / L} (unnormalised)."""
+    rng = np.random.default_rng(9)
+    nchan, L = 4, 8
+    M = 2 * nchan * L
+    x = rng.standard_normal(2 * M + 3)
+    y = o.filterbank(x, nchan, L)
+    n = np.arange(M)
+    for b in range(2):
+        xb = x[b * M:(b + 1) * M]
+        X = np.array([(xb * np.exp(-2j * np.pi * k * n / M)).sum() for k in range(M // 2)])
+        for c in range(nchan):
+            for m in range(L):
+                ref = sum(X[c * L + j] * np.exp(2j * np.pi * j * m / L) for j in range(L))
+                assert abs(y[b * L + m, c] - ref) < 1e-9 * M * L
+    assert y.shape == (2 * L, nchan)          # the 3 trailing samples are dropped
+
+
+def test_digitiser_and_rescale_definitions():
+    y = np.array([[-10.0, -6.0, -1.0, 0.0, 1.0, 5.999, 6.0, 10.0]])
+    assert o.digitise(y, 8).tolist() == [[0, 0, 106, 128, 149, 255, 255, 255]]      # floor(y*21.25 + 128)
+    assert o.digitise(y, 16).tolist() == [[0, 0, 27307, 32768, 38229, 65531, 65535, 65535]]
+    assert o.digitise(np.array([[-3.0, -0.6, 0.4, 2.0]]), 2).tolist() == [[0b11_10_01_00]]
+    d = np.arange(24, dtype=float).reshape(6, 1, 4)
+    assert np.array_equal(o.tscrunch(d, 3)[:, 0, 0], [0 + 4 + 8, 12 + 16 + 20])      # sum, not mean
+    mean, scale = o.rescale_stats(d, 4)                                               # first interval only
+    assert np.allclose(mean[0], d[:4, 0].mean(axis=0)) and np.allclose(1 / scale[0], d[:4, 0].std(axis=0))
