@@ -26,6 +26,7 @@ class Params(C.Structure):
         ("bw_mhz", C.c_double * B2F_MAX_IF), ("freq_mhz", C.c_double * B2F_MAX_IF),
         ("if_order", C.c_int32 * B2F_MAX_IF), ("dm", C.c_double), ("coherent", C.c_int32),
         ("profile", C.c_int32), ("stream", C.c_void_p),
+        ("raw_word_bits", C.c_int32), ("raw_bits", (C.c_uint8 * 4) * B2F_MAX_IF),
     ]
 
 

@@ -160,3 +160,64 @@ def base2fil(conf_path: str, *, device: int = 0, workdir_odd: str | None = None,
 if __name__ == "__main__":
     for p in base2fil(sys.argv[1]):
         print(p)
+
+
+def run_scan_raw(raw_path: str, out_path: str, *, mode: str, nif: int, bw: float, freq_lsb0: float, nchan: int,
+                 tscrunch: int = 1, pol: int = 2, nbit: int = 8, start: float = 0.0, nsec: float | None = None,
+                 keep_bandpass: bool = False, flip_if: bool = False, source: str = "unknown", ra: str | None = None,
+                 dec: str | None = None, telescope: str = "", device: int = 0, verbose: bool = True) -> dict:
+    """Raw multi-BBC recording -> band-ordered filterbank in one pass: the corner turn that
+    base2fil.sh:334-368 delegates to jive5ab (`spif2file`, recipes of spif2file.sh:31-98) is done on the
+    GPU, so no split files are written.  `mode` is base2fil's mode string (base2fil.sh:308-318)."""
+    from . import spif
+
+    W, bits = spif.recipe_for_mode(mode, nif, flip_if)
+    ifs = list(range(1, nif + 1))
+    freqs = [freq_lsb0 + (i - 1) * bw for i in ifs]
+    bws = [bw if i % 2 == 0 else -bw for i in ifs]
+    with open(raw_path, "rb") as f:
+        info = vdif.parse_header(f.read(32))
+        spf = info.payload_bytes * 8 // W
+        fps = int(round(2.0 * bw * 1e6 / spf))
+        f0 = int(round(start * fps))
+        nfr = os.path.getsize(raw_path) // info.frame_bytes - f0
+        if nsec is not None:
+            nfr = min(nfr, int(round(nsec * fps)))
+        nfr = max(nfr, 0)
+        cfg = PlanConfig(nchan=nchan, bw_mhz=bws, freq_mhz=freqs, tscrunch=max(1, tscrunch),
+                         pol_mode=pol_mode_from_reference(pol), out_nbit=nbit, in_nbit=2, frame_bytes=info.frame_bytes,
+                         header_bytes=info.header_bytes, keep_bandpass=keep_bandpass, device=device,
+                         raw_word_bits=W, raw_bits=bits)
+        f.seek(f0 * info.frame_bytes)
+        head = f.read(32)
+        f.seek(f0 * info.frame_bytes)
+        with Plan(cfg) as pl, open(out_path, "wb") as out:
+            out.write(sigproc.FilHeader(
+                source_name=source, rawdatafile=os.path.basename(raw_path),
+                telescope_id=sigproc.TELESCOPE_IDS.get(telescope.lower(), 0),
+                src_raj=sigproc.sexagesimal_to_sigproc(ra), src_dej=sigproc.sexagesimal_to_sigproc(dec),
+                tstart=vdif.frame_mjd(vdif.parse_header(head), fps) if len(head) == 32 else 0.0, tsamp=pl.tsamp_s,
+                nbits=32 if nbit == -32 else nbit, fch1=max(freqs) + bw / 2 - bw / (2 * nchan), foff=-bw / nchan,
+                nchans=nif * nchan, nifs=pl.nprod).pack())
+            cf = int(pl.chunk_frames)
+            buf = np.empty(cf * info.frame_bytes, np.uint8)
+            left, rows_out = nfr, 0
+            while left > 0:
+                got = f.readinto(memoryview(buf)[: min(cf, left) * info.frame_bytes]) // info.frame_bytes
+                if got == 0:
+                    break
+                pl.push([buf[: got * info.frame_bytes]])
+                pl.sync()
+                rows = pl.pull()
+                out.write(rows.tobytes())
+                rows_out += len(rows)
+                left -= got
+            pl.flush()
+            rows = pl.pull()
+            out.write(rows.tobytes())
+            rows_out += len(rows)
+            c = pl.counters()
+    if verbose:
+        print(f"b2f: raw {mode} -> {out_path}: {rows_out} samples x {nif * nchan} channels; frames ok/invalid/fill/bad = "
+              f"{c['frames_ok']}/{c['frames_invalid']}/{c['frames_with_fill']}/{c['frames_badhdr']}", file=sys.stderr)
+    return {"rows": rows_out, "counters": c, "nchans": nif * nchan, "tsamp_s": pl.tsamp_s}

@@ -441,7 +441,13 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
         if (std::fabs(std::fabs(prm->bw_mhz[i]) - abw) > 1e-9) return fail(B2F_EINVAL, "all IFs must share |bw|");
         if (prm->if_order[i] < 0 || prm->if_order[i] >= prm->nif) return fail(B2F_EINVAL, "if_order");
     }
-    const int64_t spf = (int64_t)payload * 8 / (prm->in_nbit * 2);
+    const int W = prm->raw_word_bits;
+    if (W != 0 && W != 16 && W != 32 && W != 64) return fail(B2F_EINVAL, "raw_word_bits must be 0, 16, 32 or 64");
+    if (W && prm->in_nbit != 2) return fail(B2F_EUNSUPPORTED, "raw multi-BBC input must be 2-bit");
+    if (W && (prm->frame_bytes % 16 || payload % (W / 2))) return fail(B2F_EUNSUPPORTED, "raw frame size");
+    if (W) for (int i = 0; i < prm->nif; ++i) for (int k = 0; k < 4; ++k)
+        if (prm->raw_bits[i][k] >= W) return fail(B2F_EINVAL, "raw_bits entry outside the word");
+    const int64_t spf = W ? (int64_t)payload * 8 / W : (int64_t)payload * 8 / (prm->in_nbit * 2);
     const double fps_d = 2.0 * abw * 1e6 / (double)spf;
     const int64_t fps = (int64_t)llround(fps_d);
     if (std::fabs(fps_d - (double)fps) > 1e-6) return fail(B2F_EINVAL, "frames per second is not an integer");
@@ -547,7 +553,7 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
     }
     const int nif = prm->nif;
     const int64_t nbt = (int64_t)nif * pl->chunk_blocks;
-    pl->slot_bytes = prm->in_nbit == 2 ? 2 * payload : payload;      // 2-bit: one index byte per time sample
+    pl->slot_bytes = W ? (int)spf : (prm->in_nbit == 2 ? 2 * payload : payload);      // 2-bit: one index byte per time sample
     pl->compact_stride = (size_t)((pl->chunk_frames * (int64_t)pl->slot_bytes + (pl->carry_mode ? pl->M : 0) + 255) / 256 * 256);
     pl->wmask_stride = (size_t)((pl->chunk_frames * pl->groups_per_slot + 255) / 256 * 256);
     pl->fstat_stride = (size_t)((pl->chunk_frames + 255) / 256 * 256);
@@ -657,7 +663,7 @@ int b2f_push(b2f_plan* pl, const void* const* frames, int64_t nframes, int on_de
     const size_t fbytes = (size_t)nframes * pl->prm.frame_bytes;
 
     if (!pl->have_base) {
-        for (int i = 0; i < nif; ++i) {
+        for (int i = 0; i < (pl->prm.raw_word_bits ? 1 : nif); ++i) {
             uint32_t w[2];
             if (on_device) CU(cudaMemcpy(w, frames[i], 8, cudaMemcpyDeviceToHost));
             else memcpy(w, frames[i], 8);
@@ -669,7 +675,7 @@ int b2f_push(b2f_plan* pl, const void* const* frames, int64_t nframes, int on_de
 
     K0Params k0{};
     if (on_device) {
-        for (int i = 0; i < nif; ++i) k0.frames[i] = static_cast<const uint8_t*>(frames[i]);
+        for (int i = 0; i < (pl->prm.raw_word_bits ? 1 : nif); ++i) k0.frames[i] = static_cast<const uint8_t*>(frames[i]);
     } else {
         const int idx = pl->stage_idx;
         if (!pl->d_stage[idx]) {
@@ -677,7 +683,8 @@ int b2f_push(b2f_plan* pl, const void* const* frames, int64_t nframes, int on_de
             CU(cudaMalloc(&pl->d_stage[idx], pl->stage_if_stride * nif));
         }
         CU(cudaStreamWaitEvent(pl->copy_stream, pl->ev_stage_free[idx], 0));
-        for (int i = 0; i < nif; ++i) {
+        const int nstreams = pl->prm.raw_word_bits ? 1 : nif;
+        for (int i = 0; i < nstreams; ++i) {
             CU(cudaMemcpyAsync(pl->d_stage[idx] + i * pl->stage_if_stride, frames[i], fbytes, cudaMemcpyHostToDevice,
                                pl->copy_stream));
             k0.frames[i] = pl->d_stage[idx] + i * pl->stage_if_stride;
@@ -709,7 +716,37 @@ int b2f_push(b2f_plan* pl, const void* const* frames, int64_t nframes, int on_de
     }
     CU(cudaMemsetAsync(pl->d_fstat, 0, pl->fstat_stride * nif, pl->stream));
     if (nblk > 0) CU(cudaMemsetAsync(pl->d_blkdirty, 0, (size_t)nif * nblk, pl->stream));
-    int rc = launch_k0(pl, k0, pl->stream, true);
+    int rc = 0;
+    if (pl->prm.raw_word_bits) {                      // corner turn + validation in one pass over the raw stream
+        K0RParams kr{};
+        kr.frames = k0.frames[0];
+        kr.compact = k0.compact; kr.compact_stride = pl->compact_stride;
+        kr.fstat = pl->d_fstat; kr.fstat_stride = pl->fstat_stride; kr.counters = pl->d_counters;
+        kr.nframes = nframes; kr.nslots = nframes;
+        kr.frame_bytes = pl->prm.frame_bytes; kr.header_bytes = pl->prm.header_bytes; kr.payload_bytes = (int)pl->payload;
+        kr.word_bits = pl->prm.raw_word_bits; kr.nif = nif; kr.time_mode = pl->prm.frame_time_mode;
+        kr.mask_faults = pl->prm.mask_faults; kr.fps = (int)pl->fps; kr.slot_bytes = pl->slot_bytes;
+        kr.base_sec = k0.base_sec[0]; kr.base_fnum = k0.base_fnum[0];
+        for (int i = 0; i < nif; ++i) for (int k = 0; k < 4; ++k) kr.bit[i][k] = pl->prm.raw_bits[i][k];
+        if (reinterpret_cast<uintptr_t>(kr.frames) & 15) return fail(B2F_EINVAL, "raw frames must be 16-byte aligned");
+        const int stage_bytes = (kr.frame_bytes + 127) & ~127;
+        const size_t smem = 128 + (size_t)kK0Stages * stage_bytes;
+        const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(nframes, 4 * pl->num_sms));
+        rc = timed(pl, B2F_K_VALIDATE, [&] {
+            if (kr.word_bits == 16) {
+                cudaFuncSetAttribute(k0r_corner_turn<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                k0r_corner_turn<16><<<grid, kK0Threads, smem, pl->stream>>>(kr);
+            } else if (kr.word_bits == 32) {
+                cudaFuncSetAttribute(k0r_corner_turn<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                k0r_corner_turn<32><<<grid, kK0Threads, smem, pl->stream>>>(kr);
+            } else {
+                cudaFuncSetAttribute(k0r_corner_turn<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                k0r_corner_turn<64><<<grid, kK0Threads, smem, pl->stream>>>(kr);
+            }
+        });
+    } else {
+        rc = launch_k0(pl, k0, pl->stream, true);
+    }
     if (rc) return rc;
     if (!on_device) {
         CU(cudaEventRecord(pl->ev_stage_free[pl->stage_idx], pl->stream));

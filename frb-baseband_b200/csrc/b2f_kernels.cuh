@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "../../include/b2f.h"
 #include "fft_inreg.cuh"
 
@@ -233,6 +235,143 @@ __global__ void __launch_bounds__(kK0Threads) k0_validate_compact(const K0Params
             }
         }
         (void)c_fillw;
+    }
+    if (tid == 0) {
+        if (c_ok) atomicAdd(&p.counters[C_OK], c_ok);
+        if (c_inv) atomicAdd(&p.counters[C_INVALID], c_inv);
+        if (c_fillf) atomicAdd(&p.counters[C_FILLFRAMES], c_fillf);
+        if (c_drop) atomicAdd(&p.counters[C_DROPPED], c_drop);
+        if (c_mis) atomicAdd(&p.counters[C_MISPLACED], c_mis);
+        if (c_bad) atomicAdd(&p.counters[C_BADHDR], c_bad);
+    }
+}
+
+// ================================================================== kernel 1r: corner turn front end
+// Raw multi-BBC VDIF (what the recorder holds before jive5ab's spif2file splits it,
+// /root/reference/spif2file.sh:31-98,178-186): every W-bit word is one time sample of all BBC
+// channels.  For IF i the recipe names the 4 source bits (sign, magnitude of pol A; sign,
+// magnitude of pol B) that form its 2-channel 2-bit sample.  This kernel validates the raw
+// frames like k0 and writes every IF's index-byte stream directly, so the split files, the FIFOs and
+// the scratch-disk round trip disappear.
+struct K0RParams {
+    const uint8_t* frames;
+    uint8_t* compact; size_t compact_stride;
+    uint8_t* fstat;   size_t fstat_stride;
+    unsigned long long* counters;
+    int64_t nframes, nslots;
+    int frame_bytes, header_bytes, payload_bytes, word_bits, nif, time_mode, mask_faults, fps, slot_bytes;
+    uint32_t base_sec, base_fnum;
+    uint8_t bit[B2F_MAX_IF][4];
+};
+
+template <typename WORD>
+__device__ __forceinline__ uint32_t gather_nibble_index(WORD w, const uint8_t (&b)[4]) {
+    return (uint32_t)(((w >> b[0]) & 1) << 3 | ((w >> b[1]) & 1) << 4 | ((w >> b[2]) & 1) << 5 | ((w >> b[3]) & 1) << 6);
+}
+
+template <int WBITS>
+__global__ void __launch_bounds__(kK0Threads) k0r_corner_turn(const K0RParams p) {
+    using WORD = typename std::conditional<WBITS == 64, unsigned long long, uint32_t>::type;
+    extern __shared__ __align__(128) uint8_t k0_smem[];
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(k0_smem);
+    const int stage_bytes = (p.frame_bytes + 127) & ~127;
+    uint8_t* bufs = k0_smem + 128;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < kK0Stages; ++s) mbar_init(&mbar[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int s = 0; s < kK0Stages; ++s) {
+            const int64_t f = blockIdx.x + (int64_t)s * gridDim.x;
+            if (f < p.nframes) {
+                mbar_expect_tx(&mbar[s], p.frame_bytes);
+                bulk_g2s(bufs + s * stage_bytes, p.frames + f * p.frame_bytes, p.frame_bytes, &mbar[s]);
+            }
+        }
+    }
+    constexpr int SPW = WBITS == 16 ? 2 : 1;                  // time samples per 32-bit payload unit (16-bit words: 2)
+    const int nquads = p.slot_bytes / 4;                      // groups of 4 consecutive time samples per frame
+    unsigned long long c_ok = 0, c_inv = 0, c_fillf = 0, c_drop = 0, c_mis = 0, c_bad = 0;
+    int it = 0;
+    for (int64_t f = blockIdx.x; f < p.nframes; f += gridDim.x, ++it) {
+        const int stage = it % kK0Stages;
+        uint8_t* buf = bufs + stage * stage_bytes;
+        mbar_wait(&mbar[stage], (it / kK0Stages) & 1);
+        const uint32_t* hw = reinterpret_cast<const uint32_t*>(buf);
+        const uint32_t w0 = hw[0], w1 = hw[1], w2 = hw[2], w3 = hw[3];
+        const bool invalid = (w0 >> 31) != 0;
+        const bool bad = ((w2 & 0xFFFFFFu) * 8u != (uint32_t)p.frame_bytes) || ((int)((w3 >> 26) & 31u) + 1 != 2) ||
+                         ((int)((w0 >> 30) & 1u) != (p.header_bytes == 16 ? 1 : 0));
+        const int64_t tslot = ((int64_t)(w0 & 0x3FFFFFFFu) - (int64_t)p.base_sec) * p.fps +
+                              ((int64_t)(w1 & 0xFFFFFFu) - (int64_t)p.base_fnum);
+        const int64_t slot = p.time_mode ? tslot : f;
+        const bool in_range = (slot >= 0 && slot < p.nslots);
+        const bool dead = invalid || bad;
+        int any_fill = 0;
+        unsigned nfill = 0;
+        if (in_range) {
+            const uint8_t* pay = buf + p.header_bytes;
+            for (int g = tid; g < nquads; g += kK0Threads) {
+                WORD w[4];
+                bool masked[4];
+                if (WBITS == 16) {
+                    const uint2 v = *reinterpret_cast<const uint2*>(pay + 8 * g);
+                    w[0] = v.x & 0xFFFFu; w[1] = v.x >> 16; w[2] = v.y & 0xFFFFu; w[3] = v.y >> 16;
+                    masked[0] = masked[1] = v.x == kFillWord;
+                    masked[2] = masked[3] = v.y == kFillWord;
+                    nfill += (v.x == kFillWord) + (v.y == kFillWord);
+                } else if (WBITS == 32) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(pay + 16 * g);
+                    w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { masked[k] = (uint32_t)w[k] == kFillWord; nfill += masked[k]; }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const uint4 v = *reinterpret_cast<const uint4*>(pay + 32 * g + 16 * k);
+                        w[2 * k] = (WORD)v.x | ((WORD)v.y << 32);
+                        w[2 * k + 1] = (WORD)v.z | ((WORD)v.w << 32);
+                        masked[2 * k] = v.x == kFillWord || v.y == kFillWord;
+                        masked[2 * k + 1] = v.z == kFillWord || v.w == kFillWord;
+                        nfill += (v.x == kFillWord) + (v.y == kFillWord) + (v.z == kFillWord) + (v.w == kFillWord);
+                    }
+                }
+                (void)SPW;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    masked[k] = p.mask_faults && (masked[k] || dead);
+                    any_fill |= masked[k] && !dead;
+                }
+                for (int i = 0; i < p.nif; ++i) {
+                    uint32_t o = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) o |= (masked[k] ? 0x80u : gather_nibble_index<WORD>(w[k], p.bit[i])) << (8 * k);
+                    *reinterpret_cast<uint32_t*>(p.compact + i * p.compact_stride + slot * (int64_t)p.slot_bytes + 4 * g) = o;
+                }
+            }
+        }
+        any_fill = __syncthreads_or(any_fill);
+        if (nfill && !dead) atomicAdd(&p.counters[C_FILLWORDS], (unsigned long long)nfill);
+        if (tid == 0) {
+            if (!in_range) {
+                ++c_drop;
+            } else {
+                for (int i = 0; i < p.nif; ++i) p.fstat[i * p.fstat_stride + slot] = dead ? 2 : (any_fill ? 3 : 1);
+                if (bad) ++c_bad;
+                else if (invalid) ++c_inv;
+                else if (any_fill) ++c_fillf;
+                else ++c_ok;
+                if (tslot != f) ++c_mis;
+            }
+            const int64_t fn = f + (int64_t)kK0Stages * gridDim.x;
+            if (fn < p.nframes) {
+                fence_proxy_async();
+                mbar_expect_tx(&mbar[stage], p.frame_bytes);
+                bulk_g2s(buf, p.frames + fn * p.frame_bytes, p.frame_bytes, &mbar[stage]);
+            }
+        }
     }
     if (tid == 0) {
         if (c_ok) atomicAdd(&p.counters[C_OK], c_ok);

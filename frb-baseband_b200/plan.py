@@ -50,6 +50,8 @@ class PlanConfig:
     stream: int | None = None
     dm: float = 0.0                          # digifil -D
     coherent: bool = False                   # digifil -F nchan:D
+    raw_word_bits: int = 0                   # 16/32/64: one raw multi-BBC VDIF stream, corner turn on the GPU
+    raw_bits: list | None = None             # per IF: 4 source bit positions (spif2file recipe)
     extra: dict = field(default_factory=dict)
 
 
@@ -88,6 +90,11 @@ class Plan:
         p.dm = cfg.dm
         p.coherent = int(cfg.coherent)
         p.profile = int(cfg.profile)
+        p.raw_word_bits = cfg.raw_word_bits
+        if cfg.raw_word_bits:
+            for i in range(nif):
+                for k in range(4):
+                    p.raw_bits[i][k] = int(cfg.raw_bits[i][k])
         p.stream = cfg.stream
         self.if_order = list(order)
         self.freq_mhz = list(freq)
@@ -131,6 +138,8 @@ class Plan:
                 ptrs[i] = int(f)
         else:
             keep = []
+            if self.cfg.raw_word_bits:
+                frames = list(frames)[:1]
             for i, f in enumerate(frames):
                 a = np.ascontiguousarray(f, dtype=np.uint8)
                 keep.append(a)

@@ -95,3 +95,27 @@ def make_vdif(nframes: int, *, seed: int, bw_mhz: float = 32.0, nbit: int = 2,
 def if_file_name(exp: str, st: str, scan: str, i: int) -> str:
     """/root/reference/base2fil.sh:336,353"""
     return f"{exp}_{st}_no0{scan}_IF{i}.vdif"
+
+
+def make_raw_vdif(codes: np.ndarray, word_bits: int, bits, *, bw_mhz: float, payload_bytes: int = 8000,
+                  ref_epoch: int = 40, sec0: int = 0) -> np.ndarray:
+    """Raw multi-BBC VDIF stream (what the recorder holds): codes[if, pol, t] in 0..3 are scattered to
+    the bit positions `bits[if] = [pol0 lsb, pol0 msb, pol1 lsb, pol1 msb]` of one word_bits-bit word per
+    time sample -- the inverse of the spif2file recipe."""
+    nif, _, nsamp = codes.shape
+    dt = {16: np.uint16, 32: np.uint32, 64: np.uint64}[word_bits]
+    w = np.zeros(nsamp, dtype=dt)
+    for i in range(nif):
+        nib = (codes[i, 0].astype(np.uint64) | (codes[i, 1].astype(np.uint64) << np.uint64(2)))
+        for k in range(4):
+            w |= (((nib >> np.uint64(k)) & np.uint64(1)) << np.uint64(bits[i][k])).astype(dt)
+    spf = payload_bytes * 8 // word_bits
+    nframes = nsamp // spf
+    fps = int(round(2 * abs(bw_mhz) * 1e6 / spf))
+    nbbc = 2 * nif
+    hdr = vdif.make_headers(nframes, frames_per_sec=fps, payload_bytes=payload_bytes, nbit=2,
+                            log2_nchan=int(np.log2(max(1, word_bits // 2))), ref_epoch=ref_epoch, sec0=sec0)
+    out = np.empty((nframes, vdif.HEADER_BYTES + payload_bytes), dtype=np.uint8)
+    out[:, : vdif.HEADER_BYTES] = hdr.view(np.uint8).reshape(nframes, vdif.HEADER_BYTES)
+    out[:, vdif.HEADER_BYTES:] = w[: nframes * spf].view(np.uint8).reshape(nframes, payload_bytes)
+    return out.reshape(-1)

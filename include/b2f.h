@@ -84,6 +84,12 @@ typedef struct b2f_params {
     int32_t coherent;              /* digifil -F nchan:D: in-channel coherent dedispersion by overlap-save (:179-180) */
     int32_t profile;               /* 1: time every kernel launch with CUDA events            */
     void* stream;                  /* cudaStream_t to launch on; NULL = plan-owned stream     */
+    int32_t raw_word_bits;         /* 0: frames[i] is the split 2-channel VDIF stream of IF i (what jive5ab's
+                                      spif2file writes, spif2file.sh:178-186).  16/32/64: frames[0] is ONE raw
+                                      multi-BBC VDIF stream whose raw_word_bits-bit words each hold one time
+                                      sample of every BBC channel; the corner turn is done on the GPU          */
+    uint8_t raw_bits[B2F_MAX_IF][4]; /* spif2file recipe (spif2file.sh:31-98): source bit of output bits 0..3
+                                      (pol0 lsb, pol0 msb, pol1 lsb, pol1 msb) of IF i                        */
 } b2f_params;
 
 typedef struct b2f_geometry {

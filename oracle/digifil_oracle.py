@@ -283,7 +283,7 @@ def digifil(vdif: np.ndarray, *, freq_mhz: float, bw_mhz: float, nchan: int,
             rescale_interval_s: float = 10.0, keep_bandpass: bool = False,
             frame_bytes: int | None = None, header_bytes: int = 32,
             dtype=np.float64, return_float: bool = False, dm: float = 0.0, coherent: bool = False,
-            nfilt: tuple[int, int] | None = None) -> dict:
+            nfilt: tuple[int, int] | None = None, x: np.ndarray | None = None) -> dict:
     """One IF: VDIF bytes -> SIGPROC samples, as `digifil -cont -c -b<nbit> -S<start> -T<nsec>
     -2 -D 0.0 [-t D] -d<..> -F<nchan>:<freq_res> [-I0]` (/root/reference/process_vdif.py:157-182).
 
@@ -305,8 +305,10 @@ def digifil(vdif: np.ndarray, *, freq_mhz: float, bw_mhz: float, nchan: int,
     nfr = vdif.size // frame_bytes - f0
     if nsec is not None:
         nfr = min(nfr, int(round(nsec * fps)))
-    x = decode_vdif(vdif[f0 * frame_bytes: (f0 + nfr) * frame_bytes], nbit=in_nbit,
-                    header_bytes=header_bytes, frame_bytes=frame_bytes)
+    if x is None:
+        x = decode_vdif(vdif[f0 * frame_bytes: (f0 + nfr) * frame_bytes], nbit=in_nbit,
+                        header_bytes=header_bytes, frame_bytes=frame_bytes)
+    # (x given: samples already decoded, e.g. by corner_turn(); vdif is then only read for its header time)
     if coherent and dm > 0:                                  # digifil -D dm -F nchan:D (process_vdif.py:177-180)
         H = chirp(nchan, freq_res, freq_mhz, bw_mhz, dm)
         yP = filterbank_dedisp(x[0], nchan, freq_res, H, nfilt[0], nfilt[1], dtype)
@@ -337,6 +339,38 @@ def digifil(vdif: np.ndarray, *, freq_mhz: float, bw_mhz: float, nchan: int,
     }
     if return_float:
         out["float"] = d
+    return out
+
+
+def corner_turn(raw: np.ndarray, word_bits: int, bits, *, frame_bytes: int = 8032, header_bytes: int = 32,
+                mask_invalid: bool = True) -> np.ndarray:
+    """jive5ab spif2file as arithmetic (/root/reference/spif2file.sh:31-98,178-186): raw multi-BBC VDIF ->
+    x[if, pol, t] decoded samples.  bits[if] = the 4 source bits of that IF's (pol0 lsb, pol0 msb, pol1 lsb,
+    pol1 msb).  Samples of invalid frames and of 32-bit payload words equal to the fill pattern are 0.0."""
+    raw = np.ascontiguousarray(raw, dtype=np.uint8)
+    nframes = raw.size // frame_bytes
+    fr = raw[: nframes * frame_bytes].reshape(nframes, frame_bytes)
+    invalid = (fr[:, 0:4].copy().view("<u4")[:, 0] >> 31).astype(bool)
+    pay = np.ascontiguousarray(fr[:, header_bytes:])
+    dt = {16: "<u2", 32: "<u4", 64: "<u8"}[word_bits]
+    w = pay.view(dt).astype(np.uint64)                                   # [frame, sample]
+    fill32 = pay.view("<u4") == VDIF_FILL_WORD
+    if word_bits == 32:
+        bad = fill32
+    elif word_bits == 16:
+        bad = np.repeat(fill32, 2, axis=1)
+    else:
+        bad = fill32[:, 0::2] | fill32[:, 1::2]
+    bad = bad | invalid[:, None]
+    out = np.empty((len(bits), 2, w.size), dtype=np.float64)
+    for i, b in enumerate(bits):
+        c0 = ((w >> np.uint64(b[0])) & np.uint64(1)) | (((w >> np.uint64(b[1])) & np.uint64(1)) << np.uint64(1))
+        c1 = ((w >> np.uint64(b[2])) & np.uint64(1)) | (((w >> np.uint64(b[3])) & np.uint64(1)) << np.uint64(1))
+        x0, x1 = LEVELS_2BIT[c0.astype(np.int64)], LEVELS_2BIT[c1.astype(np.int64)]
+        if mask_invalid:
+            x0 = np.where(bad, 0.0, x0)
+            x1 = np.where(bad, 0.0, x1)
+        out[i, 0], out[i, 1] = x0.reshape(-1), x1.reshape(-1)
     return out
 
 
