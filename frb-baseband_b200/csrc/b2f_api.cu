@@ -67,7 +67,7 @@ struct b2f_plan {
     int64_t F_if_stride = 0;
     float *d_mean = nullptr, *d_scale = nullptr;
     double2* d_partial = nullptr;
-    float2 *d_tab_g = nullptr, *d_tab_h = nullptr, *d_tab_w = nullptr, *d_tab_r = nullptr;
+    float2 *d_tab_g = nullptr, *d_tab_h = nullptr, *d_tab_w = nullptr, *d_tab_r = nullptr, *d_tab_beta = nullptr;
     unsigned long long* d_counters = nullptr;
     int* d_sm_slots = nullptr;
     int stagger_cycles = 0;
@@ -209,6 +209,15 @@ int upload_tables(b2f_plan* pl) {
             const double ph = -2.0 * M_PI * (double)(s * q) / (double)R;
             r[q * TR + s] = make_float2((float)cos(ph), (float)sin(ph));
         }
+    std::vector<float2> beta((size_t)16 * 4 * R);
+    for (int item = 0; item < 16; ++item)
+        for (int k = 0; k < 4; ++k)
+            for (int n1 = 0; n1 < R; ++n1) {
+                const double ph = (double)(1 << k) * 2.0 * M_PI * ((double)item / 512.0 - (double)n1 / M);
+                beta[((size_t)item * 4 + k) * R + n1] = make_float2((float)cos(ph), (float)sin(ph));
+            }
+    CU(cudaMalloc(&pl->d_tab_beta, beta.size() * sizeof(float2)));
+    CU(cudaMemcpy(pl->d_tab_beta, beta.data(), beta.size() * sizeof(float2), cudaMemcpyHostToDevice));
     CU(cudaMalloc(&pl->d_tab_g, g.size() * sizeof(float2)));
     CU(cudaMalloc(&pl->d_tab_h, h.size() * sizeof(float2)));
     CU(cudaMalloc(&pl->d_tab_w, w.size() * sizeof(float2)));
@@ -260,7 +269,7 @@ void free_plan(b2f_plan* pl) {
     }
     void* bufs[] = {pl->d_compact, pl->d_wmask, pl->d_fstat, pl->d_blkdirty, pl->d_inter, pl->d_colsum,
                     pl->d_eps, pl->d_F, pl->d_mean, pl->d_scale, pl->d_partial, pl->d_tab_g, pl->d_tab_h,
-                    pl->d_tab_w, pl->d_tab_r, pl->d_counters, pl->d_sm_slots, pl->d_carry, pl->d_spec, pl->d_chirp, pl->d_tw_col, pl->d_tw_row};
+                    pl->d_tab_w, pl->d_tab_r, pl->d_tab_beta, pl->d_counters, pl->d_sm_slots, pl->d_carry, pl->d_spec, pl->d_chirp, pl->d_tw_col, pl->d_tw_row};
     for (void* b : bufs)
         if (b) cudaFree(b);
     for (auto& t : pl->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
@@ -338,7 +347,7 @@ int push_dedisp(b2f_plan* pl, int64_t nblk, int64_t T) {
         ka.compact = pl->d_compact; ka.compact_stride = pl->compact_stride;
         ka.wmask = pl->d_wmask; ka.wmask_stride = pl->wmask_stride; ka.blkdirty = pl->d_blkdirty;
         ka.inter = pl->d_inter; ka.colsum = pl->d_colsum;
-        ka.tab_g = pl->d_tab_g; ka.tab_h = pl->d_tab_h; ka.tab_w = pl->d_tab_w;
+        ka.tab_g = pl->d_tab_g; ka.tab_h = pl->d_tab_h; ka.tab_w = pl->d_tab_w; ka.tab_beta = pl->d_tab_beta;
         ka.R = pl->R; ka.nstrips = pl->nstrips; ka.nblk = (int)nblk; ka.nif = nif;
         ka.payload_bytes = (int)pl->payload; ka.groups_per_slot = (int)pl->groups_per_slot;
         ka.blk_step_bytes = pl->step;                             // 1 index byte per sample
@@ -785,7 +794,7 @@ int b2f_push(b2f_plan* pl, const void* const* frames, int64_t nframes, int on_de
         ka.wmask = pl->d_wmask; ka.wmask_stride = pl->wmask_stride;
         ka.blkdirty = pl->d_blkdirty;
         ka.inter = pl->d_inter; ka.colsum = pl->d_colsum;
-        ka.tab_g = pl->d_tab_g; ka.tab_h = pl->d_tab_h; ka.tab_w = pl->d_tab_w;
+        ka.tab_g = pl->d_tab_g; ka.tab_h = pl->d_tab_h; ka.tab_w = pl->d_tab_w; ka.tab_beta = pl->d_tab_beta;
         ka.R = pl->R; ka.nstrips = pl->nstrips; ka.nblk = (int)nblk; ka.nif = nif;
         ka.payload_bytes = (int)pl->payload; ka.groups_per_slot = (int)pl->groups_per_slot;
         ka.blk_step_bytes = pl->M * (pl->prm.in_nbit == 2 ? 1 : 2);

@@ -459,6 +459,27 @@ __global__ void k_decode(const uint8_t* __restrict__ compact, const uint8_t* __r
 //   decode -> FFT_512 (16 x 32) -> * W_M^(k2 n1) -> IFFT_512 (32 x 16)  ->  B[m][n1]
 // with only two shared-memory exchanges: the 32-point forward and inverse FFTs around the
 // diagonal multiply act on the same 32 values, so they run back to back in registers.
+// pw[q] = b^q, q = 1..15, from the exactly rounded seeds b, b^2, b^4, b^8 (host table, computed in
+// double): every power is a product of at most four seeds (3 roundings), so no phase error of a base
+// is amplified by the exponent.  Computing these twiddles in registers replaces shared-memory table
+// reads, which -- not FP32 issue -- are what the column pass is short of (DESIGN.md section 5:
+// dropping every butterfly gains 18 %, dropping the table reads 20 %).
+__device__ __forceinline__ void cpowers15(const float2 (&sd)[4], float2 (&pw)[16]) {
+    pw[0] = make_float2(1.f, 0.f);
+    pw[1] = sd[0]; pw[2] = sd[1]; pw[4] = sd[2]; pw[8] = sd[3];
+    pw[3] = cmul(sd[0], sd[1]);
+    pw[5] = cmul(sd[0], sd[2]);
+    pw[6] = cmul(sd[1], sd[2]);
+    pw[7] = cmul(pw[3], sd[2]);
+    pw[9] = cmul(sd[0], sd[3]);
+    pw[10] = cmul(sd[1], sd[3]);
+    pw[11] = cmul(pw[3], sd[3]);
+    pw[12] = cmul(sd[2], sd[3]);
+    pw[13] = cmul(pw[5], sd[3]);
+    pw[14] = cmul(pw[6], sd[3]);
+    pw[15] = cmul(pw[7], sd[3]);
+}
+
 struct KAParams {
     const uint8_t* compact;  size_t compact_stride;
     const uint8_t* wmask;    size_t wmask_stride;
@@ -468,6 +489,7 @@ struct KAParams {
     const float2* tab_g;     // [16][R]  W_M^(q n1)
     const float2* tab_h;     // [32][R]  W_M^(16 p n1)
     const float2* tab_w;     // [32][16] W_512^(l q)
+    const float2* tab_beta;  // [16 items][4 seeds k = 1,2,4,8][R]  (W_M^(n1) conj W_512^(item))^k
     int R, nstrips, nblk, nif, payload_bytes, groups_per_slot;
     int64_t gb_begin, gb_end;   // this launch covers FFT blocks [gb_begin, gb_end); inter is indexed gb - gb_begin
     int64_t blk_step_bytes;     // stream bytes between the starts of consecutive blocks (= block size unless overlap-save)
@@ -556,6 +578,12 @@ __global__ void __launch_bounds__(kKAThreads, kKACtasPerSM) ka_column_pass(const
         }
     }
 
+    // P3's merged twiddle base for m1 = item: beta = W_M^(n1) * conj(W_512^(item))
+    float2 betaS[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) betaS[k] = p.tab_beta[(size_t)(item * 4 + k) * R + n1];
+    __syncthreads();
+
     const int64_t nbt = p.gb_end;
     const int64_t first = p.gb_begin + blockIdx.x / p.nstrips;
     const int64_t step = gridDim.x / p.nstrips;
@@ -643,6 +671,8 @@ __global__ void __launch_bounds__(kKAThreads, kKACtasPerSM) ka_column_pass(const
                 }
             }
             if (kFFT) { fft_inreg<16, false>(vA); fft_inreg<16, false>(vB); }
+            // (measured: computing these and the h^p powers in registers as well costs more FP than the
+            //  32 table reads it saves -- 99.6 vs 96.8 ms/step -- so they stay in shared memory)
             const float4* twA = reinterpret_cast<const float4*>(s_w + item * 16);
             const float4* twB = reinterpret_cast<const float4*>(s_w + (item + 16) * 16);
 #pragma unroll
@@ -700,13 +730,7 @@ __global__ void __launch_bounds__(kKAThreads, kKACtasPerSM) ka_column_pass(const
                 u[pp + 16] = cmul(u[pp + 16], make_float2(h.z, h.w));
             }
             if (kFFT) fft_inreg<32, true>(u);
-            const float4* tw = reinterpret_cast<const float4*>(s_wT + q * 32);
-#pragma unroll
-            for (int m1 = 0; m1 < (kTW ? 32 : 0); m1 += 2) {
-                const float4 t = tw[m1 >> 1];
-                if (m1) u[m1] = cmul_conj(u[m1], make_float2(t.x, t.y));
-                u[m1 + 1] = cmul_conj(u[m1 + 1], make_float2(t.z, t.w));
-            }
+            // (the conj W_512^(q m1) twiddle of this stage is applied in P3, merged with W_M^(q n1))
             if (kXCH) {
 #pragma unroll
                 for (int m = 0; m < 16; ++m)
@@ -734,15 +758,17 @@ __global__ void __launch_bounds__(kKAThreads, kKACtasPerSM) ka_column_pass(const
                     yB[q] = keepB[q];
                 }
             }
+            if (kTW) {
+                // twiddle of element q: W_M^(q n1) conj W_512^(q m1) = beta^q, beta = g conj(W_512^m1).
+                // Round B has m1 + 16: beta_B^q = beta_A^q conj(W_32^q), a compile-time constant factor.
+                float2 pw[16];
+                cpowers15(betaS, pw);
 #pragma unroll
-            for (int q = 0; q < (kTW ? 8 : 0); ++q) {
-                const float4 g = s_g4[q * C + lane16];
-                if (q) {
-                    yA[q] = cmul(yA[q], make_float2(g.x, g.y));
-                    yB[q] = cmul(yB[q], make_float2(g.x, g.y));
+                for (int q = 1; q < 16; ++q) {
+                    yA[q] = cmul(yA[q], pw[q]);
+                    const float2 cb = make_float2(cos64(2 * q), sin64(2 * q));      // conj(W_32^q) = exp(+2 pi i q/32)
+                    yB[q] = cmul(cmul(yB[q], cb), pw[q]);
                 }
-                yA[q + 8] = cmul(yA[q + 8], make_float2(g.z, g.w));
-                yB[q + 8] = cmul(yB[q + 8], make_float2(g.z, g.w));
             }
             if (kFFT) { fft_inreg<16, true>(yA); fft_inreg<16, true>(yB); }
             float2* dA = p.inter + ((kOneBlock ? 0 : (gb - p.gb_begin)) * (int64_t)kL + item) * R + n1;
