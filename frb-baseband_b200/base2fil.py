@@ -16,7 +16,7 @@ import sys
 
 import numpy as np
 
-from . import sigproc, vdif
+from . import handoff, sigproc, vdif
 from .conf import FrbConf, read_conf
 from .plan import Plan, PlanConfig, pol_mode_from_reference
 
@@ -122,8 +122,10 @@ def run_scan(files: dict[int, str], out_path: str, *, bw: float, freq_lsb0: floa
 
 
 def base2fil(conf_path: str, *, device: int = 0, workdir_odd: str | None = None, workdir_even: str | None = None,
-             outdir: str | None = None) -> list[str]:
-    """Filterbank stage of `base2fil <conf>` for scans whose split VDIF files already exist."""
+             outdir: str | None = None, send=None) -> list[str]:
+    """Filterbank stage of `base2fil <conf>` for scans whose split VDIF files already exist, followed by the
+    reference's per-scan hand-off (`submit2fetch`, `keepVDIF`, `flagFile`: base2fil.sh:420-447).  `send` replaces the
+    FETCH sender process (see handoff.after_scan)."""
     cfg = read_conf(conf_path)
     outdir = outdir or os.path.join(os.path.expandvars(cfg.outdir_base), cfg.experiment)
     os.makedirs(outdir, exist_ok=True)
@@ -153,6 +155,12 @@ def base2fil(conf_path: str, *, device: int = 0, workdir_odd: str | None = None,
         run_scan(files, out_path, bw=float(cfg.bw), freq_lsb0=float(cfg.freqLSB_0), nchan=int(cfg.nchan),
                  tscrunch=int(cfg.tscrunch), pol=int(cfg.pol), nbit=int(cfg.nbit), start=float(cfg.start), nsec=nsec,
                  keep_bandpass=int(cfg.keepBP) > 0, source=source, ra=ra, dec=dec, telescope=cfg.station, device=device)
+        odd = os.path.dirname(files[1])
+        even = os.path.dirname(files[2]) if int(cfg.nif) > 1 else odd
+        handoff.after_scan(out_path, flag_file=str(cfg.flagFile), submit2fetch=int(cfg.submit2fetch) != 0,
+                           keep_vdif=int(cfg.keepVDIF) != 0, send=send,
+                           vdif_globs=handoff.split_vdif_globs(cfg.experiment, station_code(cfg.station),
+                                                               "%03d" % int(scanname), odd, even))
         done.append(out_path)
     return done
 

@@ -75,8 +75,13 @@ def test_base2fil_conf_to_spliced_file(gpu, tmp_path):
     c = tmp_path / "frb.conf"
     c.write_text(f"experiment=c1test\ntarget=\"B0329+54 --ra 03:32:59.4 --dec +54:34:43.3\"\nscans=( 7 )\nskips=( 0 )\n"
                  f"lengths=( 1 )\nscannames=( 007 )\nbw=16\nnif={nif}\nfreqLSB_0=1300.0\nstation=onsala85\nnchan=32\n"
-                 f"tscrunch=32\nworkdir_odd_base={tmp_path}/s0\nworkdir_even_base={tmp_path}/s1\noutdir_base={tmp_path}/out\n")
-    done = base2fil.base2fil(str(c))
+                 f"tscrunch=32\nworkdir_odd_base={tmp_path}/s0\nworkdir_even_base={tmp_path}/s1\noutdir_base={tmp_path}/out\n"
+                 f"submit2fetch=1\nflagFile=/flags/o8.flag_1284-1348MHz_128chan\n")
+    sent = []
+    done = base2fil.base2fil(str(c), send=lambda argv: sent.append(argv) or 0)
+    # base2fil.sh:420-435: keepVDIF=0 (default) removes the split files, then "<fil> <flag>" goes to stage01_queue
+    assert not any(os.path.exists(str((odd if i % 2 else even) / f"c1test_o8_no0007_IF{i}.vdif")) for i in range(1, nif + 1))
+    assert len(sent) == 1 and sent[0][-4:] == ["-q", "stage01_queue", "-m", done[0] + " /flags/o8.flag_1284-1348MHz_128chan"]
     assert done == [str(tmp_path / "out" / "c1test" / "c1test_o8_no0007_IFall_vdif_pol2.fil")]
     h, d = sigproc.read_fil(done[0])
     ref = o.base2fil(vd, nif=nif, freq_lsb0=1300.0, bw=bw, nchan=32, tscrunch_factor=32, nsec=1.0)
