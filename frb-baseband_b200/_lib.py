@@ -49,6 +49,34 @@ class Counters(C.Structure):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
 
 
+class FilHeaderC(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("source_name", C.c_char_p), ("rawdatafile", C.c_char_p),
+        ("telescope_id", C.c_int32), ("machine_id", C.c_int32), ("src_raj", C.c_double), ("src_dej", C.c_double),
+        ("tstart_mjd", C.c_double), ("tsamp_s", C.c_double), ("nbits", C.c_int32), ("fch1_mhz", C.c_double),
+        ("foff_mhz", C.c_double), ("nchans", C.c_int32), ("nifs", C.c_int32), ("refdm", C.c_double),
+        ("write_refdm", C.c_int32),
+    ]
+
+
+class ScanIO(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("start_s", C.c_double), ("nsec", C.c_double), ("source_name", C.c_char_p),
+        ("rawdatafile", C.c_char_p), ("telescope_id", C.c_int32), ("machine_id", C.c_int32),
+        ("src_raj", C.c_double), ("src_dej", C.c_double), ("refdm", C.c_double), ("write_refdm", C.c_int32),
+        ("ring", C.c_int32), ("readers_per_file", C.c_int32),
+    ]
+
+
+class ScanResult(C.Structure):
+    _fields_ = [
+        ("frames_per_if", C.c_int64), ("rows", C.c_int64), ("bytes_in", C.c_int64), ("bytes_out", C.c_int64),
+        ("tstart_mjd", C.c_double), ("seconds_of_data", C.c_double), ("wall_s", C.c_double),
+        ("setup_s", C.c_double), ("wait_read_s", C.c_double), ("wait_gpu_s", C.c_double), ("write_s", C.c_double),
+        ("counters", Counters),
+    ]
+
+
 #: every symbol include/b2f.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "b2f_version": (C.c_int, []),
@@ -70,6 +98,14 @@ SYMBOLS = {
     "b2f_decode": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                              C.c_void_p, C.c_int, C.c_int, C.POINTER(Counters)]),
     "b2f_fp32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
+    "b2f_mark": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "b2f_wait": (C.c_int, [C.c_void_p, C.c_int64]),
+    "b2f_get_params": (C.c_int, [C.c_void_p, C.POINTER(Params)]),
+    "b2f_sigproc_header": (C.c_int, [C.POINTER(FilHeaderC), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "b2f_run_scan": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.c_char_p, C.POINTER(ScanIO),
+                               C.POINTER(ScanResult)]),
+    "b2f_release_host_cache": (C.c_int, []),
+    "b2f_run_file": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(ScanIO), C.POINTER(ScanResult)]),
     "b2f_debug_copy": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
 }
 

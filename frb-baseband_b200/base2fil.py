@@ -14,8 +14,6 @@ from __future__ import annotations
 import os
 import sys
 
-import numpy as np
-
 from . import handoff, sigproc, vdif
 from .conf import FrbConf, read_conf
 from .plan import Plan, PlanConfig, pol_mode_from_reference
@@ -62,63 +60,33 @@ def run_scan(files: dict[int, str], out_path: str, *, bw: float, freq_lsb0: floa
     nif = len(ifs)
     freqs = [freq_lsb0 + (i - 1) * bw for i in ifs]                    # base2fil.sh:54,65,254
     bws = [bw if i % 2 == 0 else -bw for i in ifs]                     # odd = LSB (-l), even = USB (-u)
-    fh = [open(files[i], "rb") for i in ifs]
-    try:
-        infos = [vdif.parse_header(f.read(32)) for f in fh]
-        info = infos[0]
-        for k, other in enumerate(infos):
-            if (other.frame_bytes, other.nbit, other.header_bytes) != (info.frame_bytes, info.nbit, info.header_bytes):
-                raise ValueError(f"{files[ifs[k]]}: frame geometry differs from {files[ifs[0]]}")
-        fps = int(round(vdif.frames_per_second(bw, info)))
-        f0 = int(round(start * fps))
-        nfr = min(os.path.getsize(files[i]) // info.frame_bytes for i in ifs) - f0
-        if nsec is not None:
-            nfr = min(nfr, int(round(nsec * fps)))
-        nfr = max(nfr, 0)
-        cfg = PlanConfig(nchan=nchan, bw_mhz=bws, freq_mhz=freqs, tscrunch=max(1, tscrunch),
-                         pol_mode=pol_mode_from_reference(pol), out_nbit=nbit, in_nbit=info.nbit,
-                         frame_bytes=info.frame_bytes, header_bytes=info.header_bytes, keep_bandpass=keep_bandpass,
-                         device=device, chunk_units=chunk_units, dm=dm, coherent=coherent and dm > 0)
-        for f in fh:
-            f.seek(f0 * info.frame_bytes)
-        head = fh[0].read(32)
-        fh[0].seek(f0 * info.frame_bytes)
-        with Plan(cfg) as pl, open(out_path, "wb") as out:
-            top = max(freqs)
-            out.write(sigproc.FilHeader(
-                source_name=source, rawdatafile=os.path.basename(files[ifs[-1]]),
-                telescope_id=sigproc.TELESCOPE_IDS.get(telescope.lower(), 0),
-                src_raj=sigproc.sexagesimal_to_sigproc(ra), src_dej=sigproc.sexagesimal_to_sigproc(dec),
-                tstart=vdif.frame_mjd(vdif.parse_header(head), fps) if len(head) == 32 else 0.0, tsamp=pl.tsamp_s,
-                nbits=32 if nbit == -32 else nbit, fch1=top + bw / 2 - bw / (2 * nchan), foff=-bw / nchan,
-                nchans=nif * nchan, nifs=pl.nprod).pack())
-            cf = int(pl.chunk_frames)
-            bufs = [np.empty(cf * info.frame_bytes, np.uint8) for _ in ifs]
-            left, rows_out = nfr, 0
-            while left > 0:
-                want = min(cf, left)
-                got = min(f.readinto(memoryview(b)[: want * info.frame_bytes]) for f, b in zip(fh, bufs)) // info.frame_bytes
-                if got == 0:
-                    break
-                pl.push([b[: got * info.frame_bytes] for b in bufs])
-                pl.sync()
-                rows = pl.pull()
-                out.write(rows.tobytes())
-                rows_out += len(rows)
-                left -= got
-            pl.flush()
-            rows = pl.pull()
-            out.write(rows.tobytes())
-            rows_out += len(rows)
-            c = pl.counters()
-        if verbose:
-            print(f"b2f: {nif} IFs x {nfr / fps:.3f} s -> {out_path}: {rows_out} samples x {nif * nchan} channels; "
-                  f"frames ok/invalid/fill/bad = {c['frames_ok']}/{c['frames_invalid']}/{c['frames_with_fill']}/"
-                  f"{c['frames_badhdr']}", file=sys.stderr)
-        return {"rows": rows_out, "counters": c, "nchans": nif * nchan, "tsamp_s": pl.tsamp_s}
-    finally:
-        for f in fh:
-            f.close()
+    infos = []
+    for i in ifs:
+        with open(files[i], "rb") as f:
+            infos.append(vdif.parse_header(f.read(32)))
+    info = infos[0]
+    for k, other in enumerate(infos):
+        if (other.frame_bytes, other.nbit, other.header_bytes) != (info.frame_bytes, info.nbit, info.header_bytes):
+            raise ValueError(f"{files[ifs[k]]}: frame geometry differs from {files[ifs[0]]}")
+    cfg = PlanConfig(nchan=nchan, bw_mhz=bws, freq_mhz=freqs, tscrunch=max(1, tscrunch),
+                     pol_mode=pol_mode_from_reference(pol), out_nbit=nbit, in_nbit=info.nbit,
+                     frame_bytes=info.frame_bytes, header_bytes=info.header_bytes, keep_bandpass=keep_bandpass,
+                     device=device, chunk_units=chunk_units, dm=dm, coherent=coherent and dm > 0)
+    with Plan(cfg) as pl:
+        r = pl.run_scan([files[i] for i in ifs], out_path, start_s=start, nsec=nsec, source_name=source,
+                        telescope_id=sigproc.TELESCOPE_IDS.get(telescope.lower(), 0),
+                        src_raj=sigproc.sexagesimal_to_sigproc(ra), src_dej=sigproc.sexagesimal_to_sigproc(dec))
+        tsamp = pl.tsamp_s
+    return _report(r, f"{nif} IFs x {r['seconds_of_data']:.3f} s", out_path, nif * nchan, tsamp, verbose)
+
+
+def _report(r: dict, what: str, out_path: str, nchans: int, tsamp: float, verbose: bool) -> dict:
+    c = r["counters"]
+    if verbose:
+        print(f"b2f: {what} -> {out_path}: {r['rows']} samples x {nchans} channels in {r['wall_s']:.2f} s; "
+              f"frames ok/invalid/fill/bad = {c['frames_ok']}/{c['frames_invalid']}/{c['frames_with_fill']}/"
+              f"{c['frames_badhdr']}", file=sys.stderr)
+    return {"rows": r["rows"], "counters": c, "nchans": nchans, "tsamp_s": tsamp, "wall_s": r["wall_s"]}
 
 
 def base2fil(conf_path: str, *, device: int = 0, workdir_odd: str | None = None, workdir_even: str | None = None,
@@ -185,47 +153,13 @@ def run_scan_raw(raw_path: str, out_path: str, *, mode: str, nif: int, bw: float
     bws = [bw if i % 2 == 0 else -bw for i in ifs]
     with open(raw_path, "rb") as f:
         info = vdif.parse_header(f.read(32))
-        spf = info.payload_bytes * 8 // W
-        fps = int(round(2.0 * bw * 1e6 / spf))
-        f0 = int(round(start * fps))
-        nfr = os.path.getsize(raw_path) // info.frame_bytes - f0
-        if nsec is not None:
-            nfr = min(nfr, int(round(nsec * fps)))
-        nfr = max(nfr, 0)
-        cfg = PlanConfig(nchan=nchan, bw_mhz=bws, freq_mhz=freqs, tscrunch=max(1, tscrunch),
-                         pol_mode=pol_mode_from_reference(pol), out_nbit=nbit, in_nbit=2, frame_bytes=info.frame_bytes,
-                         header_bytes=info.header_bytes, keep_bandpass=keep_bandpass, device=device,
-                         raw_word_bits=W, raw_bits=bits)
-        f.seek(f0 * info.frame_bytes)
-        head = f.read(32)
-        f.seek(f0 * info.frame_bytes)
-        with Plan(cfg) as pl, open(out_path, "wb") as out:
-            out.write(sigproc.FilHeader(
-                source_name=source, rawdatafile=os.path.basename(raw_path),
-                telescope_id=sigproc.TELESCOPE_IDS.get(telescope.lower(), 0),
-                src_raj=sigproc.sexagesimal_to_sigproc(ra), src_dej=sigproc.sexagesimal_to_sigproc(dec),
-                tstart=vdif.frame_mjd(vdif.parse_header(head), fps) if len(head) == 32 else 0.0, tsamp=pl.tsamp_s,
-                nbits=32 if nbit == -32 else nbit, fch1=max(freqs) + bw / 2 - bw / (2 * nchan), foff=-bw / nchan,
-                nchans=nif * nchan, nifs=pl.nprod).pack())
-            cf = int(pl.chunk_frames)
-            buf = np.empty(cf * info.frame_bytes, np.uint8)
-            left, rows_out = nfr, 0
-            while left > 0:
-                got = f.readinto(memoryview(buf)[: min(cf, left) * info.frame_bytes]) // info.frame_bytes
-                if got == 0:
-                    break
-                pl.push([buf[: got * info.frame_bytes]])
-                pl.sync()
-                rows = pl.pull()
-                out.write(rows.tobytes())
-                rows_out += len(rows)
-                left -= got
-            pl.flush()
-            rows = pl.pull()
-            out.write(rows.tobytes())
-            rows_out += len(rows)
-            c = pl.counters()
-    if verbose:
-        print(f"b2f: raw {mode} -> {out_path}: {rows_out} samples x {nif * nchan} channels; frames ok/invalid/fill/bad = "
-              f"{c['frames_ok']}/{c['frames_invalid']}/{c['frames_with_fill']}/{c['frames_badhdr']}", file=sys.stderr)
-    return {"rows": rows_out, "counters": c, "nchans": nif * nchan, "tsamp_s": pl.tsamp_s}
+    cfg = PlanConfig(nchan=nchan, bw_mhz=bws, freq_mhz=freqs, tscrunch=max(1, tscrunch),
+                     pol_mode=pol_mode_from_reference(pol), out_nbit=nbit, in_nbit=2, frame_bytes=info.frame_bytes,
+                     header_bytes=info.header_bytes, keep_bandpass=keep_bandpass, device=device,
+                     raw_word_bits=W, raw_bits=bits)
+    with Plan(cfg) as pl:
+        r = pl.run_scan([raw_path], out_path, start_s=start, nsec=nsec, source_name=source,
+                        telescope_id=sigproc.TELESCOPE_IDS.get(telescope.lower(), 0),
+                        src_raj=sigproc.sexagesimal_to_sigproc(ra), src_dej=sigproc.sexagesimal_to_sigproc(dec))
+        tsamp = pl.tsamp_s
+    return _report(r, f"raw {mode}", out_path, nif * nchan, tsamp, verbose)

@@ -33,6 +33,12 @@ int fail(int code, const std::string& msg) {
         }                                                                                       \
     } while (0)
 
+}  // namespace
+
+int b2f_internal_fail(int code, const char* msg) { return fail(code, msg); }
+
+namespace {
+
 bool is_pow2(int64_t v) { return v > 0 && (v & (v - 1)) == 0; }
 
 struct TimedLaunch {
@@ -54,6 +60,9 @@ struct b2f_plan {
     cudaStream_t stream = nullptr, copy_stream = nullptr, d2h_stream = nullptr;
     bool own_stream = false;
     cudaEvent_t ev_stage_free[2]{}, ev_h2d_done[2]{}, ev_out_free[2]{}, ev_kq_done[2]{};
+    static constexpr int kMarks = 8;                  // b2f_mark / b2f_wait tickets in flight
+    cudaEvent_t ev_mark[kMarks][3]{};
+    int64_t marks_issued = 0;
     int stage_idx = 0, out_idx = 0;
     int64_t launches = 0;
 
@@ -267,6 +276,9 @@ void free_plan(b2f_plan* pl) {
         if (pl->ev_kq_done[i]) cudaEventDestroy(pl->ev_kq_done[i]);
         if (pl->d_out_stage[i]) cudaFree(pl->d_out_stage[i]);
     }
+    for (int i = 0; i < b2f_plan::kMarks; ++i)
+        for (int k = 0; k < 3; ++k)
+            if (pl->ev_mark[i][k]) cudaEventDestroy(pl->ev_mark[i][k]);
     void* bufs[] = {pl->d_compact, pl->d_wmask, pl->d_fstat, pl->d_blkdirty, pl->d_inter, pl->d_colsum,
                     pl->d_eps, pl->d_F, pl->d_mean, pl->d_scale, pl->d_partial, pl->d_tab_g, pl->d_tab_h,
                     pl->d_tab_w, pl->d_tab_r, pl->d_tab_beta, pl->d_counters, pl->d_sm_slots, pl->d_carry, pl->d_spec, pl->d_chirp, pl->d_tw_col, pl->d_tw_row};
@@ -929,6 +941,37 @@ int b2f_sync(b2f_plan* pl) {
     CU(cudaStreamSynchronize(pl->copy_stream));
     CU(cudaStreamSynchronize(pl->stream));
     CU(cudaStreamSynchronize(pl->d2h_stream));
+    return 0;
+}
+
+int b2f_mark(b2f_plan* pl, int64_t* ticket) {
+    if (!pl || !ticket) return fail(B2F_EINVAL, "null argument");
+    CU(cudaSetDevice(pl->prm.device));
+    const int slot = (int)(pl->marks_issued % b2f_plan::kMarks);
+    cudaStream_t st[3] = {pl->copy_stream, pl->stream, pl->d2h_stream};
+    for (int k = 0; k < 3; ++k) {
+        if (!pl->ev_mark[slot][k]) CU(cudaEventCreateWithFlags(&pl->ev_mark[slot][k], cudaEventDisableTiming));
+        CU(cudaEventRecord(pl->ev_mark[slot][k], st[k]));
+    }
+    *ticket = pl->marks_issued++;
+    return 0;
+}
+
+int b2f_wait(b2f_plan* pl, int64_t ticket) {
+    if (!pl) return fail(B2F_EINVAL, "null plan");
+    if (ticket < 0 || ticket >= pl->marks_issued) return fail(B2F_EINVAL, "unknown ticket");
+    if (pl->marks_issued - ticket > b2f_plan::kMarks)          // its events were re-recorded by a newer mark
+        return fail(B2F_ESTATE, "ticket too old: at most 8 marks may be outstanding");
+    CU(cudaSetDevice(pl->prm.device));
+    const int slot = (int)(ticket % b2f_plan::kMarks);
+    for (int k = 0; k < 3; ++k) CU(cudaEventSynchronize(pl->ev_mark[slot][k]));
+    return 0;
+}
+
+int b2f_get_params(const b2f_plan* pl, b2f_params* out) {
+    if (!pl || !out) return fail(B2F_EINVAL, "null argument");
+    *out = pl->prm;
+    out->freq_res = pl->L;
     return 0;
 }
 

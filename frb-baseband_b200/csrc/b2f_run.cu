@@ -1,0 +1,525 @@
+// b2f_run.cu -- file-level runner above the streaming ABI: split VDIF files in, one SIGPROC filterbank out.
+//
+// This is the work of one `digifil ... -o <fifo> <hdr>` child per IF (/root/reference/process_vdif.py:157-191)
+// plus `splice ${splice_list} > IFall.fil` (/root/reference/base2fil.sh:420-448) as a single native call:
+// reader threads fill a ring of pinned chunks (one thread per input file), the caller's thread feeds the GPU
+// plan and writes finished rows; nothing waits for the GPU except to recycle a ring slot.  Only the public ABI
+// of include/b2f.h is used for the device side.
+#include <cuda_runtime.h>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cerrno>
+#include <chrono>
+#include <cmath>
+#include <condition_variable>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/b2f.h"
+
+int b2f_internal_fail(int code, const char* msg);
+
+namespace {
+
+int failf(int code, const std::string& s) { return b2f_internal_fail(code, s.c_str()); }
+
+// ---- VDIF header facts needed on the host (VDIF 1.1 words 0..3)
+struct FrameHead {
+    uint32_t seconds, frame_nr, epoch, frame_bytes, nbit, nchan, legacy;
+};
+
+FrameHead parse_head(const uint8_t* b) {
+    uint32_t w[4];
+    memcpy(w, b, 16);
+    FrameHead h;
+    h.seconds = w[0] & 0x3FFFFFFFu;
+    h.legacy = (w[0] >> 30) & 1u;
+    h.frame_nr = w[1] & 0xFFFFFFu;
+    h.epoch = (w[1] >> 24) & 0x3Fu;
+    h.frame_bytes = (w[2] & 0xFFFFFFu) * 8u;
+    h.nchan = 1u << ((w[2] >> 24) & 0x1Fu);
+    h.nbit = ((w[3] >> 26) & 0x1Fu) + 1u;
+    return h;
+}
+
+// MJD of 00:00 UTC on the first day of a VDIF reference epoch (six-month steps from 2000-01-01)
+int64_t epoch_mjd(uint32_t epoch) {
+    const int64_t year = 2000 + epoch / 2, month = (epoch & 1) ? 7 : 1;
+    const int64_t a = (14 - month) / 12, y = year + 4800 - a, m = month + 12 * a - 3;
+    const int64_t jdn = 1 + (153 * m + 2) / 5 + 365 * y + y / 4 - y / 100 + y / 400 - 32045;
+    return jdn - 2400001;
+}
+
+// ---- SIGPROC header (keyword strings with a 32-bit length in front)
+struct HeaderWriter {
+    std::vector<uint8_t> b;
+    void str(const char* s) {
+        const int32_t n = (int32_t)strlen(s);
+        raw(&n, 4);
+        raw(s, (size_t)n);
+    }
+    void raw(const void* p, size_t n) {
+        const uint8_t* q = static_cast<const uint8_t*>(p);
+        b.insert(b.end(), q, q + n);
+    }
+    void i32(const char* k, int32_t v) { str(k); raw(&v, 4); }
+    void f64(const char* k, double v) { str(k); raw(&v, 8); }
+    void text(const char* k, const char* v) { str(k); str(v); }
+};
+
+struct Ring {
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<int64_t> filled;      // per input file: chunks read so far
+    std::vector<int64_t> got_frames;  // [chunk % ring][file] frames actually read
+    int64_t released = 0;             // chunks whose slot may be overwritten
+    bool abort = false;
+    std::string err;
+};
+
+bool read_fully(int fd, uint8_t* dst, size_t n, off_t off, size_t* got) {
+    size_t done = 0;
+    while (done < n) {
+        const ssize_t r = pread(fd, dst + done, n - done, off + (off_t)done);
+        if (r < 0) return false;
+        if (r == 0) break;
+        done += (size_t)r;
+    }
+    *got = done;
+    return true;
+}
+
+bool write_fully(int fd, const uint8_t* src, size_t n) {
+    size_t done = 0;
+    while (done < n) {
+        const ssize_t r = write(fd, src + done, n - done);
+        if (r < 0) return false;
+        done += (size_t)r;
+    }
+    return true;
+}
+
+// Pinned blocks are expensive to make (about 1 GB/s) and a process that runs many scans wants the same sizes
+// again: finished scans hand their blocks back to this cache; b2f_release_host_cache() frees the idle ones.
+struct PinnedPool {
+    struct Block { void* p; size_t n; bool busy; };
+    std::mutex mu;
+    std::vector<Block> blocks;
+    void* acquire(size_t n) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            for (auto& b : blocks)
+                if (!b.busy && b.n >= n && b.n <= n + n / 2) { b.busy = true; return b.p; }
+        }
+        void* p = nullptr;
+        if (cudaHostAlloc(&p, n, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        std::lock_guard<std::mutex> lk(mu);
+        blocks.push_back({p, n, true});
+        return p;
+    }
+    void release(void* p) {
+        std::lock_guard<std::mutex> lk(mu);
+        for (auto& b : blocks) if (b.p == p) b.busy = false;
+    }
+    void trim() {
+        std::lock_guard<std::mutex> lk(mu);
+        std::vector<Block> keep;
+        for (auto& b : blocks) {
+            if (b.busy) keep.push_back(b);
+            else cudaFreeHost(b.p);
+        }
+        blocks.swap(keep);
+    }
+};
+PinnedPool g_pool;
+
+struct Closer {
+    std::vector<int> fds;
+    std::vector<void*> pinned;
+    ~Closer() {
+        for (int f : fds) if (f >= 0) close(f);
+        for (void* p : pinned) if (p) g_pool.release(p);
+    }
+};
+
+// Finished rows go to the file on their own thread, in the order they were queued.
+struct Writer {
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<std::pair<int, size_t>> q;      // (buffer index, bytes), FIFO
+    std::vector<int> free_bufs;
+    bool done = false, failed = false;
+    std::string err;
+};
+
+}  // namespace
+
+extern "C" int b2f_release_host_cache(void) {
+    g_pool.trim();
+    return 0;
+}
+
+extern "C" int b2f_sigproc_header(const b2f_fil_header* h, void* buf, size_t cap, size_t* nbytes) {
+    if (!h || !nbytes) return failf(B2F_EINVAL, "null argument");
+    if (h->struct_size != sizeof(b2f_fil_header)) return failf(B2F_EINVAL, "b2f_fil_header.struct_size mismatch");
+    HeaderWriter w;
+    w.str("HEADER_START");
+    w.i32("telescope_id", h->telescope_id);
+    w.i32("machine_id", h->machine_id);
+    w.i32("data_type", 1);
+    w.text("rawdatafile", h->rawdatafile ? h->rawdatafile : "");
+    w.text("source_name", h->source_name ? h->source_name : "unknown");
+    w.i32("barycentric", 0);
+    w.i32("pulsarcentric", 0);
+    w.f64("az_start", 0.0);
+    w.f64("za_start", 0.0);
+    w.f64("src_raj", h->src_raj);
+    w.f64("src_dej", h->src_dej);
+    w.f64("tstart", h->tstart_mjd);
+    w.f64("tsamp", h->tsamp_s);
+    w.i32("nbits", h->nbits);
+    w.f64("fch1", h->fch1_mhz);
+    w.f64("foff", h->foff_mhz);
+    w.i32("nchans", h->nchans);
+    w.i32("nifs", h->nifs);
+    if (h->write_refdm) w.f64("refdm", h->refdm);
+    w.str("HEADER_END");
+    *nbytes = w.b.size();
+    if (buf) {
+        if (cap < w.b.size()) return failf(B2F_EINVAL, "header buffer too small");
+        memcpy(buf, w.b.data(), w.b.size());
+    }
+    return 0;
+}
+
+extern "C" int b2f_run_scan(b2f_plan* pl, int nfiles, const char* const* vdif_paths, const char* out_path,
+                            const b2f_scan_io* io_in, b2f_scan_result* res) {
+    if (!pl || !vdif_paths || !out_path) return failf(B2F_EINVAL, "null argument");
+    b2f_scan_io io{};
+    if (io_in) {
+        if (io_in->struct_size != sizeof(b2f_scan_io)) return failf(B2F_EINVAL, "b2f_scan_io.struct_size mismatch");
+        io = *io_in;
+    }
+    b2f_params prm;
+    b2f_geometry g;
+    int rc = b2f_get_params(pl, &prm);
+    if (rc) return rc;
+    rc = b2f_get_geometry(pl, &g);
+    if (rc) return rc;
+    const int nstreams = prm.raw_word_bits ? 1 : prm.nif;
+    if (nfiles != nstreams)
+        return failf(B2F_EINVAL, "the plan expects " + std::to_string(nstreams) + " input file(s), got " + std::to_string(nfiles));
+    const auto t_begin = std::chrono::steady_clock::now();
+    const size_t fb = (size_t)prm.frame_bytes;
+    const double fps_d = 2.0 * std::fabs(prm.bw_mhz[0]) * 1e6 / (double)g.samples_per_frame;
+    const int64_t fps = llround(fps_d);
+    if (std::fabs(fps_d - (double)fps) > 1e-6)
+        return failf(B2F_EINVAL, "frames per second is not an integer for this bandwidth and frame size");
+
+    Closer own;
+    // ---- inputs: size, window (-S / -T), geometry check against the plan
+    const int64_t f0 = llround(io.start_s * (double)fps);
+    int64_t nfr = INT64_MAX;
+    for (int i = 0; i < nfiles; ++i) {
+        const int fd = open(vdif_paths[i], O_RDONLY);
+        if (fd < 0) return failf(B2F_EINVAL, std::string("cannot open ") + vdif_paths[i] + ": " + strerror(errno));
+        own.fds.push_back(fd);
+        struct stat st;
+        if (fstat(fd, &st)) return failf(B2F_EINVAL, std::string("cannot stat ") + vdif_paths[i]);
+        nfr = std::min<int64_t>(nfr, (int64_t)(st.st_size / (off_t)fb) - f0);
+        uint8_t head[32];
+        size_t got = 0;
+        if (read_fully(fd, head, 32, 0, &got) && got == 32) {
+            const FrameHead h = parse_head(head);
+            if (h.frame_bytes != fb || (int)(h.legacy ? 16 : 32) != prm.header_bytes ||
+                (!prm.raw_word_bits && (int)h.nbit != prm.in_nbit))
+                return failf(B2F_EINVAL, std::string(vdif_paths[i]) + ": frame geometry differs from the plan (" +
+                                             std::to_string(h.frame_bytes) + " B frames, " + std::to_string(h.nbit) + " bit)");
+        }
+    }
+    if (io.nsec > 0) nfr = std::min<int64_t>(nfr, llround(io.nsec * (double)fps));
+    nfr = std::max<int64_t>(nfr, 0);
+
+    double tstart = 0.0;
+    {
+        uint8_t head[32];
+        size_t got = 0;
+        if (read_fully(own.fds[0], head, 32, (off_t)(f0 * (int64_t)fb), &got) && got == 32) {
+            const FrameHead h = parse_head(head);
+            tstart = (double)epoch_mjd(h.epoch) + ((double)h.seconds + (double)h.frame_nr / (double)fps) / 86400.0;
+        }
+    }
+
+    // ---- output: an existing FIFO (base2fil.sh:348-349) is opened as it is, never unlinked (process_vdif.py:146-149)
+    int ofd;
+    {
+        struct stat st;
+        if (stat(out_path, &st) == 0 && S_ISFIFO(st.st_mode)) ofd = open(out_path, O_WRONLY);
+        else ofd = open(out_path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+        if (ofd < 0) return failf(B2F_EINVAL, std::string("cannot open ") + out_path + " for writing: " + strerror(errno));
+        own.fds.push_back(ofd);
+    }
+    int64_t bytes_out = 0;
+    {
+        double top = prm.freq_mhz[0];
+        for (int i = 1; i < prm.nif; ++i) top = std::max(top, prm.freq_mhz[i]);
+        const double abw = std::fabs(prm.bw_mhz[0]);
+        std::string base = vdif_paths[nfiles - 1];
+        base = base.substr(base.find_last_of('/') == std::string::npos ? 0 : base.find_last_of('/') + 1);
+        b2f_fil_header fh{};
+        fh.struct_size = sizeof fh;
+        fh.source_name = io.source_name;
+        fh.rawdatafile = io.rawdatafile ? io.rawdatafile : base.c_str();
+        fh.telescope_id = io.telescope_id;
+        fh.machine_id = io.machine_id;
+        fh.src_raj = io.src_raj;
+        fh.src_dej = io.src_dej;
+        fh.tstart_mjd = tstart;
+        fh.tsamp_s = g.tsamp_s;
+        fh.nbits = prm.out_nbit == -32 ? 32 : prm.out_nbit;
+        fh.fch1_mhz = top + abw / 2 - abw / (2.0 * prm.nchan);
+        fh.foff_mhz = -abw / prm.nchan;
+        fh.nchans = prm.nif * prm.nchan;
+        fh.nifs = g.nprod;
+        fh.refdm = io.refdm;
+        fh.write_refdm = io.write_refdm;
+        uint8_t hb[1024];
+        size_t hn = 0;
+        rc = b2f_sigproc_header(&fh, hb, sizeof hb, &hn);
+        if (rc) return rc;
+        if (!write_fully(ofd, hb, hn)) return failf(B2F_EINVAL, std::string("write failed: ") + strerror(errno));
+        bytes_out += (int64_t)hn;
+    }
+
+    // ---- pinned ring + output buffers
+    const int ring = io.ring > 0 ? std::min(std::max(io.ring, 2), 6) : 3;   // < 2 cannot overlap reading with the GPU
+    const int64_t cf = g.chunk_frames;
+    const size_t file_stride = ((size_t)cf * fb + 255) / 256 * 256;
+    const size_t slot_bytes = file_stride * (size_t)nfiles;
+    const int64_t max_rows = std::max<int64_t>(4 * g.chunk_rows, 4096);      // rows per pull; a backlog takes several
+    if (cudaSetDevice(prm.device) != cudaSuccess) return failf(B2F_ECUDA, "cudaSetDevice failed");
+    std::vector<uint8_t*> slot(ring, nullptr);
+    for (int s = 0; s < ring; ++s) {
+        void* p = g_pool.acquire(slot_bytes);
+        if (!p) return failf(B2F_ENOMEM, "cannot allocate pinned input ring");
+        own.pinned.push_back(p);
+        slot[s] = static_cast<uint8_t*>(p);
+    }
+    constexpr int kOut = 4;
+    uint8_t* outb[kOut];
+    for (int s = 0; s < kOut; ++s) {
+        void* p = g_pool.acquire((size_t)max_rows * (size_t)g.row_bytes);
+        if (!p) return failf(B2F_ENOMEM, "cannot allocate pinned output buffers");
+        own.pinned.push_back(p);
+        outb[s] = static_cast<uint8_t*>(p);
+    }
+
+    // ---- readers: file i, chunk k -> slot[k % ring] + i * file_stride
+    const int64_t nchunks = (nfr + cf - 1) / cf;
+    // Several threads per file: a page-cache read is a single-core memcpy (about 5 GB/s), far below what PCIe takes.
+    const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
+    const int parts = io.readers_per_file > 0 ? std::min(io.readers_per_file, 8)
+                                              : std::max(1, std::min(4, hw / std::max(1, nfiles)));
+    const int nreaders = nfiles * parts;
+    Ring R;
+    R.filled.assign(nreaders, 0);
+    R.got_frames.assign((size_t)ring * nreaders, 0);
+    std::vector<std::thread> readers;
+    for (int t = 0; t < nreaders; ++t) {
+        readers.emplace_back([&, t] {
+            const int i = t / parts, j = t % parts;
+            for (int64_t k = 0; k < nchunks; ++k) {
+                {
+                    std::unique_lock<std::mutex> lk(R.mu);
+                    R.cv.wait(lk, [&] { return R.abort || k < R.released + ring; });
+                    if (R.abort) return;
+                }
+                const int64_t want = std::min<int64_t>(cf, nfr - k * cf);
+                const int64_t a = want * j / parts, b = want * (j + 1) / parts;      // this thread's frames of the chunk
+                size_t got = 0;
+                const bool ok = read_fully(own.fds[i], slot[k % ring] + (size_t)i * file_stride + (size_t)a * fb,
+                                           (size_t)(b - a) * fb, (off_t)((f0 + k * cf + a) * (int64_t)fb), &got);
+                std::lock_guard<std::mutex> lk(R.mu);
+                if (!ok) {
+                    R.abort = true;
+                    R.err = std::string("read failed on ") + vdif_paths[i] + ": " + strerror(errno);
+                }
+                // frames of this chunk that are contiguous from its start as far as this part knows
+                R.got_frames[(size_t)(k % ring) * nreaders + t] = (int64_t)(got / fb) == b - a ? want : a + (int64_t)(got / fb);
+                R.filled[t] = k + 1;
+                R.cv.notify_all();
+                if (!ok) return;
+            }
+        });
+    }
+    auto stop_readers = [&] {
+        {
+            std::lock_guard<std::mutex> lk(R.mu);
+            R.abort = true;
+        }
+        R.cv.notify_all();
+        for (auto& t : readers) if (t.joinable()) t.join();
+    };
+
+    // ---- feed the plan; rows of chunk k are written while chunk k+1 is on the GPU
+    int64_t rows_total = 0, frames_done = 0;
+    double t_wait_read = 0, t_wait_gpu = 0, t_write = 0;
+    auto since = [](std::chrono::steady_clock::time_point t0) {
+        return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    };
+    const double t_setup = since(t_begin);
+    Writer W;
+    for (int s = 0; s < kOut; ++s) W.free_bufs.push_back(s);
+    std::thread writer([&] {
+        for (;;) {
+            std::pair<int, size_t> job;
+            {
+                std::unique_lock<std::mutex> lk(W.mu);
+                W.cv.wait(lk, [&] { return W.done || !W.q.empty(); });
+                if (W.q.empty()) return;
+                job = W.q.front();
+                W.q.erase(W.q.begin());
+            }
+            const auto t0 = std::chrono::steady_clock::now();
+            const bool ok = W.failed || write_fully(ofd, outb[job.first], job.second);
+            std::lock_guard<std::mutex> lk(W.mu);
+            t_write += since(t0);
+            if (!ok && !W.failed) {
+                W.failed = true;
+                W.err = std::string("write failed: ") + strerror(errno);
+            }
+            W.free_bufs.push_back(job.first);
+            W.cv.notify_all();
+        }
+    });
+    auto take_buffer = [&]() -> int {
+        std::unique_lock<std::mutex> lk(W.mu);
+        W.cv.wait(lk, [&] { return !W.free_bufs.empty(); });
+        const int b = W.free_bufs.back();
+        W.free_bufs.pop_back();
+        return b;
+    };
+    auto queue_write = [&](int buf, int64_t rows) {
+        {
+            std::lock_guard<std::mutex> lk(W.mu);
+            if (rows > 0) W.q.emplace_back(buf, (size_t)rows * (size_t)g.row_bytes);
+            else W.free_bufs.push_back(buf);
+        }
+        W.cv.notify_all();
+        bytes_out += rows * g.row_bytes;
+        rows_total += rows;
+    };
+    int64_t pend_rows[2] = {0, 0}, pend_ticket[2] = {-1, -1};
+    int pend_buf[2] = {-1, -1};
+    auto drain = [&](int b) -> int {        // rows queued into pend_buf[b] by the GPU -> writer
+        if (pend_ticket[b] < 0) return 0;
+        const auto t0 = std::chrono::steady_clock::now();
+        const int r = b2f_wait(pl, pend_ticket[b]);
+        t_wait_gpu += since(t0);
+        pend_ticket[b] = -1;
+        queue_write(pend_buf[b], r ? 0 : pend_rows[b]);
+        pend_buf[b] = -1;
+        pend_rows[b] = 0;
+        return r;
+    };
+    rc = b2f_reset(pl);
+    for (int64_t k = 0; rc == 0 && k < nchunks; ++k) {
+        int64_t got = INT64_MAX;
+        const auto tw = std::chrono::steady_clock::now();
+        {
+            std::unique_lock<std::mutex> lk(R.mu);
+            R.cv.wait(lk, [&] {
+                if (R.abort) return true;
+                for (int t = 0; t < nreaders; ++t) if (R.filled[t] <= k) return false;
+                return true;
+            });
+            if (R.abort) { rc = failf(B2F_EINVAL, R.err); break; }
+            for (int t = 0; t < nreaders; ++t) got = std::min(got, R.got_frames[(size_t)(k % ring) * nreaders + t]);
+        }
+        t_wait_read += since(tw);
+        if (got <= 0) break;
+        const void* ptrs[B2F_MAX_IF];
+        for (int i = 0; i < nfiles; ++i) ptrs[i] = slot[k % ring] + (size_t)i * file_stride;
+        const int b = (int)(k & 1);
+        rc = b2f_push(pl, ptrs, got, 0);
+        if (rc) break;
+        // while the GPU has chunk k queued: finish chunk k-1 (its copies and kernels are then behind us, so its
+        // ring slot can be recycled) and write its rows, which keeps the file in time order
+        rc = drain(b ^ 1);
+        if (rc) break;
+        for (;;) {                           // normally one pull; the first rescale interval comes out as a backlog
+            int64_t n = 0;
+            pend_buf[b] = take_buffer();
+            rc = b2f_pull(pl, outb[pend_buf[b]], max_rows, 2, &n);
+            if (rc) { queue_write(pend_buf[b], 0); pend_buf[b] = -1; break; }
+            pend_rows[b] = n;
+            rc = b2f_mark(pl, &pend_ticket[b]);
+            if (rc || n < max_rows) break;
+            rc = drain(b);
+            if (rc) break;
+        }
+        if (rc) break;
+        frames_done += got;
+        {
+            std::lock_guard<std::mutex> lk(R.mu);
+            R.released = k;                  // chunks < k are consumed; chunk k's slot stays until the next turn
+        }
+        R.cv.notify_all();
+        if (got < std::min<int64_t>(cf, nfr - k * cf)) break;      // short read: a file ended early
+    }
+    stop_readers();
+    if (rc == 0) rc = drain((int)(nchunks & 1));          // older of the two pending buffers first
+    if (rc == 0) rc = drain((int)(nchunks & 1) ^ 1);
+    if (rc == 0) rc = b2f_flush(pl);
+    while (rc == 0) {                        // rows still held (first rescale interval, tail)
+        int64_t n = 0;
+        const int buf = take_buffer();
+        rc = b2f_pull(pl, outb[buf], max_rows, 0, &n);
+        queue_write(buf, rc ? 0 : n);
+        if (rc || n == 0) break;
+    }
+    {
+        std::lock_guard<std::mutex> lk(W.mu);
+        W.done = true;
+    }
+    W.cv.notify_all();
+    writer.join();
+    if (rc == 0 && W.failed) rc = failf(B2F_EINVAL, W.err);
+    if (rc) {
+        b2f_sync(pl);                        // nothing may still be reading the pinned buffers when they are freed
+        return rc;
+    }
+    rc = b2f_sync(pl);
+    if (rc) return rc;
+    if (res) {
+        memset(res, 0, sizeof *res);
+        res->frames_per_if = frames_done;
+        res->rows = rows_total;
+        res->bytes_in = frames_done * (int64_t)fb * nfiles;
+        res->bytes_out = bytes_out;
+        res->tstart_mjd = tstart;
+        res->seconds_of_data = (double)frames_done / (double)fps;
+        res->wall_s = since(t_begin);
+        res->setup_s = t_setup;
+        res->wait_read_s = t_wait_read;
+        res->wait_gpu_s = t_wait_gpu;
+        res->write_s = t_write;
+        rc = b2f_get_counters(pl, &res->counters);
+    }
+    return rc;
+}
+
+extern "C" int b2f_run_file(b2f_plan* pl, const char* vdif_path, const char* fil_path, const b2f_scan_io* io,
+                            b2f_scan_result* res) {
+    const char* paths[1] = {vdif_path};
+    if (!vdif_path) return failf(B2F_EINVAL, "null argument");
+    return b2f_run_scan(pl, 1, paths, fil_path, io, res);
+}

@@ -5,6 +5,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -180,6 +181,40 @@ class Plan:
 
     def sync(self):
         _lib.check(_lib.lib().b2f_sync(self._h))
+
+    def mark(self) -> int:
+        t = C.c_int64(0)
+        _lib.check(_lib.lib().b2f_mark(self._h, C.byref(t)))
+        return t.value
+
+    def wait(self, ticket: int):
+        _lib.check(_lib.lib().b2f_wait(self._h, int(ticket)))
+
+    def run_scan(self, paths, out_path: str, *, start_s: float = 0.0, nsec: float | None = None,
+                 source_name: str = "unknown", rawdatafile: str | None = None, telescope_id: int = 0,
+                 machine_id: int = 0, src_raj: float = 0.0, src_dej: float = 0.0, refdm: float | None = None,
+                 ring: int = 0, readers_per_file: int = 0) -> dict:
+        """Files in, filterbank file out, entirely inside libb2f (b2f_run_scan): threaded readers, pinned ring,
+        pipelined pushes/pulls.  `paths`: one split VDIF file per IF in plan order (or the one raw recording)."""
+        io = _lib.ScanIO()
+        io.struct_size = C.sizeof(_lib.ScanIO)
+        io.start_s = float(start_s)
+        io.nsec = -1.0 if nsec is None else float(nsec)
+        io.source_name = source_name.encode()
+        io.rawdatafile = None if rawdatafile is None else rawdatafile.encode()
+        io.telescope_id, io.machine_id = int(telescope_id), int(machine_id)
+        io.src_raj, io.src_dej = float(src_raj), float(src_dej)
+        io.refdm = 0.0 if refdm is None else float(refdm)
+        io.write_refdm = int(refdm is not None)
+        io.ring = ring
+        io.readers_per_file = readers_per_file
+        arr = (C.c_char_p * len(paths))(*[os.fsencode(p) for p in paths])
+        res = _lib.ScanResult()
+        _lib.check(_lib.lib().b2f_run_scan(self._h, len(paths), arr, os.fsencode(out_path), C.byref(io), C.byref(res)))
+        return {"rows": int(res.rows), "frames_per_if": int(res.frames_per_if), "bytes_in": int(res.bytes_in),
+                "bytes_out": int(res.bytes_out), "tstart_mjd": res.tstart_mjd, "seconds_of_data": res.seconds_of_data,
+                "wall_s": res.wall_s, "setup_s": res.setup_s, "wait_read_s": res.wait_read_s,
+                "wait_gpu_s": res.wait_gpu_s, "write_s": res.write_s, "counters": res.counters.as_dict()}
 
     def reset(self):
         _lib.check(_lib.lib().b2f_reset(self._h))

@@ -18,7 +18,6 @@ import stat
 import subprocess
 import sys
 
-import numpy as np
 
 # (flags, argparse keywords, option group) -- one row per option of the reference CLI
 _G, _D, _P = "General info about the data.", "Input to digifil.", "Input to prepdata/prepsubband"
@@ -156,44 +155,19 @@ def run_digifil(hdr, fil_out_dir=None, start=1, nsecs=120, nchan=128, overwrite=
     try:
         with open(datafile, "rb") as src:
             info = vdif.parse_header(src.read(32))
-            fps = vdif.frames_per_second(bw, info)
-            if abs(fps - round(fps)) > 1e-6:
-                raise InputError(f"{datafile}: {fps} frames per second is not an integer for bw={bw}")
-            fps = int(round(fps))
-            first_frame = int(round(start * fps))
-            nframes = os.fstat(src.fileno()).st_size // info.frame_bytes - first_frame
-            nframes = max(0, min(nframes, int(round(nsecs * fps))))
-            cfg = PlanConfig(nchan=nchan, bw_mhz=[bw], freq_mhz=[freq], tscrunch=max(1, tscrunch),
-                             pol_mode=pol_mode_from_reference(pol), out_nbit=nbit, in_nbit=info.nbit,
-                             frame_bytes=info.frame_bytes, header_bytes=info.header_bytes, keep_bandpass=keepBP,
-                             device=device, dm=float(dm), coherent=bool(coherent and dm > 0.0))
-            src.seek(first_frame * info.frame_bytes)
-            head = src.read(32)
-            src.seek(first_frame * info.frame_bytes)
-            with Plan(cfg) as pl, open(fil, "wb") as out:
-                out.write(sigproc.FilHeader(
-                    source_name=kv.get("SOURCE", "unknown"), rawdatafile=os.path.basename(datafile),
-                    telescope_id=sigproc.TELESCOPE_IDS.get(kv.get("TELESCOPE", "").lower(), 0),
-                    src_raj=sigproc.sexagesimal_to_sigproc(kv.get("RA")),
-                    src_dej=sigproc.sexagesimal_to_sigproc(kv.get("DEC")),
-                    tstart=vdif.frame_mjd(vdif.parse_header(head), fps) if len(head) == 32 else 0.0,
-                    tsamp=pl.tsamp_s, nbits=32 if nbit == -32 else nbit,
-                    fch1=freq + abs(bw) / 2 - abs(bw) / (2 * nchan), foff=-abs(bw) / nchan, nchans=nchan,
-                    nifs=pl.nprod, refdm=dm).pack())
-                chunk = np.empty(int(pl.chunk_frames) * info.frame_bytes, np.uint8)
-                left = nframes
-                while left > 0:
-                    want = min(int(pl.chunk_frames), left) * info.frame_bytes
-                    got = src.readinto(memoryview(chunk)[:want]) // info.frame_bytes
-                    if got == 0:
-                        break
-                    pl.push([chunk[: got * info.frame_bytes]])
-                    pl.sync()                                  # `chunk` is refilled by the next read
-                    out.write(pl.pull().tobytes())
-                    left -= got
-                pl.flush()
-                out.write(pl.pull().tobytes())
-                c = pl.counters()
+        fps = vdif.frames_per_second(bw, info)
+        if abs(fps - round(fps)) > 1e-6:
+            raise InputError(f"{datafile}: {fps} frames per second is not an integer for bw={bw}")
+        cfg = PlanConfig(nchan=nchan, bw_mhz=[bw], freq_mhz=[freq], tscrunch=max(1, tscrunch),
+                         pol_mode=pol_mode_from_reference(pol), out_nbit=nbit, in_nbit=info.nbit,
+                         frame_bytes=info.frame_bytes, header_bytes=info.header_bytes, keep_bandpass=keepBP,
+                         device=device, dm=float(dm), coherent=bool(coherent and dm > 0.0))
+        with Plan(cfg) as pl:
+            # the digifil child process (reference :191): file in, .fil (or FIFO) out, inside libb2f
+            c = pl.run_scan([datafile], fil, start_s=start, nsec=nsecs, source_name=kv.get("SOURCE", "unknown"),
+                            telescope_id=sigproc.TELESCOPE_IDS.get(kv.get("TELESCOPE", "").lower(), 0),
+                            src_raj=sigproc.sexagesimal_to_sigproc(kv.get("RA")),
+                            src_dej=sigproc.sexagesimal_to_sigproc(kv.get("DEC")), refdm=dm)["counters"]
         if c["frames_invalid"] or c["frames_with_fill"] or c["frames_badhdr"]:
             print("b2f: masked {frames_invalid} invalid, {frames_with_fill} fill-pattern and {frames_badhdr} "
                   "malformed frames".format(**c), file=sys.stderr)

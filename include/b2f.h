@@ -6,7 +6,8 @@
  * so every entry point below cites the reference call site whose work it replaces:
  *
  *   digifil argv built at      process_vdif.py:156-182   -> b2f_params fields
- *   digifil process run at     process_vdif.py:191        -> b2f_push / b2f_pull (per chunk)
+ *   digifil process run at     process_vdif.py:191        -> b2f_run_file, or b2f_push / b2f_pull per chunk
+ *   fan-out + FIFOs + splice   base2fil.sh:404-448        -> b2f_run_scan
  *   .hdr semantics             process_vdif.py:115-139   -> freq_mhz / bw_mhz (sign = sideband)
  *   one digifil per IF         base2fil.sh:60-66          -> nif > 1 batches the IFs in one plan
  *   splice ${splice_list}      base2fil.sh:422-446        -> spliced row layout written by b2f_pull
@@ -164,6 +165,74 @@ int b2f_get_rescale(struct b2f_plan* plan, float* mean, float* scale);
  * the timers; requires params.profile = 1 */
 int b2f_kernel_time(struct b2f_plan* plan, int kernel_id, double* ms, int64_t* launches);
 int b2f_reset_timers(struct b2f_plan* plan);
+
+/* Ordering points for callers that pipeline pushes and pulls without b2f_sync: b2f_mark returns a ticket for
+ * "everything queued on this plan so far" (host->device copies, kernels, device->host copies); b2f_wait blocks
+ * until that point has been reached.  After waiting on a ticket taken after push k / pull k, the host buffers
+ * given to push k may be overwritten and the rows of pull k (mode 2) may be read.  At most 8 tickets may be
+ * outstanding. */
+int b2f_mark(struct b2f_plan* plan, int64_t* ticket);
+int b2f_wait(struct b2f_plan* plan, int64_t ticket);
+
+/* The parameters the plan was created with (freq_res resolved to its effective value). */
+int b2f_get_params(const struct b2f_plan* plan, b2f_params* out);
+
+/* ---- file level: what one `digifil` process per IF plus `splice` do with files ------------------------------- */
+
+/* SIGPROC filterbank header as digifil writes it at the top of every .fil (process_vdif.py:143-145) and splice
+ * re-emits with nchans summed (base2fil.sh:422); the fields dm_utils.py:108-125 reads back are source_name and
+ * nchans. */
+typedef struct b2f_fil_header {
+    uint32_t struct_size;
+    const char* source_name;       /* SOURCE of the .hdr (process_vdif.py:125); NULL = "unknown" */
+    const char* rawdatafile;
+    int32_t telescope_id, machine_id;
+    double src_raj, src_dej;       /* hhmmss.s / ddmmss.s */
+    double tstart_mjd, tsamp_s;
+    int32_t nbits;                 /* 2, 8, 16 or 32 (float) */
+    double fch1_mhz, foff_mhz;     /* centre of the first channel; foff < 0: descending frequency */
+    int32_t nchans, nifs;
+    double refdm;
+    int32_t write_refdm;
+} b2f_fil_header;
+
+/* Serialise the header; buf may be NULL to query the size. Pure host code. */
+int b2f_sigproc_header(const b2f_fil_header* h, void* buf, size_t cap, size_t* nbytes);
+
+typedef struct b2f_scan_io {
+    uint32_t struct_size;          /* = sizeof(b2f_scan_io) */
+    double start_s;                /* digifil -S: seconds skipped at the head of every input (process_vdif.py:157-161) */
+    double nsec;                   /* digifil -T: seconds processed; <= 0: to the end of the shortest input */
+    const char* source_name;       /* SIGPROC header fields, see b2f_fil_header */
+    const char* rawdatafile;       /* NULL = basename of the last input path */
+    int32_t telescope_id, machine_id;
+    double src_raj, src_dej;
+    double refdm;
+    int32_t write_refdm;
+    int32_t ring;                  /* pinned input chunks in flight, 2..6; 0 = 3 */
+    int32_t readers_per_file;      /* reader threads per input, 1..8; 0 = as many as the host cores allow, up to 4 */
+} b2f_scan_io;
+
+typedef struct b2f_scan_result {
+    int64_t frames_per_if, rows, bytes_in, bytes_out;
+    double tstart_mjd, seconds_of_data, wall_s;
+    double setup_s, wait_read_s, wait_gpu_s, write_s;   /* where the calling thread spent wall_s */
+    b2f_counters counters;
+} b2f_scan_result;
+
+/* All subbands of a scan -> one band-ordered filterbank file: vdif_paths[i] is the split file of plan IF i
+ * (base2fil.sh:336,353), or the single raw recording when the plan does the corner turn (raw_word_bits != 0).
+ * Replaces base2fil.sh:404-448 (run_process_vdif per IF, FIFOs, splice).  out_path may be an existing FIFO: it
+ * is then opened for writing as it is (process_vdif.py:146-149, INSTALL.md:32-35).  One reader thread per input
+ * fills a ring of pinned chunks while the calling thread feeds the GPU and writes finished rows.  io and result
+ * may be NULL.  The plan is reset first, so one plan serves consecutive scans. */
+int b2f_run_scan(struct b2f_plan* plan, int nfiles, const char* const* vdif_paths, const char* out_path,
+                 const b2f_scan_io* io, b2f_scan_result* result);
+/* b2f_run_scan keeps its pinned host buffers in a process-wide cache for the next scan; this frees the idle ones. */
+int b2f_release_host_cache(void);
+/* One subband -> its own filterbank: the `digifil` child process of process_vdif.py:191 (plan with nif = 1). */
+int b2f_run_file(struct b2f_plan* plan, const char* vdif_path, const char* fil_path, const b2f_scan_io* io,
+                 b2f_scan_result* result);
 
 /* Stand-alone decode of VDIF frames (host or device) -> planar float samples
  * out[2][nframes*samples_per_frame] on the device or host (kernel 1 of the path without the

@@ -55,3 +55,27 @@ def test_no_cpu_fallback():
     with pytest.raises(_lib.B2FError) as e:
         Plan(PlanConfig(nchan=128, bw_mhz=[-32.0]))
     assert e.value.code == _lib.ECUDA and "no CPU fallback" in e.value.message
+
+
+def test_sigproc_header_matches_python_writer():
+    """b2f_sigproc_header (pure host code inside libb2f) == sigproc.FilHeader.pack byte for byte."""
+    import ctypes as C
+    from frb_baseband_b200 import sigproc
+    for refdm in (None, 560.0):
+        h = _lib.FilHeaderC()
+        h.struct_size = C.sizeof(h)
+        h.source_name, h.rawdatafile, h.telescope_id = b"R3", b"ek048c_ef_no0001_IF8.vdif", 8
+        h.src_raj, h.src_dej, h.tstart_mjd, h.tsamp_s = 15800.7502, 654300.3152, 58849.123456789, 6.4e-5
+        h.nbits, h.fch1_mhz, h.foff_mhz, h.nchans, h.nifs = 8, 1509.875, -0.25, 1024, 4
+        h.write_refdm, h.refdm = int(refdm is not None), refdm or 0.0
+        n = C.c_size_t()
+        _lib.check(_lib.lib().b2f_sigproc_header(C.byref(h), None, 0, C.byref(n)))
+        buf = C.create_string_buffer(n.value)
+        _lib.check(_lib.lib().b2f_sigproc_header(C.byref(h), buf, n.value, C.byref(n)))
+        py = sigproc.FilHeader(source_name="R3", rawdatafile="ek048c_ef_no0001_IF8.vdif", telescope_id=8,
+                               src_raj=15800.7502, src_dej=654300.3152, tstart=58849.123456789, tsamp=6.4e-5, nbits=8,
+                               fch1=1509.875, foff=-0.25, nchans=1024, nifs=4, refdm=refdm).pack()
+        assert buf.raw == py
+        hh, off = sigproc.read_header(buf.raw)
+        assert off == n.value and hh.nchans == 1024 and hh.source_name == "R3"
+    assert _lib.lib().b2f_sigproc_header(C.byref(h), buf, 8, C.byref(n)) == _lib.EINVAL

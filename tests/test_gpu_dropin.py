@@ -88,3 +88,49 @@ def test_base2fil_conf_to_spliced_file(gpu, tmp_path):
     assert h.nchans == 128 and h.fch1 == pytest.approx(ref["fch1"]) and h.source_name == "B0329+54"
     assert d.shape[0] == ref["data"].shape[0] and d.shape[2] == 128
     assert np.abs(d[:, 0, :].astype(int) - ref["data"].astype(int)).max() <= 1
+
+
+def test_native_runner_equals_streaming_calls(gpu, tmp_path):
+    """b2f_run_scan (threaded readers, pinned ring, pipelined push/pull) writes exactly the rows the caller gets
+    from b2f_push/b2f_pull chunk by chunk, for a -S/-T window that ends inside a chunk, files of unequal length,
+    and every ring depth."""
+    from frb_baseband_b200.plan import Plan, PlanConfig
+    from helpers import run_plan
+    nif, bw, fb = 2, 16.0, 8032
+    nfr = [4 * 1000 + 650, 4 * 1000 + 900]
+    paths, vd = [], []
+    for i in range(nif):
+        p = tmp_path / f"x_IF{i + 1}.vdif"
+        vd.append(_write_vdif(str(p), nfr[i], 40 + i, bw, tone_frac=0.2 + 0.3 * i, invalid_frac=0.002))
+        paths.append(str(p))
+    bws, freqs = [-bw, bw], [1300.0, 1316.0]
+    start, nsec = 0.25, 1.7                                   # 2000 frames/s at 16 MHz: frames 500 .. 3900
+    f0, n = 500, 3400
+    ref, info = run_plan([v[f0 * fb:(f0 + n) * fb] for v in vd], nchan=32, bw=bws, freq=freqs, tscrunch=32, interval=0.5)
+    for ring in (2, 5, 0):
+        out = tmp_path / f"o{ring}.fil"
+        with Plan(PlanConfig(nchan=32, bw_mhz=bws, freq_mhz=freqs, tscrunch=32, rescale_interval_s=0.5)) as pl:
+            r = pl.run_scan(paths, str(out), start_s=start, nsec=nsec, source_name="SRC", ring=ring)
+            r2 = pl.run_scan(paths, str(tmp_path / "again.fil"), start_s=start, nsec=nsec, source_name="SRC", ring=ring)
+        h, d = sigproc.read_fil(str(out))
+        assert r["frames_per_if"] == n and r["rows"] == len(ref) == d.shape[0]
+        assert np.array_equal(d.reshape(len(ref), -1), ref)
+        assert h.nchans == 64 and h.fch1 == pytest.approx(1316.0 + 8 - 0.25) and h.foff == pytest.approx(-0.5)
+        assert h.tstart == pytest.approx(vdif_mjd(vd[0][f0 * fb:f0 * fb + 32], 2000))
+        assert r["counters"]["frames_invalid"] == info["counters"]["frames_invalid"] > 0
+        assert open(out, "rb").read() == open(tmp_path / "again.fil", "rb").read()      # a plan serves consecutive scans
+    # to the end of the shortest file when -T is not given
+    with Plan(PlanConfig(nchan=32, bw_mhz=bws, freq_mhz=freqs, tscrunch=32, rescale_interval_s=0.5)) as pl:
+        r = pl.run_scan(paths, str(tmp_path / "all.fil"))
+        assert r["frames_per_if"] == min(nfr)
+        with pytest.raises(Exception) as e:
+            pl.run_scan(paths[:1], str(tmp_path / "bad.fil"))
+        assert "expects 2 input" in str(e.value)
+        with pytest.raises(Exception) as e:
+            pl.run_scan([paths[0], str(tmp_path / "missing.vdif")], str(tmp_path / "bad.fil"))
+        assert "cannot open" in str(e.value)
+
+
+def vdif_mjd(head, fps):
+    from frb_baseband_b200 import vdif
+    return vdif.frame_mjd(vdif.parse_header(bytes(head)), fps)
