@@ -327,10 +327,12 @@ int push_dedisp(b2f_plan* pl, int64_t nblk, int64_t T) {
         kg.tw_col = pl->d_tw_col; kg.tw_row = pl->d_tw_row;
         kg.F = pl->d_F; kg.F_if_stride = pl->F_if_stride; kg.row0 = pl->rows_off + pl->rows_held;
         kg.L = pl->L; kg.lgL = 31 - __builtin_clz(pl->L); kg.R = pl->R; kg.lgR = 31 - __builtin_clz(pl->R);
-        kg.C = std::min(16, 16384 / pl->L);
+        kg.C = std::min(16, 8192 / pl->L);                    // 64 KiB of column data per CTA, two CTAs per SM
+        kg.lgC = 31 - __builtin_clz(kg.C);
         kg.nblk = (int)nblk; kg.nif = nif; kg.D = pl->D; kg.mode = pl->prm.pol_mode; kg.M = pl->M;
-        const size_t smem_col = ((size_t)pl->L * kg.C + pl->L / 2 + 32) * sizeof(float2);
-        const size_t smem_row = ((size_t)pl->R + pl->R / 2) * sizeof(float2);
+        const int RB = std::max(1, std::min(16, 4096 / pl->R));
+        const size_t smem_col = ((size_t)pl->L + 32 + kg_padded((size_t)pl->L * kg.C)) * sizeof(float2);
+        const size_t smem_row = ((size_t)pl->R + kg_padded((size_t)RB * pl->R)) * sizeof(float2);
         CU(cudaFuncSetAttribute(kg_column_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_col));
         CU(cudaFuncSetAttribute(kg_row_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row));
         for (int64_t b0 = 0; b0 < nbt; b0 += NB) {
@@ -338,7 +340,7 @@ int push_dedisp(b2f_plan* pl, int64_t nblk, int64_t T) {
             kg.gb_begin = b0; kg.gb_end = b0 + nb;
             const int64_t work = nb * (pl->R / kg.C);
             rc = timed(pl, B2F_K_COLUMN, [&] {
-                kg_column_pass<<<(unsigned)std::min<int64_t>(work, pl->num_sms), 256, smem_col, pl->stream>>>(kg);
+                kg_column_pass<<<(unsigned)std::min<int64_t>(work, 2 * (int64_t)pl->num_sms), 256, smem_col, pl->stream>>>(kg);
             });
             if (rc) return rc;
             rc = timed(pl, B2F_K_EPS, [&] {
@@ -346,9 +348,9 @@ int push_dedisp(b2f_plan* pl, int64_t nblk, int64_t T) {
                                                                                        pl->d_eps + b0 * pl->N, pl->R);
             });
             if (rc) return rc;
-            const int64_t ngroups = nb * (pl->L / pl->D);
+            const int64_t nunits = nb * (pl->L / std::max(pl->D, RB));
             rc = timed(pl, B2F_K_ROW, [&] {
-                kg_row_pass<<<(unsigned)std::min<int64_t>(ngroups, (int64_t)pl->num_sms * 4), 256, smem_row, pl->stream>>>(kg);
+                kg_row_pass<<<(unsigned)std::min<int64_t>(nunits, (int64_t)pl->num_sms * 2), 256, smem_row, pl->stream>>>(kg);
             });
             if (rc) return rc;
         }
@@ -595,9 +597,9 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
     CUB(cudaMalloc(&pl->d_sm_slots, 1024 * sizeof(int)));
     if (pl->carry_mode) CUB(cudaMalloc(&pl->d_carry, (size_t)pl->M * nif));
     if (generic) {
-        std::vector<float2> tc(L / 2), tr(R / 2);
-        for (int k = 0; k < L / 2; ++k) tc[k] = make_float2((float)cos(-2.0 * M_PI * k / L), (float)sin(-2.0 * M_PI * k / L));
-        for (int k = 0; k < R / 2; ++k) tr[k] = make_float2((float)cos(-2.0 * M_PI * k / R), (float)sin(-2.0 * M_PI * k / R));
+        std::vector<float2> tc(L), tr(R);
+        for (int k = 0; k < L; ++k) tc[k] = make_float2((float)cos(-2.0 * M_PI * k / L), (float)sin(-2.0 * M_PI * k / L));
+        for (int k = 0; k < R; ++k) tr[k] = make_float2((float)cos(-2.0 * M_PI * k / R), (float)sin(-2.0 * M_PI * k / R));
         CUB(cudaMalloc(&pl->d_tw_col, tc.size() * sizeof(float2)));
         CUB(cudaMalloc(&pl->d_tw_row, tr.size() * sizeof(float2)));
         CUB(cudaMemcpy(pl->d_tw_col, tc.data(), tc.size() * sizeof(float2), cudaMemcpyHostToDevice));

@@ -1166,32 +1166,140 @@ __global__ void __launch_bounds__(256, 2) kc_dedisp_back(const KCParams p) {
 
 // ================================================================== generic channeliser
 // Any power-of-two freq_res (L) and row length (R = 2 nchan) outside the tuned 512-point kernels,
-// e.g. process_vdif's default --nchan 512 -> -F512:1024 (/root/reference/process_vdif.py:46,162).
-// Same algebra as the tuned path, iterative radix-2 FFTs in shared memory:
-// forward DIF leaves the spectrum bit-reversed, the diagonal is applied in that order and the
-// inverse DIT consumes it, so no reordering pass is needed.  2-bit input (index stream) only.
+// e.g. process_vdif's default --nchan 512 -> -F512:1024 (/root/reference/process_vdif.py:46,162) and the
+// 1024 channels per IF that submit_job.py:58-76 asks for at DM 560.  Same algebra as the tuned path
+// (DESIGN.md section 3).  FFTs are in-place Sande-Tukey passes of radix 16 held in registers: a pass
+// over segments of length n = 16 m computes y_q[lo] = W_n^(lo q) * sum_j x[j m + lo] W_16^(j q) and
+// stores it at q m + lo, so after all passes frequency k sits at its digit-reversed position.  The
+// inverse undoes the passes in reverse order, so the diagonal W_M^(k2 n1) is applied in that order
+// and no reordering pass exists.  The innermost pass (radix 2..16, m = 1) of the forward transform,
+// the diagonal and the innermost inverse pass act on the same values and run back to back in registers.
+// 2-bit input (index stream) only.
 struct KGParams {
     const uint8_t* compact; size_t compact_stride;
     float2* inter;               // [gb - gb_begin][L][R]
     float2* colsum;              // [nif*nblk][R]
     const float2* eps;           // [nif*nblk][R/2]
-    const float2* tw_col;        // [L/2]  exp(-2 pi i k / L)
-    const float2* tw_row;        // [R/2]  exp(-2 pi i k / R)
+    const float2* tw_col;        // [L]  exp(-2 pi i k / L)
+    const float2* tw_row;        // [R]  exp(-2 pi i k / R)
     float* F; int64_t F_if_stride; int64_t row0;
-    int L, lgL, R, lgR, C, nblk, nif, D, mode;
+    int L, lgL, R, lgR, C, lgC, nblk, nif, D, mode;
     int64_t M, gb_begin, gb_end;
 };
 
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 
-static __global__ void __launch_bounds__(256) kg_column_pass(const KGParams p) {
+// shared-memory index with one pad element per 16: strided passes stay (nearly) conflict-free
+__device__ __forceinline__ int kg_phys(int e) { return e + (e >> 4); }
+__host__ __device__ constexpr size_t kg_padded(size_t n) { return n + n / 16 + 1; }
+
+// number of radix-16 passes outside the innermost one, and the innermost radix, for a 2^lg point FFT
+__host__ __device__ __forceinline__ int kg_outer_passes(int lg) { return (lg - 1) / 4; }
+__host__ __device__ __forceinline__ int kg_inner_lg(int lg) { return lg - 4 * ((lg - 1) / 4); }
+
+// frequency index <-> position after the forward passes (base-16 digits of the segment number reversed)
+__device__ __forceinline__ int kg_freq_of_pos(int pos, int lg) {
+    const int nf = kg_outer_passes(lg), lgi = kg_inner_lg(lg);
+    const int seg = pos >> lgi, q = pos & ((1 << lgi) - 1);
+    int k = 0;
+    for (int f = 0; f < nf; ++f) k |= ((seg >> (4 * (nf - 1 - f))) & 15) << (4 * f);
+    return k | (q << (4 * nf));
+}
+__device__ __forceinline__ int kg_pos_of_freq(int k, int lg) {
+    const int nf = kg_outer_passes(lg), lgi = kg_inner_lg(lg);
+    int seg = 0;
+    for (int f = 0; f < nf; ++f) seg |= ((k >> (4 * f)) & 15) << (4 * (nf - 1 - f));
+    return (seg << lgi) | (k >> (4 * nf));
+}
+
+// One radix-16 pass over `cnt` transforms.  Sequences are interleaved [index][1 << lgC] (columns) or stored one
+// after the other with lgC = 0 and `seq_len` elements each (rows).  SRC: 0 shared, 1 index bytes (decode),
+// 2 global float2.  DST: 0 shared, 1 global float2.
+template <bool INV, int SRC, int DST>
+__device__ __forceinline__ void kg_pass16(float2* sm, const float2* tw, int lgLen, int lgn, int lgC, int cnt,
+                                          const uint8_t* gsrc_b, const float2* gsrc_f, float2* gdst, int64_t gstride,
+                                          const float2* lut) {
+    const int lgm = lgn - 4, m = 1 << lgm, lgT = lgLen - 4;         // transforms per sequence = 2^lgT
+    for (int t = threadIdx.x; t < cnt; t += blockDim.x) {
+        const int cl = t & ((1 << lgC) - 1), u = t >> lgC;
+        const int seq = u >> lgT, w = u & ((1 << lgT) - 1);          // seq > 0 only for rows (lgC = 0)
+        const int lo = w & (m - 1), seg = w >> lgm;
+        const int base = (seq << lgLen) + (seg << lgn) + lo;
+        const int step = lo << (lgLen - lgn);
+        float2 v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int idx = base + j * m;
+            if (SRC == 1) v[j] = *reinterpret_cast<const float2*>(reinterpret_cast<const uint8_t*>(lut) + gsrc_b[(int64_t)idx * gstride + cl]);
+            else if (SRC == 2) v[j] = gsrc_f[(int64_t)seq * gstride + (idx & ((1 << lgLen) - 1))];
+            else v[j] = sm[kg_phys((idx << lgC) + cl)];
+        }
+        if (INV) {
+#pragma unroll
+            for (int q = 1; q < 16; ++q) v[q] = cmul_conj(v[q], tw[q * step]);
+            fft_inreg<16, true>(v);
+        } else {
+            fft_inreg<16, false>(v);
+#pragma unroll
+            for (int q = 1; q < 16; ++q) v[q] = cmul(v[q], tw[q * step]);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int idx = base + j * m;
+            if (DST == 1) gdst[(int64_t)idx * gstride + cl] = v[j];
+            else sm[kg_phys((idx << lgC) + cl)] = v[j];
+        }
+    }
+}
+
+// innermost step of the column pass: FFT_RM, diagonal, IFFT_RM on the RM values of one segment
+template <int RM, bool GLOBAL>
+__device__ __forceinline__ void kg_column_inner(float2* sm, const KGParams& p, int n1_0, float2* colsum, const uint8_t* gsrc_b,
+                                                float2* gdst, const float2* lut) {
+    constexpr int LGI = ilog2(RM);
+    const int lgC = p.lgC, cnt = (p.L >> LGI) << lgC;
+    const int nf = kg_outer_passes(p.lgL);
+    const float inv_half_m = 2.0f / (float)p.M;
+    for (int t = threadIdx.x; t < cnt; t += blockDim.x) {
+        const int cl = t & ((1 << lgC) - 1), seg = t >> lgC;
+        float2 v[RM];
+#pragma unroll
+        for (int q = 0; q < RM; ++q) {
+            const int idx = seg * RM + q;
+            if (GLOBAL) v[q] = *reinterpret_cast<const float2*>(reinterpret_cast<const uint8_t*>(lut) + gsrc_b[(int64_t)idx * p.R + cl]);
+            else v[q] = sm[kg_phys((idx << lgC) + cl)];
+        }
+        fft_inreg<RM, false>(v);
+        if (seg == 0) colsum[cl] = v[0];                            // A[k2 = 0]
+        int kseg = 0;
+        for (int f = 0; f < nf; ++f) kseg |= ((seg >> (4 * (nf - 1 - f))) & 15) << (4 * f);
+        const int n1 = n1_0 + cl;
+#pragma unroll
+        for (int q = 0; q < RM; ++q) {                              // * W_M^(k2 n1), phase reduced exactly in integers
+            const int k2 = kseg | (q << (4 * nf));
+            const int ph = (int)(((int64_t)k2 * n1) & (p.M - 1));
+            float sn, cs;
+            sincospif(-(float)ph * inv_half_m, &sn, &cs);
+            v[q] = cmul(v[q], make_float2(cs, sn));
+        }
+        fft_inreg<RM, true>(v);
+#pragma unroll
+        for (int q = 0; q < RM; ++q) {
+            const int idx = seg * RM + q;
+            if (GLOBAL) gdst[(int64_t)idx * p.R + cl] = v[q];
+            else sm[kg_phys((idx << lgC) + cl)] = v[q];
+        }
+    }
+}
+
+static __global__ void __launch_bounds__(256, 2) kg_column_pass(const KGParams p) {
     extern __shared__ __align__(16) uint8_t kg_smem[];
-    float2* data = reinterpret_cast<float2*>(kg_smem);                   // [L][C]
-    float2* tw = data + (size_t)p.L * p.C;                                // [L/2]
-    float2* lut = tw + p.L / 2;                                           // [32]
-    const int tid = threadIdx.x, L = p.L, C = p.C, R = p.R, lgL = p.lgL;
-    for (int i = tid; i < L / 2; i += 256) tw[i] = p.tw_col[i];
+    float2* tw = reinterpret_cast<float2*>(kg_smem);                     // [L]
+    float2* lut = tw + p.L;                                               // [32]
+    float2* data = lut + 32;                                              // [L][C], padded
+    const int tid = threadIdx.x, L = p.L, C = p.C, R = p.R, lgL = p.lgL, lgC = p.lgC;
+    for (int i = tid; i < L; i += 256) tw[i] = p.tw_col[i];
     if (tid < 32) {
         const int c0 = tid & 3, c1 = (tid >> 2) & 3;
         const float m0 = (c0 == 0 || c0 == 3) ? kLevHi : kLevLo, m1 = (c1 == 0 || c1 == 3) ? kLevHi : kLevLo;
@@ -1199,128 +1307,149 @@ static __global__ void __launch_bounds__(256) kg_column_pass(const KGParams p) {
     }
     __syncthreads();
     const int nstrips = R / C;
+    const int nf = kg_outer_passes(lgL), lgi = kg_inner_lg(lgL);
     const int64_t nwork = (p.gb_end - p.gb_begin) * nstrips;
-    const int nel = L * C, nbf = (L / 2) * C;
+    const int cnt16 = (L >> 4) << lgC;
     for (int64_t w = blockIdx.x; w < nwork; w += gridDim.x) {
         const int64_t lb = w / nstrips, gb = p.gb_begin + lb;
         const int strip = (int)(w % nstrips);
         const int ifi = (int)(gb / p.nblk);
         const int64_t blk = gb % p.nblk;
         const uint8_t* src = p.compact + ifi * p.compact_stride + blk * p.M + (int64_t)strip * C;
-        for (int i = tid; i < nel; i += 256) {
-            const int n2 = i / C, cl = i % C;
-            data[i] = *reinterpret_cast<const float2*>(reinterpret_cast<const uint8_t*>(lut) + src[(int64_t)n2 * R + cl]);
-        }
-        __syncthreads();
-        for (int s = lgL - 1; s >= 0; --s) {                 // forward DIF: natural in, bit-reversed out
-            const int half = 1 << s;
-            for (int i = tid; i < nbf; i += 256) {
-                const int cl = i % C, b = i / C;
-                const int j = b & (half - 1);
-                const int i0 = (((b >> s) << (s + 1)) + j) * C + cl, i1 = i0 + half * C;
-                const float2 x = data[i0], y = data[i1];
-                data[i0] = cadd(x, y);
-                data[i1] = cmul(csub(x, y), tw[j << (lgL - 1 - s)]);
-            }
-            __syncthreads();
-        }
-        if (tid < C) p.colsum[gb * R + strip * C + tid] = data[tid];            // A[k2 = 0] sits at position 0
-        for (int i = tid; i < nel; i += 256) {               // * W_M^(k2 n1), k2 = bitrev(position)
-            const int pos = i / C, cl = i % C;
-            const unsigned k2 = __brev((unsigned)pos) >> (32 - lgL);
-            const long long ph = ((long long)k2 * (strip * C + cl)) % p.M;
-            float sn, cs;
-            sincospif(-2.0f * (float)((double)ph / (double)p.M), &sn, &cs);
-            data[i] = cmul(data[i], make_float2(cs, sn));
-        }
-        __syncthreads();
-        for (int s = 0; s < lgL; ++s) {                      // inverse DIT: bit-reversed in, natural out
-            const int half = 1 << s;
-            for (int i = tid; i < nbf; i += 256) {
-                const int cl = i % C, b = i / C;
-                const int j = b & (half - 1);
-                const int i0 = (((b >> s) << (s + 1)) + j) * C + cl, i1 = i0 + half * C;
-                const float2 x = data[i0], t = cmul_conj(data[i1], tw[j << (lgL - 1 - s)]);
-                data[i0] = cadd(x, t);
-                data[i1] = csub(x, t);
-            }
-            __syncthreads();
-        }
         float2* dst = p.inter + lb * (int64_t)L * R + strip * C;
-        for (int i = tid; i < nel; i += 256) dst[(int64_t)(i / C) * R + (i % C)] = data[i];
+        float2* colsum = p.colsum + gb * R + strip * C;
+        if (nf == 0) {                                       // L = 16: one register-resident step, no shared memory
+            kg_column_inner<16, true>(data, p, strip * C, colsum, src, dst, lut);
+            continue;
+        }
+        for (int f = 0; f < nf; ++f) {                       // forward, outermost first
+            if (f == 0) kg_pass16<false, 1, 0>(data, tw, lgL, lgL, lgC, cnt16, src, nullptr, nullptr, R, lut);
+            else kg_pass16<false, 0, 0>(data, tw, lgL, lgL - 4 * f, lgC, cnt16, nullptr, nullptr, nullptr, 0, lut);
+            __syncthreads();
+        }
+        switch (lgi) {
+            case 1: kg_column_inner<2, false>(data, p, strip * C, colsum, nullptr, nullptr, lut); break;
+            case 2: kg_column_inner<4, false>(data, p, strip * C, colsum, nullptr, nullptr, lut); break;
+            case 3: kg_column_inner<8, false>(data, p, strip * C, colsum, nullptr, nullptr, lut); break;
+            default: kg_column_inner<16, false>(data, p, strip * C, colsum, nullptr, nullptr, lut); break;
+        }
         __syncthreads();
+        for (int f = nf - 1; f >= 0; --f) {                  // inverse, innermost first
+            if (f == 0) kg_pass16<true, 0, 1>(data, tw, lgL, lgL, lgC, cnt16, nullptr, nullptr, dst, R, lut);
+            else kg_pass16<true, 0, 0>(data, tw, lgL, lgL - 4 * f, lgC, cnt16, nullptr, nullptr, nullptr, 0, lut);
+            __syncthreads();
+        }
     }
 }
 
-// generic row pass: one CTA walks the D rows of an output sample; row FFT in shared memory
-static __global__ void __launch_bounds__(256) kg_row_pass(const KGParams p) {
+template <int RM>
+__device__ __forceinline__ void kg_row_inner(float2* sm, int lgR, int cnt) {
+    constexpr int LGI = ilog2(RM);
+    (void)lgR;
+    for (int t = threadIdx.x; t < cnt; t += blockDim.x) {           // t = global segment number over all rows of the batch
+        float2 v[RM];
+#pragma unroll
+        for (int q = 0; q < RM; ++q) v[q] = sm[kg_phys((t << LGI) + q)];
+        fft_inreg<RM, false>(v);
+#pragma unroll
+        for (int q = 0; q < RM; ++q) sm[kg_phys((t << LGI) + q)] = v[q];
+    }
+}
+
+// generic row pass: a CTA holds RB rows of a block in shared memory, transforms them together, detects and
+// integrates D rows per output sample
+static __global__ void __launch_bounds__(256, 2) kg_row_pass(const KGParams p) {
     extern __shared__ __align__(16) uint8_t kg_smem[];
-    float2* row = reinterpret_cast<float2*>(kg_smem);                    // [R]
-    float2* tw = row + p.R;                                               // [R/2]
+    float2* tw = reinterpret_cast<float2*>(kg_smem);                     // [R]
+    float2* rows = tw + p.R;                                              // [RB][R], padded
     const int tid = threadIdx.x, R = p.R, N = R / 2, lgR = p.lgR, L = p.L, D = p.D;
-    for (int i = tid; i < R / 2; i += 256) tw[i] = p.tw_row[i];
+    for (int i = tid; i < R; i += 256) tw[i] = p.tw_row[i];
     __syncthreads();
     const int nprod = nprod_of_mode(p.mode);
-    const int groups_per_blk = L / D;
-    const int64_t ngroups = (p.gb_end - p.gb_begin) * groups_per_blk;
+    const int RB = min(16, 4096 / R) < 1 ? 1 : min(16, 4096 / R);        // rows per batch
+    const int U = max(D, RB);                                            // rows per work unit (whole output samples)
+    const int units_per_blk = L / U;
+    const int64_t nunits = (p.gb_end - p.gb_begin) * units_per_blk;
+    const int nf = kg_outer_passes(lgR), lgi = kg_inner_lg(lgR);
+    const int cnt16 = RB * (R >> 4);
     constexpr int CPT = 4;                                               // channels per thread: nchan <= 1024
-    for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
-        const int64_t lb = g / groups_per_blk, gb = p.gb_begin + lb;
-        const int g0 = (int)(g % groups_per_blk) * D;
+    int posA[CPT], posB[CPT];
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+        const int c = tid + 256 * k;
+        posA[k] = c < N ? kg_pos_of_freq(c, lgR) : 0;
+        posB[k] = c < N ? kg_pos_of_freq(R - 1 - c, lgR) : 0;
+    }
+    for (int64_t g = blockIdx.x; g < nunits; g += gridDim.x) {
+        const int64_t lb = g / units_per_blk, gb = p.gb_begin + lb;
+        const int r0 = (int)(g % units_per_blk) * U;
+        const int ifi = (int)(gb / p.nblk);
+        const int64_t blk = gb % p.nblk;
         float acc[CPT][4];
 #pragma unroll
         for (int k = 0; k < CPT; ++k)
 #pragma unroll
             for (int q = 0; q < 4; ++q) acc[k][q] = 0.f;
-        for (int r = 0; r < D; ++r) {
-            const float2* src = p.inter + (lb * (int64_t)L + g0 + r) * R;
-            for (int i = tid; i < R; i += 256) row[i] = src[i];
-            __syncthreads();
-            for (int s = lgR - 1; s >= 0; --s) {             // forward DIF, output bit-reversed
-                const int half = 1 << s;
-                for (int b = tid; b < R / 2; b += 256) {
-                    const int j = b & (half - 1);
-                    const int i0 = ((b >> s) << (s + 1)) + j, i1 = i0 + half;
-                    const float2 x = row[i0], y = row[i1];
-                    row[i0] = cadd(x, y);
-                    row[i1] = cmul(csub(x, y), tw[j << (lgR - 1 - s)]);
+        for (int b0 = 0; b0 < U; b0 += RB) {
+            const float2* src = p.inter + (lb * (int64_t)L + r0 + b0) * R;
+            if (nf == 0) {                                   // R = 16: rows go straight to the innermost step
+                for (int i = tid; i < RB * R; i += 256) rows[kg_phys(i)] = src[i];
+            } else {
+                for (int f = 0; f < nf; ++f) {
+                    if (f == 0) kg_pass16<false, 2, 0>(rows, tw, lgR, lgR, 0, cnt16, nullptr, src, nullptr, R, nullptr);
+                    else kg_pass16<false, 0, 0>(rows, tw, lgR, lgR - 4 * f, 0, cnt16, nullptr, nullptr, nullptr, 0, nullptr);
+                    __syncthreads();
                 }
-                __syncthreads();
             }
+            if (nf == 0) __syncthreads();
+            switch (lgi) {
+                case 1: kg_row_inner<2>(rows, lgR, RB * (R >> 1)); break;
+                case 2: kg_row_inner<4>(rows, lgR, RB * (R >> 2)); break;
+                case 3: kg_row_inner<8>(rows, lgR, RB * (R >> 3)); break;
+                default: kg_row_inner<16>(rows, lgR, RB * (R >> 4)); break;
+            }
+            __syncthreads();
+            for (int r = 0; r < RB; ++r) {
+                const float2* row = rows;
+                const int rbase = r << lgR;
 #pragma unroll
-            for (int k = 0; k < CPT; ++k) {
-                const int c = tid + 256 * k;
-                if (c < N) {
-                    const float2 a = row[__brev((unsigned)c) >> (32 - lgR)];
-                    const float2 b = row[__brev((unsigned)(R - 1 - c)) >> (32 - lgR)];
-                    const float2 e = p.eps[gb * N + c];
-                    const float2 bp = make_float2(b.x - e.x, -b.y - e.y);
-                    const float2 P = cadd(a, bp), Q = csub(a, bp);
-                    const float pp = 0.25f * (P.x * P.x + P.y * P.y), qq = 0.25f * (Q.x * Q.x + Q.y * Q.y);
-                    const float xr = P.x * Q.x + P.y * Q.y, xi = P.y * Q.x - P.x * Q.y;
-                    const float re = -0.25f * xi, im = 0.25f * xr;
-                    switch (p.mode) {
-                        case B2F_POL_P0: acc[k][0] += pp; break;
-                        case B2F_POL_P1: acc[k][0] += qq; break;
-                        case B2F_POL_I: acc[k][0] += pp + qq; break;
-                        case B2F_POL_I2: acc[k][0] += (pp + qq) * (pp + qq); break;
-                        case B2F_POL_PPQQ: acc[k][0] += pp; acc[k][1] += qq; break;
-                        case B2F_POL_COHERENCE: acc[k][0] += pp; acc[k][1] += qq; acc[k][2] += re; acc[k][3] += im; break;
-                        default: acc[k][0] += pp + qq; acc[k][1] += 2.f * re; acc[k][2] += 2.f * im; acc[k][3] += pp - qq; break;
+                for (int k = 0; k < CPT; ++k) {
+                    const int c = tid + 256 * k;
+                    if (c < N) {
+                        const float2 a = row[kg_phys(rbase + posA[k])];
+                        const float2 b = row[kg_phys(rbase + posB[k])];
+                        const float2 e = p.eps[gb * N + c];
+                        const float2 bp = make_float2(b.x - e.x, -b.y - e.y);
+                        const float2 P = cadd(a, bp), Q = csub(a, bp);
+                        const float pp = 0.25f * (P.x * P.x + P.y * P.y), qq = 0.25f * (Q.x * Q.x + Q.y * Q.y);
+                        const float xr = P.x * Q.x + P.y * Q.y, xi = P.y * Q.x - P.x * Q.y;
+                        const float re = -0.25f * xi, im = 0.25f * xr;
+                        switch (p.mode) {
+                            case B2F_POL_P0: acc[k][0] += pp; break;
+                            case B2F_POL_P1: acc[k][0] += qq; break;
+                            case B2F_POL_I: acc[k][0] += pp + qq; break;
+                            case B2F_POL_I2: acc[k][0] += (pp + qq) * (pp + qq); break;
+                            case B2F_POL_PPQQ: acc[k][0] += pp; acc[k][1] += qq; break;
+                            case B2F_POL_COHERENCE: acc[k][0] += pp; acc[k][1] += qq; acc[k][2] += re; acc[k][3] += im; break;
+                            default: acc[k][0] += pp + qq; acc[k][1] += 2.f * re; acc[k][2] += 2.f * im; acc[k][3] += pp - qq; break;
+                        }
+                    }
+                }
+                const int rr = r0 + b0 + r;                  // row of the block
+                if (((rr + 1) & (D - 1)) == 0) {             // an output sample is complete
+                    const int64_t t = p.row0 + (blk * L + rr) / D;
+                    float* dst = p.F + ifi * p.F_if_stride + t * (int64_t)(nprod * N);
+#pragma unroll
+                    for (int k = 0; k < CPT; ++k) {
+                        const int c = tid + 256 * k;
+                        if (c < N)
+                            for (int q = 0; q < nprod; ++q) dst[q * N + c] = acc[k][q];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) acc[k][q] = 0.f;
                     }
                 }
             }
             __syncthreads();
-        }
-        const int ifi = (int)(gb / p.nblk);
-        const int64_t blk = gb % p.nblk;
-        const int64_t t = p.row0 + (blk * L + g0) / D;
-        float* dst = p.F + ifi * p.F_if_stride + t * (int64_t)(nprod * N);
-#pragma unroll
-        for (int k = 0; k < CPT; ++k) {
-            const int c = tid + 256 * k;
-            if (c < N)
-                for (int q = 0; q < nprod; ++q) dst[q * N + c] = acc[k][q];
         }
     }
 }

@@ -246,7 +246,8 @@ def test_unsupported_requests_fail_loudly(gpu):
         assert e.value.code == _lib.EUNSUPPORTED
 
 
-@pytest.mark.parametrize("nchan,freq_res,D,nframes", [(512, 0, 4, 1500), (1024, 0, 2, 1100), (128, 64, 16, 300), (32, 2048, 32, 700)])
+@pytest.mark.parametrize("nchan,freq_res,D,nframes", [(512, 0, 4, 1500), (1024, 0, 2, 1100), (128, 64, 16, 300), (32, 2048, 32, 700),
+                                                        (8, 16, 1, 40), (16, 32, 2, 60), (512, 512, 4, 500), (64, 256, 256, 200)])
 def test_generic_channeliser(gpu, nchan, freq_res, D, nframes):
     """freq_res / nchan outside the tuned kernels, e.g. process_vdif's default --nchan 512 ->
     digifil -F512:1024 (process_vdif.py:46,162).  Pushes are 1024-frame pieces that do not align
