@@ -93,7 +93,7 @@ def read_header(buf: bytes) -> tuple[FilHeader, int]:
         nonlocal pos
         (n,) = struct.unpack_from("<i", buf, pos)
         pos += 4
-        if n < 1 or n > 80:
+        if n < 0 or n > 80:
             raise ValueError("not a SIGPROC header")
         s = buf[pos:pos + n].decode()
         pos += n

@@ -65,3 +65,21 @@ def test_after_scan_order_and_failure(tmp_path):
         handoff.after_scan(str(fil), submit2fetch=True, keep_vdif=False, send=lambda a: 1,
                            vdif_globs=[str(tmp_path / "*.vdif")], log=lambda m: None)
     assert not any(f.exists() for f in v)                                    # removal precedes the submit, as in the shell
+
+
+def test_dm_catalogue_matches_reference(tmp_path):
+    """source_dm.get_dm == the table of the reference's dm_utils.get_dm (fixture: tests/golden/dm_utils_reference.json,
+    extracted from /root/reference/dm_utils.py:12-93), same int/float types; R1 absent; unknown -> None."""
+    from frb_baseband_b200 import sigproc, source_dm
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "dm_utils_reference.json")))["table"]
+    assert source_dm.FRB_DMS == gold and all(type(source_dm.FRB_DMS[k]) is type(v) for k, v in gold.items())
+    assert source_dm.get_dm("R3") == 349.7 and source_dm.get_dm("R1", psrcat="/nonexistent/psrcat") is None
+    assert source_dm.isPulsar is False
+    fake = tmp_path / "psrcat"                                  # a stand-in psrcat that knows one pulsar
+    fake.write_text("#!/bin/sh\n[ \"$7\" = B0329+54 ] && echo ' 26.7641 ' || exit 1\n")
+    fake.chmod(0o755)
+    assert source_dm.get_dm("B0329+54", psrcat=str(fake)) == pytest.approx(26.7641) and source_dm.isPulsar is True
+    assert source_dm.get_dm("J0000+0000", psrcat=str(fake)) is None
+    fil = tmp_path / "x.fil"
+    fil.write_bytes(sigproc.FilHeader(source_name="R3", nchans=1024, nbits=8, nifs=1).pack() + bytes(2048))
+    assert source_dm.get_src(str(fil)) == "R3" and source_dm.get_nchan(str(fil)) == 1024          # dm_utils.py:108-125
