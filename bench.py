@@ -169,6 +169,7 @@ def main():
     ap.add_argument("--seconds", type=float, default=60.0, help="seconds of sky data per step (C2: 60)")
     ap.add_argument("--impl", default="b2f", choices=["b2f", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--chunk-units", type=int, default=4, help="frames per push in units of 1024 (0 = library default of 2048 frames)")
     ap.add_argument("--nccl-gather", action="store_true", help="splice with an NCCL gather instead of peer stores")
     ap.add_argument("--cpu-sample", type=float, default=1.024, help="seconds of data for the cpu_baseline leg")
     args = ap.parse_args()
@@ -211,7 +212,7 @@ def main():
     _, bws, freqs = rank_if_plan(NIF * world, world, rank, FREQ_LSB0, BW)   # rank r owns the next 8 subbands up
     stream = torch.cuda.current_stream(dev)
     cfg = PlanConfig(nchan=NCHAN, bw_mhz=bws, freq_mhz=freqs, tscrunch=TSCRUNCH, out_nbit=8, freq_res=FREQ_RES,
-                     device=local_rank, profile=True, stream=stream.cuda_stream)
+                     device=local_rank, profile=True, stream=stream.cuda_stream, chunk_units=args.chunk_units)
     pl = Plan(cfg)
     cf = int(pl.chunk_frames)
     rows_total = (nframes * 16000 // (2 * NCHAN * FREQ_RES)) * FREQ_RES // TSCRUNCH   # only an upper bound
@@ -317,9 +318,22 @@ def main():
         cfg_pos = pl.cfg   # positional frames: the cycled 12 s hold repeats header seconds, samples are what is timed
         ms_e2e, rows_e, _, _ = timed(step_host, max(1, min(args.steps, 3)), 1)
         h2d = sum(n for _, n in chunks) * NIF * FRAME_BYTES
+        # the ceiling of that number: a bare pinned-host -> device copy of the same buffers (PCIe), nothing else
+        scratch = torch.empty_like(vd[0][:hold_frames])
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        scratch.copy_(host[0], non_blocking=True)
+        torch.cuda.synchronize(dev)
+        c0.record(stream)
+        for i in range(NIF):
+            scratch.copy_(host[i], non_blocking=True)
+        c1.record(stream)
+        torch.cuda.synchronize(dev)
+        h2d_copy = NIF * hold_frames * FRAME_BYTES / (c0.elapsed_time(c1) * 1e-3) / 1e9
+        del scratch
         e2e = {"value": world * in_bytes / (ms_e2e * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(rows_e * NIF * NCHAN), "ms_per_step": ms_e2e,
                "rt_factor": world * data_sec / (ms_e2e * 1e-3),
+               "h2d_copy_GBps_per_gpu": h2d_copy, "frac_of_h2d_copy": in_bytes / (ms_e2e * 1e-3) / 1e9 / h2d_copy,
                "note": "pinned host VDIF pushed chunk by chunk through b2f_push, rows pulled to pinned host memory; "
                        "12 s of host-resident VDIF cycled to cover the 60 s scan"}
 

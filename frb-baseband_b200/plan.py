@@ -44,7 +44,7 @@ class PlanConfig:
     mask_faults: bool = True
     keep_bandpass: bool = False
     splice_pol_major: bool = False
-    chunk_units: int = 0                     # 0 = library default (about 1024 frames per IF and push)
+    chunk_units: int = 0                     # 0 = library default (about 2048 frames per IF and push)
     rescale_interval_s: float = 10.0
     device: int = 0
     profile: bool = False

@@ -34,7 +34,7 @@ def test_column_pass_stages(gpu):
         v = synth.make_vdif(int(pl.chunk_frames), seed=11, bw_mhz=bw)
         pl.push([v])
         R, L = 2 * nchan, 512
-        nblk = int(pl.geometry.unit_blocks)
+        nblk = int(pl.geometry.unit_blocks * (pl.chunk_frames // pl.geometry.unit_frames))
         inter = pl.debug(4, np.complex64).reshape(nblk, L, R)
         colsum = pl.debug(5, np.complex64).reshape(nblk, R)
         eps = pl.debug(6, np.complex64).reshape(nblk, nchan)
