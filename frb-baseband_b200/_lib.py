@@ -43,7 +43,7 @@ class Counters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "frames_ok", "frames_invalid", "frames_with_fill", "fill_words", "frames_dropped",
         "frames_misplaced", "frames_badhdr", "slots_missing", "rows_produced", "rows_emitted",
-        "blocks_dirty", "kernel_launches")]
+        "blocks_dirty", "kernel_launches", "rescale_frozen", "rescale_preset")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
@@ -64,7 +64,8 @@ class ScanIO(C.Structure):
         ("struct_size", C.c_uint32), ("start_s", C.c_double), ("nsec", C.c_double), ("source_name", C.c_char_p),
         ("rawdatafile", C.c_char_p), ("telescope_id", C.c_int32), ("machine_id", C.c_int32),
         ("src_raj", C.c_double), ("src_dej", C.c_double), ("refdm", C.c_double), ("write_refdm", C.c_int32),
-        ("ring", C.c_int32), ("readers_per_file", C.c_int32),
+        ("ring", C.c_int32), ("readers_per_file", C.c_int32), ("part_index", C.c_int32), ("part_count", C.c_int32),
+        ("stats_only", C.c_int32),
     ]
 
 
@@ -93,6 +94,7 @@ SYMBOLS = {
     "b2f_reset": (C.c_int, [C.c_void_p]),
     "b2f_get_counters": (C.c_int, [C.c_void_p, C.POINTER(Counters)]),
     "b2f_get_rescale": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b2f_set_rescale": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "b2f_kernel_time": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "b2f_reset_timers": (C.c_int, [C.c_void_p]),
     "b2f_decode": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -101,6 +101,7 @@ struct b2f_plan {
     int64_t rows_held = 0;
     int64_t rows_produced = 0, rows_emitted = 0;
     bool stats_ready = false, flushed = false, have_base = false;
+    bool preset_stats = false;        // rescale given by the caller (b2f_set_rescale): survives b2f_reset
     int64_t frames_pushed = 0;
     uint32_t base_sec0[B2F_MAX_IF]{}, base_fnum0[B2F_MAX_IF]{};
     int64_t last_nblk = 0, last_nframes = 0;
@@ -294,7 +295,7 @@ void free_plan(b2f_plan* pl) {
 
 int init_state(b2f_plan* pl) {
     pl->rows_base = pl->rows_off = pl->rows_held = pl->rows_produced = pl->rows_emitted = 0;
-    pl->stats_ready = pl->prm.keep_bandpass != 0;
+    pl->stats_ready = pl->prm.keep_bandpass != 0 || pl->preset_stats;
     pl->flushed = false;
     pl->have_base = false;
     pl->frames_pushed = 0;
@@ -303,9 +304,11 @@ int init_state(b2f_plan* pl) {
     pl->last_nblk = pl->last_nframes = 0;
     const int ncol = pl->nprod * pl->N;
     CU(cudaMemsetAsync(pl->d_counters, 0, C_COUNT * sizeof(unsigned long long), pl->stream));
-    CU(cudaMemsetAsync(pl->d_mean, 0, (size_t)pl->prm.nif * ncol * sizeof(float), pl->stream));
-    std::vector<float> ones((size_t)pl->prm.nif * ncol, 1.0f);
-    CU(cudaMemcpyAsync(pl->d_scale, ones.data(), ones.size() * sizeof(float), cudaMemcpyHostToDevice, pl->stream));
+    if (!pl->preset_stats) {
+        CU(cudaMemsetAsync(pl->d_mean, 0, (size_t)pl->prm.nif * ncol * sizeof(float), pl->stream));
+        std::vector<float> ones((size_t)pl->prm.nif * ncol, 1.0f);
+        CU(cudaMemcpyAsync(pl->d_scale, ones.data(), ones.size() * sizeof(float), cudaMemcpyHostToDevice, pl->stream));
+    }
     CU(cudaStreamSynchronize(pl->stream));
     return 0;
 }
@@ -994,6 +997,8 @@ int b2f_get_counters(b2f_plan* pl, b2f_counters* c) {
     c->frames_badhdr = h[C_BADHDR]; c->slots_missing = h[C_MISSING];
     c->rows_produced = pl->rows_produced; c->rows_emitted = pl->rows_emitted; c->blocks_dirty = h[C_DIRTY];
     c->kernel_launches = (uint64_t)pl->launches;
+    c->rescale_frozen = pl->stats_ready ? 1 : 0;
+    c->rescale_preset = pl->preset_stats ? 1 : 0;
     return 0;
 }
 
@@ -1004,6 +1009,24 @@ int b2f_get_rescale(b2f_plan* pl, float* mean, float* scale) {
     const size_t n = (size_t)pl->prm.nif * pl->nprod * pl->N * sizeof(float);
     CU(cudaMemcpy(mean, pl->d_mean, n, cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(scale, pl->d_scale, n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int b2f_set_rescale(b2f_plan* pl, const float* mean, const float* scale) {
+    if (!pl) return fail(B2F_EINVAL, "null plan");
+    if ((mean == nullptr) != (scale == nullptr)) return fail(B2F_EINVAL, "mean and scale must both be given or both be NULL");
+    CU(cudaSetDevice(pl->prm.device));
+    if (!mean) {
+        pl->preset_stats = false;
+        pl->stats_ready = pl->prm.keep_bandpass != 0;
+        return 0;
+    }
+    const size_t n = (size_t)pl->prm.nif * pl->nprod * pl->N * sizeof(float);
+    CU(cudaStreamSynchronize(pl->stream));
+    CU(cudaMemcpy(pl->d_mean, mean, n, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(pl->d_scale, scale, n, cudaMemcpyHostToDevice));
+    pl->preset_stats = true;
+    pl->stats_ready = true;
     return 0;
 }
 

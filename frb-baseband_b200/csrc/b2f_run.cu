@@ -19,6 +19,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <numeric>
 #include <string>
 #include <thread>
 #include <vector>
@@ -97,10 +98,10 @@ bool read_fully(int fd, uint8_t* dst, size_t n, off_t off, size_t* got) {
     return true;
 }
 
-bool write_fully(int fd, const uint8_t* src, size_t n) {
+bool write_fully(int fd, const uint8_t* src, size_t n, off_t pos = -1) {      // pos >= 0: at that file offset
     size_t done = 0;
     while (done < n) {
-        const ssize_t r = write(fd, src + done, n - done);
+        const ssize_t r = pos >= 0 ? pwrite(fd, src + done, n - done, pos + (off_t)done) : write(fd, src + done, n - done);
         if (r < 0) return false;
         done += (size_t)r;
     }
@@ -202,12 +203,17 @@ extern "C" int b2f_sigproc_header(const b2f_fil_header* h, void* buf, size_t cap
 
 extern "C" int b2f_run_scan(b2f_plan* pl, int nfiles, const char* const* vdif_paths, const char* out_path,
                             const b2f_scan_io* io_in, b2f_scan_result* res) {
-    if (!pl || !vdif_paths || !out_path) return failf(B2F_EINVAL, "null argument");
+    if (!pl || !vdif_paths) return failf(B2F_EINVAL, "null argument");
     b2f_scan_io io{};
     if (io_in) {
         if (io_in->struct_size != sizeof(b2f_scan_io)) return failf(B2F_EINVAL, "b2f_scan_io.struct_size mismatch");
         io = *io_in;
     }
+    const bool stats_only = io.stats_only != 0;
+    const bool in_parts = io.part_count > 1;
+    if (!out_path && !stats_only) return failf(B2F_EINVAL, "null output path");
+    if (in_parts && (io.part_index < 0 || io.part_index >= io.part_count)) return failf(B2F_EINVAL, "part_index out of range");
+    if (in_parts && stats_only) return failf(B2F_EINVAL, "stats_only measures the head of the whole window: do not combine it with parts");
     b2f_params prm;
     b2f_geometry g;
     int rc = b2f_get_params(pl, &prm);
@@ -226,7 +232,7 @@ extern "C" int b2f_run_scan(b2f_plan* pl, int nfiles, const char* const* vdif_pa
 
     Closer own;
     // ---- inputs: size, window (-S / -T), geometry check against the plan
-    const int64_t f0 = llround(io.start_s * (double)fps);
+    int64_t f0 = llround(io.start_s * (double)fps);
     int64_t nfr = INT64_MAX;
     for (int i = 0; i < nfiles; ++i) {
         const int fd = open(vdif_paths[i], O_RDONLY);
@@ -258,17 +264,46 @@ extern "C" int b2f_run_scan(b2f_plan* pl, int nfiles, const char* const* vdif_pa
         }
     }
 
+    // ---- time segment of this call: cut where frames, FFT blocks (overlap-save steps) and output samples coincide
+    int64_t row0 = 0, rows_limit = INT64_MAX;
+    if (in_parts) {
+        b2f_counters c0;
+        rc = b2f_get_counters(pl, &c0);
+        if (rc) return rc;
+        if (!prm.keep_bandpass && !c0.rescale_preset)
+            return failf(B2F_ESTATE, "a scan processed in parts needs the statistics of its first interval: call b2f_set_rescale first");
+        const int64_t D = std::max(1, prm.tscrunch), spf = g.samples_per_frame, M = g.block_samples;
+        const int64_t keep = g.freq_res - g.nfilt_pos - g.nfilt_neg, step = keep * 2 * prm.nchan;
+        const int64_t T = nfr * spf, NB = T >= M ? (T - M) / step + 1 : 0;
+        const int64_t gg = std::gcd(spf, step), ub = spf / gg;           // blocks between aligned boundaries
+        const int64_t A = NB / ub, k = io.part_index, n = io.part_count;
+        const int64_t b_lo = A * k / n * ub, b_hi = k == n - 1 ? NB : A * (k + 1) / n * ub;
+        const int64_t skip = b_lo * step / spf;                           // exact: b_lo is a multiple of ub
+        int64_t take = nfr - skip;
+        if (k < n - 1) take = std::min(take, ((b_hi - b_lo - 1) * step + M + spf - 1) / spf);   // includes the overlap halo
+        if (b_hi <= b_lo) take = 0;
+        f0 += skip;
+        nfr = std::max<int64_t>(take, 0);
+        row0 = b_lo * keep / D;
+        rows_limit = (b_hi - b_lo) * keep / D;
+    }
+
     // ---- output: an existing FIFO (base2fil.sh:348-349) is opened as it is, never unlinked (process_vdif.py:146-149)
-    int ofd;
-    {
+    int ofd = -1;
+    bool positioned = false;                  // parts write at their final offset (pwrite) into a file nobody truncates
+    if (!stats_only) {
         struct stat st;
-        if (stat(out_path, &st) == 0 && S_ISFIFO(st.st_mode)) ofd = open(out_path, O_WRONLY);
-        else ofd = open(out_path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+        const bool fifo = stat(out_path, &st) == 0 && S_ISFIFO(st.st_mode);
+        if (fifo && in_parts) return failf(B2F_EINVAL, "parts of a scan cannot be written to a FIFO");
+        if (fifo) ofd = open(out_path, O_WRONLY);
+        else ofd = open(out_path, in_parts ? (O_WRONLY | O_CREAT) : (O_WRONLY | O_CREAT | O_TRUNC), 0644);
         if (ofd < 0) return failf(B2F_EINVAL, std::string("cannot open ") + out_path + " for writing: " + strerror(errno));
         own.fds.push_back(ofd);
+        positioned = in_parts;
     }
     int64_t bytes_out = 0;
-    {
+    off_t out_pos = 0;
+    if (!stats_only) {
         double top = prm.freq_mhz[0];
         for (int i = 1; i < prm.nif; ++i) top = std::max(top, prm.freq_mhz[i]);
         const double abw = std::fabs(prm.bw_mhz[0]);
@@ -295,8 +330,11 @@ extern "C" int b2f_run_scan(b2f_plan* pl, int nfiles, const char* const* vdif_pa
         size_t hn = 0;
         rc = b2f_sigproc_header(&fh, hb, sizeof hb, &hn);
         if (rc) return rc;
-        if (!write_fully(ofd, hb, hn)) return failf(B2F_EINVAL, std::string("write failed: ") + strerror(errno));
-        bytes_out += (int64_t)hn;
+        if (!positioned || io.part_index == 0) {
+            if (!write_fully(ofd, hb, hn, positioned ? 0 : -1)) return failf(B2F_EINVAL, std::string("write failed: ") + strerror(errno));
+            bytes_out += (int64_t)hn;
+        }
+        out_pos = (off_t)hn + (off_t)(row0 * g.row_bytes);
     }
 
     // ---- pinned ring + output buffers
@@ -389,7 +427,8 @@ extern "C" int b2f_run_scan(b2f_plan* pl, int nfiles, const char* const* vdif_pa
                 W.q.erase(W.q.begin());
             }
             const auto t0 = std::chrono::steady_clock::now();
-            const bool ok = W.failed || write_fully(ofd, outb[job.first], job.second);
+            const bool ok = W.failed || write_fully(ofd, outb[job.first], job.second, positioned ? out_pos : -1);
+            out_pos += (off_t)job.second;
             std::lock_guard<std::mutex> lk(W.mu);
             t_write += since(t0);
             if (!ok && !W.failed) {
@@ -408,6 +447,7 @@ extern "C" int b2f_run_scan(b2f_plan* pl, int nfiles, const char* const* vdif_pa
         return b;
     };
     auto queue_write = [&](int buf, int64_t rows) {
+        rows = std::max<int64_t>(0, std::min(rows, rows_limit - rows_total));       // a part ends at its last own row
         {
             std::lock_guard<std::mutex> lk(W.mu);
             if (rows > 0) W.q.emplace_back(buf, (size_t)rows * (size_t)g.row_bytes);
@@ -451,6 +491,24 @@ extern "C" int b2f_run_scan(b2f_plan* pl, int nfiles, const char* const* vdif_pa
         const int b = (int)(k & 1);
         rc = b2f_push(pl, ptrs, got, 0);
         if (rc) break;
+        if (stats_only) {                    // measure, emit nothing; stop once the interval is complete
+            int64_t n = 0;
+            rc = b2f_pull(pl, nullptr, 0, 0, &n);
+            if (rc) break;
+            rc = b2f_sync(pl);               // the ring slot is reused right away
+            if (rc) break;
+            b2f_counters c;
+            rc = b2f_get_counters(pl, &c);
+            if (rc) break;
+            frames_done += got;
+            {
+                std::lock_guard<std::mutex> lk(R.mu);
+                R.released = k + 1;
+            }
+            R.cv.notify_all();
+            if (c.rescale_frozen || got < std::min<int64_t>(cf, nfr - k * cf)) break;
+            continue;
+        }
         // while the GPU has chunk k queued: finish chunk k-1 (its copies and kernels are then behind us, so its
         // ring slot can be recycled) and write its rows, which keeps the file in time order
         rc = drain(b ^ 1);
@@ -479,7 +537,11 @@ extern "C" int b2f_run_scan(b2f_plan* pl, int nfiles, const char* const* vdif_pa
     if (rc == 0) rc = drain((int)(nchunks & 1));          // older of the two pending buffers first
     if (rc == 0) rc = drain((int)(nchunks & 1) ^ 1);
     if (rc == 0) rc = b2f_flush(pl);
-    while (rc == 0) {                        // rows still held (first rescale interval, tail)
+    if (rc == 0 && stats_only) {             // a window shorter than the interval: statistics of what there is
+        int64_t n = 0;
+        rc = b2f_pull(pl, nullptr, 0, 0, &n);
+    }
+    while (rc == 0 && !stats_only) {         // rows still held (first rescale interval, tail)
         int64_t n = 0;
         const int buf = take_buffer();
         rc = b2f_pull(pl, outb[buf], max_rows, 0, &n);

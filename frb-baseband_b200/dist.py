@@ -73,3 +73,52 @@ class PeerSplice:
     def result(self):
         """the spliced rows (valid on the owner after every rank has synchronised)"""
         return self.buf if self.rank == self.owner else None
+
+
+# ---------------------------------------------------------------------------------------------
+# Time sharding: one long scan (BASELINE config 5: 3600 s) cut into consecutive segments, one per
+# rank.  Segments start where frames, FFT blocks and output samples coincide, so every rank's rows
+# are exactly the rows a single GPU would produce for that stretch, and each rank writes them at
+# their final offset of the same file.  The one thing the segments share is digifil's `-c` rescale
+# (/root/reference/process_vdif.py:181-182: mean and sigma of the first 10 s, then frozen): the rank
+# that holds the head of the scan measures it and broadcasts 2 * nif * npol * nchan floats.
+def broadcast_rescale(plan, rank: int, src: int = 0, group=None, device=None):
+    """Every rank ends up with src's measured (mean, scale) set on its plan."""
+    import torch
+    import torch.distributed as dist
+
+    n = plan.nif * plan.nprod * plan.cfg.nchan
+    buf = torch.empty(2 * n, dtype=torch.float32, device=device or "cpu")
+    if rank == src:
+        mean, scale = plan.rescale()
+        buf[:n] = torch.from_numpy(mean.reshape(-1))
+        buf[n:] = torch.from_numpy(scale.reshape(-1))
+    dist.broadcast(buf, src=src, group=group)
+    host = buf.cpu().numpy()
+    plan.set_rescale(host[:n], host[n:])
+    return host[:n].copy(), host[n:].copy()
+
+
+def run_scan_time_sharded(plan, paths, out_path: str, world: int, rank: int, *, group=None, device=None,
+                          **scan_kw) -> dict:
+    """Rank `rank` of `world` processes its time segment of the scan into `out_path` (shared file system).
+    Collective: call on every rank with the same arguments.  Returns this rank's b2f_run_scan result."""
+    import os
+
+    import torch.distributed as dist
+
+    if world == 1:
+        return plan.run_scan(paths, out_path, **scan_kw)
+    keep_bp = bool(plan.cfg.keep_bandpass)
+    if rank == 0:
+        if os.path.exists(out_path):
+            os.remove(out_path)                 # parts never truncate: start from nothing
+        if not keep_bp:
+            plan.run_scan(paths, None, stats_only=True, **scan_kw)
+    if not keep_bp:
+        broadcast_rescale(plan, rank, 0, group, device)
+    else:
+        dist.barrier(group=group)               # nobody writes before the stale file is gone
+    res = plan.run_scan(paths, out_path, part=(rank, world), **scan_kw)
+    dist.barrier(group=group)
+    return res

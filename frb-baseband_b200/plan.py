@@ -193,9 +193,12 @@ class Plan:
     def run_scan(self, paths, out_path: str, *, start_s: float = 0.0, nsec: float | None = None,
                  source_name: str = "unknown", rawdatafile: str | None = None, telescope_id: int = 0,
                  machine_id: int = 0, src_raj: float = 0.0, src_dej: float = 0.0, refdm: float | None = None,
-                 ring: int = 0, readers_per_file: int = 0) -> dict:
+                 ring: int = 0, readers_per_file: int = 0, part: tuple[int, int] | None = None,
+                 stats_only: bool = False) -> dict:
         """Files in, filterbank file out, entirely inside libb2f (b2f_run_scan): threaded readers, pinned ring,
-        pipelined pushes/pulls.  `paths`: one split VDIF file per IF in plan order (or the one raw recording)."""
+        pipelined pushes/pulls.  `paths`: one split VDIF file per IF in plan order (or the one raw recording).
+        `part=(k, n)`: only time segment k of n, written at its final offset of `out_path` (needs set_rescale
+        unless keep_bandpass); `stats_only`: measure the first rescale interval, write nothing."""
         io = _lib.ScanIO()
         io.struct_size = C.sizeof(_lib.ScanIO)
         io.start_s = float(start_s)
@@ -208,9 +211,12 @@ class Plan:
         io.write_refdm = int(refdm is not None)
         io.ring = ring
         io.readers_per_file = readers_per_file
+        io.part_index, io.part_count = part if part else (0, 0)
+        io.stats_only = int(stats_only)
         arr = (C.c_char_p * len(paths))(*[os.fsencode(p) for p in paths])
         res = _lib.ScanResult()
-        _lib.check(_lib.lib().b2f_run_scan(self._h, len(paths), arr, os.fsencode(out_path), C.byref(io), C.byref(res)))
+        _lib.check(_lib.lib().b2f_run_scan(self._h, len(paths), arr, None if out_path is None else os.fsencode(out_path),
+                                           C.byref(io), C.byref(res)))
         return {"rows": int(res.rows), "frames_per_if": int(res.frames_per_if), "bytes_in": int(res.bytes_in),
                 "bytes_out": int(res.bytes_out), "tstart_mjd": res.tstart_mjd, "seconds_of_data": res.seconds_of_data,
                 "wall_s": res.wall_s, "setup_s": res.setup_s, "wait_read_s": res.wait_read_s,
@@ -232,6 +238,16 @@ class Plan:
         _lib.check(_lib.lib().b2f_get_rescale(self._h, mean.ctypes.data, scale.ctypes.data))
         shp = (self.nif, self.nprod, self.cfg.nchan)
         return mean.reshape(shp), scale.reshape(shp)
+
+    def set_rescale(self, mean: np.ndarray | None, scale: np.ndarray | None = None):
+        """Freeze the digitiser's mean/scale (arrays as `rescale()` returns them); None returns to measuring."""
+        if mean is None:
+            _lib.check(_lib.lib().b2f_set_rescale(self._h, None, None))
+            return
+        m = np.ascontiguousarray(mean, np.float32).reshape(-1)
+        s = np.ascontiguousarray(scale, np.float32).reshape(-1)
+        assert m.size == s.size == self.nif * self.nprod * self.cfg.nchan
+        _lib.check(_lib.lib().b2f_set_rescale(self._h, m.ctypes.data, s.ctypes.data))
 
     def kernel_times(self) -> dict:
         out = {}

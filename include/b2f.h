@@ -113,6 +113,8 @@ typedef struct b2f_counters {
     uint64_t frames_dropped, frames_misplaced, frames_badhdr, slots_missing;
     uint64_t rows_produced, rows_emitted, blocks_dirty;
     uint64_t kernel_launches;     /* kernels this plan has launched since it was created */
+    uint64_t rescale_frozen;      /* 1 once mean/scale are fixed for this scan (measured, preset, or keep_bandpass) */
+    uint64_t rescale_preset;      /* 1 while b2f_set_rescale values are in force */
 } b2f_counters;
 
 /* kernel ids for b2f_kernel_time */
@@ -161,6 +163,11 @@ int b2f_reset(struct b2f_plan* plan);        /* new scan, same parameters */
 int b2f_get_counters(struct b2f_plan* plan, b2f_counters* out);
 /* mean/scale the digitiser applies: arrays of nif*nprod*nchan floats, natural channel order */
 int b2f_get_rescale(struct b2f_plan* plan, float* mean, float* scale);
+/* Freeze the digitiser's mean/scale from outside instead of measuring them on the first rescale interval: a scan
+ * cut into time segments (several GPUs, or several calls) must requantise every segment with the statistics of the
+ * scan's first interval, which is what digifil -c does (process_vdif.py:181-182).  Arrays as b2f_get_rescale
+ * returns them.  Stays in force across b2f_reset; NULL, NULL returns to measuring. */
+int b2f_set_rescale(struct b2f_plan* plan, const float* mean, const float* scale);
 /* accumulated device time (ms) and launch count of one kernel kind since the last reset of
  * the timers; requires params.profile = 1 */
 int b2f_kernel_time(struct b2f_plan* plan, int kernel_id, double* ms, int64_t* launches);
@@ -211,6 +218,14 @@ typedef struct b2f_scan_io {
     int32_t write_refdm;
     int32_t ring;                  /* pinned input chunks in flight, 2..6; 0 = 3 */
     int32_t readers_per_file;      /* reader threads per input, 1..8; 0 = as many as the host cores allow, up to 4 */
+    int32_t part_index, part_count; /* time segment part_index of part_count (0, 0 or 0, 1 = the whole window): the
+                                      window is cut on boundaries where frames, FFT blocks and output samples
+                                      coincide; every part writes its rows at their final offset of the same
+                                      out_path (regular file, not truncated; part 0 also writes the header), so
+                                      parts may run concurrently on different GPUs.  Unless keep_bandpass is set
+                                      the plan needs b2f_set_rescale first (statistics of the scan's first interval) */
+    int32_t stats_only;            /* 1: stop as soon as the first rescale interval is measured, write nothing
+                                      (out_path may be NULL); read the result with b2f_get_rescale */
 } b2f_scan_io;
 
 typedef struct b2f_scan_result {

@@ -134,3 +134,44 @@ def test_native_runner_equals_streaming_calls(gpu, tmp_path):
 def vdif_mjd(head, fps):
     from frb_baseband_b200 import vdif
     return vdif.frame_mjd(vdif.parse_header(bytes(head)), fps)
+
+
+@pytest.mark.parametrize("kind", ["tuned", "dedisp", "generic", "float_bandpass"])
+def test_scan_in_time_parts_is_bit_identical(gpu, tmp_path, kind):
+    """SURVEY 8e time sharding: a scan processed as n consecutive parts -- each with the statistics of the scan's
+    first interval preset and writing at its final file offset -- gives the file a single run gives, byte for byte
+    (parts run one after the other here; on several GPUs they run concurrently, dist.run_scan_time_sharded)."""
+    from frb_baseband_b200.plan import Plan, PlanConfig
+    bw, nfr = 32.0, 3 * 1024 + 700
+    kw = dict(nchan=128, bw_mhz=[-bw, bw], freq_mhz=[1300.0, 1332.0], tscrunch=16, rescale_interval_s=0.3)
+    if kind == "dedisp":
+        kw.update(dm=300.0, coherent=True)
+    elif kind == "generic":
+        kw.update(nchan=64, freq_res=256, tscrunch=8)
+    elif kind == "float_bandpass":
+        kw.update(out_nbit=-32, keep_bandpass=True, pol_mode=4)
+    paths = []
+    for i in range(2):
+        p = tmp_path / f"t_IF{i + 1}.vdif"
+        _write_vdif(str(p), nfr + 37 * i, 70 + i, bw, tone_frac=0.15 + 0.5 * i, rho=0.3)
+        paths.append(str(p))
+    whole = tmp_path / "whole.fil"
+    with Plan(PlanConfig(**kw)) as pl:
+        r = pl.run_scan(paths, str(whole), source_name="S")
+        assert r["rows"] > 0
+    ref = open(whole, "rb").read()
+    for n in (2, 3):
+        out = tmp_path / f"parts{n}.fil"
+        with Plan(PlanConfig(**kw)) as pl:
+            if kind != "float_bandpass":
+                with pytest.raises(Exception) as e:
+                    pl.run_scan(paths, str(out), source_name="S", part=(0, n))
+                assert "b2f_set_rescale" in str(e.value)
+                pl.run_scan(paths, None, stats_only=True)
+                assert pl.counters()["rescale_frozen"] == 1
+                pl.set_rescale(*pl.rescale())
+            rows = 0
+            for k in reversed(range(n)):                     # any order: every part knows its offset
+                rows += pl.run_scan(paths, str(out), source_name="S", part=(k, n))["rows"]
+        assert rows == r["rows"]
+        assert open(out, "rb").read() == ref, f"{kind}: {n} parts differ from the single run"
