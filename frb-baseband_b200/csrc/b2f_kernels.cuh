@@ -20,7 +20,14 @@ constexpr int kL = 512;                 // column FFT length (= digifil freq_res
 constexpr int kStripCols = B2F_STRIP_COLS;   // columns per column-pass CTA (8 or 16)
 constexpr int kKAThreads = 16 * kStripCols;  // 16 work items x columns
 constexpr int kKACtasPerSM = 32 / kStripCols;  // 4 x 128 threads or 2 x 256 threads: 16 warps per SM either way
-constexpr int kKBThreads = 256;
+#ifndef B2F_KB_THREADS
+#define B2F_KB_THREADS 256
+#endif
+#ifndef B2F_KB_STAGES
+#define B2F_KB_STAGES 2
+#endif
+constexpr int kKBThreads = B2F_KB_THREADS;
+constexpr int kKBStages = B2F_KB_STAGES;        // TMA ring depth per warp: kKBStages - 1 row tiles in flight
 constexpr uint32_t kFillWord = 0x11223344u;
 constexpr float kLevLo = 1.0f;          // standard VLBI optimal 2-bit reconstruction levels
 constexpr float kLevHi = 3.3359f;
@@ -878,9 +885,10 @@ struct KBSmem {
     static constexpr int kBody = kRows > kXch ? kRows : kXch;
     static constexpr int kEps = N * (int)sizeof(float2);
     static constexpr int kStage = (kBody + kEps + 127) / 128 * 128;
-    static constexpr int kWarpBytes = 2 * kStage;
+    static constexpr int kWarpBytes = kKBStages * kStage;
     static constexpr int kTw = PT * TR * (int)sizeof(float2);
-    static constexpr size_t kBytes = 128 + (size_t)kWarps * kWarpBytes + kTw;
+    static constexpr int kBarBytes = (kWarps * kKBStages * 8 + 127) / 128 * 128;
+    static constexpr size_t kBytes = kBarBytes + (size_t)kWarps * kWarpBytes + kTw;
 };
 
 // Every warp is its own pipeline: it owns whole time-integration groups (D consecutive rows
@@ -895,14 +903,13 @@ __global__ void __launch_bounds__(kKBThreads, 2) kb_row_pass(const KBParams p) {
     extern __shared__ __align__(128) uint8_t kb_smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int s = lane % TR, rsw = lane / TR;
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(kb_smem) + 2 * warp;
-    uint8_t* stage0 = kb_smem + 128 + (size_t)warp * S::kWarpBytes;
-    float2* s_tw = reinterpret_cast<float2*>(kb_smem + 128 + (size_t)S::kWarps * S::kWarpBytes);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(kb_smem) + kKBStages * warp;
+    uint8_t* stage0 = kb_smem + S::kBarBytes + (size_t)warp * S::kWarpBytes;
+    float2* s_tw = reinterpret_cast<float2*>(kb_smem + S::kBarBytes + (size_t)S::kWarps * S::kWarpBytes);
 
     for (int i = tid; i < PT * TR; i += kKBThreads) s_tw[i] = p.tab_r[i];
     if (lane == 0) {
-        mbar_init(&mbar[0], 1);
-        mbar_init(&mbar[1], 1);
+        for (int k = 0; k < kKBStages; ++k) mbar_init(&mbar[k], 1);
         mbar_fence_init();
     }
     __syncthreads();
@@ -936,20 +943,31 @@ __global__ void __launch_bounds__(kKBThreads, 2) kb_row_pass(const KBParams p) {
 
     int64_t grp_cur = (int64_t)blockIdx.x * S::kWarps + warp;
     int pass_cur = 0;
-    if (grp_cur < ngroups) issue(grp_cur, 0, 0);
+    auto advance = [&](int64_t& g, int& ps) {
+        if (++ps == passes) { ps = 0; g += wstride; }
+    };
+    // the issue pointer runs kKBStages - 1 tiles ahead of the tile being transformed
+    int64_t grp_iss = grp_cur;
+    int pass_iss = 0, iss = 0;
+    for (int k = 0; k < kKBStages - 1 && grp_iss < ngroups; ++k) {
+        issue(grp_iss, pass_iss, iss % kKBStages);
+        ++iss;
+        advance(grp_iss, pass_iss);
+    }
 
     float acc[QPT][HP][NPROD];
     float2 e[QPT][HP];
     int it = 0;
     while (grp_cur < ngroups) {
-        const int buf = it & 1;
-        int64_t grp_nxt = grp_cur;
-        int pass_nxt = pass_cur + 1;
-        if (pass_nxt == passes) { pass_nxt = 0; grp_nxt += wstride; }
-        // stage buf^1 was last touched by this warp one iteration ago (program order): refill it
-        if (grp_nxt < ngroups) issue(grp_nxt, pass_nxt, buf ^ 1);
+        const int buf = it % kKBStages;
+        // the stage consumed one iteration ago (program order) is free: refill it
+        if (grp_iss < ngroups) {
+            issue(grp_iss, pass_iss, iss % kKBStages);
+            ++iss;
+            advance(grp_iss, pass_iss);
+        }
 
-        mbar_wait(&mbar[buf], (it >> 1) & 1);
+        mbar_wait(&mbar[buf], (it / kKBStages) & 1);
         uint8_t* st = stage0 + buf * S::kStage;
         const float2* tile = reinterpret_cast<const float2*>(st + rsw * S::kPitch);
         if (pass_cur == 0 && MODE != kModeSpectrum) {
@@ -991,8 +1009,7 @@ __global__ void __launch_bounds__(kKBThreads, 2) kb_row_pass(const KBParams p) {
             for (int j = 0; j < QPT; ++j)
 #pragma unroll
                 for (int pp = 0; pp < TR; ++pp) dst[(s + TR * j) + PT * pp] = z[j][pp];
-            grp_cur = grp_nxt;
-            pass_cur = pass_nxt;
+            advance(grp_cur, pass_cur);
             ++it;
             continue;
         }
@@ -1035,8 +1052,7 @@ __global__ void __launch_bounds__(kKBThreads, 2) kb_row_pass(const KBParams p) {
                         for (int pp = 0; pp < HP; ++pp) dst[k * N + (s + TR * j) + PT * pp] = acc[j][pp][k];
             }
         }
-        grp_cur = grp_nxt;
-        pass_cur = pass_nxt;
+        advance(grp_cur, pass_cur);
         ++it;
     }
 }

@@ -175,3 +175,37 @@ def test_scan_in_time_parts_is_bit_identical(gpu, tmp_path, kind):
                 rows += pl.run_scan(paths, str(out), source_name="S", part=(k, n))["rows"]
         assert rows == r["rows"]
         assert open(out, "rb").read() == ref, f"{kind}: {n} parts differ from the single run"
+
+
+def test_edge_inputs_empty_short_and_widest(gpu, tmp_path):
+    """Inputs at the edges of what base2fil can hand over: an empty split file (base2fil.sh:391-394 writes an
+    empty .fil for it; the runner writes a header-only one), a file shorter than one FFT block (no samples), a
+    window that starts beyond the end, and the widest plan (32 IFs, the B2F_MAX_IF of include/b2f.h)."""
+    from frb_baseband_b200.plan import Plan, PlanConfig
+    bw = 16.0
+    empty, short = tmp_path / "e_IF1.vdif", tmp_path / "s_IF1.vdif"
+    empty.write_bytes(b"")
+    _write_vdif(str(short), 1, 3, bw)                       # 16000 samples < one 32768-sample block
+    with Plan(PlanConfig(nchan=32, bw_mhz=[-bw], tscrunch=32)) as pl:
+        for src in (empty, short):
+            out = tmp_path / (src.name + ".fil")
+            r = pl.run_scan([str(src)], str(out), source_name="X")
+            h, off = sigproc.read_header(open(out, "rb").read())
+            assert r["rows"] == 0 and os.path.getsize(out) == off and h.nchans == 32 and h.source_name == "X"
+        r = pl.run_scan([str(short)], str(tmp_path / "late.fil"), start_s=5.0)
+        assert r["rows"] == 0 and r["frames_per_if"] == 0
+    nif, nfr = 32, 64
+    vd, paths = [], []
+    for i in range(nif):
+        p = tmp_path / f"w_IF{i + 1}.vdif"
+        vd.append(_write_vdif(str(p), nfr, 900 + i, bw, tone_frac=0.03 * i))
+        paths.append(str(p))
+    bws = [bw if (i + 1) % 2 == 0 else -bw for i in range(nif)]
+    freqs = [1000.0 + i * bw for i in range(nif)]
+    with Plan(PlanConfig(nchan=8, bw_mhz=bws, freq_mhz=freqs, tscrunch=64, rescale_interval_s=0.01)) as pl:
+        r = pl.run_scan(paths, str(tmp_path / "wide.fil"))
+    h, d = sigproc.read_fil(str(tmp_path / "wide.fil"))
+    ref = o.base2fil({i + 1: vd[i] for i in range(nif)}, nif=nif, freq_lsb0=1000.0, bw=bw, nchan=8, tscrunch_factor=64,
+                     rescale_interval_s=0.01)
+    assert h.nchans == 256 and d.shape[0] == ref["data"].shape[0] == r["rows"] > 0
+    assert np.abs(d[:, 0, :].astype(int) - ref["data"].astype(int)).max() <= 1
