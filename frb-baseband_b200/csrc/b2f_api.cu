@@ -246,7 +246,8 @@ int launch_k0(b2f_plan* pl, const K0Params& kp, cudaStream_t st, bool profile_ok
     for (int i = 0; i < nif; ++i) aligned = aligned && ((reinterpret_cast<uintptr_t>(kp.frames[i]) & 15) == 0);
     const int stage_bytes = (kp.frame_bytes + 127) & ~127;
     int sms = pl ? pl->num_sms : 148;
-    int gx = (int)std::max<int64_t>(1, std::min<int64_t>(kp.nframes, (4 * sms + nif - 1) / nif));
+    static const int per_sm = [] { const char* e = getenv("B2F_K0_CTAS_PER_SM"); return e ? std::max(1, atoi(e)) : 4; }();
+    int gx = (int)std::max<int64_t>(1, std::min<int64_t>(kp.nframes, (per_sm * sms + nif - 1) / nif));
     dim3 grid(gx, nif);
     auto body = [&] {
         if (vec && aligned) {

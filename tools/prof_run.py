@@ -13,7 +13,8 @@ from frb_baseband_b200.plan import Plan, PlanConfig  # noqa: E402
 nchunks = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 dev = torch.device("cuda", 0)
 bws, freqs = bench.if_plan()
-pl = Plan(PlanConfig(nchan=bench.NCHAN, bw_mhz=bws, freq_mhz=freqs, tscrunch=bench.TSCRUNCH, rescale_interval_s=0.2))
+pl = Plan(PlanConfig(nchan=bench.NCHAN, bw_mhz=bws, freq_mhz=freqs, tscrunch=bench.TSCRUNCH, rescale_interval_s=0.2,
+                     chunk_units=4))          # 4096 frames per IF and push, like bench.py
 cf = int(pl.chunk_frames)
 vd = [bench.make_device_vdif(torch, dev, cf * nchunks, 1 + i) for i in range(bench.NIF)]
 out = torch.empty((pl.chunk_rows * (nchunks + 1), bench.NIF * bench.NCHAN), dtype=torch.uint8, device=dev)
