@@ -7,6 +7,8 @@
 // of include/b2f.h is used for the device side.
 #include <cuda_runtime.h>
 #include <fcntl.h>
+#include <pthread.h>
+#include <signal.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -142,6 +144,29 @@ struct PinnedPool {
 };
 PinnedPool g_pool;
 
+// A reader that closes base2fil's FIFO early must surface as an error (EPIPE), not kill the caller: SIGPIPE is
+// blocked for the duration of a run (threads started meanwhile inherit the mask) and a pending one is consumed
+// before the caller's mask is restored.
+struct SigpipeGuard {
+    sigset_t old{};
+    bool active = false;
+    SigpipeGuard() {
+        sigset_t s;
+        sigemptyset(&s);
+        sigaddset(&s, SIGPIPE);
+        active = pthread_sigmask(SIG_BLOCK, &s, &old) == 0;
+    }
+    ~SigpipeGuard() {
+        if (!active) return;
+        sigset_t s;
+        sigemptyset(&s);
+        sigaddset(&s, SIGPIPE);
+        const timespec zero{0, 0};
+        while (sigtimedwait(&s, nullptr, &zero) > 0) {}
+        pthread_sigmask(SIG_SETMASK, &old, nullptr);
+    }
+};
+
 struct Closer {
     std::vector<int> fds;
     std::vector<void*> pinned;
@@ -230,6 +255,7 @@ extern "C" int b2f_run_scan(b2f_plan* pl, int nfiles, const char* const* vdif_pa
     if (std::fabs(fps_d - (double)fps) > 1e-6)
         return failf(B2F_EINVAL, "frames per second is not an integer for this bandwidth and frame size");
 
+    SigpipeGuard no_sigpipe;
     Closer own;
     // ---- inputs: size, window (-S / -T), geometry check against the plan
     int64_t f0 = llround(io.start_s * (double)fps);

@@ -32,6 +32,8 @@ extern "C" {
 #define B2F_VERSION 100            /* 0.1.0 */
 #define B2F_MAX_IF 32
 
+struct b2f_plan;                   /* opaque: created by b2f_plan_create, owned by the library */
+
 enum b2f_error {
     B2F_OK = 0,
     B2F_EINVAL = -1,               /* bad parameter (InputError in process_vdif.py:236) */

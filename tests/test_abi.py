@@ -79,3 +79,22 @@ def test_sigproc_header_matches_python_writer():
         hh, off = sigproc.read_header(buf.raw)
         assert off == n.value and hh.nchans == 1024 and hh.source_name == "R3"
     assert _lib.lib().b2f_sigproc_header(C.byref(h), buf, 8, C.byref(n)) == _lib.EINVAL
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/b2f.h compiles as strict C99 and a C program links against libb2f.so: the boundary a digifil- or
+    splice-like tool written in C would use (examples/b2f_scan.c is mode B of INTEGRATION.md from C)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "b2f_scan")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(root, "include"),
+                           os.path.join(root, "examples", "b2f_scan.c"), "-o", exe, "-L", libdir, "-lb2f",
+                           "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe, "--version"], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.startswith("libb2f 0.1.0")
+    bad = subprocess.run([exe, str(tmp_path / "o.fil")], capture_output=True, text=True)
+    assert bad.returncode == 2 and "usage" in bad.stderr

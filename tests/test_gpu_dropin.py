@@ -209,3 +209,30 @@ def test_edge_inputs_empty_short_and_widest(gpu, tmp_path):
                      rescale_interval_s=0.01)
     assert h.nchans == 256 and d.shape[0] == ref["data"].shape[0] == r["rows"] > 0
     assert np.abs(d[:, 0, :].astype(int) - ref["data"].astype(int)).max() <= 1
+
+
+def test_c_program_through_the_abi(gpu, tmp_path):
+    """examples/b2f_scan.c (plain C against include/b2f.h) writes the file the Python host writes."""
+    import shutil
+    import subprocess
+    from frb_baseband_b200 import _lib
+    from frb_baseband_b200.plan import Plan, PlanConfig
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe, libdir = str(tmp_path / "b2f_scan"), os.path.dirname(_lib.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "b2f_scan.c"),
+                           "-o", exe, "-L", libdir, "-lb2f", "-Wl,-rpath," + libdir])
+    bw, paths = 32.0, []
+    for i in range(2):
+        p = tmp_path / f"c_IF{i + 1}.vdif"
+        _write_vdif(str(p), 1300, 300 + i, bw, tone_frac=0.2 + 0.4 * i)
+        paths.append(str(p))
+    out_c, out_py = tmp_path / "c.fil", tmp_path / "py.fil"
+    r = subprocess.run([exe, "--nchan", "128", "--tscrunch", "16", "--bw", "32", "--freq-lsb0", "1254", "--nsec", "0.3",
+                        "--source", "R3", str(out_c)] + paths, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "2 IFs x 0.300 s" in r.stderr
+    with Plan(PlanConfig(nchan=128, bw_mhz=[-bw, bw], freq_mhz=[1254.0, 1286.0], tscrunch=16)) as pl:
+        pl.run_scan(paths, str(out_py), nsec=0.3, source_name="R3")
+    assert open(out_c, "rb").read() == open(out_py, "rb").read()
