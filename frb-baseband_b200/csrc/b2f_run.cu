@@ -322,6 +322,10 @@ extern "C" int b2f_run_scan(b2f_plan* pl, int nfiles, const char* const* vdif_pa
         const bool fifo = stat(out_path, &st) == 0 && S_ISFIFO(st.st_mode);
         if (fifo && in_parts) return failf(B2F_EINVAL, "parts of a scan cannot be written to a FIFO");
         if (fifo) ofd = open(out_path, O_WRONLY);
+#ifdef F_SETPIPE_SZ
+        // what setfifo.perl does for every FIFO of the splice list (setfifo.perl:10, base2fil.sh:417-419): 1 MiB pipe
+        if (fifo && ofd >= 0) (void)fcntl(ofd, F_SETPIPE_SZ, 1048576);
+#endif
         else ofd = open(out_path, in_parts ? (O_WRONLY | O_CREAT) : (O_WRONLY | O_CREAT | O_TRUNC), 0644);
         if (ofd < 0) return failf(B2F_EINVAL, std::string("cannot open ") + out_path + " for writing: " + strerror(errno));
         own.fds.push_back(ofd);
