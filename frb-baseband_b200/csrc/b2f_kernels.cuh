@@ -1129,6 +1129,7 @@ __global__ void __launch_bounds__(256, 2) kc_dedisp_back(const KCParams p) {
 
     const int nstrips = N / 8;
     const int nprod = nprod_of_mode(p.mode);
+    const bool own_only = p.mode == B2F_POL_P0 || p.mode == B2F_POL_P1 || p.mode == B2F_POL_I || p.mode == B2F_POL_PPQQ;
     const int64_t nwork = (p.gb_end - p.gb_begin) * nstrips;
     for (int64_t w = blockIdx.x; w < nwork; w += gridDim.x) {
         const int64_t lb = w / nstrips;
@@ -1185,6 +1186,12 @@ __global__ void __launch_bounds__(256, 2) kc_dedisp_back(const KCParams p) {
             }
             fft_inreg<32, true>(u);
             __syncthreads();                   // everyone has its u[]: the exchange buffer becomes the power buffer
+            if (own_only) {
+                // products without a cross term: every lane squares its own polarisation, [m][ch][pol]
+#pragma unroll
+                for (int mh = 0; mh < 32; ++mh)
+                    pw[(size_t)(item + 16 * mh) * 16 + lane16] = u[mh].x * u[mh].x + u[mh].y * u[mh].y;
+            } else {
 #pragma unroll
             for (int mh = 0; mh < 32; ++mh) {
                 const float ox = __shfl_xor_sync(0xffffffffu, u[mh].x, 1), oy = __shfl_xor_sync(0xffffffffu, u[mh].y, 1);
@@ -1195,15 +1202,12 @@ __global__ void __launch_bounds__(256, 2) kc_dedisp_back(const KCParams p) {
                     float* dst = pw + (size_t)(item + 16 * mh) * 8 + ch8;
                     constexpr size_t PS = (size_t)kL * 8;        // product stride
                     switch (p.mode) {
-                        case B2F_POL_P0: dst[0] = pp; break;
-                        case B2F_POL_P1: dst[0] = qq; break;
-                        case B2F_POL_I: dst[0] = pp + qq; break;
                         case B2F_POL_I2: dst[0] = (pp + qq) * (pp + qq); break;
-                        case B2F_POL_PPQQ: dst[0] = pp; dst[PS] = qq; break;
                         case B2F_POL_COHERENCE: dst[0] = pp; dst[PS] = qq; dst[2 * PS] = re; dst[3 * PS] = im; break;
                         default: dst[0] = pp + qq; dst[PS] = 2.f * re; dst[2 * PS] = 2.f * im; dst[3 * PS] = pp - qq; break;
                     }
                 }
+            }
             }
         }
         __syncthreads();
@@ -1212,9 +1216,20 @@ __global__ void __launch_bounds__(256, 2) kc_dedisp_back(const KCParams p) {
         const int64_t t0 = p.row0 + blk * nrow;
         for (int o = tid; o < nprod * nrow * 8; o += 256) {
             const int ch = o & 7, r = (o >> 3) % nrow, k = (o >> 3) / nrow;
-            const float* src = pw + ((size_t)k * kL + p.nfilt_pos + r * p.D) * 8 + ch;
             float sum = 0.f;
-            for (int i = 0; i < p.D; ++i) sum += src[i * 8];
+            if (own_only) {
+                const float2* src = reinterpret_cast<const float2*>(pw) + (size_t)(p.nfilt_pos + r * p.D) * 8 + ch;
+                float s0 = 0.f, s1 = 0.f;
+                for (int i = 0; i < p.D; ++i) {
+                    const float2 v = src[i * 8];
+                    s0 += v.x;
+                    s1 += v.y;
+                }
+                sum = p.mode == B2F_POL_I ? s0 + s1 : p.mode == B2F_POL_P0 ? s0 : p.mode == B2F_POL_P1 ? s1 : (k == 0 ? s0 : s1);
+            } else {
+                const float* src = pw + ((size_t)k * kL + p.nfilt_pos + r * p.D) * 8 + ch;
+                for (int i = 0; i < p.D; ++i) sum += src[i * 8];
+            }
             p.F[ifi * p.F_if_stride + (t0 + r) * (int64_t)(nprod * N) + k * N + (int)(w % nstrips) * 8 + ch] = sum;
         }
         __syncthreads();
