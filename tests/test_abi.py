@@ -98,3 +98,20 @@ def test_header_is_plain_c_and_links(tmp_path):
     assert out.returncode == 0 and out.stdout.startswith("libb2f 0.1.0")
     bad = subprocess.run([exe, str(tmp_path / "o.fil")], capture_output=True, text=True)
     assert bad.returncode == 2 and "usage" in bad.stderr
+
+
+def test_ctypes_structs_match_the_c_layout(tmp_path):
+    """sizeof of every struct of include/b2f.h as gcc lays it out == the ctypes mirror in _lib.py."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "b2f.h"\nint main(void) { printf("%zu %zu %zu %zu %zu %zu\\n", '
+                   "sizeof(b2f_params), sizeof(b2f_geometry), sizeof(b2f_counters), sizeof(b2f_fil_header), "
+                   "sizeof(b2f_scan_io), sizeof(b2f_scan_result)); return 0; }\n")
+    exe = str(tmp_path / "sizes")
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", exe])
+    got = [int(x) for x in subprocess.check_output([exe], text=True).split()]
+    want = [C.sizeof(t) for t in (_lib.Params, _lib.Geometry, _lib.Counters, _lib.FilHeaderC, _lib.ScanIO, _lib.ScanResult)]
+    assert got == want
