@@ -338,7 +338,8 @@ int push_dedisp(b2f_plan* pl, int64_t nblk, int64_t T) {
         const size_t smem_col = ((size_t)pl->L + 32 + kg_padded((size_t)pl->L * kg.C)) * sizeof(float2);
         const size_t smem_row = ((size_t)pl->R + kg_padded((size_t)RB * pl->R)) * sizeof(float2);
         CU(cudaFuncSetAttribute(kg_column_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_col));
-        CU(cudaFuncSetAttribute(kg_row_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row));
+        CU(cudaFuncSetAttribute(kg_row_pass<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row));
+        CU(cudaFuncSetAttribute(kg_row_pass<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row));
         for (int64_t b0 = 0; b0 < nbt; b0 += NB) {
             const int64_t nb = std::min(NB, nbt - b0);
             kg.gb_begin = b0; kg.gb_end = b0 + nb;
@@ -348,13 +349,14 @@ int push_dedisp(b2f_plan* pl, int64_t nblk, int64_t T) {
             });
             if (rc) return rc;
             rc = timed(pl, B2F_K_EPS, [&] {
-                ke_eps<<<(unsigned)nb, pl->R / 2, pl->R * sizeof(float2), pl->stream>>>(pl->d_colsum + b0 * pl->R,
+                ke_eps<<<(unsigned)nb, std::min(pl->R / 2, 512), pl->R * sizeof(float2), pl->stream>>>(pl->d_colsum + b0 * pl->R,
                                                                                        pl->d_eps + b0 * pl->N, pl->R);
             });
             if (rc) return rc;
             const int64_t nunits = nb * (pl->L / std::max(pl->D, RB));
             rc = timed(pl, B2F_K_ROW, [&] {
-                kg_row_pass<<<(unsigned)std::min<int64_t>(nunits, (int64_t)pl->num_sms * 2), 256, smem_row, pl->stream>>>(kg);
+                if (pl->N > 1024) kg_row_pass<8><<<(unsigned)std::min<int64_t>(nunits, (int64_t)pl->num_sms * 2), 256, smem_row, pl->stream>>>(kg);
+                else kg_row_pass<4><<<(unsigned)std::min<int64_t>(nunits, (int64_t)pl->num_sms * 2), 256, smem_row, pl->stream>>>(kg);
             });
             if (rc) return rc;
         }
@@ -449,8 +451,8 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
     if (prm->nchan < 1) return fail(B2F_EINVAL, "nchan");
     const int L = prm->freq_res > 0 ? prm->freq_res : (prm->nchan <= 128 ? 512 : 2 * prm->nchan);
     const int R = 2 * prm->nchan;
-    if (!is_pow2(R) || R < 16 || R > 2048) return fail(B2F_EUNSUPPORTED, "nchan must be a power of two in 8..1024");
-    if (!is_pow2(L) || L < 16 || L > 2048) return fail(B2F_EUNSUPPORTED, "freq_res must be a power of two in 16..2048");
+    if (!is_pow2(R) || R < 16 || R > 4096) return fail(B2F_EUNSUPPORTED, "nchan must be a power of two in 8..2048");
+    if (!is_pow2(L) || L < 16 || L > 4096) return fail(B2F_EUNSUPPORTED, "freq_res must be a power of two in 16..4096");
     const bool generic = !(L == kL && R <= 512);        // tuned kernels: 512-point columns, rows up to 512
     if (generic && prm->in_nbit != 2) return fail(B2F_EUNSUPPORTED, "freq_res != 512 or nchan > 256 needs 2-bit input in this build");
     const int D = prm->tscrunch < 1 ? 1 : prm->tscrunch;
@@ -841,7 +843,7 @@ int b2f_push(b2f_plan* pl, const void* const* frames, int64_t nframes, int on_de
             rc = launch_ka(pl, ka, (unsigned)grid);
             if (rc) return rc;
             rc = timed(pl, B2F_K_EPS, [&] {
-                ke_eps<<<(unsigned)nb, pl->R / 2, pl->R * sizeof(float2), pl->stream>>>(pl->d_colsum + b0 * pl->R,
+                ke_eps<<<(unsigned)nb, std::min(pl->R / 2, 512), pl->R * sizeof(float2), pl->stream>>>(pl->d_colsum + b0 * pl->R,
                                                                                        pl->d_eps + b0 * pl->N, pl->R);
             });
             if (rc) return rc;

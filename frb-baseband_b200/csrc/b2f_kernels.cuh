@@ -837,25 +837,28 @@ __global__ void __launch_bounds__(kKAThreads, kKACtasPerSM) ka_column_pass(const
 // term that separating the two real polarisations after the row pass needs.
 static __global__ void ke_eps(const float2* __restrict__ colsum, float2* __restrict__ eps, int R) {
     extern __shared__ float2 ke_s[];
-    const int t = threadIdx.x;                      // R/2 threads
     const int lg = 31 - __clz(R);
     const float2* src = colsum + (int64_t)blockIdx.x * R;
-    for (int i = t; i < R; i += blockDim.x) ke_s[__brev(i) >> (32 - lg)] = src[i];
+    for (int i = threadIdx.x; i < R; i += blockDim.x) ke_s[__brev(i) >> (32 - lg)] = src[i];
     __syncthreads();
     for (int s = 1; s <= lg; ++s) {
         const int half = 1 << (s - 1);
-        const int j = t & (half - 1);
-        const int i0 = ((t >> (s - 1)) << s) + j, i1 = i0 + half;
-        float sn, cs;
-        sincospif(-(float)j / (float)half, &sn, &cs);
-        const float2 a = ke_s[i0], b = ke_s[i1];
-        const float2 wb = make_float2(b.x * cs - b.y * sn, b.x * sn + b.y * cs);
-        ke_s[i0] = make_float2(a.x + wb.x, a.y + wb.y);
-        ke_s[i1] = make_float2(a.x - wb.x, a.y - wb.y);
+        for (int t = threadIdx.x; t < R / 2; t += blockDim.x) {      // one butterfly per thread and pass
+            const int j = t & (half - 1);
+            const int i0 = ((t >> (s - 1)) << s) + j, i1 = i0 + half;
+            float sn, cs;
+            sincospif(-(float)j / (float)half, &sn, &cs);
+            const float2 a = ke_s[i0], b = ke_s[i1];
+            const float2 wb = make_float2(b.x * cs - b.y * sn, b.x * sn + b.y * cs);
+            ke_s[i0] = make_float2(a.x + wb.x, a.y + wb.y);
+            ke_s[i1] = make_float2(a.x - wb.x, a.y - wb.y);
+        }
         __syncthreads();
     }
-    const float2 g0 = ke_s[R - 1 - t], g1 = ke_s[(R - t) & (R - 1)];
-    eps[(int64_t)blockIdx.x * (R / 2) + t] = make_float2(g0.x - g1.x, -(g0.y - g1.y));
+    for (int t = threadIdx.x; t < R / 2; t += blockDim.x) {
+        const float2 g0 = ke_s[R - 1 - t], g1 = ke_s[(R - t) & (R - 1)];
+        eps[(int64_t)blockIdx.x * (R / 2) + t] = make_float2(g0.x - g1.x, -(g0.y - g1.y));
+    }
 }
 
 // ================================================================== kernel 3c+4: row pass
@@ -1430,7 +1433,8 @@ __device__ __forceinline__ void kg_row_inner(float2* sm, int lgR, int cnt) {
 
 // generic row pass: a CTA holds RB rows of a block in shared memory, transforms them together, detects and
 // integrates D rows per output sample
-static __global__ void __launch_bounds__(256, 2) kg_row_pass(const KGParams p) {
+template <int CPT>                                                       // channels per thread: nchan <= 256 * CPT
+__global__ void __launch_bounds__(256, 2) kg_row_pass(const KGParams p) {
     extern __shared__ __align__(16) uint8_t kg_smem[];
     float2* tw = reinterpret_cast<float2*>(kg_smem);                     // [R]
     float2* rows = tw + p.R;                                              // [RB][R], padded
@@ -1444,7 +1448,6 @@ static __global__ void __launch_bounds__(256, 2) kg_row_pass(const KGParams p) {
     const int64_t nunits = (p.gb_end - p.gb_begin) * units_per_blk;
     const int nf = kg_outer_passes(lgR), lgi = kg_inner_lg(lgR);
     const int cnt16 = RB * (R >> 4);
-    constexpr int CPT = 4;                                               // channels per thread: nchan <= 1024
     int posA[CPT], posB[CPT];
 #pragma unroll
     for (int k = 0; k < CPT; ++k) {

@@ -239,7 +239,7 @@ def test_other_row_lengths(gpu, nchan, bw, D):
 
 
 def test_unsupported_requests_fail_loudly(gpu):
-    for kw in (dict(nchan=2048), dict(nchan=128, tscrunch=3), dict(nchan=128, tscrunch=1024), dict(nchan=4),
+    for kw in (dict(nchan=4096), dict(nchan=128, tscrunch=3), dict(nchan=128, tscrunch=1024), dict(nchan=4),
                dict(nchan=512, in_nbit=8), dict(nchan=512, dm=100.0, coherent=True)):
         with pytest.raises(_lib.B2FError) as e:
             Plan(PlanConfig(bw_mhz=[-32.0], **kw))
@@ -247,7 +247,8 @@ def test_unsupported_requests_fail_loudly(gpu):
 
 
 @pytest.mark.parametrize("nchan,freq_res,D,nframes", [(512, 0, 4, 1500), (1024, 0, 2, 1100), (128, 64, 16, 300), (32, 2048, 32, 700),
-                                                        (8, 16, 1, 40), (16, 32, 2, 60), (512, 512, 4, 500), (64, 256, 256, 200)])
+                                                        (8, 16, 1, 40), (16, 32, 2, 60), (512, 512, 4, 500), (64, 256, 256, 200),
+                                                        (2048, 0, 1, 2300)])
 def test_generic_channeliser(gpu, nchan, freq_res, D, nframes):
     """freq_res / nchan outside the tuned kernels, e.g. process_vdif's default --nchan 512 ->
     digifil -F512:1024 (process_vdif.py:46,162).  Pushes are 1024-frame pieces that do not align
