@@ -22,6 +22,7 @@ CONFIGS = {
     "C3 (C2 with PP,QQ,Re,Im float32, 20 s)": dict(nif=8, bw=32.0, nchan=128, D=16, seconds=20.0, mode=_lib.POL_COHERENCE, nbit=-32),
     "C3b (C2 with Stokes IQUV float32, 20 s)": dict(nif=8, bw=32.0, nchan=128, D=16, seconds=20.0, mode=_lib.POL_IQUV, nbit=-32),
     "C4 (C2 + coherent dedispersion DM 560, 20 s)": dict(nif=8, bw=32.0, nchan=128, D=16, seconds=20.0, dm=560.0),
+    "C5 (16 IF x 32 MHz = 4096 Mbps, nchan 128, D 16, 8-bit I, 10 s sample of the 3600 s scan)": dict(nif=16, bw=32.0, nchan=128, D=16, seconds=10.0),
     "generic (1 IF x 32 MHz, nchan 512 -> -F512:1024, D 4, 10 s)": dict(nif=1, bw=32.0, nchan=512, D=4, seconds=10.0),
     "generic policy (8 IF x 32 MHz, nchan 1024 -> -F1024:2048, D 2: submit_job.py at DM 560, 10 s)": dict(nif=8, bw=32.0, nchan=1024, D=2, seconds=10.0),
 }
