@@ -1,4 +1,6 @@
 """Parity of the CUDA path (through the C ABI) with the oracle.  Runs on the B200 box."""
+import os
+
 import numpy as np
 import pytest
 
@@ -282,7 +284,9 @@ def test_property_random_configurations(gpu):
     modes = [(_lib.POL_P0, "P0"), (_lib.POL_P1, "P1"), (_lib.POL_I, "I"), (_lib.POL_I2, "I2"),
              (_lib.POL_COHERENCE, "coherence"), (_lib.POL_IQUV, "IQUV"), (_lib.POL_PPQQ, "PPQQ")]
 
-    @settings(max_examples=10, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True,
+    # B2F_PROPERTY_EXAMPLES / B2F_PROPERTY_RANDOM=1: a wider, non-repeating sweep for one-off hunting
+    @settings(max_examples=int(os.environ.get("B2F_PROPERTY_EXAMPLES", "10")), deadline=None,
+              suppress_health_check=list(HealthCheck), derandomize=os.environ.get("B2F_PROPERTY_RANDOM", "0") != "1",
               phases=[Phase.generate])          # no shrinking: every example costs GPU time
     @given(lg_nchan=st.integers(3, 8), lg_d=st.integers(0, 6), usb=st.booleans(), mode=st.sampled_from(modes),
            bw=st.sampled_from([16.0, 32.0]), seed=st.integers(0, 2 ** 16), faults=st.booleans(), units=st.integers(1, 2))
