@@ -609,9 +609,20 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
     CUB(cudaMalloc(&pl->d_sm_slots, 1024 * sizeof(int)));
     if (pl->carry_mode) CUB(cudaMalloc(&pl->d_carry, (size_t)pl->M * nif));
     if (generic) {
-        std::vector<float2> tc(L), tr(R);
-        for (int k = 0; k < L; ++k) tc[k] = make_float2((float)cos(-2.0 * M_PI * k / L), (float)sin(-2.0 * M_PI * k / L));
-        for (int k = 0; k < R; ++k) tr[k] = make_float2((float)cos(-2.0 * M_PI * k / R), (float)sin(-2.0 * M_PI * k / R));
+        auto pass_tables = [](int len) {                 // layout of kg_tw_offset: per outer pass, [q - 1][lo]
+            std::vector<float2> t((size_t)len, make_float2(1.f, 0.f));
+            const int lg = 31 - __builtin_clz(len);
+            for (int f = 0; f < kg_outer_passes(lg); ++f) {
+                const int n = len >> (4 * f), m = n / 16, off = kg_tw_offset(lg, f);
+                for (int q = 1; q < 16; ++q)
+                    for (int lo = 0; lo < m; ++lo) {
+                        const double ph = -2.0 * M_PI * (double)lo * q / n;
+                        t[(size_t)off + (size_t)(q - 1) * m + lo] = make_float2((float)cos(ph), (float)sin(ph));
+                    }
+            }
+            return t;
+        };
+        std::vector<float2> tc = pass_tables(L), tr = pass_tables(R);
         CUB(cudaMalloc(&pl->d_tw_col, tc.size() * sizeof(float2)));
         CUB(cudaMalloc(&pl->d_tw_row, tr.size() * sizeof(float2)));
         CUB(cudaMemcpy(pl->d_tw_col, tc.data(), tc.size() * sizeof(float2), cudaMemcpyHostToDevice));

@@ -1255,8 +1255,8 @@ struct KGParams {
     float2* inter;               // [gb - gb_begin][L][R]
     float2* colsum;              // [nif*nblk][R]
     const float2* eps;           // [nif*nblk][R/2]
-    const float2* tw_col;        // [L]  exp(-2 pi i k / L)
-    const float2* tw_row;        // [R]  exp(-2 pi i k / R)
+    const float2* tw_col;        // [L]  per-pass twiddle rows for L-point FFTs, see kg_tw_offset
+    const float2* tw_row;        // [R]  the same for R-point FFTs
     float* F; int64_t F_if_stride; int64_t row0;
     int L, lgL, R, lgR, C, lgC, nblk, nif, D, mode;
     int64_t M, gb_begin, gb_end;
@@ -1265,13 +1265,33 @@ struct KGParams {
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 
-// shared-memory index with one pad element per 16: strided passes stay (nearly) conflict-free
-__device__ __forceinline__ int kg_phys(int e) { return e + (e >> 4); }
-__host__ __device__ constexpr size_t kg_padded(size_t n) { return n + n / 16 + 1; }
+// Shared-memory index swizzles (XOR within aligned 16-element groups, so buffers need no padding).  Every pass
+// reads 64-bit elements either contiguously or at the stride of the innermost passes; the swizzle keeps the 16
+// lanes of a half-warp on 16 different 8-byte banks in both cases:
+//   columns, layout [index][C] with C < 16: the innermost passes step 32 elements between neighbouring segments
+//     -> bits 5..6 of the element number are folded into bits 2..3;
+//   rows, layout [row][R]: the innermost pass steps RM = 2..16 elements, the one before it R/16
+//     -> bits 4..6 are folded into bits 0..2 and bit 7 into bit 3.
+// (ncu before: 45 % of the column kernel's and 65 % of the row kernel's shared wavefronts were bank conflicts
+// with one pad element per 16.)
+template <bool ROWS>
+__device__ __forceinline__ int kg_phys(int e) {
+    return ROWS ? (e ^ ((e >> 4) & 7) ^ (((e >> 7) & 1) << 3)) : (e ^ (((e >> 5) & 3) << 2));
+}
+__host__ __device__ constexpr size_t kg_padded(size_t n) { return (n + 15) / 16 * 16; }
 
 // number of radix-16 passes outside the innermost one, and the innermost radix, for a 2^lg point FFT
 __host__ __device__ __forceinline__ int kg_outer_passes(int lg) { return (lg - 1) / 4; }
 __host__ __device__ __forceinline__ int kg_inner_lg(int lg) { return lg - 4 * ((lg - 1) / 4); }
+
+// Twiddles of outer pass f (segments of n = len >> 4f points, m = n / 16): 15 rows of m entries,
+// table[offset(f) + (q - 1) m + lo] = exp(-2 pi i lo q / n), so the lanes of a warp (consecutive lo) read
+// consecutive entries.  All passes together need fewer than `len` entries.
+__host__ __device__ __forceinline__ int kg_tw_offset(int lg, int f) {
+    int off = 0;
+    for (int g = 0; g < f; ++g) off += 15 << (lg - 4 * g - 4);
+    return off;
+}
 
 // frequency index <-> position after the forward passes (base-16 digits of the segment number reversed)
 __device__ __forceinline__ int kg_freq_of_pos(int pos, int lg) {
@@ -1291,7 +1311,7 @@ __device__ __forceinline__ int kg_pos_of_freq(int k, int lg) {
 // One radix-16 pass over `cnt` transforms.  Sequences are interleaved [index][1 << lgC] (columns) or stored one
 // after the other with lgC = 0 and `seq_len` elements each (rows).  SRC: 0 shared, 1 index bytes (decode),
 // 2 global float2.  DST: 0 shared, 1 global float2.
-template <bool INV, int SRC, int DST>
+template <bool INV, int SRC, int DST, bool ROWS>
 __device__ __forceinline__ void kg_pass16(float2* sm, const float2* tw, int lgLen, int lgn, int lgC, int cnt,
                                           const uint8_t* gsrc_b, const float2* gsrc_f, float2* gdst, int64_t gstride,
                                           const float2* lut) {
@@ -1301,29 +1321,29 @@ __device__ __forceinline__ void kg_pass16(float2* sm, const float2* tw, int lgLe
         const int seq = u >> lgT, w = u & ((1 << lgT) - 1);          // seq > 0 only for rows (lgC = 0)
         const int lo = w & (m - 1), seg = w >> lgm;
         const int base = (seq << lgLen) + (seg << lgn) + lo;
-        const int step = lo << (lgLen - lgn);
+        const float2* twl = tw + lo;                                 // this pass's table, [q - 1][lo]: lanes read neighbours
         float2 v[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const int idx = base + j * m;
             if (SRC == 1) v[j] = *reinterpret_cast<const float2*>(reinterpret_cast<const uint8_t*>(lut) + gsrc_b[(int64_t)idx * gstride + cl]);
             else if (SRC == 2) v[j] = gsrc_f[(int64_t)seq * gstride + (idx & ((1 << lgLen) - 1))];
-            else v[j] = sm[kg_phys((idx << lgC) + cl)];
+            else v[j] = sm[kg_phys<ROWS>((idx << lgC) + cl)];
         }
         if (INV) {
 #pragma unroll
-            for (int q = 1; q < 16; ++q) v[q] = cmul_conj(v[q], tw[q * step]);
+            for (int q = 1; q < 16; ++q) v[q] = cmul_conj(v[q], twl[(q - 1) << lgm]);
             fft_inreg<16, true>(v);
         } else {
             fft_inreg<16, false>(v);
 #pragma unroll
-            for (int q = 1; q < 16; ++q) v[q] = cmul(v[q], tw[q * step]);
+            for (int q = 1; q < 16; ++q) v[q] = cmul(v[q], twl[(q - 1) << lgm]);
         }
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const int idx = base + j * m;
             if (DST == 1) gdst[(int64_t)idx * gstride + cl] = v[j];
-            else sm[kg_phys((idx << lgC) + cl)] = v[j];
+            else sm[kg_phys<ROWS>((idx << lgC) + cl)] = v[j];
         }
     }
 }
@@ -1343,7 +1363,7 @@ __device__ __forceinline__ void kg_column_inner(float2* sm, const KGParams& p, i
         for (int q = 0; q < RM; ++q) {
             const int idx = seg * RM + q;
             if (GLOBAL) v[q] = *reinterpret_cast<const float2*>(reinterpret_cast<const uint8_t*>(lut) + gsrc_b[(int64_t)idx * p.R + cl]);
-            else v[q] = sm[kg_phys((idx << lgC) + cl)];
+            else v[q] = sm[kg_phys<false>((idx << lgC) + cl)];
         }
         fft_inreg<RM, false>(v);
         if (seg == 0) colsum[cl] = v[0];                            // A[k2 = 0]
@@ -1363,7 +1383,7 @@ __device__ __forceinline__ void kg_column_inner(float2* sm, const KGParams& p, i
         for (int q = 0; q < RM; ++q) {
             const int idx = seg * RM + q;
             if (GLOBAL) gdst[(int64_t)idx * p.R + cl] = v[q];
-            else sm[kg_phys((idx << lgC) + cl)] = v[q];
+            else sm[kg_phys<false>((idx << lgC) + cl)] = v[q];
         }
     }
 }
@@ -1398,8 +1418,8 @@ static __global__ void __launch_bounds__(256, 2) kg_column_pass(const KGParams p
             continue;
         }
         for (int f = 0; f < nf; ++f) {                       // forward, outermost first
-            if (f == 0) kg_pass16<false, 1, 0>(data, tw, lgL, lgL, lgC, cnt16, src, nullptr, nullptr, R, lut);
-            else kg_pass16<false, 0, 0>(data, tw, lgL, lgL - 4 * f, lgC, cnt16, nullptr, nullptr, nullptr, 0, lut);
+            if (f == 0) kg_pass16<false, 1, 0, false>(data, tw, lgL, lgL, lgC, cnt16, src, nullptr, nullptr, R, lut);
+            else kg_pass16<false, 0, 0, false>(data, tw + kg_tw_offset(lgL, f), lgL, lgL - 4 * f, lgC, cnt16, nullptr, nullptr, nullptr, 0, lut);
             __syncthreads();
         }
         switch (lgi) {
@@ -1410,8 +1430,8 @@ static __global__ void __launch_bounds__(256, 2) kg_column_pass(const KGParams p
         }
         __syncthreads();
         for (int f = nf - 1; f >= 0; --f) {                  // inverse, innermost first
-            if (f == 0) kg_pass16<true, 0, 1>(data, tw, lgL, lgL, lgC, cnt16, nullptr, nullptr, dst, R, lut);
-            else kg_pass16<true, 0, 0>(data, tw, lgL, lgL - 4 * f, lgC, cnt16, nullptr, nullptr, nullptr, 0, lut);
+            if (f == 0) kg_pass16<true, 0, 1, false>(data, tw, lgL, lgL, lgC, cnt16, nullptr, nullptr, dst, R, lut);
+            else kg_pass16<true, 0, 0, false>(data, tw + kg_tw_offset(lgL, f), lgL, lgL - 4 * f, lgC, cnt16, nullptr, nullptr, nullptr, 0, lut);
             __syncthreads();
         }
     }
@@ -1424,10 +1444,10 @@ __device__ __forceinline__ void kg_row_inner(float2* sm, int lgR, int cnt) {
     for (int t = threadIdx.x; t < cnt; t += blockDim.x) {           // t = global segment number over all rows of the batch
         float2 v[RM];
 #pragma unroll
-        for (int q = 0; q < RM; ++q) v[q] = sm[kg_phys((t << LGI) + q)];
+        for (int q = 0; q < RM; ++q) v[q] = sm[kg_phys<true>((t << LGI) + q)];
         fft_inreg<RM, false>(v);
 #pragma unroll
-        for (int q = 0; q < RM; ++q) sm[kg_phys((t << LGI) + q)] = v[q];
+        for (int q = 0; q < RM; ++q) sm[kg_phys<true>((t << LGI) + q)] = v[q];
     }
 }
 
@@ -1468,11 +1488,11 @@ __global__ void __launch_bounds__(256, 2) kg_row_pass(const KGParams p) {
         for (int b0 = 0; b0 < U; b0 += RB) {
             const float2* src = p.inter + (lb * (int64_t)L + r0 + b0) * R;
             if (nf == 0) {                                   // R = 16: rows go straight to the innermost step
-                for (int i = tid; i < RB * R; i += 256) rows[kg_phys(i)] = src[i];
+                for (int i = tid; i < RB * R; i += 256) rows[kg_phys<true>(i)] = src[i];
             } else {
                 for (int f = 0; f < nf; ++f) {
-                    if (f == 0) kg_pass16<false, 2, 0>(rows, tw, lgR, lgR, 0, cnt16, nullptr, src, nullptr, R, nullptr);
-                    else kg_pass16<false, 0, 0>(rows, tw, lgR, lgR - 4 * f, 0, cnt16, nullptr, nullptr, nullptr, 0, nullptr);
+                    if (f == 0) kg_pass16<false, 2, 0, true>(rows, tw, lgR, lgR, 0, cnt16, nullptr, src, nullptr, R, nullptr);
+                    else kg_pass16<false, 0, 0, true>(rows, tw + kg_tw_offset(lgR, f), lgR, lgR - 4 * f, 0, cnt16, nullptr, nullptr, nullptr, 0, nullptr);
                     __syncthreads();
                 }
             }
@@ -1491,8 +1511,8 @@ __global__ void __launch_bounds__(256, 2) kg_row_pass(const KGParams p) {
                 for (int k = 0; k < CPT; ++k) {
                     const int c = tid + 256 * k;
                     if (c < N) {
-                        const float2 a = row[kg_phys(rbase + posA[k])];
-                        const float2 b = row[kg_phys(rbase + posB[k])];
+                        const float2 a = row[kg_phys<true>(rbase + posA[k])];
+                        const float2 b = row[kg_phys<true>(rbase + posB[k])];
                         const float2 e = p.eps[gb * N + c];
                         const float2 bp = make_float2(b.x - e.x, -b.y - e.y);
                         const float2 P = cadd(a, bp), Q = csub(a, bp);
