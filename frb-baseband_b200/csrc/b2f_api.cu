@@ -336,7 +336,7 @@ int push_dedisp(b2f_plan* pl, int64_t nblk, int64_t T) {
         kg.nblk = (int)nblk; kg.nif = nif; kg.D = pl->D; kg.mode = pl->prm.pol_mode; kg.M = pl->M;
         const int RB = std::max(1, std::min(16, 4096 / pl->R));
         const size_t smem_col = ((size_t)pl->L + 32 + kg_padded((size_t)pl->L * kg.C)) * sizeof(float2);
-        const size_t smem_row = ((size_t)pl->R + kg_padded((size_t)RB * pl->R)) * sizeof(float2);
+        const size_t smem_row = ((size_t)pl->R + kg_padded((size_t)RB * pl->R) + 2 * (size_t)RB * pl->R) * sizeof(float2);
         CU(cudaFuncSetAttribute(kg_column_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_col));
         CU(cudaFuncSetAttribute(kg_row_pass<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row));
         CU(cudaFuncSetAttribute(kg_row_pass<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row));

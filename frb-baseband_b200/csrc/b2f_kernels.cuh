@@ -1270,13 +1270,14 @@ __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(
 // lanes of a half-warp on 16 different 8-byte banks in both cases:
 //   columns, layout [index][C] with C < 16: the innermost passes step 32 elements between neighbouring segments
 //     -> bits 5..6 of the element number are folded into bits 2..3;
-//   rows, layout [row][R]: the innermost pass steps RM = 2..16 elements, the one before it R/16
-//     -> bits 4..6 are folded into bits 0..2 and bit 7 into bit 3.
+//   rows, layout [row][R]: the innermost pass steps RM = 2..16 elements, the one before it R/256, and detection
+//     reads digit-reversed positions (neighbouring channels are R/16 elements apart)
+//     -> bits 4..6 and 8..10 are folded into bits 0..2 and bit 7 into bit 3.
 // (ncu before: 45 % of the column kernel's and 65 % of the row kernel's shared wavefronts were bank conflicts
 // with one pad element per 16.)
 template <bool ROWS>
 __device__ __forceinline__ int kg_phys(int e) {
-    return ROWS ? (e ^ ((e >> 4) & 7) ^ (((e >> 7) & 1) << 3)) : (e ^ (((e >> 5) & 3) << 2));
+    return ROWS ? (e ^ (((e >> 4) ^ (e >> 8)) & 7) ^ (((e >> 7) & 1) << 3)) : (e ^ (((e >> 5) & 3) << 2));
 }
 __host__ __device__ constexpr size_t kg_padded(size_t n) { return (n + 15) / 16 * 16; }
 
@@ -1457,7 +1458,7 @@ template <int CPT>                                                       // chan
 __global__ void __launch_bounds__(256, 2) kg_row_pass(const KGParams p) {
     extern __shared__ __align__(16) uint8_t kg_smem[];
     float2* tw = reinterpret_cast<float2*>(kg_smem);                     // [R]
-    float2* rows = tw + p.R;                                              // [RB][R], padded
+    float2* rows = tw + p.R;                                              // [RB][R], swizzled
     const int tid = threadIdx.x, R = p.R, N = R / 2, lgR = p.lgR, L = p.L, D = p.D;
     for (int i = tid; i < R; i += 256) tw[i] = p.tw_row[i];
     __syncthreads();
@@ -1475,18 +1476,42 @@ __global__ void __launch_bounds__(256, 2) kg_row_pass(const KGParams p) {
         posA[k] = c < N ? kg_pos_of_freq(c, lgR) : 0;
         posB[k] = c < N ? kg_pos_of_freq(R - 1 - c, lgR) : 0;
     }
+    // the next batch of rows is copied into shared memory (cp.async, two buffers) while this one is transformed
+    const int batch = RB * R;
+    float2* stage = rows + kg_padded((size_t)batch);                     // [2][RB][R], natural order
+    auto prefetch = [&](int64_t g, int b0, int buf) {
+        const int64_t lb = g / units_per_blk;
+        const float2* src = p.inter + (lb * (int64_t)L + (int)(g % units_per_blk) * U + b0) * R;
+        float2* dst = stage + (size_t)buf * batch;
+        for (int i = tid * 2; i < batch; i += 512) cp_async16(dst + i, src + i);
+    };
+    int it = 0;
+    if (blockIdx.x < nunits) prefetch(blockIdx.x, 0, 0);
+    cp_async_commit();
     for (int64_t g = blockIdx.x; g < nunits; g += gridDim.x) {
         const int64_t lb = g / units_per_blk, gb = p.gb_begin + lb;
         const int r0 = (int)(g % units_per_blk) * U;
         const int ifi = (int)(gb / p.nblk);
         const int64_t blk = gb % p.nblk;
         float acc[CPT][4];
+        float2 epsr[CPT];
 #pragma unroll
-        for (int k = 0; k < CPT; ++k)
+        for (int k = 0; k < CPT; ++k) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) acc[k][q] = 0.f;
-        for (int b0 = 0; b0 < U; b0 += RB) {
-            const float2* src = p.inter + (lb * (int64_t)L + r0 + b0) * R;
+            epsr[k] = tid + 256 * k < N ? p.eps[gb * N + tid + 256 * k] : make_float2(0.f, 0.f);
+        }
+        for (int b0 = 0; b0 < U; b0 += RB, ++it) {
+            {
+                int64_t gn = g;
+                int bn = b0 + RB;
+                if (bn >= U) { bn = 0; gn += gridDim.x; }
+                if (gn < nunits) prefetch(gn, bn, (it + 1) & 1);
+                cp_async_commit();
+                cp_async_wait<1>();
+                __syncthreads();
+            }
+            const float2* src = stage + (size_t)(it & 1) * batch;
             if (nf == 0) {                                   // R = 16: rows go straight to the innermost step
                 for (int i = tid; i < RB * R; i += 256) rows[kg_phys<true>(i)] = src[i];
             } else {
@@ -1513,7 +1538,7 @@ __global__ void __launch_bounds__(256, 2) kg_row_pass(const KGParams p) {
                     if (c < N) {
                         const float2 a = row[kg_phys<true>(rbase + posA[k])];
                         const float2 b = row[kg_phys<true>(rbase + posB[k])];
-                        const float2 e = p.eps[gb * N + c];
+                        const float2 e = epsr[k];
                         const float2 bp = make_float2(b.x - e.x, -b.y - e.y);
                         const float2 P = cadd(a, bp), Q = csub(a, bp);
                         const float pp = 0.25f * (P.x * P.x + P.y * P.y), qq = 0.25f * (Q.x * Q.x + Q.y * Q.y);
@@ -1547,6 +1572,7 @@ __global__ void __launch_bounds__(256, 2) kg_row_pass(const KGParams p) {
             __syncthreads();
         }
     }
+    cp_async_wait<0>();
 }
 
 // ================================================================== kernel 5a: statistics
