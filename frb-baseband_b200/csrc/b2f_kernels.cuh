@@ -1349,6 +1349,103 @@ __device__ __forceinline__ void kg_pass16(float2* sm, const float2* tw, int lgLe
     }
 }
 
+// Column passes with two neighbouring columns per thread: one 128-bit shared access and one twiddle read serve
+// both (the shared-memory instruction queue is what the column kernel runs out of first), and the two
+// independent 16-point transforms interleave.  SRC: 0 shared, 1 index bytes.  DST: 0 shared, 1 global.
+template <bool INV, int SRC, int DST>
+__device__ __forceinline__ void kg_pass16_pair(float2* sm, const float2* tw, int lgLen, int lgn, int lgC, int cnt,
+                                               const uint8_t* gsrc_b, float2* gdst, int64_t gstride, const float2* lut) {
+    const int lgm = lgn - 4, m = 1 << lgm, lgP = lgC - 1;           // 2^lgP column pairs per strip
+    for (int t = threadIdx.x; t < cnt; t += blockDim.x) {
+        const int c2 = (t & ((1 << lgP) - 1)) * 2, w = t >> lgP;
+        const int lo = w & (m - 1), seg = w >> lgm;
+        const int base = (seg << lgn) + lo;
+        const float2* twl = tw + lo;
+        float2 a[16], b[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int idx = base + j * m;
+            if (SRC == 1) {
+                const uint32_t two = *reinterpret_cast<const uint16_t*>(gsrc_b + (int64_t)idx * gstride + c2);
+                a[j] = *reinterpret_cast<const float2*>(reinterpret_cast<const uint8_t*>(lut) + (two & 255u));
+                b[j] = *reinterpret_cast<const float2*>(reinterpret_cast<const uint8_t*>(lut) + (two >> 8));
+            } else {
+                const float4 v4 = *reinterpret_cast<const float4*>(&sm[kg_phys<false>((idx << lgC) + c2)]);
+                a[j] = make_float2(v4.x, v4.y);
+                b[j] = make_float2(v4.z, v4.w);
+            }
+        }
+        if (INV) {
+#pragma unroll
+            for (int q = 1; q < 16; ++q) {
+                const float2 wq = twl[(q - 1) << lgm];
+                a[q] = cmul_conj(a[q], wq);
+                b[q] = cmul_conj(b[q], wq);
+            }
+            fft_inreg<16, true>(a);
+            fft_inreg<16, true>(b);
+        } else {
+            fft_inreg<16, false>(a);
+            fft_inreg<16, false>(b);
+#pragma unroll
+            for (int q = 1; q < 16; ++q) {
+                const float2 wq = twl[(q - 1) << lgm];
+                a[q] = cmul(a[q], wq);
+                b[q] = cmul(b[q], wq);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int idx = base + j * m;
+            const float4 v4 = make_float4(a[j].x, a[j].y, b[j].x, b[j].y);
+            if (DST == 1) *reinterpret_cast<float4*>(gdst + (int64_t)idx * gstride + c2) = v4;
+            else *reinterpret_cast<float4*>(&sm[kg_phys<false>((idx << lgC) + c2)]) = v4;
+        }
+    }
+}
+
+template <int RM>
+__device__ __forceinline__ void kg_column_inner_pair(float2* sm, const KGParams& p, int n1_0, float2* colsum) {
+    constexpr int LGI = ilog2(RM);
+    const int lgC = p.lgC, lgP = lgC - 1, cnt = (p.L >> LGI) << lgP;
+    const int nf = kg_outer_passes(p.lgL);
+    const float inv_half_m = 2.0f / (float)p.M;
+    for (int t = threadIdx.x; t < cnt; t += blockDim.x) {
+        const int c2 = (t & ((1 << lgP) - 1)) * 2, seg = t >> lgP;
+        float2 a[RM], b[RM];
+#pragma unroll
+        for (int q = 0; q < RM; ++q) {
+            const float4 v4 = *reinterpret_cast<const float4*>(&sm[kg_phys<false>(((seg * RM + q) << lgC) + c2)]);
+            a[q] = make_float2(v4.x, v4.y);
+            b[q] = make_float2(v4.z, v4.w);
+        }
+        fft_inreg<RM, false>(a);
+        fft_inreg<RM, false>(b);
+        if (seg == 0) {                                             // A[k2 = 0]
+            colsum[c2] = a[0];
+            colsum[c2 + 1] = b[0];
+        }
+        int kseg = 0;
+        for (int f = 0; f < nf; ++f) kseg |= ((seg >> (4 * (nf - 1 - f))) & 15) << (4 * f);
+        const int n1 = n1_0 + c2;
+#pragma unroll
+        for (int q = 0; q < RM; ++q) {                              // * W_M^(k2 n1), phase reduced exactly in integers
+            const int k2 = kseg | (q << (4 * nf));
+            const int pa = (int)(((int64_t)k2 * n1) & (p.M - 1)), pb = (int)(((int64_t)pa + k2) & (p.M - 1));
+            float sn, cs;
+            sincospif(-(float)pa * inv_half_m, &sn, &cs);
+            a[q] = cmul(a[q], make_float2(cs, sn));
+            sincospif(-(float)pb * inv_half_m, &sn, &cs);
+            b[q] = cmul(b[q], make_float2(cs, sn));
+        }
+        fft_inreg<RM, true>(a);
+        fft_inreg<RM, true>(b);
+#pragma unroll
+        for (int q = 0; q < RM; ++q)
+            *reinterpret_cast<float4*>(&sm[kg_phys<false>(((seg * RM + q) << lgC) + c2)]) = make_float4(a[q].x, a[q].y, b[q].x, b[q].y);
+    }
+}
+
 // innermost step of the column pass: FFT_RM, diagonal, IFFT_RM on the RM values of one segment
 template <int RM, bool GLOBAL>
 __device__ __forceinline__ void kg_column_inner(float2* sm, const KGParams& p, int n1_0, float2* colsum, const uint8_t* gsrc_b,
@@ -1418,21 +1515,22 @@ static __global__ void __launch_bounds__(256, 2) kg_column_pass(const KGParams p
             kg_column_inner<16, true>(data, p, strip * C, colsum, src, dst, lut);
             continue;
         }
+        const int cnt2 = cnt16 >> 1;                         // two neighbouring columns per thread
         for (int f = 0; f < nf; ++f) {                       // forward, outermost first
-            if (f == 0) kg_pass16<false, 1, 0, false>(data, tw, lgL, lgL, lgC, cnt16, src, nullptr, nullptr, R, lut);
-            else kg_pass16<false, 0, 0, false>(data, tw + kg_tw_offset(lgL, f), lgL, lgL - 4 * f, lgC, cnt16, nullptr, nullptr, nullptr, 0, lut);
+            if (f == 0) kg_pass16_pair<false, 1, 0>(data, tw, lgL, lgL, lgC, cnt2, src, nullptr, R, lut);
+            else kg_pass16_pair<false, 0, 0>(data, tw + kg_tw_offset(lgL, f), lgL, lgL - 4 * f, lgC, cnt2, nullptr, nullptr, 0, lut);
             __syncthreads();
         }
         switch (lgi) {
-            case 1: kg_column_inner<2, false>(data, p, strip * C, colsum, nullptr, nullptr, lut); break;
-            case 2: kg_column_inner<4, false>(data, p, strip * C, colsum, nullptr, nullptr, lut); break;
-            case 3: kg_column_inner<8, false>(data, p, strip * C, colsum, nullptr, nullptr, lut); break;
-            default: kg_column_inner<16, false>(data, p, strip * C, colsum, nullptr, nullptr, lut); break;
+            case 1: kg_column_inner_pair<2>(data, p, strip * C, colsum); break;
+            case 2: kg_column_inner_pair<4>(data, p, strip * C, colsum); break;
+            case 3: kg_column_inner_pair<8>(data, p, strip * C, colsum); break;
+            default: kg_column_inner_pair<16>(data, p, strip * C, colsum); break;
         }
         __syncthreads();
         for (int f = nf - 1; f >= 0; --f) {                  // inverse, innermost first
-            if (f == 0) kg_pass16<true, 0, 1, false>(data, tw, lgL, lgL, lgC, cnt16, nullptr, nullptr, dst, R, lut);
-            else kg_pass16<true, 0, 0, false>(data, tw + kg_tw_offset(lgL, f), lgL, lgL - 4 * f, lgC, cnt16, nullptr, nullptr, nullptr, 0, lut);
+            if (f == 0) kg_pass16_pair<true, 0, 1>(data, tw, lgL, lgL, lgC, cnt2, nullptr, dst, R, lut);
+            else kg_pass16_pair<true, 0, 0>(data, tw + kg_tw_offset(lgL, f), lgL, lgL - 4 * f, lgC, cnt2, nullptr, nullptr, 0, lut);
             __syncthreads();
         }
     }
