@@ -126,7 +126,7 @@ __device__ __forceinline__ uint2 expand_word_2bit(uint32_t w, bool masked) {
     return make_uint2(lo << 3, hi << 3);
 }
 
-constexpr int kK0Threads = 128;
+constexpr int kK0Threads = 256;
 constexpr int kK0Stages = 4;
 
 template <bool VEC>
