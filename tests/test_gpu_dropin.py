@@ -236,3 +236,51 @@ def test_c_program_through_the_abi(gpu, tmp_path):
     with Plan(PlanConfig(nchan=128, bw_mhz=[-bw, bw], freq_mhz=[1254.0, 1286.0], tscrunch=16)) as pl:
         pl.run_scan(paths, str(out_py), nsec=0.3, source_name="R3")
     assert open(out_c, "rb").read() == open(out_py, "rb").read()
+
+
+def test_mode_a_concurrent_processes_share_the_gpu(gpu, tmp_path):
+    """Mode A of INTEGRATION.md as base2fil.sh:60-66 runs it: one `process_vdif` OS process per IF, all at once on
+    the same GPU, each into the FIFO base2fil made, with a splice-like reader joining them highest frequency first."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "bin", "process_vdif")
+    nif, bw, nfr = 4, 16.0, 2600
+    vd, procs, fifos = {}, [], []
+    for i in range(1, nif + 1):
+        p = tmp_path / f"ma_o8_no0003_IF{i}.vdif"
+        vd[i] = _write_vdif(str(p), nfr, 600 + i, bw, tone_frac=0.1 * i)
+        fifo = tmp_path / f"ma_o8_no0003_IF{i}.vdif_pol2.fil"
+        os.mkfifo(fifo)                                                       # base2fil.sh:348-349
+        fifos.append(str(fifo))
+        freq = 1300.0 + (i - 1) * bw
+        # the target of frb.conf carries --ra/--dec (frb.conf:3-6); without them the wrapper asks psrcat like the reference
+        procs.append(subprocess.Popen([sys.executable, exe, "B0329+54", "--ra", "03:32:59.4", "--dec", "+54:34:43.3", str(p),
+                                       "-f", str(freq), "-b", str(bw),
+                                       "-l" if i % 2 else "-u", "--nchan", "32", "--nsec", "1", "--start", "0", "--force",
+                                       "-t", "onsala85", "--pol", "2", "--tscrunch", "32", "--fil_out_dir", str(tmp_path),
+                                       "--nbit=8"], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE))
+    got = {}
+
+    def reader(k, path):
+        with open(path, "rb") as f:
+            got[k] = f.read()
+
+    threads = [threading.Thread(target=reader, args=(k, f), daemon=True) for k, f in enumerate(fifos)]
+    for t in threads:
+        t.start()
+    for pr in procs:
+        _, err = pr.communicate(timeout=120)
+        assert pr.returncode == 0, err.decode()[-600:]
+    for t in threads:
+        t.join(60)
+        assert not t.is_alive()
+    ref = o.base2fil(vd, nif=nif, freq_lsb0=1300.0, bw=bw, nchan=32, tscrunch_factor=32, nsec=1.0)
+    tiles = []
+    for k in reversed(range(nif)):                                            # splice order: highest frequency first
+        h, off = sigproc.read_header(got[k])
+        tiles.append(np.frombuffer(got[k], np.uint8, offset=off).reshape(-1, 32))
+        assert all(os.path.exists(f) for f in fifos)                          # FIFOs are never unlinked (:146-149)
+    rows = np.concatenate(tiles, axis=1)
+    assert rows.shape == ref["data"].shape
+    assert np.abs(rows.astype(int) - ref["data"].astype(int)).max() <= 1
