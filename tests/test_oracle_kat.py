@@ -198,3 +198,32 @@ def test_digitiser_and_rescale_definitions():
     assert np.array_equal(o.tscrunch(d, 3)[:, 0, 0], [0 + 4 + 8, 12 + 16 + 20])      # sum, not mean
     mean, scale = o.rescale_stats(d, 4)                                               # first interval only
     assert np.allclose(mean[0], d[:4, 0].mean(axis=0)) and np.allclose(1 / scale[0], d[:4, 0].std(axis=0))
+
+
+def _golden_scans():
+    import base64
+    import json
+    import os
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "oracle_small_scans.json")))
+    for c in g["cases"]:
+        rows = np.frombuffer(base64.b64decode(c["rows_b64"]), np.uint8).reshape(c["shape"])
+        yield c, rows, g["rescale_interval_s"]
+
+
+def test_oracle_reproduces_committed_small_scans():
+    """The seeded synthetic scans of tests/golden/oracle_small_scans.json (made by make_oracle_golden.py): same VDIF
+    bytes from the seed, same 8-bit rows from the oracle (+-1 LSB allowed for a different FFT library build)."""
+    import hashlib
+    from frb_baseband_b200 import synth
+    n = 0
+    for c, rows, interval in _golden_scans():
+        v = synth.make_vdif(c["nframes"], seed=c["seed"], bw_mhz=c["bw"], **c["sig"])
+        assert hashlib.sha256(v.tobytes()).hexdigest() == c["vdif_sha256"], c["name"]
+        sbw = c["bw"] if c["usb"] else -c["bw"]
+        r = o.digifil(v, freq_mhz=1400.0, bw_mhz=sbw, nchan=c["nchan"], tscrunch_factor=c["D"], pol_mode=c["pol_mode"],
+                      out_nbit=8, rescale_interval_s=interval)
+        d = np.abs(r["data"].reshape(rows.shape).astype(int) - rows.astype(int))
+        assert d.max() <= 1 and (d > 0).mean() < 1e-3, c["name"]
+        assert r["fch1"] == pytest.approx(c["fch1"]) and r["tsamp_s"] == pytest.approx(c["tsamp_s"])
+        n += 1
+    assert n == 3
