@@ -320,4 +320,4 @@ def test_committed_small_scans(gpu):
         rows, _ = run_plan([v], nchan=c["nchan"], bw=[sbw], tscrunch=c["D"], pol_mode=modes[c["pol_mode"]], out_nbit=8,
                            interval=g["rescale_interval_s"])
         d = np.abs(rows.reshape(want.shape).astype(int) - want.astype(int))
-        assert d.max() <= 1 and (d > 0).mean() < 2e-3, c["name"]
+        assert d.max() <= 1 and (d > 0).sum() <= max(5, 2e-3 * d.size), c["name"]
