@@ -1068,7 +1068,16 @@ __global__ void __launch_bounds__(kKBThreads, 2) kb_row_pass(const KBParams p) {
                 const float bx = __shfl_xor_sync(0xffffffffu, bs.x, TR - 1);
                 const float by = __shfl_xor_sync(0xffffffffu, bs.y, TR - 1);
                 const float2 bp = make_float2(bx - e[j][pp].x, -by - e[j][pp].y);
-                detect_acc<MODE == kModeSpectrum ? B2F_POL_I : MODE>(acc[j][pp], make_float2(a.x + bp.x, a.y + bp.y), make_float2(a.x - bp.x, a.y - bp.y));
+                if (MODE == B2F_POL_I) {
+                    // |yP|^2 + |yQ|^2 = (|a + b'|^2 + |a - b'|^2) / 4 = (|a|^2 + |b'|^2) / 2: no need to form P and Q
+                    float t = a.x * a.x;
+                    t = fmaf(a.y, a.y, t);
+                    t = fmaf(bp.x, bp.x, t);
+                    t = fmaf(bp.y, bp.y, t);
+                    acc[j][pp][0] = fmaf(0.5f, t, acc[j][pp][0]);
+                } else {
+                    detect_acc<MODE == kModeSpectrum ? B2F_POL_P0 : MODE>(acc[j][pp], make_float2(a.x + bp.x, a.y + bp.y), make_float2(a.x - bp.x, a.y - bp.y));
+                }
             }
         if (pass_cur == passes - 1) {
             // add up the row slots that integrate into the same output sample
