@@ -12,6 +12,7 @@
 #include <string>
 #include <vector>
 
+#define B2F_API_TU
 #include "b2f_launch.h"
 
 using namespace b2f;

@@ -410,6 +410,7 @@ struct K0bParams {
     int64_t nslots; int nif, nblk, groups_per_slot, samples_per_frame; int64_t block_samples;
     uint8_t* compact; size_t compact_stride; int slot_bytes, in_nbit;   // 2-bit: missing slots get the zero-entry index
 };
+#ifdef B2F_API_TU        // non-template kernels are launched from b2f_api.cu only: compile them once
 static __global__ void k0b_finish_slots(const K0bParams p) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= p.nslots * p.nif) return;
@@ -430,6 +431,7 @@ static __global__ void k0b_finish_slots(const K0bParams p) {
     const int64_t b0 = s0 / p.block_samples, b1 = (s0 + p.samples_per_frame - 1) / p.block_samples;
     for (int64_t b = b0; b <= b1 && b < p.nblk; ++b) p.blkdirty[ifi * (int64_t)p.nblk + b] = 1;
 }
+#endif
 
 // ================================================================== stand-alone decode
 // compact payload (+ word mask) -> planar float samples out[2][nsamp].  HBM-bound expansion
@@ -835,6 +837,7 @@ __global__ void __launch_bounds__(kKAThreads, kKACtasPerSM) ka_column_pass(const
 // ================================================================== kernel 3b: eps
 // eps_c = conj(G[R-1-c] - G[(R-c) mod R]),  G = FFT_R(column sums): the one block-constant
 // term that separating the two real polarisations after the row pass needs.
+#ifdef B2F_API_TU        // non-template kernels are launched from b2f_api.cu only: compile them once
 static __global__ void ke_eps(const float2* __restrict__ colsum, float2* __restrict__ eps, int R) {
     extern __shared__ float2 ke_s[];
     const int lg = 31 - __clz(R);
@@ -860,6 +863,7 @@ static __global__ void ke_eps(const float2* __restrict__ colsum, float2* __restr
         eps[(int64_t)blockIdx.x * (R / 2) + t] = make_float2(g0.x - g1.x, -(g0.y - g1.y));
     }
 }
+#endif
 
 // ================================================================== kernel 3c+4: row pass
 // FFT_R across the R columns of every row m of the column-pass output, separation of the two
@@ -1495,6 +1499,7 @@ __device__ __forceinline__ void kg_column_inner(float2* sm, const KGParams& p, i
     }
 }
 
+#ifdef B2F_API_TU        // non-template kernels are launched from b2f_api.cu only: compile them once
 static __global__ void __launch_bounds__(256, 2) kg_column_pass(const KGParams p) {
     extern __shared__ __align__(16) uint8_t kg_smem[];
     float2* tw = reinterpret_cast<float2*>(kg_smem);                     // [L]
@@ -1544,6 +1549,7 @@ static __global__ void __launch_bounds__(256, 2) kg_column_pass(const KGParams p
         }
     }
 }
+#endif
 
 template <int RM>
 __device__ __forceinline__ void kg_row_inner(float2* sm, int lgR, int cnt) {
@@ -1685,6 +1691,7 @@ __global__ void __launch_bounds__(256, 2) kg_row_pass(const KGParams p) {
 // ================================================================== kernel 5a: statistics
 // mean / sigma per (IF, product, channel) over the first rescale interval, fp64 accumulators,
 // deterministic two-level reduction.
+#ifdef B2F_API_TU        // non-template kernels are launched from b2f_api.cu only: compile them once
 static __global__ void ks_partial(const float* __restrict__ F, int64_t F_if_stride, int64_t rows, int ncol,
                            double2* __restrict__ partial) {
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1700,6 +1707,8 @@ static __global__ void ks_partial(const float* __restrict__ F, int64_t F_if_stri
     }
     partial[((int64_t)ifi * nsplit + split) * ncol + col] = make_double2(s, ss);
 }
+#endif
+#ifdef B2F_API_TU        // non-template kernels are launched from b2f_api.cu only: compile them once
 static __global__ void ks_final(const double2* __restrict__ partial, int nsplit, int64_t rows, int ncol,
                          float* __restrict__ mean, float* __restrict__ scale) {
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1716,6 +1725,7 @@ static __global__ void ks_final(const double2* __restrict__ partial, int nsplit,
     mean[ifi * ncol + col] = (float)m;
     scale[ifi * ncol + col] = var > 0.0 ? (float)(1.0 / sqrt(var)) : 1.0f;
 }
+#endif
 
 // ================================================================== kernel 5b: requantise + flip + splice
 // One thread = 4 consecutive output channels of one output row.  The band flip of USB
@@ -1735,6 +1745,7 @@ __device__ __forceinline__ float quant(float y, float dscale, float dmean, float
     return fminf(fmaxf(floorf(fmaf(y, dscale, dmean + 0.5f)), 0.f), dmax);
 }
 
+#ifdef B2F_API_TU        // non-template kernels are launched from b2f_api.cu only: compile them once
 static __global__ void kq_quantise(const KQParams p) {
     const int64_t quads_per_row = p.out_row_elems / 4;
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -1786,5 +1797,6 @@ static __global__ void kq_quantise(const KQParams p) {
         *reinterpret_cast<float4*>(orow + 4 * (int64_t)j) = make_float4(y[0], y[1], y[2], y[3]);
     }
 }
+#endif
 
 }  // namespace b2f
