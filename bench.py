@@ -355,6 +355,10 @@ def main():
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
     col_ms, col_n = ktimes["column"]
     row_ms, row_n = ktimes["row"]
+    fused = ktimes.get("fused", (0.0, 0))[1] > 0
+    if fused:                      # one persistent kernel does both halves
+        col_ms, col_n = ktimes["fused"]
+        row_ms, row_n = ktimes["fused"]
     blocks_per_step = NIF * (nframes * 16000 // (2 * NCHAN * FREQ_RES))
     R, L = 2 * NCHAN, FREQ_RES
     # algorithmic bytes of the column pass per launch: 2-bit payload in + (the path's output share is
@@ -364,7 +368,7 @@ def main():
     launches_per_step = col_n / args.steps
     alg_bytes_launch = alg_bytes_step / launches_per_step
     achieved = alg_bytes_launch / (col_launch_ms * 1e-3) / 1e9
-    roofline = {"kernel": "ka_column_pass<2>", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+    roofline = {"kernel": "kf_fused<256,I>" if fused else "ka_column_pass<2>", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
                 "avg_launch_ms": col_launch_ms, "share_of_step": col_ms / args.steps / ms_step,
                 "note": "path is FP32-FFT bound (AI ~245 FLOP/B, SURVEY 8d); see roofline_fp32"}
@@ -378,8 +382,8 @@ def main():
     row_flops = blocks_per_step * L * 5.0 * R * 8
     roofline_fp32 = {
         "bound": "fp32", "unit": "TFLOP/s", "peak": fp32_peak, "peak_source": "measured live: FMA loop (b2f_fp32_peak)",
-        "column": {"achieved": col_flops / (col_ms / args.steps * 1e-3) / 1e12},
-        "row": {"achieved": row_flops / (row_ms / args.steps * 1e-3) / 1e12},
+        "column": {"achieved": (col_flops + (row_flops if fused else 0)) / (col_ms / args.steps * 1e-3) / 1e12},
+        "row": {"achieved": (row_flops + (col_flops if fused else 0)) / (row_ms / args.steps * 1e-3) / 1e12},
         "step": {"achieved": (col_flops + row_flops) / (ms_step * 1e-3) / 1e12},
         "convention": "5 N log2 N per complex FFT (SURVEY 8d): 17.04 MFLOP per 131072-sample dual-pol block",
     }

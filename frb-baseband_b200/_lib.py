@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libb2f.so")
 
 POL_P0, POL_P1, POL_I, POL_I2, POL_COHERENCE, POL_IQUV, POL_PPQQ = range(7)
 K_VALIDATE, K_COLUMN, K_EPS, K_ROW, K_STATS, K_QUANT, K_DECODE, K_DEDISP = range(8)
-KERNEL_NAMES = ["validate", "column", "eps", "row", "stats", "quant", "decode", "dedisp"]
+KERNEL_NAMES = ["validate", "column", "eps", "row", "stats", "quant", "decode", "dedisp", "fused", "tsum"]
 
 EINVAL, ECUDA, ENOMEM, ESTATE, EUNSUPPORTED = -1, -2, -3, -4, -5
 
@@ -103,6 +103,7 @@ SYMBOLS = {
     "b2f_mark": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "b2f_wait": (C.c_int, [C.c_void_p, C.c_int64]),
     "b2f_get_params": (C.c_int, [C.c_void_p, C.POINTER(Params)]),
+    "b2f_channeliser_path": (C.c_int, [C.c_void_p]),
     "b2f_sigproc_header": (C.c_int, [C.POINTER(FilHeaderC), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "b2f_run_scan": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.c_char_p, C.POINTER(ScanIO),
                                C.POINTER(ScanResult)]),

@@ -13,6 +13,7 @@
 #include <vector>
 
 #define B2F_API_TU
+#include "b2f_fused.cuh"
 #include "b2f_launch.h"
 
 using namespace b2f;
@@ -95,6 +96,15 @@ struct b2f_plan {
     float2* d_chirp = nullptr;
     uint8_t* d_out_stage[2]{};
     size_t out_stage_bytes[2]{};
+    // round-2 channeliser (b2f_fused.cuh): 0 = round-1 kernels, 1 = new kernels as two launches, 2 = fused
+    int path = 0;
+    uint8_t* d_tstream = nullptr;  size_t tstream_stride = 0;   // block-transposed index bytes
+    int* d_fillflag = nullptr;     size_t fillflag_stride = 0;
+    float* d_part = nullptr;       int64_t part_if_stride = 0;  // partial rows when tscrunch > 1024 / R
+    int Dp = 0;                    // rows a warp integrates itself
+    unsigned* d_fsync = nullptr;   // per-lane arrival counters + abort flag (last word)
+    int f_grid = 0, f_lanes = 0, f_nslot = 2;
+    bool f_aborted = false;
 
     // state
     int64_t rows_base = 0;         // rows already emitted and dropped from the front of F
@@ -284,7 +294,8 @@ void free_plan(b2f_plan* pl) {
             if (pl->ev_mark[i][k]) cudaEventDestroy(pl->ev_mark[i][k]);
     void* bufs[] = {pl->d_compact, pl->d_wmask, pl->d_fstat, pl->d_blkdirty, pl->d_inter, pl->d_colsum,
                     pl->d_eps, pl->d_F, pl->d_mean, pl->d_scale, pl->d_partial, pl->d_tab_g, pl->d_tab_h,
-                    pl->d_tab_w, pl->d_tab_r, pl->d_tab_beta, pl->d_counters, pl->d_sm_slots, pl->d_carry, pl->d_spec, pl->d_chirp, pl->d_tw_col, pl->d_tw_row};
+                    pl->d_tab_w, pl->d_tab_r, pl->d_tab_beta, pl->d_counters, pl->d_sm_slots, pl->d_carry, pl->d_spec, pl->d_chirp, pl->d_tw_col, pl->d_tw_row,
+                    pl->d_tstream, pl->d_fillflag, pl->d_part, pl->d_fsync};
     for (void* b : bufs)
         if (b) cudaFree(b);
     for (auto& t : pl->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
@@ -304,6 +315,8 @@ int init_state(b2f_plan* pl) {
     pl->carry_len = 0;
     pl->blocks_dirty = 0;
     pl->last_nblk = pl->last_nframes = 0;
+    pl->f_aborted = false;
+    if (pl->d_fsync) CU(cudaMemsetAsync(pl->d_fsync, 0, ((size_t)pl->f_lanes + 1) * FS_STRIDE * sizeof(unsigned), pl->stream));
     const int ncol = pl->nprod * pl->N;
     CU(cudaMemsetAsync(pl->d_counters, 0, C_COUNT * sizeof(unsigned long long), pl->stream));
     if (!pl->preset_stats) {
@@ -424,6 +437,119 @@ cudaError_t b2f_launch_kb(int R, int mode, const KBParams& p, int grid, cudaStre
     if (R == 256) return b2f_launch_kb_part2(R, mode, p, grid, st);
     return b2f_launch_kb_part1(R, mode, p, grid, st);
 }
+
+cudaError_t b2f_launch_kf(int R, int mode, const FParams& p, int grid, int cooperative, cudaStream_t st, int* occ) {
+    switch (R) {
+        case 16: return b2f_launch_kf_16(mode, p, grid, cooperative, st, occ);
+        case 32: return b2f_launch_kf_32(mode, p, grid, cooperative, st, occ);
+        case 64: return b2f_launch_kf_64(mode, p, grid, cooperative, st, occ);
+        case 128: return b2f_launch_kf_128(mode, p, grid, cooperative, st, occ);
+        case 256: return b2f_launch_kf_256(mode, p, grid, cooperative, st, occ);
+        case 512: return b2f_launch_kf_512(mode, p, grid, cooperative, st, occ);
+    }
+    return cudaErrorInvalidValue;
+}
+
+namespace {
+
+// the fused kernel gives up (instead of hanging the GPU) if a warp waits ~1 s for another one: surface that
+int check_fused_abort(b2f_plan* pl) {
+    if (pl->path != 2 || !pl->d_fsync) return 0;
+    if (!pl->f_aborted) {
+        unsigned flag = 0;
+        CU(cudaMemcpyAsync(&flag, pl->d_fsync + (size_t)pl->f_lanes * FS_STRIDE, sizeof(flag), cudaMemcpyDeviceToHost, pl->stream));
+        CU(cudaStreamSynchronize(pl->stream));
+        if (flag) pl->f_aborted = true;
+    }
+    if (pl->f_aborted) return fail(B2F_ECUDA, "fused channeliser: inter-warp wait timed out (results of this scan are invalid)");
+    return 0;
+}
+
+// Round-2 channeliser of one push: header check, transposing de-framer, then either the fused kernel or its two
+// halves as separate launches, then the sum of partial rows where tscrunch spans several warps' rows.
+int push_fused(b2f_plan* pl, const K0Params& k0, int64_t nframes, int64_t nblk) {
+    const int nif = pl->prm.nif;
+    const int64_t nbt = (int64_t)nif * nblk;
+    int rc = 0;
+    for (int i = 0; i < nif; ++i)
+        if (reinterpret_cast<uintptr_t>(k0.frames[i]) & 15) return fail(B2F_EINVAL, "frames must be 16-byte aligned");
+    K0HParams kh{};
+    K0TParams kt{};
+    for (int i = 0; i < nif; ++i) {
+        kh.frames[i] = k0.frames[i]; kt.frames[i] = k0.frames[i];
+        kh.base_sec[i] = k0.base_sec[i]; kh.base_fnum[i] = k0.base_fnum[i];
+    }
+    kh.fstat = pl->d_fstat; kh.fstat_stride = pl->fstat_stride; kh.counters = pl->d_counters;
+    kh.nframes = nframes; kh.frame_bytes = pl->prm.frame_bytes; kh.header_bytes = pl->prm.header_bytes;
+    kh.in_nbit = pl->prm.in_nbit; kh.fps = (int)pl->fps; kh.nif = nif;
+    kt.fstat = pl->d_fstat; kt.fstat_stride = pl->fstat_stride;
+    kt.fillflag = pl->d_fillflag; kt.fillflag_stride = pl->fillflag_stride;
+    kt.tstream = pl->d_tstream; kt.tstream_if_stride = pl->tstream_stride; kt.counters = pl->d_counters;
+    kt.nblk = (int)nblk; kt.nif = nif; kt.R = pl->R; kt.frame_bytes = pl->prm.frame_bytes;
+    kt.header_bytes = pl->prm.header_bytes; kt.payload_bytes = (int)pl->payload; kt.mask_faults = pl->prm.mask_faults;
+    CU(cudaMemsetAsync(pl->d_fillflag, 0, pl->fillflag_stride * nif * sizeof(int), pl->stream));
+    rc = timed(pl, B2F_K_VALIDATE, [&] {
+        const int64_t n = nframes * nif;
+        k0h_headers<<<(unsigned)((n + 255) / 256), 256, 0, pl->stream>>>(kh);
+        if (nblk > 0) {
+            const int sc = std::min(32, pl->R);
+            const int64_t units = nbt * (pl->R / sc);
+            const unsigned grid = (unsigned)std::min<int64_t>(units, (int64_t)pl->num_sms * 8);
+            if (sc == 32) k0t_transpose<32><<<grid, 256, 0, pl->stream>>>(kt);
+            else k0t_transpose<16><<<grid, 256, 0, pl->stream>>>(kt);
+        }
+    });
+    if (rc) return rc;
+    pl->launches++;                                   // two kernels in one timed region
+    if (nblk == 0) return 0;
+
+    FParams fp{};
+    fp.tstream = pl->d_tstream; fp.tstream_if_stride = pl->tstream_stride;
+    fp.ring = pl->d_inter; fp.colsum = pl->d_colsum; fp.eps = pl->d_eps;
+    fp.tab_h = pl->d_tab_h; fp.tab_w = pl->d_tab_w; fp.tab_beta = pl->d_tab_beta; fp.tab_r = pl->d_tab_r;
+    const bool direct = pl->Dp == pl->D;
+    fp.out = direct ? pl->d_F : pl->d_part;
+    fp.out_if_stride = direct ? pl->F_if_stride : pl->part_if_stride;
+    fp.out_row0 = direct ? pl->rows_off + pl->rows_held : 0;
+    fp.Dp = pl->Dp; fp.nblk = (int)nblk; fp.nif = nif;
+    fp.gb_begin = 0; fp.gb_end = nbt;
+    fp.sync = pl->d_fsync; fp.abort_flag = pl->d_fsync + (size_t)pl->f_lanes * FS_STRIDE;
+    fp.nslot = pl->f_nslot;
+    cudaError_t e = cudaSuccess;
+    if (pl->path == 2) {
+        CU(cudaMemsetAsync(pl->d_fsync, 0, (size_t)pl->f_lanes * FS_STRIDE * sizeof(unsigned), pl->stream));
+        fp.phase = 0;
+        rc = timed(pl, B2F_K_FUSED, [&] { e = b2f_launch_kf(pl->R, pl->prm.pol_mode, fp, pl->f_grid, 1, pl->stream, nullptr); });
+        if (rc) return rc;
+        if (e != cudaSuccess) return fail(B2F_ECUDA, std::string("fused channeliser launch: ") + cudaGetErrorString(e));
+    } else {
+        fp.phase = 1;
+        rc = timed(pl, B2F_K_COLUMN, [&] { e = b2f_launch_kf(pl->R, pl->prm.pol_mode, fp, pl->f_grid, 0, pl->stream, nullptr); });
+        if (rc) return rc;
+        if (e != cudaSuccess) return fail(B2F_ECUDA, std::string("column half launch: ") + cudaGetErrorString(e));
+        rc = timed(pl, B2F_K_EPS, [&] {
+            ke_eps<<<(unsigned)nbt, std::min(pl->R / 2, 512), pl->R * sizeof(float2), pl->stream>>>(pl->d_colsum, pl->d_eps, pl->R);
+        });
+        if (rc) return rc;
+        fp.phase = 2;
+        rc = timed(pl, B2F_K_ROW, [&] { e = b2f_launch_kf(pl->R, pl->prm.pol_mode, fp, pl->f_grid, 0, pl->stream, nullptr); });
+        if (rc) return rc;
+        if (e != cudaSuccess) return fail(B2F_ECUDA, std::string("row half launch: ") + cudaGetErrorString(e));
+    }
+    if (!direct) {
+        const int ncol = pl->nprod * pl->N;
+        const int64_t rows = nblk * kL / pl->D;
+        const int64_t n4 = rows * (ncol / 4);
+        rc = timed(pl, B2F_K_TSUM, [&] {
+            kt_sum_partials<<<dim3((unsigned)((n4 + 255) / 256), nif), 256, 0, pl->stream>>>(
+                pl->d_part, pl->part_if_stride, pl->d_F, pl->F_if_stride, pl->rows_off + pl->rows_held, rows, ncol, pl->D / pl->Dp);
+        });
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -562,6 +688,34 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, prm->device) != cudaSuccess) { free_plan(pl); return fail(B2F_ECUDA, "device properties"); }
     pl->num_sms = prop.multiProcessorCount;
+    {
+        // which channeliser: the fused kernel wherever it applies (2-bit split streams, frames in order, 512-point
+        // columns, no dedispersion); B2F_PATH=legacy|split|fused overrides (split = the new kernels as two launches)
+        const bool eligible = !generic && !dedisp && prm->in_nbit == 2 && W == 0 && prm->frame_time_mode == B2F_FRAMES_POSITIONAL &&
+                              payload % 16 == 0 && prm->frame_bytes % 16 == 0 && prop.cooperativeLaunch;
+        const char* e = getenv("B2F_PATH");
+        int want = 2;
+        if (e && !strcmp(e, "legacy")) want = 0;
+        else if (e && !strcmp(e, "split")) want = 1;
+        pl->path = eligible ? want : 0;
+        if (pl->path) {
+            int occ = 0;
+            FParams dummy{};
+            if (b2f_launch_kf(R, prm->pol_mode, dummy, 0, 0, nullptr, &occ) != cudaSuccess || occ < 1) {
+                cudaGetLastError();
+                pl->path = 0;
+            } else {
+                const int npair = R / 2;
+                const int cpl = std::max(1, npair / kFWarps);              // CTAs per lane (one block per lane and round)
+                pl->f_grid = std::max(1, (std::min(occ, 1) * pl->num_sms) / cpl) * cpl;
+                if (pl->f_grid > occ * pl->num_sms) pl->path = 0;          // fewer SMs than one lane needs
+                pl->f_lanes = pl->f_grid * kFWarps / npair;
+                const char* ns = getenv("B2F_RING_SLOTS");
+                pl->f_nslot = ns ? std::max(2, std::min(4, atoi(ns))) : 2;
+                pl->Dp = std::min(D, 1024 / R);
+            }
+        }
+    }
 
     auto bail = [&](int rc) { free_plan(pl); return rc; };
 #define CUB(x)                                                                                      \
@@ -593,11 +747,25 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
     pl->compact_stride = (size_t)((pl->chunk_frames * (int64_t)pl->slot_bytes + (pl->carry_mode ? pl->M : 0) + 255) / 256 * 256);
     pl->wmask_stride = (size_t)((pl->chunk_frames * pl->groups_per_slot + 255) / 256 * 256);
     pl->fstat_stride = (size_t)((pl->chunk_frames + 255) / 256 * 256);
-    CUB(cudaMalloc(&pl->d_compact, pl->compact_stride * nif));
-    CUB(cudaMalloc(&pl->d_wmask, pl->wmask_stride * nif));
+    if (!pl->path) {
+        CUB(cudaMalloc(&pl->d_compact, pl->compact_stride * nif));
+        CUB(cudaMalloc(&pl->d_wmask, pl->wmask_stride * nif));
+        CUB(cudaMalloc(&pl->d_blkdirty, (size_t)nbt));
+    } else {
+        pl->tstream_stride = (size_t)((pl->chunk_blocks * pl->M + 255) / 256 * 256);
+        pl->fillflag_stride = (size_t)((pl->chunk_frames + 63) / 64 * 64);
+        CUB(cudaMalloc(&pl->d_tstream, pl->tstream_stride * nif));
+        CUB(cudaMalloc(&pl->d_fillflag, pl->fillflag_stride * nif * sizeof(int)));
+        CUB(cudaMalloc(&pl->d_fsync, ((size_t)pl->f_lanes + 1) * FS_STRIDE * sizeof(unsigned)));
+        CUB(cudaMemset(pl->d_fsync, 0, ((size_t)pl->f_lanes + 1) * FS_STRIDE * sizeof(unsigned)));
+        if (pl->Dp < D) {
+            pl->part_if_stride = pl->chunk_blocks * (L / pl->Dp) * nprod * pl->N;
+            CUB(cudaMalloc(&pl->d_part, (size_t)pl->part_if_stride * nif * sizeof(float)));
+        }
+    }
     CUB(cudaMalloc(&pl->d_fstat, pl->fstat_stride * nif));
-    CUB(cudaMalloc(&pl->d_blkdirty, (size_t)nbt));
-    const int64_t inter_blocks = pl->batch_blocks > 0 ? std::min<int64_t>(pl->batch_blocks, nbt) : nbt;
+    int64_t inter_blocks = pl->batch_blocks > 0 ? std::min<int64_t>(pl->batch_blocks, nbt) : nbt;
+    if (pl->path == 2) inter_blocks = (int64_t)pl->f_lanes * pl->f_nslot;         // the ring: it lives in L2
     CUB(cudaMalloc(&pl->d_inter, (size_t)inter_blocks * L * R * sizeof(float2)));
     CUB(cudaMalloc(&pl->d_colsum, (size_t)nbt * R * sizeof(float2)));
     CUB(cudaMalloc(&pl->d_eps, (size_t)nbt * pl->N * sizeof(float2)));
@@ -761,9 +929,23 @@ int b2f_push(b2f_plan* pl, const void* const* frames, int64_t nframes, int on_de
             CU(cudaMemcpyAsync(pl->d_compact + i * pl->compact_stride, pl->d_carry + (size_t)i * pl->M, (size_t)pl->carry_len,
                                cudaMemcpyDeviceToDevice, pl->stream));
     }
+    int rc = 0;
+    if (pl->path) {
+        rc = push_fused(pl, k0, nframes, nblk);
+        if (rc) return rc;
+        if (!on_device) {
+            CU(cudaEventRecord(pl->ev_stage_free[pl->stage_idx], pl->stream));
+            pl->stage_idx ^= 1;
+        }
+        pl->rows_held += rows;
+        pl->rows_produced += rows;
+        pl->frames_pushed += nframes;
+        pl->last_nblk = nblk;
+        pl->last_nframes = nframes;
+        return 0;
+    }
     CU(cudaMemsetAsync(pl->d_fstat, 0, pl->fstat_stride * nif, pl->stream));
     if (nblk > 0) CU(cudaMemsetAsync(pl->d_blkdirty, 0, (size_t)nif * nblk, pl->stream));
-    int rc = 0;
     if (pl->prm.raw_word_bits) {                      // corner turn + validation in one pass over the raw stream
         K0RParams kr{};
         kr.frames = k0.frames[0];
@@ -952,7 +1134,11 @@ static int pull_impl(b2f_plan* pl, void* out, int64_t max_rows, int out_on_devic
         CU(cudaMemcpyAsync(out, dst, bytes, cudaMemcpyDeviceToHost, pl->d2h_stream));
         CU(cudaEventRecord(pl->ev_out_free[oi], pl->d2h_stream));
         pl->out_idx ^= 1;
-        if (out_on_device == 0) CU(cudaStreamSynchronize(pl->d2h_stream));
+        if (out_on_device == 0) {
+            CU(cudaStreamSynchronize(pl->d2h_stream));
+            int rc2 = check_fused_abort(pl);
+            if (rc2) return rc2;
+        }
     }
     pl->rows_held -= n;
     pl->rows_emitted += n;
@@ -967,7 +1153,7 @@ int b2f_sync(b2f_plan* pl) {
     CU(cudaStreamSynchronize(pl->copy_stream));
     CU(cudaStreamSynchronize(pl->stream));
     CU(cudaStreamSynchronize(pl->d2h_stream));
-    return 0;
+    return check_fused_abort(pl);
 }
 
 int b2f_mark(b2f_plan* pl, int64_t* ticket) {
@@ -994,6 +1180,8 @@ int b2f_wait(b2f_plan* pl, int64_t ticket) {
     return 0;
 }
 
+int b2f_channeliser_path(const b2f_plan* pl) { return pl ? pl->path : B2F_EINVAL; }
+
 int b2f_get_params(const b2f_plan* pl, b2f_params* out) {
     if (!pl || !out) return fail(B2F_EINVAL, "null argument");
     *out = pl->prm;
@@ -1006,6 +1194,7 @@ int b2f_get_counters(b2f_plan* pl, b2f_counters* c) {
     CU(cudaSetDevice(pl->prm.device));
     unsigned long long h[C_COUNT];
     CU(cudaStreamSynchronize(pl->stream));
+    { int rc = check_fused_abort(pl); if (rc) return rc; }
     CU(cudaMemcpy(h, pl->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
     c->frames_ok = h[C_OK]; c->frames_invalid = h[C_INVALID]; c->frames_with_fill = h[C_FILLFRAMES];
     c->fill_words = h[C_FILLWORDS]; c->frames_dropped = h[C_DROPPED]; c->frames_misplaced = h[C_MISPLACED];
@@ -1204,12 +1393,16 @@ int b2f_debug_copy(b2f_plan* pl, int which, void* dst, size_t nbytes, size_t* ne
     const void* src = nullptr;
     size_t n = 0;
     switch (which) {
-        case 0: src = pl->d_compact; n = pl->compact_stride * nif; break;
+        case 0:
+            if (pl->path) { src = pl->d_tstream; n = pl->tstream_stride * nif; }
+            else { src = pl->d_compact; n = pl->compact_stride * nif; }
+            break;
         case 1: src = pl->d_wmask; n = pl->wmask_stride * nif; break;
         case 2: src = pl->d_fstat; n = pl->fstat_stride * nif; break;
         case 3: src = pl->d_blkdirty; n = (size_t)nbt; break;
         case 4: {       // intermediate of the last sub-batch only (whole push when batching is off)
-            const int64_t nbk = pl->batch_blocks > 0 ? std::min<int64_t>(pl->batch_blocks, nbt) : nbt;
+            int64_t nbk = pl->batch_blocks > 0 ? std::min<int64_t>(pl->batch_blocks, nbt) : nbt;
+            if (pl->path == 2) nbk = (int64_t)pl->f_lanes * pl->f_nslot;     // the ring ([pair][512][2] slots), not the whole push
             src = pl->d_inter; n = (size_t)nbk * pl->L * pl->R * sizeof(float2); break;
         }
         case 5: src = pl->d_colsum; n = (size_t)nbt * pl->R * sizeof(float2); break;
@@ -1217,6 +1410,7 @@ int b2f_debug_copy(b2f_plan* pl, int which, void* dst, size_t nbytes, size_t* ne
         case 7: src = pl->d_F; n = (size_t)pl->F_if_stride * nif * sizeof(float); break;
         default: return fail(B2F_EINVAL, "which");
     }
+    if (!src) return fail(B2F_EINVAL, "this buffer is not used by the plan's channeliser path");
     if (needed) *needed = n;
     if (!dst) return 0;
     CU(cudaMemcpy(dst, src, std::min(n, nbytes), cudaMemcpyDeviceToHost));

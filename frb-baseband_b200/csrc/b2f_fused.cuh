@@ -1,0 +1,646 @@
+// Round-2 channeliser: warp-autonomous column pass fused with the row pass through an L2-resident ring.
+//
+// What it replaces: ka_column_pass + ke_eps + kb_row_pass of b2f_kernels.cuh for 2-bit input without
+// dedispersion (the arithmetic of `digifil -F<nchan>:512 -d<n> -t<D>`, /root/reference/process_vdif.py:156-176).
+// Same algebra, different mapping onto the machine:
+//
+//   * one WARP owns two neighbouring columns of a block: lane = 2 * item + col, item = 0..15.  The two
+//     shared-memory exchanges of the 512-point FFT / diagonal / inverse FFT happen inside the warp
+//     (__syncwarp only), so no block barrier exists anywhere and the 16 warps of an SM drift into
+//     different phases: one warp's exchanges hide under another's butterflies.
+//   * the exchange buffer is a padded 16 x 17 matrix of float4 per column: column access (P1 write,
+//     P3 read) and row access (middle section) are both bank-conflict free with base + immediate
+//     addresses.  The column-dependent twiddle table is 2 columns wide, i.e. a broadcast.
+//   * input is the block-transposed index stream k0t_transpose writes: every lane gets its 32 samples
+//     with two 128-bit loads, prefetched one work item ahead (no shared-memory staging, no cp.async).
+//   * the column result goes to a ring of 1 MiB block slots that stays in L2 ([pair][row][2] float2, so a
+//     warp's 8 KiB are contiguous); the warps of the same "lane" (R/2 warps = one block) then run that
+//     block's rows one round later, reading 16-byte pieces with cp.async.  Per-lane arrival counters
+//     (fence + relaxed atomic / acquire load) order the two; the [blk][512][R] intermediate never
+//     reaches HBM.
+//   * eps (the block-constant term) is computed by one rotating warp per lane and round.
+//   * every warp integrates only its own 1024/R rows; if tscrunch spans more, kt_sum_partials adds the
+//     partial rows in a fixed order (deterministic; no float atomics).
+//
+// phase 1 / phase 2 run the two halves as separate launches over a full-size intermediate (same device
+// functions): kept as a debugging and profiling aid (B2F_PATH=split).
+#pragma once
+#include "b2f_kernels.cuh"
+
+namespace b2f {
+
+constexpr int kFWarps = 16;                 // one 512-thread CTA per SM: 16 autonomous warps, 128 registers each
+constexpr int kFThreads = kFWarps * 32;
+constexpr unsigned kFSpinLimit = 1u << 22;  // polls (with nanosleep) before a waiting warp gives up: ~1 s
+
+enum FSync { FS_COL = 0, FS_ROW = 1, FS_EPS = 2, FS_STRIDE = 32 };   // counters of one lane, 128 bytes apart
+
+template <int R> struct FShape;
+template <> struct FShape<16>  { static constexpr int TR = 4,  PT = 4;  };
+template <> struct FShape<32>  { static constexpr int TR = 4,  PT = 8;  };
+template <> struct FShape<64>  { static constexpr int TR = 8,  PT = 8;  };
+template <> struct FShape<128> { static constexpr int TR = 8,  PT = 16; };
+template <> struct FShape<256> { static constexpr int TR = 16, PT = 16; };
+template <> struct FShape<512> { static constexpr int TR = 16, PT = 32; };
+
+template <int R>
+struct FGeo {
+    static constexpr int TR = FShape<R>::TR, PT = FShape<R>::PT;
+    static constexpr int N = R / 2, NPAIR = R / 2;
+    static constexpr int RPW = 1024 / R;                       // rows of a block one warp transforms
+    static constexpr int RW = 32 / TR;                         // rows per warp pass
+    static constexpr int NPASS = RPW / RW;
+    static constexpr int kPitch = R * 8 + (TR < 16 ? TR * 8 : 0);     // bytes between rows of the row tile
+    static constexpr int kXch = RW * TR * (PT + 1) * 8;               // transposition buffer of one pass
+    static constexpr int kRowBuf = RPW * kPitch + (kXch > RW * kPitch ? kXch - RW * kPitch : 0);
+    static constexpr int kColBuf = 16 * 34 * 16;                      // 16 x 17 float4 per column, two columns
+    static constexpr int kWarpBuf = ((kRowBuf > kColBuf ? kRowBuf : kColBuf) + 127) / 128 * 128;
+    static constexpr int kOffW4 = 0;                                  // [8][32] float4  W_512^(l q), q pairs
+    static constexpr int kOffLut = kOffW4 + 8 * 32 * 16;              // 17 x float2 (+ pad)
+    static constexpr int kOffTw = kOffLut + 256;                      // [PT][TR] float2 W_R^(s q)
+    static constexpr int kOffH = kOffTw + R * 8;                      // per warp [16][2] float4 (h^p, h^(p+16))
+    static constexpr int kOffBuf = (kOffH + kFWarps * 512 + 127) / 128 * 128;
+    static constexpr size_t kBytes = (size_t)kOffBuf + (size_t)kFWarps * kWarpBuf;
+};
+
+struct FParams {
+    const uint8_t* tstream;        // [if][blk][pair][half][lane][16] index bytes (k0t_transpose)
+    size_t tstream_if_stride;
+    float2* ring;                  // fused: [2 * lanes][M]; split: [blocks of the launch][M]; slot layout [pair][512][2]
+    float2* colsum;                // [nif*nblk][R]
+    float2* eps;                   // [nif*nblk][R/2]
+    const float2 *tab_h, *tab_w, *tab_beta, *tab_r;
+    float* out;                    // F (Dp == D) or the partial-row buffer
+    int64_t out_if_stride;         // floats between IFs
+    int64_t out_row0;              // first row of this push inside `out`, in units of Dp input rows
+    int Dp;                        // rows integrated per output row here: min(tscrunch, 1024 / R)
+    int nblk, nif;
+    int64_t gb_begin, gb_end;
+    unsigned* sync;                // [lanes][FS_STRIDE]
+    unsigned* abort_flag;
+    int phase;                     // 0 fused, 1 column halves only, 2 row halves only
+    int nslot;                     // ring slots per lane (fused): 2 or 3
+};
+
+// ------------------------------------------------------------------ inter-warp ordering through L2
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// the whole warp calls; true when *ctr >= target was observed (acquire), false on abort / timeout
+__device__ __forceinline__ bool warp_wait_ge(const unsigned* ctr, unsigned target, unsigned* abort_flag, int lane) {
+    int ok = 1;
+    if (lane == 0) {
+        unsigned spins = 0;
+        while (ld_acquire_u32(ctr) < target) {
+            if (++spins > kFSpinLimit || ((spins & 63u) == 0 && ld_relaxed_u32(abort_flag) != 0)) {
+                atomicExch(abort_flag, 1u);
+                ok = 0;
+                break;
+            }
+            __nanosleep(spins < 64 ? 32 : 256);
+        }
+    }
+    ok = __shfl_sync(0xffffffffu, ok, 0);
+    return ok != 0;
+}
+// all lanes have finished their global stores / loads; one release-ordered increment for the warp
+__device__ __forceinline__ void warp_arrive(unsigned* ctr, int lane) {
+    __syncwarp();
+    if (lane == 0) {
+        __threadfence();
+        atomicAdd(ctr, 1u);
+    }
+}
+__device__ __forceinline__ float2 ldcg_f2(const float2* p) {
+    float2 v;
+    asm volatile("ld.global.cg.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 ldg_stream16(const void* p) {       // read-once input: do not keep it in L1
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+// ------------------------------------------------------------------ column half of one work item
+// lane = 2 * item + col.  xb: this warp's exchange buffer, E[a][b] of column c at float4 index a * 34 + 2 b + c.
+// dst: this warp's 8 KiB of the block slot, float2 index 2 * row + col.
+template <int R>
+__device__ __forceinline__ void f_col_front(const uint4 rawA, const uint4 rawB, float4* xb, const float4* s_w4,
+                                            const uint8_t* s_lut, const float4* s_h4w, const int lane, float2* colsum_n1) {
+    const int item = lane >> 1, col = lane & 1;
+    // ---- P1: decode, FFT_16 over r (n2 = 32 r + l) for l = item (A) and item + 16 (B), twiddle W_512^(l q)
+    {
+        float2 vA[16], vB[16];
+        const uint32_t wa[4] = {rawA.x, rawA.y, rawA.z, rawA.w}, wb[4] = {rawB.x, rawB.y, rawB.z, rawB.w};
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const uint32_t ia = __byte_perm(wa[r >> 2], 0u, 0x4440 + (r & 3));
+            const uint32_t ib = __byte_perm(wb[r >> 2], 0u, 0x4440 + (r & 3));
+            vA[r] = *reinterpret_cast<const float2*>(s_lut + ia);
+            vB[r] = *reinterpret_cast<const float2*>(s_lut + ib);
+        }
+        fft_inreg<16, false>(vA);
+        fft_inreg<16, false>(vB);
+#pragma unroll
+        for (int qp = 0; qp < 8; ++qp) {
+            const float4 ta = s_w4[qp * 32 + item], tb = s_w4[qp * 32 + item + 16];
+            if (qp) vA[2 * qp] = cmul(vA[2 * qp], make_float2(ta.x, ta.y));
+            vA[2 * qp + 1] = cmul(vA[2 * qp + 1], make_float2(ta.z, ta.w));
+            if (qp) vB[2 * qp] = cmul(vB[2 * qp], make_float2(tb.x, tb.y));
+            vB[2 * qp + 1] = cmul(vB[2 * qp + 1], make_float2(tb.z, tb.w));
+        }
+#pragma unroll
+        for (int q = 0; q < 16; ++q) xb[q * 34 + lane] = make_float4(vA[q].x, vA[q].y, vB[q].x, vB[q].y);
+    }
+    __syncwarp();
+    // ---- middle: FFT_32 over l -> p;  * W_M^(16 p n1);  IFFT_32 over p -> m1   (thread q = item, in place on row q)
+    {
+        float2 u[32];
+        float4* row = xb + item * 34 + col;
+#pragma unroll
+        for (int l = 0; l < 16; ++l) {
+            const float4 t = row[2 * l];
+            u[l] = make_float2(t.x, t.y);
+            u[l + 16] = make_float2(t.z, t.w);
+        }
+        fft_inreg<32, false>(u);
+        if (item == 0) *colsum_n1 = u[0];                       // A[k2 = 0]: column sum
+#pragma unroll
+        for (int pp = 0; pp < 16; ++pp) {
+            const float4 h = s_h4w[pp * 2 + col];
+            if (pp) u[pp] = cmul(u[pp], make_float2(h.x, h.y));
+            u[pp + 16] = cmul(u[pp + 16], make_float2(h.z, h.w));
+        }
+        fft_inreg<32, true>(u);
+#pragma unroll
+        for (int m = 0; m < 16; ++m) row[2 * m] = make_float4(u[m].x, u[m].y, u[m + 16].x, u[m + 16].y);
+    }
+    __syncwarp();
+}
+
+// ---- P3: * beta^q (W_M^(q n1) conj W_512^(q m1));  IFFT_16 over q -> m2;  rows m1 + 32 m2, m1 = item, item + 16
+__device__ __forceinline__ void f_col_back(const float4* xb, const float2 (&betaS)[4], const int lane, float2* dst) {
+    {
+        float2 pw[16];
+        cpowers15(betaS, pw);
+        float2 yA[16], yB[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const float4 t = xb[q * 34 + lane];
+            yA[q] = make_float2(t.x, t.y);
+            yB[q] = make_float2(t.z, t.w);
+        }
+#pragma unroll
+        for (int q = 1; q < 16; ++q) {
+            yA[q] = cmul(yA[q], pw[q]);
+            const float2 cb = make_float2(cos64(2 * q), sin64(2 * q));      // conj(W_32^q): m1 + 16
+            yB[q] = cmul(cmul(yB[q], cb), pw[q]);
+        }
+        fft_inreg<16, true>(yA);
+        fft_inreg<16, true>(yB);
+#pragma unroll
+        for (int m2 = 0; m2 < 16; ++m2) {
+            dst[64 * m2 + lane] = yA[m2];                       // row item + 32 m2
+            dst[64 * m2 + 32 + lane] = yB[m2];                  // row item + 16 + 32 m2
+        }
+    }
+}
+
+// ------------------------------------------------------------------ row half
+// FFT_R of RW rows held in shared memory (TR lanes per row, PT points per lane): radix PT in registers,
+// transposition through `myx` (which may overwrite the rows once everybody has loaded them), radix TR.
+// z[j][t] = Z_c at c = (s + TR j) + PT t.
+template <int TR, int PT>
+__device__ __forceinline__ void f_row_fft(const float2* tile, float2* myx, const float2* s_tw, const int s,
+                                          float2 (&z)[PT / TR][TR]) {
+    constexpr int QPT = PT / TR;
+    float2 v[PT];
+#pragma unroll
+    for (int a = 0; a < PT; ++a) v[a] = tile[s + TR * a];
+    fft_inreg<PT, false>(v);
+#pragma unroll
+    for (int q = 1; q < PT; ++q) v[q] = cmul(v[q], s_tw[q * TR + s]);
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < PT; ++q) myx[s * (PT + 1) + q] = v[q];
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < QPT; ++j)
+#pragma unroll
+        for (int t = 0; t < TR; ++t) z[j][t] = myx[t * (PT + 1) + s + TR * j];
+#pragma unroll
+    for (int j = 0; j < QPT; ++j) fft_inreg<TR, false>(z[j]);
+}
+
+// 16-byte pieces of rows [m0, m0 + RPW) of a block slot -> this warp's row tile
+template <int R>
+__device__ __forceinline__ void f_row_load(const float2* slot, const int m0, uint8_t* wbuf, const int lane) {
+    using G = FGeo<R>;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {                              // RPW * NPAIR = 512 pieces
+        const int idx = lane + 32 * k;
+        const int r = idx % G::RPW, pp = idx / G::RPW;
+        cp_async16(wbuf + r * G::kPitch + pp * 16, slot + ((int64_t)pp * kL + m0 + r) * 2);
+    }
+    cp_async_commit();
+}
+
+// transform, un-mix, detect and integrate the RPW rows in the tile; write whole (partial) output rows
+template <int R, int MODE>
+__device__ __forceinline__ void f_row_compute(const FParams& p, uint8_t* wbuf, const float2* s_tw, const float2* eps_blk,
+                                              const int64_t gb, const int m0, const int lane) {
+    using G = FGeo<R>;
+    constexpr int TR = G::TR, PT = G::PT, RW = G::RW, QPT = PT / TR, HP = TR / 2, N = G::N;
+    constexpr int NPROD = nprod_of_mode(MODE);
+    const int s = lane % TR, rsw = lane / TR;
+    const int Dp = p.Dp;
+    const int GW = Dp > RW ? Dp : RW;               // rows per integration group inside this task
+    const int ppg = GW / RW;                        // passes per group
+    const int nout = GW / Dp;                       // output rows per group (> 1 only if Dp < RW)
+    const int spo = RW / nout;                      // row slots that add up to one output row
+    float2 e[QPT][HP];
+#pragma unroll
+    for (int j = 0; j < QPT; ++j)
+#pragma unroll
+        for (int pp = 0; pp < HP; ++pp) e[j][pp] = ldcg_f2(eps_blk + (s + TR * j) + PT * pp);
+    const int ifi = (int)(gb / p.nblk);
+    const int64_t blk = gb % p.nblk;
+    float acc[QPT][HP][NPROD];
+    // passes run from the last rows to the first: the transposition buffer of pass k may then spill into the
+    // (already consumed) rows of pass k + 1
+#pragma unroll 1
+    for (int k = G::NPASS - 1; k >= 0; --k) {
+        if (k % ppg == ppg - 1) {
+#pragma unroll
+            for (int j = 0; j < QPT; ++j)
+#pragma unroll
+                for (int pp = 0; pp < HP; ++pp)
+#pragma unroll
+                    for (int c = 0; c < NPROD; ++c) acc[j][pp][c] = 0.f;
+        }
+        float2 z[QPT][TR];
+        f_row_fft<TR, PT>(reinterpret_cast<const float2*>(wbuf + (k * RW + rsw) * G::kPitch),
+                          reinterpret_cast<float2*>(wbuf + k * RW * G::kPitch) + rsw * TR * (PT + 1), s_tw, s, z);
+        // mirror channel R-1-c lives in lane s ^ (TR-1), register [QPT-1-j][TR-1-pp]
+#pragma unroll
+        for (int j = 0; j < QPT; ++j)
+#pragma unroll
+            for (int pp = 0; pp < HP; ++pp) {
+                const float2 a = z[j][pp];
+                const float2 bs = z[QPT - 1 - j][TR - 1 - pp];
+                const float bx = __shfl_xor_sync(0xffffffffu, bs.x, TR - 1);
+                const float by = __shfl_xor_sync(0xffffffffu, bs.y, TR - 1);
+                const float2 bp = make_float2(bx - e[j][pp].x, -by - e[j][pp].y);
+                if (MODE == B2F_POL_I) {
+                    float t = a.x * a.x;
+                    t = fmaf(a.y, a.y, t);
+                    t = fmaf(bp.x, bp.x, t);
+                    t = fmaf(bp.y, bp.y, t);
+                    acc[j][pp][0] = fmaf(0.5f, t, acc[j][pp][0]);
+                } else {
+                    detect_acc<MODE>(acc[j][pp], make_float2(a.x + bp.x, a.y + bp.y), make_float2(a.x - bp.x, a.y - bp.y));
+                }
+            }
+        if (k % ppg == 0) {
+            for (int m = TR; m < TR * spo; m <<= 1) {
+#pragma unroll
+                for (int j = 0; j < QPT; ++j)
+#pragma unroll
+                    for (int pp = 0; pp < HP; ++pp)
+#pragma unroll
+                        for (int c = 0; c < NPROD; ++c) acc[j][pp][c] += __shfl_xor_sync(0xffffffffu, acc[j][pp][c], m);
+            }
+            if (rsw % spo == 0) {
+                const int g0 = m0 + (k / ppg) * GW;             // first row of this group inside the block
+                const int64_t t = p.out_row0 + (blk * kL + g0) / Dp + rsw / spo;
+                float* dst = p.out + ifi * p.out_if_stride + t * (int64_t)(NPROD * N);
+#pragma unroll
+                for (int c = 0; c < NPROD; ++c)
+#pragma unroll
+                    for (int j = 0; j < QPT; ++j)
+#pragma unroll
+                        for (int pp = 0; pp < HP; ++pp) dst[c * N + (s + TR * j) + PT * pp] = acc[j][pp][c];
+            }
+        }
+    }
+}
+
+// eps_c = conj(G[R-1-c] - G[(R-c) mod R]), G = FFT_R(column sums), by one warp
+template <int R>
+__device__ __forceinline__ void f_eps(const float2* colsum_blk, float2* eps_blk, uint8_t* wbuf, const float2* s_tw,
+                                      const int lane) {
+    using G = FGeo<R>;
+    constexpr int TR = G::TR, PT = G::PT, RW = G::RW, QPT = PT / TR;
+    const int s = lane % TR, rsw = lane / TR;
+    for (int i = lane; i < R; i += 32) {
+        const float2 v = ldcg_f2(colsum_blk + i);
+#pragma unroll
+        for (int rs = 0; rs < RW; ++rs) reinterpret_cast<float2*>(wbuf + rs * G::kPitch)[i] = v;
+    }
+    __syncwarp();
+    float2 z[QPT][TR];
+    f_row_fft<TR, PT>(reinterpret_cast<const float2*>(wbuf + rsw * G::kPitch),
+                      reinterpret_cast<float2*>(wbuf) + rsw * TR * (PT + 1), s_tw, s, z);
+    __syncwarp();
+    float2* Gs = reinterpret_cast<float2*>(wbuf);
+    if (rsw == 0) {
+#pragma unroll
+        for (int j = 0; j < QPT; ++j)
+#pragma unroll
+            for (int t = 0; t < TR; ++t) Gs[(s + TR * j) + PT * t] = z[j][t];
+    }
+    __syncwarp();
+    for (int c = lane; c < R / 2; c += 32) {
+        const float2 g0 = Gs[R - 1 - c], g1 = Gs[(R - c) & (R - 1)];
+        eps_blk[c] = make_float2(g0.x - g1.x, -(g0.y - g1.y));
+    }
+    __syncwarp();
+}
+
+template <int R, int MODE>
+__global__ void __launch_bounds__(kFThreads, 1) kf_fused(const FParams p) {
+    using G = FGeo<R>;
+    extern __shared__ __align__(128) uint8_t kf_smem[];
+    float4* s_w4 = reinterpret_cast<float4*>(kf_smem + G::kOffW4);
+    uint8_t* s_lut = kf_smem + G::kOffLut;
+    float2* s_tw = reinterpret_cast<float2*>(kf_smem + G::kOffTw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float4* s_h4w = reinterpret_cast<float4*>(kf_smem + G::kOffH + warp * 512);
+    uint8_t* wbuf = kf_smem + G::kOffBuf + (size_t)warp * G::kWarpBuf;
+
+    // ---- tables shared by the CTA
+    for (int i = tid; i < 8 * 32; i += kFThreads) {
+        const int qp = i >> 5, l = i & 31;
+        const float2 w0 = p.tab_w[l * 16 + 2 * qp], w1 = p.tab_w[l * 16 + 2 * qp + 1];
+        s_w4[i] = make_float4(w0.x, w0.y, w1.x, w1.y);
+    }
+    if (tid < 32) {
+        const int c0 = tid & 3, c1 = (tid >> 2) & 3;
+        const float m0 = (c0 == 0 || c0 == 3) ? kLevHi : kLevLo;
+        const float m1 = (c1 == 0 || c1 == 3) ? kLevHi : kLevLo;
+        if (tid <= 16)
+            reinterpret_cast<float2*>(s_lut)[tid] = tid < 16 ? make_float2((c0 & 2) ? m0 : -m0, (c1 & 2) ? m1 : -m1) : make_float2(0.f, 0.f);
+    }
+    for (int i = tid; i < G::PT * G::TR; i += kFThreads) s_tw[i] = p.tab_r[i];
+
+    // ---- this warp's static place: lane `lam` (one block per round), column pair `pr`
+    const int gw = blockIdx.x * kFWarps + warp;
+    const int nl = (int)(gridDim.x * kFWarps) / G::NPAIR;
+    const int lam = gw / G::NPAIR, pr = gw % G::NPAIR;
+    const int item = lane >> 1, col = lane & 1;
+    const int n1 = 2 * pr + col;
+    {
+        const int pp = lane >> 1;                                // 16 entries x 2 columns
+        const float2 h0 = p.tab_h[pp * R + 2 * pr + (lane & 1)], h1 = p.tab_h[(pp + 16) * R + 2 * pr + (lane & 1)];
+        s_h4w[pp * 2 + (lane & 1)] = make_float4(h0.x, h0.y, h1.x, h1.y);
+    }
+    float2 betaS[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) betaS[k] = p.tab_beta[(size_t)(item * 4 + k) * R + n1];
+    __syncthreads();
+    if (lam >= nl) return;
+
+    const int64_t nb = p.gb_end - p.gb_begin;
+    const int64_t M = (int64_t)R * kL;
+    unsigned* sy = p.sync + (size_t)lam * FS_STRIDE;
+    const int phase = p.phase, ns = p.nslot;
+
+    auto raw_ptr = [&](int64_t lb) {
+        const int64_t gb = p.gb_begin + lb;
+        const int ifi = (int)(gb / p.nblk);
+        const int64_t blk = gb % p.nblk;
+        return p.tstream + ifi * p.tstream_if_stride + blk * M + (size_t)pr * 1024 + (size_t)lane * 16;
+    };
+    uint4 rawA = make_uint4(0, 0, 0, 0), rawB = rawA;
+    if (phase != 2 && lam < nb) {
+        const uint8_t* q = raw_ptr(lam);
+        rawA = ldg_stream16(q);
+        rawB = ldg_stream16(q + 512);
+    }
+
+#pragma unroll 1
+    for (int i = 0;; ++i) {
+        const int64_t lbc = (int64_t)i * nl + lam;                         // block whose columns run this round
+        const int64_t lbr = phase == 2 ? lbc : lbc - nl;                   // block whose rows run this round
+        const bool vc = phase != 2 && lbc < nb;
+        const bool vr = phase != 1 && lbr >= 0 && lbr < nb;
+        if (!vc && !vr) break;
+        __syncwarp();
+        // ---- eps of last round's block, by one rotating warp, before its own column work
+        if (phase == 0 && vr && pr == (i % G::NPAIR)) {
+            if (!warp_wait_ge(sy + FS_COL, (unsigned)(G::NPAIR * i), p.abort_flag, lane)) return;
+            const int64_t gb = p.gb_begin + lbr;
+            f_eps<R>(p.colsum + gb * R, p.eps + gb * G::N, wbuf, s_tw, lane);
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence();
+                atomicMax(sy + FS_EPS, (unsigned)i);
+            }
+        }
+        if (vc) {
+            const int64_t gb = p.gb_begin + lbc;
+            const int64_t slot = phase == 0 ? (int64_t)lam * ns + (i % ns) : lbc;
+            f_col_front<R>(rawA, rawB, reinterpret_cast<float4*>(wbuf), s_w4, s_lut, s_h4w, lane, p.colsum + gb * R + n1);
+            // the slot written now was read by the row halves `ns` rounds ago (they ran one round later)
+            if (phase == 0 && i >= ns) {
+                if (!warp_wait_ge(sy + FS_ROW, (unsigned)(G::NPAIR * (i - ns + 1)), p.abort_flag, lane)) return;
+            }
+            f_col_back(reinterpret_cast<const float4*>(wbuf), betaS, lane, p.ring + slot * M + (size_t)pr * 1024);
+            if (phase == 0) warp_arrive(sy + FS_COL, lane);
+            if (lbc + nl < nb) {
+                const uint8_t* q = raw_ptr(lbc + nl);
+                rawA = ldg_stream16(q);
+                rawB = ldg_stream16(q + 512);
+            }
+        }
+        if (vr) {
+            const int64_t gb = p.gb_begin + lbr;
+            const int64_t slot = phase == 0 ? (int64_t)lam * ns + ((i - 1) % ns) : lbr;
+            if (phase == 0) {
+                if (!warp_wait_ge(sy + FS_COL, (unsigned)(G::NPAIR * i), p.abort_flag, lane)) return;
+            }
+            __syncwarp();
+            f_row_load<R>(p.ring + slot * M, pr * G::RPW, wbuf, lane);
+            if (phase == 0) {
+                if (!warp_wait_ge(sy + FS_EPS, (unsigned)i, p.abort_flag, lane)) return;
+            }
+            cp_async_wait<0>();
+            __syncwarp();
+            if (phase == 0) warp_arrive(sy + FS_ROW, lane);               // the slot has been read
+            f_row_compute<R, MODE>(p, wbuf, s_tw, p.eps + gb * G::N, gb, pr * G::RPW, lane);
+            __syncwarp();
+        }
+    }
+}
+
+// ================================================================== front end of the fused path
+// Header-only validation: one thread per frame.  fstat = 1 usable, 2 dead (invalid bit or bad header).
+struct K0HParams {
+    const uint8_t* frames[B2F_MAX_IF];
+    uint8_t* fstat; size_t fstat_stride;
+    unsigned long long* counters;
+    int64_t nframes;
+    int frame_bytes, header_bytes, in_nbit, fps, nif;
+    uint32_t base_sec[B2F_MAX_IF], base_fnum[B2F_MAX_IF];
+};
+
+// Validation + fill masking + block transposition: the 2-bit payload of one FFT block (512 rows of R time
+// samples) becomes the index-byte stream the fused kernel reads, [pair][half][lane = 2 item + col][r]:
+// byte r = sample (row 32 r + item + 16 half, column 2 pair + col), value (code1 << 2 | code0) << 3,
+// 0x80 for samples that decode to 0.0.  One CTA handles a strip of SC = min(32, R) columns of one block:
+// pieces of SC/2 payload bytes never straddle a frame.
+struct K0TParams {
+    const uint8_t* frames[B2F_MAX_IF];
+    const uint8_t* fstat; size_t fstat_stride;
+    int* fillflag; size_t fillflag_stride;                       // one int per frame: set when a fill word was seen
+    uint8_t* tstream; size_t tstream_if_stride;
+    unsigned long long* counters;
+    int nblk, nif, R, frame_bytes, header_bytes, payload_bytes, mask_faults;
+};
+
+#ifdef B2F_API_TU
+static __global__ void k0h_headers(const K0HParams p) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const bool in = i < p.nframes * p.nif;
+    int bad = 0, inv = 0, mis = 0, alive = 0;
+    if (in) {
+        const int ifi = (int)(i / p.nframes);
+        const int64_t f = i % p.nframes;
+        const uint4 h = *reinterpret_cast<const uint4*>(p.frames[ifi] + f * p.frame_bytes);
+        const bool invalid = (h.x >> 31) != 0;
+        const bool badh = ((h.z & 0xFFFFFFu) * 8u != (uint32_t)p.frame_bytes) || ((int)((h.w >> 26) & 31u) + 1 != p.in_nbit) ||
+                          ((int)((h.x >> 30) & 1u) != (p.header_bytes == 16 ? 1 : 0));
+        const int64_t tslot = ((int64_t)(h.x & 0x3FFFFFFFu) - (int64_t)p.base_sec[ifi]) * p.fps +
+                              ((int64_t)(h.y & 0xFFFFFFu) - (int64_t)p.base_fnum[ifi]);
+        p.fstat[ifi * p.fstat_stride + f] = (invalid || badh) ? 2 : 1;
+        bad = badh;
+        inv = !badh && invalid;
+        alive = !badh && !invalid;
+        mis = tslot != f;
+    }
+    const unsigned nb = __popc(__ballot_sync(0xffffffffu, bad)), ni = __popc(__ballot_sync(0xffffffffu, inv));
+    const unsigned nm = __popc(__ballot_sync(0xffffffffu, mis)), na = __popc(__ballot_sync(0xffffffffu, alive));
+    if ((threadIdx.x & 31) == 0) {
+        if (nb) atomicAdd(&p.counters[C_BADHDR], (unsigned long long)nb);
+        if (ni) atomicAdd(&p.counters[C_INVALID], (unsigned long long)ni);
+        if (nm) atomicAdd(&p.counters[C_MISPLACED], (unsigned long long)nm);
+        if (na) atomicAdd(&p.counters[C_OK], (unsigned long long)na);      // frames with fill are moved out by k0t
+    }
+}
+
+template <int SC>
+static __global__ void __launch_bounds__(256) k0t_transpose(const K0TParams p) {
+    constexpr int PB = SC / 2;                   // payload bytes per row piece
+    constexpr int NW = PB / 4;                   // 32-bit words per piece
+    constexpr int PITCH = SC + 8;                // bytes between rows of expanded index bytes: conflict-free word reads
+    __shared__ __align__(16) uint8_t s_exp[kL * PITCH];
+    const int tid = threadIdx.x;
+    const int R = p.R, nstrip = R / SC;
+    const int64_t M = (int64_t)R * kL;
+    const int64_t nunits = (int64_t)p.nif * p.nblk * nstrip;
+    unsigned long long nfill_total = 0;
+    for (int64_t u = blockIdx.x; u < nunits; u += gridDim.x) {
+        const int strip = (int)(u % nstrip);
+        const int64_t gb = u / nstrip;
+        const int ifi = (int)(gb / p.nblk);
+        const int64_t blk = gb % p.nblk;
+        const uint8_t* frames = p.frames[ifi];
+        // ---- load, validate, expand: two rows per thread
+#pragma unroll
+        for (int k = 0; k < kL / 256; ++k) {
+            const int row = tid + 256 * k;
+            const int64_t pb = (blk * M + (int64_t)R * row + (int64_t)strip * SC) >> 1;     // payload byte of the stream
+            const int64_t f = pb / p.payload_bytes;
+            const int off = (int)(pb - f * p.payload_bytes);
+            const uint8_t* src = frames + f * p.frame_bytes + p.header_bytes + off;
+            uint32_t w[NW];
+            if (NW == 4) {
+                const uint4 v = ldg_stream16(src);
+                w[0] = v.x; w[1] = v.y; w[2 % NW] = v.z; w[3 % NW] = v.w;
+            } else {
+                const uint2 v = *reinterpret_cast<const uint2*>(src);
+                w[0] = v.x; w[1] = v.y;
+            }
+            const bool dead = p.fstat[ifi * p.fstat_stride + f] == 2;
+            unsigned fm = 0;
+#pragma unroll
+            for (int j = 0; j < NW; ++j) fm |= (unsigned)(w[j] == kFillWord) << j;
+            if (fm && !dead) {
+                nfill_total += __popc(fm);
+                if (p.mask_faults && atomicExch(&p.fillflag[ifi * p.fillflag_stride + f], 1) == 0) {
+                    atomicAdd(&p.counters[C_FILLFRAMES], 1ull);
+                    atomicAdd(&p.counters[C_OK], ~0ull);                    // -1: alive, but not clean
+                }
+            }
+            const unsigned mask = !p.mask_faults ? 0u : (dead ? 0xFu : fm);
+            uint2* d = reinterpret_cast<uint2*>(s_exp + row * PITCH);
+#pragma unroll
+            for (int j = 0; j < NW; ++j) d[j] = expand_word_2bit(w[j], (mask >> j) & 1);
+        }
+        __syncthreads();
+        // ---- transposed read-out: thread = (half, column quad, item); 16 rows x 4 columns -> 4 outputs of 16 bytes
+        {
+            const int lane = tid & 31, wrp = tid >> 5;
+            const int item = lane & 15;
+            const int cq = (wrp & 3) * 2 + (lane >> 4);
+            const int half = wrp >> 2;
+            if (cq < SC / 4) {
+                uint32_t o[4][4];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    uint32_t a[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        a[j] = *reinterpret_cast<const uint32_t*>(s_exp + (32 * (4 * g + j) + item + 16 * half) * PITCH + 4 * cq);
+                    const uint32_t t0 = __byte_perm(a[0], a[1], 0x5140), t1 = __byte_perm(a[2], a[3], 0x5140);
+                    const uint32_t t2 = __byte_perm(a[0], a[1], 0x7362), t3 = __byte_perm(a[2], a[3], 0x7362);
+                    o[0][g] = __byte_perm(t0, t1, 0x5410);
+                    o[1][g] = __byte_perm(t0, t1, 0x7632);
+                    o[2][g] = __byte_perm(t2, t3, 0x5410);
+                    o[3][g] = __byte_perm(t2, t3, 0x7632);
+                }
+                uint8_t* tb = p.tstream + ifi * p.tstream_if_stride + blk * M;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int pair = strip * (SC / 2) + 2 * cq + (j >> 1), col = j & 1;
+                    *reinterpret_cast<uint4*>(tb + ((size_t)(pair * 2 + half) * 32 + 2 * item + col) * 16) =
+                        make_uint4(o[j][0], o[j][1], o[j][2], o[j][3]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // fill words: one atomic per warp
+    for (int m = 16; m; m >>= 1) nfill_total += __shfl_xor_sync(0xffffffffu, nfill_total, m);
+    if ((tid & 31) == 0 && nfill_total) atomicAdd(&p.counters[C_FILLWORDS], nfill_total);
+}
+
+// F[row][col] = sum of `ratio` consecutive partial rows, fixed order
+static __global__ void kt_sum_partials(const float* __restrict__ part, int64_t part_if_stride, float* __restrict__ F,
+                                       int64_t F_if_stride, int64_t F_row0, int64_t rows, int ncol, int ratio) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;        // one float4 of one output row
+    const int q = ncol / 4;
+    if (i >= rows * q) return;
+    const int ifi = blockIdx.y;
+    const int64_t row = i / q;
+    const int c4 = (int)(i % q);
+    const float4* src = reinterpret_cast<const float4*>(part + ifi * part_if_stride + row * ratio * (int64_t)ncol) + c4;
+    float4 s = src[0];
+    for (int k = 1; k < ratio; ++k) {
+        const float4 v = src[(int64_t)k * q];
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    reinterpret_cast<float4*>(F + ifi * F_if_stride + (F_row0 + row) * (int64_t)ncol)[c4] = s;
+}
+#endif
+
+}  // namespace b2f

@@ -11,3 +11,14 @@ cudaError_t b2f_launch_ka_8(int R, const b2f::KAParams& p, unsigned grid, cudaSt
 cudaError_t b2f_launch_kb_part0(int R, int mode, const b2f::KBParams& p, int grid, cudaStream_t st);   // R = 16, 32, 64
 cudaError_t b2f_launch_kb_part1(int R, int mode, const b2f::KBParams& p, int grid, cudaStream_t st);   // R = 128, 512
 cudaError_t b2f_launch_kb_part2(int R, int mode, const b2f::KBParams& p, int grid, cudaStream_t st);   // R = 256
+
+// fused column + row kernel (b2f_fused.cuh), one translation unit per row length.  With max_ctas_per_sm != NULL the
+// call only reports how many CTAs of the kernel fit on one SM.
+namespace b2f { struct FParams; }
+cudaError_t b2f_launch_kf(int R, int mode, const b2f::FParams& p, int grid, int cooperative, cudaStream_t st, int* max_ctas_per_sm);
+cudaError_t b2f_launch_kf_16(int mode, const b2f::FParams& p, int grid, int cooperative, cudaStream_t st, int* max_ctas_per_sm);
+cudaError_t b2f_launch_kf_32(int mode, const b2f::FParams& p, int grid, int cooperative, cudaStream_t st, int* max_ctas_per_sm);
+cudaError_t b2f_launch_kf_64(int mode, const b2f::FParams& p, int grid, int cooperative, cudaStream_t st, int* max_ctas_per_sm);
+cudaError_t b2f_launch_kf_128(int mode, const b2f::FParams& p, int grid, int cooperative, cudaStream_t st, int* max_ctas_per_sm);
+cudaError_t b2f_launch_kf_256(int mode, const b2f::FParams& p, int grid, int cooperative, cudaStream_t st, int* max_ctas_per_sm);
+cudaError_t b2f_launch_kf_512(int mode, const b2f::FParams& p, int grid, int cooperative, cudaStream_t st, int* max_ctas_per_sm);

@@ -110,6 +110,8 @@ class Plan:
         self.chunk_frames = g.chunk_frames
         self.chunk_rows = g.chunk_rows
         self.tsamp_s = g.tsamp_s
+        #: 2 = fused column + row kernel (L2 ring), 1 = the same as two launches, 0 = round-1 kernels
+        self.path = _lib.lib().b2f_channeliser_path(self._h)
 
     # ------------------------------------------------------------------ lifecycle
     def close(self):

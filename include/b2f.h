@@ -129,7 +129,9 @@ enum b2f_kernel_id {
     B2F_K_QUANT = 5,               /* rescale + requantise + sideband flip + splice           */
     B2F_K_DECODE = 6,              /* stand-alone decode (tests / roofline)                   */
     B2F_K_DEDISP = 7,              /* un-mix + chirp + backward FFT + overlap discard + detect */
-    B2F_K_COUNT = 8
+    B2F_K_FUSED = 8,               /* decode + column pass + row pass + detection in one persistent kernel */
+    B2F_K_TSUM = 9,                /* sum of partial rows when tscrunch spans the rows of several warps */
+    B2F_K_COUNT = 10
 };
 
 int b2f_version(void);
@@ -182,6 +184,12 @@ int b2f_reset_timers(struct b2f_plan* plan);
  * outstanding. */
 int b2f_mark(struct b2f_plan* plan, int64_t* ticket);
 int b2f_wait(struct b2f_plan* plan, int64_t ticket);
+
+/* Which channeliser kernels the plan runs: 2 = fused column + row kernel with the block intermediate kept in an
+ * L2-resident ring (2-bit split streams, frames in order, freq_res 512, no dedispersion); 1 = the same kernels as
+ * two launches over a full intermediate; 0 = the round-1 kernels (everything else).  B2F_PATH=legacy|split|fused in
+ * the environment overrides the choice where the fused kernel applies. */
+int b2f_channeliser_path(const struct b2f_plan* plan);
 
 /* The parameters the plan was created with (freq_res resolved to its effective value). */
 int b2f_get_params(const struct b2f_plan* plan, b2f_params* out);
@@ -264,7 +272,8 @@ int b2f_fp32_peak(int device, double* tflops);
 
 /* Test hooks: copy an internal device buffer of the most recent push to the host.
  * which: 0 compact payload, 1 word mask, 2 frame status, 3 block dirty flags,
- *        4 column-pass output [blk][L][R] float2, 5 column sums [blk][R] float2,
+ *        4 column-pass output [blk][L][R] float2 (paths 1, 2: slots of [R/2][L][2] float2; path 2: only the ring),
+ *        5 column sums [blk][R] float2,
  *        6 eps [blk][nchan] float2, 7 detected floats of held rows [if][row][prod][chan]. */
 int b2f_debug_copy(struct b2f_plan* plan, int which, void* dst, size_t nbytes, size_t* needed);
 

@@ -37,7 +37,12 @@ def test_column_pass_stages(gpu):
         pl.push([v])
         R, L = 2 * nchan, 512
         nblk = int(pl.geometry.unit_blocks * (pl.chunk_frames // pl.geometry.unit_frames))
-        inter = pl.debug(4, np.complex64).reshape(nblk, L, R)
+        if pl.path == 2:                                   # fused kernel: the intermediate only exists as a ring in L2
+            inter = None
+        elif pl.path == 1:                                 # block slots are [pair][row][2]
+            inter = pl.debug(4, np.complex64).reshape(nblk, R // 2, L, 2).transpose(0, 2, 1, 3).reshape(nblk, L, R)
+        else:
+            inter = pl.debug(4, np.complex64).reshape(nblk, L, R)
         colsum = pl.debug(5, np.complex64).reshape(nblk, R)
         eps = pl.debug(6, np.complex64).reshape(nblk, nchan)
         x = o.decode_vdif(v)
@@ -46,7 +51,8 @@ def test_column_pass_stages(gpu):
         for b in (0, 1, nblk - 1):
             B, S = ap.column_pass(z[b * M:(b + 1) * M], R, L)
             sc = np.abs(B).max()
-            assert np.abs(inter[b] - B).max() <= 2e-6 * sc, f"column pass block {b}"
+            if inter is not None:
+                assert np.abs(inter[b] - B).max() <= 2e-6 * sc, f"column pass block {b}"
             assert np.abs(colsum[b] - S).max() <= 1e-6 * np.abs(S).max() + 1e-3
             e = ap.eps_from_colsum(S, R)
             assert np.abs(eps[b] - e).max() <= 1e-5 * np.abs(e).max()
