@@ -30,12 +30,39 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-NIF, BW, NCHAN, FREQ_RES, TSCRUNCH = 8, 32.0, 128, 512, 16
 FRAME_BYTES, PAYLOAD = 8032, 8000
-FPS = 4000                                  # frames per second per IF
-BYTES_PER_DATA_SEC = NIF * FPS * FRAME_BYTES   # 257.024 MB of VDIF per second of sky
 FREQ_LSB0 = 1254.0
 METRIC = "input baseband GB/s (VDIF bytes, headers included) per B200, 2 Gbps 16x32 MHz 2-bit -> 8-bit Stokes I"
+
+#: BASELINE.json `configs`, in its order.  C2 is the configuration the metric is quoted on and the default.
+CONFIGS = {
+    "C1": dict(nif=4, bw=16.0, nchan=32, tscrunch=32, seconds=10.0, pol="I", out_nbit=8,
+               what="C1: 4 IF x 16 MHz dual-pol 2-bit VDIF (512 Mbps; the reading of '8 subbands (512 Mbps)' that "
+                    "base2fil.sh:251 gives), 10 s, nchan 32, freq_res 512, tscrunch 32 (64 us), 8-bit Stokes I"),
+    "C2": dict(nif=8, bw=32.0, nchan=128, tscrunch=16, seconds=60.0, pol="I", out_nbit=8,
+               what="C2: 8 IF x 32 MHz dual-pol 2-bit VDIF (2 Gbps), {sec:.0f} s, nchan 128, freq_res 512 (digifil -F128:512), "
+                    "tscrunch 16, 8-bit Stokes I spliced to 1024 channels"),
+    "C3": dict(nif=8, bw=32.0, nchan=128, tscrunch=16, seconds=60.0, pol="coherence", out_nbit=-32,
+               what="C3: the C2 input to PP, QQ, Re PQ*, Im PQ* (digifil -d4), 32-bit float output, {sec:.0f} s"),
+    "C4": dict(nif=8, bw=32.0, nchan=128, tscrunch=16, seconds=60.0, pol="I", out_nbit=8, dm=560.0,
+               what="C4: C2 + coherent in-channel dedispersion at DM 560 (overlap-save), {sec:.0f} s"),
+    "C5": dict(nif=16, bw=32.0, nchan=128, tscrunch=16, seconds=3600.0, sample_seconds=30.0, pol="I", out_nbit=8,
+               what="C5: 16 IF x 32 MHz 2-bit (4 Gbps) streaming Stokes I; bounded sample of {sec:.0f} s of the 3600 s scan "
+                    "(the scan is 120 such stretches; nothing carries over between them but the frozen rescale)"),
+}
+# module-level geometry of the selected configuration (set by select_config; tools/ import these)
+NIF, BW, NCHAN, FREQ_RES, TSCRUNCH = 8, 32.0, 128, 512, 16
+FPS = 4000                                  # frames per second per IF
+BYTES_PER_DATA_SEC = NIF * FPS * FRAME_BYTES   # 257.024 MB of VDIF per second of sky
+
+
+def select_config(name: str) -> dict:
+    global NIF, BW, NCHAN, TSCRUNCH, FPS, BYTES_PER_DATA_SEC
+    c = CONFIGS[name]
+    NIF, BW, NCHAN, TSCRUNCH = c["nif"], c["bw"], c["nchan"], c["tscrunch"]
+    FPS = int(round(2 * BW * 1e6 / 16000))
+    BYTES_PER_DATA_SEC = NIF * FPS * FRAME_BYTES
+    return c
 
 
 def if_plan():
@@ -119,15 +146,15 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------
-# CPU arm: the oracle port, one single-threaded worker process per IF (base2fil.sh:60-66,219)
+# CPU arm: the oracle port, one worker process per IF (base2fil.sh:60-66,219)
 # --------------------------------------------------------------------------------------------
 def _cpu_worker(args):
-    seed, nframes, fc, sbw, nthr = args
+    seed, nframes, fc, sbw, nthr, cfg = args
     os.environ["OMP_NUM_THREADS"] = "1"
     import contextlib
     from frb_baseband_b200 import synth
     from oracle import digifil_oracle as o
-    v = synth.make_vdif(nframes, seed=seed, bw_mhz=BW)
+    v = synth.make_vdif(nframes, seed=seed, bw_mhz=abs(sbw))
     try:                      # digifil -threads K (process_vdif.py --nthreads): FFT batches over K threads
         import scipy.fft
         pool = scipy.fft.set_workers(nthr)
@@ -135,37 +162,65 @@ def _cpu_worker(args):
         pool = contextlib.nullcontext()
     t0 = time.perf_counter()
     with pool:
-        r = o.digifil(v, freq_mhz=fc, bw_mhz=sbw, nchan=NCHAN, freq_res=FREQ_RES, tscrunch_factor=TSCRUNCH,
-                      out_nbit=8, dtype=np.float32)
+        r = o.digifil(v, freq_mhz=fc, bw_mhz=sbw, nchan=cfg["nchan"], freq_res=FREQ_RES, tscrunch_factor=cfg["tscrunch"],
+                      pol_mode=cfg["pol"], out_nbit=cfg["out_nbit"], dm=cfg.get("dm", 0.0), coherent=cfg.get("dm", 0.0) > 0,
+                      dtype=np.float32)
     return time.perf_counter() - t0, r["data"].shape[0]
 
 
-def cpu_arm(sample_seconds: float, steps: int = 1):
+def cpu_arm(cfg: dict, sample_seconds: float, steps: int = 1):
     """Time the oracle (CPU restatement of digifil+splice) on this box's host cores."""
     import multiprocessing as mp
     from frb_baseband_b200 import synth
     cores = len(os.sched_getaffinity(0))
     workers = min(NIF, cores)
     nthr = max(1, cores // workers)        # all host cores: one process per IF, digifil_nthreads = cores / nif
-    nframes = int(round(sample_seconds * FPS / 1024)) * 1024 or 1024
+    unit = 1024 if BW >= 32 else 256       # frames holding whole FFT blocks
+    nframes = int(round(sample_seconds * FPS / unit)) * unit or unit
     bws, freqs = if_plan()
-    jobs = [(synth.config_seed(2, i + 1), nframes, freqs[i], bws[i], nthr) for i in range(NIF)]
+    jobs = [(synth.config_seed(2, i + 1), nframes, freqs[i], bws[i], nthr, cfg) for i in range(NIF)]
     ctx = mp.get_context("spawn")      # the parent may hold a CUDA context: never fork it
     times = []
     with ctx.Pool(workers) as pool:
         for _ in range(steps):
-            t0 = time.perf_counter()
             res = pool.map(_cpu_worker, jobs)
             # splice: concatenate per-IF rows, highest frequency first (trivial next to digifil)
             wall = max(r[0] for r in res) if workers >= NIF else sum(r[0] for r in res) / workers
             times.append(max(wall, 1e-9))
-            _ = time.perf_counter() - t0
     t = float(np.median(times))
     data_sec = nframes / FPS
     return {"value": NIF * nframes * FRAME_BYTES / t / 1e9, "unit": "GB/s", "cores": workers * nthr, "kind": "port",
-            "sample": f"{data_sec:.3f} s of all {NIF} IFs of the C2 workload, one oracle process per IF with {nthr} FFT "
-                      f"thread(s) each (NumPy/SciPy-pocketfft float32 restatement of digifil+splice, not DSPSR itself)",
+            "sample": f"{data_sec:.3f} s of all {NIF} IFs of the workload, one oracle process per IF with {nthr} FFT "
+                      f"thread(s) each (NumPy/SciPy-pocketfft float32 restatement of digifil+splice, NOT DSPSR/FFTW "
+                      f"digifil itself: ratios against it would shrink by a small integer factor against the real thing)",
             "rt_factor": data_sec / t, "seconds_per_step": t}
+
+
+def parity_check(torch, vd0, cfg: dict, bw_signed: float, freq: float, device: int):
+    """The bench's own input through the same kernels vs the oracle: the first frames of one IF, float output
+    (digifil -b-32 -I0), so a timed kernel that wrote garbage cannot score."""
+    from frb_baseband_b200 import _lib
+    from frb_baseband_b200.plan import Plan, PlanConfig
+    from oracle import digifil_oracle as o
+    nfr = 1024 if BW >= 32 else 512
+    v = vd0[:nfr].cpu().numpy().reshape(-1)
+    dm = cfg.get("dm", 0.0)
+    mode = {"I": _lib.POL_I, "coherence": _lib.POL_COHERENCE, "IQUV": _lib.POL_IQUV}[cfg["pol"]]
+    with Plan(PlanConfig(nchan=cfg["nchan"], bw_mhz=[bw_signed], freq_mhz=[freq], tscrunch=cfg["tscrunch"], pol_mode=mode,
+                         out_nbit=-32, keep_bandpass=True, dm=dm, coherent=dm > 0, device=device)) as pl:
+        path = pl.path
+        pl.push([v])
+        pl.flush()
+        rows = pl.pull().view(np.float32).astype(np.float64)
+    ref = o.digifil(v, freq_mhz=freq, bw_mhz=bw_signed, nchan=cfg["nchan"], tscrunch_factor=cfg["tscrunch"], pol_mode=cfg["pol"],
+                    out_nbit=-32, keep_bandpass=True, dm=dm, coherent=dm > 0)["data"].astype(np.float64)
+    n = min(rows.shape[0], ref.shape[0])
+    ref = ref[:n]
+    got = rows[:n].reshape(ref.shape)
+    rms = np.sqrt((ref ** 2).mean(axis=(0, 2), keepdims=True))
+    err = float((np.abs(got - ref) / np.maximum(np.abs(ref), rms)).max()) if n else float("nan")
+    return {"max_rel": err, "tol": 1e-5, "ok": bool(n > 0 and err <= 1e-5), "rows": int(n), "frames": nfr,
+            "channeliser_path": path, "what": "first frames of IF 1 of the timed input, float path vs the NumPy oracle"}
 
 
 # --------------------------------------------------------------------------------------------
@@ -174,13 +229,18 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--seconds", type=float, default=60.0, help="seconds of sky data per step (C2: 60)")
+    ap.add_argument("--config", default="C2", choices=sorted(CONFIGS), help="BASELINE.json configuration (default: C2, the headline)")
+    ap.add_argument("--seconds", type=float, default=None, help="seconds of sky data per step (default: the configuration's)")
     ap.add_argument("--impl", default="b2f", choices=["b2f", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--chunk-units", type=int, default=4, help="frames per push in units of 1024 (0 = library default of 2048 frames)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg of a multi-GPU run")
+    ap.add_argument("--chunk-units", type=int, default=4, help="frames per push in units of whole-block frame groups (0 = library default)")
     ap.add_argument("--nccl-gather", action="store_true", help="splice with an NCCL gather instead of peer stores")
     ap.add_argument("--cpu-sample", type=float, default=1.024, help="seconds of data for the cpu_baseline leg")
     args = ap.parse_args()
+    cfg = select_config(args.config)
+    seconds = args.seconds if args.seconds else cfg.get("sample_seconds", cfg["seconds"])
+    workload = cfg["what"].format(sec=seconds)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -190,13 +250,12 @@ def main():
         if rank != 0:
             return 0
         W = max(args.warmup, 0)
-        r = cpu_arm(args.cpu_sample, steps=max(1, args.steps + min(W, 1)))
+        r = cpu_arm(cfg, args.cpu_sample, steps=max(1, args.steps + min(W, 1)))
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "GB/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["seconds_per_step"] * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "rt_factor": r["rt_factor"],
-                "config": {"workload": "C2: 8 IF x 32 MHz dual-pol 2-bit VDIF (2 Gbps), nchan 128, freq_res 512, "
-                                       "tscrunch 16, 8-bit Stokes I; bounded sample per step: " + r["sample"]},
+                "config": {"workload": workload + "; bounded sample per step: " + r["sample"]},
                 "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": r["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -216,62 +275,79 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    nframes = int(round(args.seconds * FPS))
-    _, bws, freqs = rank_if_plan(NIF * world, world, rank, FREQ_LSB0, BW)   # rank r owns the next 8 subbands up
+    nframes = int(round(seconds * FPS))
+    unit = 1024 if BW >= 32 else 256
+    nframes -= nframes % unit
+    _, bws, freqs = rank_if_plan(NIF * world, world, rank, FREQ_LSB0, BW)   # rank r owns the next NIF subbands up
     stream = torch.cuda.current_stream(dev)
-    cfg = PlanConfig(nchan=NCHAN, bw_mhz=bws, freq_mhz=freqs, tscrunch=TSCRUNCH, out_nbit=8, freq_res=FREQ_RES,
-                     device=local_rank, profile=True, stream=stream.cuda_stream, chunk_units=args.chunk_units)
-    pl = Plan(cfg)
+    mode = {"I": _lib.POL_I, "coherence": _lib.POL_COHERENCE, "IQUV": _lib.POL_IQUV}[cfg["pol"]]
+    dm = cfg.get("dm", 0.0)
+    out_nbit = cfg["out_nbit"]
+
+    def make_plan(bws_, freqs_, chunk_units):
+        return Plan(PlanConfig(nchan=NCHAN, bw_mhz=bws_, freq_mhz=freqs_, tscrunch=TSCRUNCH, out_nbit=out_nbit, freq_res=FREQ_RES,
+                               pol_mode=mode, dm=dm, coherent=dm > 0, device=local_rank, profile=True, stream=stream.cuda_stream,
+                               chunk_units=chunk_units))
+
+    pl = make_plan(bws, freqs, 0 if dm > 0 else args.chunk_units)
     cf = int(pl.chunk_frames)
-    rows_total = (nframes * 16000 // (2 * NCHAN * FREQ_RES)) * FREQ_RES // TSCRUNCH   # only an upper bound
+    row_bytes = int(pl.row_bytes)
+    rows_total = int(seconds / pl.tsamp_s) + 8          # only an upper bound
     vd = [make_device_vdif(torch, dev, nframes, 20121102 + 2000 + 100 * rank + i) for i in range(NIF)]
-    out_dev = torch.empty((rows_total + cf, NIF * NCHAN), dtype=torch.uint8, device=dev)
+    out_dev = torch.empty((rows_total + int(pl.chunk_rows), row_bytes), dtype=torch.uint8, device=dev)
+    cap_rows = out_dev.shape[0]
     gathered = None
     peer = None
     if world > 1 and not args.nccl_gather:
         try:       # splice by peer stores over NVLink from the requantise kernel itself
-            peer = PeerSplice(rows_total + cf, NIF * NCHAN, world, rank, dev)
+            peer = PeerSplice(cap_rows, row_bytes, world, rank, dev)
         except Exception as ex:
             if rank == 0:
                 print(f"peer splice unavailable ({ex!r}); falling back to an NCCL gather", file=sys.stderr)
     if world > 1 and peer is None and rank == 0:
-        gathered = torch.empty((world, rows_total + cf, NIF * NCHAN), dtype=torch.uint8, device=dev)
-    chunks = [(f0, min(cf, nframes - f0)) for f0 in range(0, nframes, cf)]
+        gathered = torch.empty((world, cap_rows, row_bytes), dtype=torch.uint8, device=dev)
 
-    def step_device():
-        pl.reset()
-        got = 0
-        cap = rows_total + cf
-        for f0, n in chunks:
-            pl.push([v[f0].data_ptr() for v in vd], nframes=n, on_device=True)
-            if peer is not None:
-                got += pl.pull_strided(peer.dst(got), cap - got, peer.pitch)
+    def make_step(plan, vds, out, peer_):
+        cfr = int(plan.chunk_frames)
+        chunks_ = [(f0, min(cfr, nframes - f0)) for f0 in range(0, nframes, cfr)]
+        cap = out.shape[0]
+
+        def step():
+            plan.reset()
+            got = 0
+            for f0, n in chunks_:
+                plan.push([v[f0].data_ptr() for v in vds], nframes=n, on_device=True)
+                if peer_ is not None:
+                    got += plan.pull_strided(peer_.dst(got), cap - got, peer_.pitch)
+                else:
+                    got += plan.pull_device(out[got].data_ptr(), cap - got)
+            plan.flush()
+            if peer_ is not None:
+                got += plan.pull_strided(peer_.dst(got), cap - got, peer_.pitch)
             else:
-                got += pl.pull_device(out_dev[got].data_ptr(), cap - got)
-        pl.flush()
-        if peer is not None:
-            got += pl.pull_strided(peer.dst(got), cap - got, peer.pitch)
-        else:
-            got += pl.pull_device(out_dev[got].data_ptr(), cap - got)
-            if world > 1:   # fallback: gather every rank's 8-bit tile into rank 0's band-ordered rows
-                gather_splice(out_dev, world, rank, dst=0, out=gathered)
-        return got
+                got += plan.pull_device(out[got].data_ptr(), cap - got)
+                if world > 1 and plan is pl:   # fallback: gather every rank's tile into rank 0's band-ordered rows
+                    gather_splice(out, world, rank, dst=0, out=gathered)
+            return got
+        return step, chunks_
 
-    def timed(fn, steps, warmup, sampler=None):
+    step_device, chunks = make_step(pl, vd, out_dev, peer)
+
+    def timed(plan, fn, steps, warmup):
         for _ in range(warmup):
             fn()
-        pl.sync(); torch.cuda.synchronize(dev)
-        pl.reset_timers()
+        plan.sync(); torch.cuda.synchronize(dev)
+        plan.reset_timers()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.time()
-        l0 = pl.counters()["kernel_launches"]
+        l0 = plan.counters()["kernel_launches"]
         e0.record(stream)
         for _ in range(steps):
             rows = fn()
-        pl.sync()
+        plan.sync()
         e1.record(stream)
         torch.cuda.synchronize(dev)
         if world > 1:
@@ -282,29 +358,54 @@ def main():
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        launches = pl.counters()["kernel_launches"] - l0
+        launches = plan.counters()["kernel_launches"] - l0
         return ms / steps, rows, launches, (t0, t1)
 
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.3)
-    ms_step, rows, launches, (t0, t1) = timed(step_device, args.steps, max(args.warmup, 3))
+    ms_step, rows, launches, (t0, t1) = timed(pl, step_device, args.steps, max(args.warmup, 3))
     clocks = sampler.stop(t0, t1)
     ktimes = pl.kernel_times()
     data_sec = nframes / FPS
     in_bytes = NIF * nframes * FRAME_BYTES
     value = world * in_bytes / (ms_step * 1e-3) / 1e9
 
+    # ---- strong scaling: the SAME band cut over the ranks (base2fil.sh:60-66 runs one process per IF; here 1/N of the
+    # IFs per GPU), pushes N times longer so that a launch still holds as many FFT blocks as the grid needs
+    strong = None
+    if world > 1 and not args.no_strong and NIF % world == 0:
+        per = NIF // world
+        sl = slice(rank * per, (rank + 1) * per)
+        _, bws1, freqs1 = rank_if_plan(NIF, 1, 0, FREQ_LSB0, BW)
+        pls = make_plan(bws1[sl], freqs1[sl], 0 if dm > 0 else args.chunk_units * world)
+        outs = torch.empty((cap_rows, int(pls.row_bytes)), dtype=torch.uint8, device=dev)
+        peers = None
+        if peer is not None:
+            try:
+                peers = PeerSplice(cap_rows, int(pls.row_bytes), world, rank, dev)
+            except Exception:
+                peers = None
+        step_s, _ = make_step(pls, vd[:per], outs, peers)
+        ms_s, rows_s, _, _ = timed(pls, step_s, max(1, min(args.steps, 3)), 2)
+        strong = {"ifs_per_gpu": per, "ms_per_step": ms_s, "value": in_bytes / (ms_s * 1e-3) / 1e9, "unit": "GB/s",
+                  "rt_factor": data_sec / (ms_s * 1e-3), "efficiency_vs_this_runs_weak_per_gpu_rate": ms_step / (world * ms_s),
+                  "chunk_frames": int(pls.chunk_frames), "rows_per_step": int(rows_s),
+                  "note": "the configuration's own band (not N bands): every GPU takes nif/N subbands, splice by peer stores"}
+        pls.close()
+        del outs
+
     # ---- e2e: pinned host VDIF -> C ABI -> rows back in pinned host memory
     e2e = None
     if not args.no_e2e:
         hold_frames = min(nframes, 12 * FPS)            # pinned host copy of 12 s, cycled through the scan
         hold_frames -= hold_frames % cf
+        hold_frames = max(hold_frames, cf)
         host = [torch.empty((hold_frames, FRAME_BYTES), dtype=torch.uint8, pin_memory=True) for _ in range(NIF)]
         for i in range(NIF):
             host[i].copy_(vd[i][:hold_frames])
         torch.cuda.synchronize(dev)
-        out_host = torch.empty((rows_total + cf, NIF * NCHAN), dtype=torch.uint8, pin_memory=True)
+        out_host = torch.empty((cap_rows, row_bytes), dtype=torch.uint8, pin_memory=True)
         hptr = [h.data_ptr() for h in host]
         import ctypes as C
 
@@ -317,14 +418,13 @@ def main():
                     n = hold_frames - h0
                 ptrs = (C.c_void_p * NIF)(*[p + h0 * FRAME_BYTES for p in hptr])
                 _lib.check(_lib.lib().b2f_push(pl._h, ptrs, n, 0))
-                got += pl.pull_async(out_host[got].data_ptr(), rows_total + cf - got)
+                got += pl.pull_async(out_host[got].data_ptr(), cap_rows - got)
             pl.flush()
-            got += pl.pull_async(out_host[got].data_ptr(), rows_total + cf - got)
+            got += pl.pull_async(out_host[got].data_ptr(), cap_rows - got)
             pl.sync()
             return got
 
-        cfg_pos = pl.cfg   # positional frames: the cycled 12 s hold repeats header seconds, samples are what is timed
-        ms_e2e, rows_e, _, _ = timed(step_host, max(1, min(args.steps, 3)), 1)
+        ms_e2e, rows_e, _, _ = timed(pl, step_host, max(1, min(args.steps, 3)), 1)
         h2d = sum(n for _, n in chunks) * NIF * FRAME_BYTES
         # the ceiling of that number: a bare pinned-host -> device copy of the same buffers (PCIe), nothing else
         scratch = torch.empty_like(vd[0][:hold_frames])
@@ -339,13 +439,14 @@ def main():
         h2d_copy = NIF * hold_frames * FRAME_BYTES / (c0.elapsed_time(c1) * 1e-3) / 1e9
         del scratch
         e2e = {"value": world * in_bytes / (ms_e2e * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(rows_e * NIF * NCHAN), "ms_per_step": ms_e2e,
+               "d2h_bytes_per_step": int(rows_e * row_bytes), "ms_per_step": ms_e2e,
                "rt_factor": world * data_sec / (ms_e2e * 1e-3),
                "h2d_copy_GBps_per_gpu": h2d_copy, "frac_of_h2d_copy": in_bytes / (ms_e2e * 1e-3) / 1e9 / h2d_copy,
                "note": "pinned host VDIF pushed chunk by chunk through b2f_push, rows pulled to pinned host memory; "
-                       "12 s of host-resident VDIF cycled to cover the 60 s scan"}
+                       "12 s of host-resident VDIF cycled to cover the scan"}
 
-    # ---- roofline of the dominant kernel (column pass) + the FP32 view that actually binds
+    # ---- roofline of the dominant kernel.  The path is FP32-FFT bound (AI ~245 FLOP/B): `roofline` is that
+    # view; `roofline_hbm` is the algorithmic-bytes view the spec also asks for (small by construction).
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -353,60 +454,67 @@ def main():
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
-    col_ms, col_n = ktimes["column"]
-    row_ms, row_n = ktimes["row"]
     fused = ktimes.get("fused", (0.0, 0))[1] > 0
-    if fused:                      # one persistent kernel does both halves
-        col_ms, col_n = ktimes["fused"]
-        row_ms, row_n = ktimes["fused"]
-    blocks_per_step = NIF * (nframes * 16000 // (2 * NCHAN * FREQ_RES))
     R, L = 2 * NCHAN, FREQ_RES
-    # algorithmic bytes of the column pass per launch: 2-bit payload in + (the path's output share is
-    # written by later kernels) -> SURVEY 8(d): input 32.128 MB + output 2 MB per IF-second
-    alg_bytes_step = in_bytes + rows * NIF * NCHAN
-    col_launch_ms = col_ms / max(col_n, 1)
-    launches_per_step = col_n / args.steps
-    alg_bytes_launch = alg_bytes_step / launches_per_step
-    achieved = alg_bytes_launch / (col_launch_ms * 1e-3) / 1e9
-    roofline = {"kernel": "kf_fused<256,I>" if fused else "ka_column_pass<2>", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
-                "avg_launch_ms": col_launch_ms, "share_of_step": col_ms / args.steps / ms_step,
-                "note": "path is FP32-FFT bound (AI ~245 FLOP/B, SURVEY 8d); see roofline_fp32"}
+    blocks_per_step = NIF * (nframes * 16000 // (R * L))
+    col_flops = blocks_per_step * 2.0 * R * 5 * L * 9            # FFT_512 + IFFT_512 per column, 5 N log2 N
+    row_flops = blocks_per_step * L * 5.0 * R * np.log2(R)
+    if fused:
+        dom, dom_name = ktimes["fused"], f"kf_fused<{R},{cfg['pol']}> (decode + column pass + row pass + detection, one persistent kernel)"
+        dom_flops = col_flops + row_flops
+    else:
+        dom, dom_name = ktimes["column"], "ka_column_pass (decode + column pass)"
+        dom_flops = col_flops
+    dom_ms, dom_n = dom
+    dom_launch_ms = dom_ms / max(dom_n, 1)
+    launches_per_step = max(dom_n, 1) / args.steps
+    fp32_peak = fp32_peak_tflops(local_rank)
+    traffic = None
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        roofline["traffic"] = prof.get("ka_column_pass_dram_bytes_per_launch")
+        traffic = prof.get("kf_fused_dram_bytes_per_launch" if fused else "ka_column_pass_dram_bytes_per_launch")
     except Exception:
         pass
-    fp32_peak = fp32_peak_tflops(local_rank)
-    col_flops = blocks_per_step * 2.0 * R * 5 * L * 9            # FFT_512 + IFFT_512 per column, 5 N log2 N
-    row_flops = blocks_per_step * L * 5.0 * R * 8
-    roofline_fp32 = {
-        "bound": "fp32", "unit": "TFLOP/s", "peak": fp32_peak, "peak_source": "measured live: FMA loop (b2f_fp32_peak)",
-        "column": {"achieved": (col_flops + (row_flops if fused else 0)) / (col_ms / args.steps * 1e-3) / 1e12},
-        "row": {"achieved": (row_flops + (col_flops if fused else 0)) / (row_ms / args.steps * 1e-3) / 1e12},
-        "step": {"achieved": (col_flops + row_flops) / (ms_step * 1e-3) / 1e12},
-        "convention": "5 N log2 N per complex FFT (SURVEY 8d): 17.04 MFLOP per 131072-sample dual-pol block",
-    }
-    for k in ("column", "row", "step"):
-        roofline_fp32[k]["frac"] = roofline_fp32[k]["achieved"] / fp32_peak
+    ach = dom_flops / launches_per_step / (dom_launch_ms * 1e-3) / 1e12
+    roofline = {"kernel": dom_name, "bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak,
+                "traffic": traffic, "traffic_source": "ncu --set full of tools/prof_run.py (same push size), profiles/traffic.json",
+                "peak_source": "measured live: FP32 FMA loop (b2f_fp32_peak); MEASURED_PEAKS.json holds no FP32 CUDA-core figure "
+                               "(nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4)",
+                "avg_launch_ms": dom_launch_ms, "share_of_step": dom_ms / args.steps / ms_step,
+                "convention": "5 N log2 N per complex FFT (SURVEY 8d)",
+                "whole_step": {"achieved": (col_flops + row_flops) / (ms_step * 1e-3) / 1e12,
+                               "frac": (col_flops + row_flops) / (ms_step * 1e-3) / 1e12 / fp32_peak}}
+    alg_bytes_step = in_bytes + rows * row_bytes
+    ach_b = alg_bytes_step / launches_per_step / (dom_launch_ms * 1e-3) / 1e9
+    roofline_hbm = {"kernel": dom_name, "bound": "hbm", "achieved": ach_b, "peak": hbm_peak, "unit": "GB/s", "frac": ach_b / hbm_peak,
+                    "peak_source": peak_src, "note": "algorithmic bytes (VDIF in + rows out) / dominant kernel time: not the binding roofline"}
+
+    par = None
+    if rank == 0:
+        try:
+            par = parity_check(torch, vd[0], cfg, bws[0], freqs[0], local_rank)
+        except Exception as ex:
+            par = {"ok": False, "error": repr(ex)}
 
     line = {
         "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "rt_factor": world * data_sec / (ms_step * 1e-3),
-        "config": {"workload": "C2: 8 IF x 32 MHz dual-pol 2-bit VDIF (2 Gbps), %.0f s, nchan 128, freq_res 512 "
-                               "(digifil -F128:512), tscrunch 16, 8-bit Stokes I spliced to 1024 channels" % data_sec,
-                   "nif_per_gpu": NIF, "chunk_frames": cf, "l2": "inputs (15.4 GB/step) and intermediates larger than L2",
-                   "parallelism": (f"subband groups x{world}, " + ("splice by NVLink peer stores from the requantise kernel" if peer is not None else "NCCL gather of 8-bit tiles")) if world > 1 else "1 GPU"},
+        "config": {"workload": workload, "name": args.config, "nif_per_gpu": NIF, "chunk_frames": cf,
+                   "channeliser_path": {0: "round-1 kernels", 1: "round-2 kernels, two launches", 2: "fused kernel, L2 ring"}.get(pl.path),
+                   "l2": "inputs (%.1f GB/step) larger than L2" % (in_bytes / 1e9),
+                   "parallelism": (f"subband groups x{world} (weak: every GPU its own {NIF}-IF band), " + ("splice by NVLink peer stores from the requantise kernel" if peer is not None else "NCCL gather of 8-bit tiles")) if world > 1 else "1 GPU"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-        "roofline": roofline, "roofline_fp32": roofline_fp32,
+        "roofline": roofline, "roofline_hbm": roofline_hbm, "parity_check": par,
         "kernel_ms_per_step": {k: v[0] / args.steps for k, v in ktimes.items() if v[1]},
         "rows_per_step": int(rows),
     }
+    if strong is not None:
+        line["strong"] = strong
     if rank == 0 and world == 1:
         try:
-            line["cpu_baseline"] = {k: v for k, v in cpu_arm(args.cpu_sample).items() if k != "seconds_per_step"}
+            line["cpu_baseline"] = {k: v for k, v in cpu_arm(cfg, args.cpu_sample).items() if k != "seconds_per_step"}
         except Exception as ex:      # never lose the GPU number to a host-side hiccup
             line["cpu_baseline"] = {"error": repr(ex)}
     if rank == 0:

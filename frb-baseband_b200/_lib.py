@@ -7,13 +7,15 @@ import os
 
 B2F_MAX_IF = 32
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb2f.so")
+LIB_PATH = os.environ.get("B2F_LIB") or os.path.join(_HERE, "libb2f.so")   # B2F_LIB: an alternative build (A/B kernel experiments)
 
 POL_P0, POL_P1, POL_I, POL_I2, POL_COHERENCE, POL_IQUV, POL_PPQQ = range(7)
 K_VALIDATE, K_COLUMN, K_EPS, K_ROW, K_STATS, K_QUANT, K_DECODE, K_DEDISP = range(8)
 KERNEL_NAMES = ["validate", "column", "eps", "row", "stats", "quant", "decode", "dedisp", "fused", "tsum"]
 
 EINVAL, ECUDA, ENOMEM, ESTATE, EUNSUPPORTED = -1, -2, -3, -4, -5
+DECODE_STATIC, DECODE_JA98 = 0, 1
+RESCALE_CONSTANT, RESCALE_RUNNING = 0, 1
 
 
 class Params(C.Structure):
@@ -27,6 +29,8 @@ class Params(C.Structure):
         ("if_order", C.c_int32 * B2F_MAX_IF), ("dm", C.c_double), ("coherent", C.c_int32),
         ("profile", C.c_int32), ("stream", C.c_void_p),
         ("raw_word_bits", C.c_int32), ("raw_bits", (C.c_uint8 * 4) * B2F_MAX_IF),
+        ("decode_mode", C.c_int32), ("in8_offset_mode", C.c_int32), ("fft_normalised", C.c_int32),
+        ("rescale_mode", C.c_int32), ("digi_sigma", C.c_double),
     ]
 
 

@@ -103,8 +103,10 @@ struct b2f_plan {
     float* d_part = nullptr;       int64_t part_if_stride = 0;  // partial rows when tscrunch > 1024 / R
     int Dp = 0;                    // rows a warp integrates itself
     unsigned* d_fsync = nullptr;   // per-lane arrival counters + abort flag (last word)
-    int f_grid = 0, f_lanes = 0, f_nslot = 2;
+    int f_grid = 0, f_lanes = 0, f_nslot = 3, f_lag = 2;
     bool f_aborted = false;
+    float4* d_levels = nullptr;                                 // JA98 decode: output magnitudes per window of 512 samples
+    unsigned long long* d_fprof = nullptr;                      // B2F_FUSED_PROF=1: per-warp cycle breakdown of the fused kernel
 
     // state
     int64_t rows_base = 0;         // rows already emitted and dropped from the front of F
@@ -112,6 +114,7 @@ struct b2f_plan {
     int64_t rows_held = 0;
     int64_t rows_produced = 0, rows_emitted = 0;
     bool stats_ready = false, flushed = false, have_base = false;
+    int64_t rows_this_interval = 0;   // B2F_RESCALE_RUNNING: rows still to be emitted with the statistics in force
     bool preset_stats = false;        // rescale given by the caller (b2f_set_rescale): survives b2f_reset
     int64_t frames_pushed = 0;
     uint32_t base_sec0[B2F_MAX_IF]{}, base_fnum0[B2F_MAX_IF]{};
@@ -295,7 +298,7 @@ void free_plan(b2f_plan* pl) {
     void* bufs[] = {pl->d_compact, pl->d_wmask, pl->d_fstat, pl->d_blkdirty, pl->d_inter, pl->d_colsum,
                     pl->d_eps, pl->d_F, pl->d_mean, pl->d_scale, pl->d_partial, pl->d_tab_g, pl->d_tab_h,
                     pl->d_tab_w, pl->d_tab_r, pl->d_tab_beta, pl->d_counters, pl->d_sm_slots, pl->d_carry, pl->d_spec, pl->d_chirp, pl->d_tw_col, pl->d_tw_row,
-                    pl->d_tstream, pl->d_fillflag, pl->d_part, pl->d_fsync};
+                    pl->d_tstream, pl->d_fillflag, pl->d_part, pl->d_fsync, pl->d_fprof, pl->d_levels};
     for (void* b : bufs)
         if (b) cudaFree(b);
     for (auto& t : pl->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
@@ -315,13 +318,20 @@ int init_state(b2f_plan* pl) {
     pl->carry_len = 0;
     pl->blocks_dirty = 0;
     pl->last_nblk = pl->last_nframes = 0;
+    pl->rows_this_interval = 0;
     pl->f_aborted = false;
     if (pl->d_fsync) CU(cudaMemsetAsync(pl->d_fsync, 0, ((size_t)pl->f_lanes + 1) * FS_STRIDE * sizeof(unsigned), pl->stream));
     const int ncol = pl->nprod * pl->N;
     CU(cudaMemsetAsync(pl->d_counters, 0, C_COUNT * sizeof(unsigned long long), pl->stream));
     if (!pl->preset_stats) {
         CU(cudaMemsetAsync(pl->d_mean, 0, (size_t)pl->prm.nif * ncol * sizeof(float), pl->stream));
-        std::vector<float> ones((size_t)pl->prm.nif * ncol, 1.0f);
+        // keep_bandpass with normalised transforms (D4): the "scale" the digitiser applies is 1 / (M * freq_res), squared for -d3
+        float unit = 1.0f;
+        if (pl->prm.keep_bandpass && pl->prm.fft_normalised) {
+            const double nrm = 1.0 / ((double)pl->M * pl->L);
+            unit = (float)(pl->prm.pol_mode == B2F_POL_I2 ? nrm * nrm : nrm);
+        }
+        std::vector<float> ones((size_t)pl->prm.nif * ncol, unit);
         CU(cudaMemcpyAsync(pl->d_scale, ones.data(), ones.size() * sizeof(float), cudaMemcpyHostToDevice, pl->stream));
     }
     CU(cudaStreamSynchronize(pl->stream));
@@ -432,6 +442,11 @@ int push_dedisp(b2f_plan* pl, int64_t nblk, int64_t T) {
 cudaError_t b2f_launch_ka(int in_nbit, int R, const KAParams& p, unsigned grid, cudaStream_t st) {
     return in_nbit == 2 ? b2f_launch_ka_2(R, p, grid, st) : b2f_launch_ka_8(R, p, grid, st);
 }
+cudaError_t b2f_launch_kr(int R, int mode, const KBParams& p, int grid, cudaStream_t st) {
+    if (R <= 64) return b2f_launch_kr_part0(R, mode, p, grid, st);
+    if (R == 256) return b2f_launch_kr_part2(R, mode, p, grid, st);
+    return b2f_launch_kr_part1(R, mode, p, grid, st);
+}
 cudaError_t b2f_launch_kb(int R, int mode, const KBParams& p, int grid, cudaStream_t st) {
     if (R <= 64) return b2f_launch_kb_part0(R, mode, p, grid, st);
     if (R == 256) return b2f_launch_kb_part2(R, mode, p, grid, st);
@@ -492,29 +507,40 @@ int push_fused(b2f_plan* pl, const K0Params& k0, int64_t nframes, int64_t nblk) 
         const int64_t n = nframes * nif;
         k0h_headers<<<(unsigned)((n + 255) / 256), 256, 0, pl->stream>>>(kh);
         if (nblk > 0) {
-            const int sc = std::min(32, pl->R);
+            const int sc = std::min(64, pl->R);
             const int64_t units = nbt * (pl->R / sc);
-            const unsigned grid = (unsigned)std::min<int64_t>(units, (int64_t)pl->num_sms * 8);
-            if (sc == 32) k0t_transpose<32><<<grid, 256, 0, pl->stream>>>(kt);
+            const unsigned grid = (unsigned)std::min<int64_t>(units, (int64_t)pl->num_sms * (sc == 64 ? 6 : 8));
+            if (sc == 64) k0t_transpose<64><<<grid, 256, 0, pl->stream>>>(kt);
+            else if (sc == 32) k0t_transpose<32><<<grid, 256, 0, pl->stream>>>(kt);
             else k0t_transpose<16><<<grid, 256, 0, pl->stream>>>(kt);
         }
     });
     if (rc) return rc;
     pl->launches++;                                   // two kernels in one timed region
     if (nblk == 0) return 0;
+    if (pl->d_levels) {
+        KJParams kj{};
+        for (int i = 0; i < nif; ++i) kj.frames[i] = k0.frames[i];
+        kj.fstat = pl->d_fstat; kj.fstat_stride = pl->fstat_stride; kj.levels = pl->d_levels;
+        kj.nblk = (int)nblk; kj.nif = nif; kj.R = pl->R; kj.frame_bytes = pl->prm.frame_bytes;
+        kj.header_bytes = pl->prm.header_bytes; kj.payload_bytes = (int)pl->payload; kj.mask_faults = pl->prm.mask_faults;
+        const int64_t nthreads = nbt * pl->R * 32;
+        rc = timed(pl, B2F_K_VALIDATE, [&] { kj_ja98_levels<<<(unsigned)((nthreads + 255) / 256), 256, 0, pl->stream>>>(kj); });
+        if (rc) return rc;
+    }
 
     FParams fp{};
     fp.tstream = pl->d_tstream; fp.tstream_if_stride = pl->tstream_stride;
     fp.ring = pl->d_inter; fp.colsum = pl->d_colsum; fp.eps = pl->d_eps;
     fp.tab_h = pl->d_tab_h; fp.tab_w = pl->d_tab_w; fp.tab_beta = pl->d_tab_beta; fp.tab_r = pl->d_tab_r;
-    const bool direct = pl->Dp == pl->D;
+    const bool direct = pl->Dp == pl->D || pl->path == 1;
     fp.out = direct ? pl->d_F : pl->d_part;
     fp.out_if_stride = direct ? pl->F_if_stride : pl->part_if_stride;
     fp.out_row0 = direct ? pl->rows_off + pl->rows_held : 0;
     fp.Dp = pl->Dp; fp.nblk = (int)nblk; fp.nif = nif;
     fp.gb_begin = 0; fp.gb_end = nbt;
     fp.sync = pl->d_fsync; fp.abort_flag = pl->d_fsync + (size_t)pl->f_lanes * FS_STRIDE;
-    fp.nslot = pl->f_nslot;
+    fp.nslot = pl->f_nslot; fp.lag = pl->f_lag; fp.prof = pl->d_fprof; fp.levels = pl->d_levels;
     cudaError_t e = cudaSuccess;
     if (pl->path == 2) {
         CU(cudaMemsetAsync(pl->d_fsync, 0, (size_t)pl->f_lanes * FS_STRIDE * sizeof(unsigned), pl->stream));
@@ -531,10 +557,20 @@ int push_fused(b2f_plan* pl, const K0Params& k0, int64_t nframes, int64_t nblk) 
             ke_eps<<<(unsigned)nbt, std::min(pl->R / 2, 512), pl->R * sizeof(float2), pl->stream>>>(pl->d_colsum, pl->d_eps, pl->R);
         });
         if (rc) return rc;
-        fp.phase = 2;
-        rc = timed(pl, B2F_K_ROW, [&] { e = b2f_launch_kf(pl->R, pl->prm.pol_mode, fp, pl->f_grid, 0, pl->stream, nullptr); });
+        // row pass over the [pair][row][2] blocks: per-warp cp.async ring, whole integration groups per warp -> F directly
+        int TR, PT;
+        kb_shape(pl->R, &TR, &PT);
+        const int RW = 32 / TR, GW = std::max(pl->D, RW);
+        KBParams kb{};
+        kb.inter = pl->d_inter; kb.eps = pl->d_eps; kb.tab_r = pl->d_tab_r;
+        kb.F = pl->d_F; kb.F_if_stride = pl->F_if_stride; kb.row0 = pl->rows_off + pl->rows_held;
+        kb.nblk = (int)nblk; kb.nif = nif; kb.D = pl->D; kb.gb_begin = 0; kb.gb_end = nbt;
+        const int64_t ngroups = nbt * (kL / GW);
+        const int64_t ctas = (ngroups + kKBThreads / 32 - 1) / (kKBThreads / 32);
+        rc = timed(pl, B2F_K_ROW, [&] { e = b2f_launch_kr(pl->R, pl->prm.pol_mode, kb, (int)std::min<int64_t>(ctas, (int64_t)pl->num_sms * 2), pl->stream); });
         if (rc) return rc;
-        if (e != cudaSuccess) return fail(B2F_ECUDA, std::string("row half launch: ") + cudaGetErrorString(e));
+        if (e != cudaSuccess) return fail(B2F_ECUDA, std::string("row pass launch: ") + cudaGetErrorString(e));
+        return 0;
     }
     if (!direct) {
         const int ncol = pl->nprod * pl->N;
@@ -597,6 +633,10 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
         if (std::fabs(std::fabs(prm->bw_mhz[i]) - abw) > 1e-9) return fail(B2F_EINVAL, "all IFs must share |bw|");
         if (prm->if_order[i] < 0 || prm->if_order[i] >= prm->nif) return fail(B2F_EINVAL, "if_order");
     }
+    if (prm->decode_mode != B2F_DECODE_STATIC && prm->decode_mode != B2F_DECODE_JA98) return fail(B2F_EINVAL, "decode_mode");
+    if (prm->decode_mode == B2F_DECODE_JA98 && prm->in_nbit != 2) return fail(B2F_EINVAL, "decode_mode JA98 is a 2-bit unpacker");
+    if (prm->rescale_mode != B2F_RESCALE_CONSTANT && prm->rescale_mode != B2F_RESCALE_RUNNING) return fail(B2F_EINVAL, "rescale_mode");
+    if (prm->digi_sigma < 0) return fail(B2F_EINVAL, "digi_sigma");
     const int W = prm->raw_word_bits;
     if (W != 0 && W != 16 && W != 32 && W != 64) return fail(B2F_EINVAL, "raw_word_bits must be 0, 16, 32 or 64");
     if (W && prm->in_nbit != 2) return fail(B2F_EUNSUPPORTED, "raw multi-BBC input must be 2-bit");
@@ -689,15 +729,26 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
     if (cudaGetDeviceProperties(&prop, prm->device) != cudaSuccess) { free_plan(pl); return fail(B2F_ECUDA, "device properties"); }
     pl->num_sms = prop.multiProcessorCount;
     {
-        // which channeliser: the fused kernel wherever it applies (2-bit split streams, frames in order, 512-point
-        // columns, no dedispersion); B2F_PATH=legacy|split|fused overrides (split = the new kernels as two launches)
+        // Which channeliser.  Measured on B200 for C2 (20 s of 8 IF x 32 MHz): round-1 kernels 46.1 ms (column 31.1 + row 15.0),
+        // round-2 kernels as two launches 54.5 (column 25.7, 25 % faster and free of bank conflicts, but its [pair][row][2]
+        // block layout halves the row pass's HBM efficiency: 28.8), fused kernel 61.6 with 12x less DRAM traffic (0.79 GB
+        // instead of 9.75 GB per push: the intermediate stays in the L2 ring) -- its inter-warp ordering costs more than the
+        // HBM round trip saved.  So the round-1 kernels stay the default; B2F_PATH=split|fused selects the others where
+        // they apply (2-bit split streams, frames in order, 512-point columns, no dedispersion), and the JA98 decode, which
+        // only the round-2 column kernel implements, selects the fused kernel by itself.
         const bool eligible = !generic && !dedisp && prm->in_nbit == 2 && W == 0 && prm->frame_time_mode == B2F_FRAMES_POSITIONAL &&
                               payload % 16 == 0 && prm->frame_bytes % 16 == 0 && prop.cooperativeLaunch;
         const char* e = getenv("B2F_PATH");
-        int want = 2;
+        int want = prm->decode_mode == B2F_DECODE_JA98 ? 2 : 0;
         if (e && !strcmp(e, "legacy")) want = 0;
         else if (e && !strcmp(e, "split")) want = 1;
+        else if (e && !strcmp(e, "fused")) want = 2;
         pl->path = eligible ? want : 0;
+        if (prm->decode_mode == B2F_DECODE_JA98 && (!eligible || want == 0)) {
+            delete pl;
+            return fail(B2F_EUNSUPPORTED, "decode_mode JA98 is implemented in the round-2 column kernel only: 2-bit split streams, frames in "
+                                          "order, freq_res 512, nchan <= 256, no dedispersion");
+        }
         if (pl->path) {
             int occ = 0;
             FParams dummy{};
@@ -705,13 +756,13 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
                 cudaGetLastError();
                 pl->path = 0;
             } else {
-                const int npair = R / 2;
-                const int cpl = std::max(1, npair / kFWarps);              // CTAs per lane (one block per lane and round)
-                pl->f_grid = std::max(1, (std::min(occ, 1) * pl->num_sms) / cpl) * cpl;
-                if (pl->f_grid > occ * pl->num_sms) pl->path = 0;          // fewer SMs than one lane needs
+                const int npair = R / 2;                                   // warps per lane (one block per lane and round)
+                pl->f_grid = pl->num_sms;                                  // one 16-warp CTA per SM
                 pl->f_lanes = pl->f_grid * kFWarps / npair;
-                const char* ns = getenv("B2F_RING_SLOTS");
-                pl->f_nslot = ns ? std::max(2, std::min(4, atoi(ns))) : 2;
+                if (pl->f_lanes < 1) pl->path = 0;
+                const char* lg = getenv("B2F_ROW_LAG");
+                pl->f_lag = lg ? std::max(1, std::min(3, atoi(lg))) : 2;
+                { const char* e2 = getenv("B2F_RING_SLOTS"); pl->f_nslot = e2 ? std::max(pl->f_lag + 1, std::min(6, atoi(e2))) : pl->f_lag + 1; }
                 pl->Dp = std::min(D, 1024 / R);
             }
         }
@@ -758,7 +809,12 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
         CUB(cudaMalloc(&pl->d_fillflag, pl->fillflag_stride * nif * sizeof(int)));
         CUB(cudaMalloc(&pl->d_fsync, ((size_t)pl->f_lanes + 1) * FS_STRIDE * sizeof(unsigned)));
         CUB(cudaMemset(pl->d_fsync, 0, ((size_t)pl->f_lanes + 1) * FS_STRIDE * sizeof(unsigned)));
-        if (pl->Dp < D) {
+        if (prm->decode_mode == B2F_DECODE_JA98) CUB(cudaMalloc(&pl->d_levels, (size_t)nbt * R * sizeof(float4)));
+        if (getenv("B2F_FUSED_PROF")) {
+            CUB(cudaMalloc(&pl->d_fprof, (size_t)pl->f_grid * kFWarps * 8 * sizeof(unsigned long long)));
+            CUB(cudaMemset(pl->d_fprof, 0, (size_t)pl->f_grid * kFWarps * 8 * sizeof(unsigned long long)));
+        }
+        if (pl->Dp < D && pl->path == 2) {
             pl->part_if_stride = pl->chunk_blocks * (L / pl->Dp) * nprod * pl->N;
             CUB(cudaMalloc(&pl->d_part, (size_t)pl->part_if_stride * nif * sizeof(float)));
         }
@@ -873,6 +929,19 @@ int b2f_push(b2f_plan* pl, const void* const* frames, int64_t nframes, int on_de
     const int64_t nblk = pl->carry_mode ? (T >= pl->M ? (T - pl->M) / pl->step + 1 : 0) : nframes * pl->spf / pl->M;
     const int64_t rows = nblk * pl->keep / pl->D;
     if (nblk == 0 && !pl->carry_mode) return 0;
+    if (pl->rows_off + pl->rows_held + rows > pl->F_cap_rows && pl->rows_off > 0 && pl->rows_held + rows <= pl->F_cap_rows) {
+        // running rescale keeps the rows of an unfinished interval: move them to the front of the buffer, in pieces no
+        // longer than the gap so that source and destination of one copy never overlap
+        const int64_t ncolF = (int64_t)pl->nprod * pl->N;
+        for (int i = 0; i < pl->prm.nif; ++i)
+            for (int64_t r0 = 0; r0 < pl->rows_held; r0 += pl->rows_off) {
+                const int64_t n = std::min(pl->rows_off, pl->rows_held - r0);
+                float* base = pl->d_F + i * pl->F_if_stride;
+                CU(cudaMemcpyAsync(base + r0 * ncolF, base + (pl->rows_off + r0) * ncolF, (size_t)n * ncolF * sizeof(float),
+                                   cudaMemcpyDeviceToDevice, pl->stream));
+            }
+        pl->rows_off = 0;
+    }
     if (pl->rows_off + pl->rows_held + rows > pl->F_cap_rows)
         return fail(B2F_ESTATE, "row buffer full: call b2f_pull before pushing more");
     const size_t fbytes = (size_t)nframes * pl->prm.frame_bytes;
@@ -1000,8 +1069,8 @@ int b2f_push(b2f_plan* pl, const void* const* frames, int64_t nframes, int on_de
         rc = push_dedisp(pl, nblk, T);
         if (rc) return rc;
     } else
-    // ---- channeliser in L2-sized sub-batches: the column pass writes [nb][512][R] float2 and the
-    // row pass reads it straight back, so the intermediate never has to reach HBM.
+    // ---- round-1 channeliser: the column pass writes the whole [nb][512][R] float2 intermediate to HBM and the row pass
+    // streams it back (97 % of the step's DRAM traffic; L2-sized sub-batches were measured slower, see plan_create)
     {
         const int64_t nbt = (int64_t)nif * nblk;
         const int64_t NB = pl->batch_blocks > 0 ? std::min<int64_t>(pl->batch_blocks, nbt) : nbt;
@@ -1019,6 +1088,7 @@ int b2f_push(b2f_plan* pl, const void* const* frames, int64_t nframes, int on_de
         ka.payload_bytes = (int)pl->payload; ka.groups_per_slot = (int)pl->groups_per_slot;
         ka.blk_step_bytes = pl->M * (pl->prm.in_nbit == 2 ? 1 : 2);
         ka.sm_slots = pl->d_sm_slots; ka.stagger_cycles = pl->stagger_cycles;
+        ka.in8_offset = pl->prm.in8_offset_mode ? 128.0f : 127.5f;
         {
             const char* e = getenv("B2F_KA_VARIANT");      // timing ablations only (tools/ablate.py)
             ka.variant = e ? atoi(e) : 0;
@@ -1070,7 +1140,12 @@ int b2f_pull(b2f_plan* pl, void* out, int64_t max_rows, int out_on_device, int64
 
 int b2f_pull_strided(b2f_plan* pl, void* out, int64_t max_rows, int64_t row_pitch_bytes, int64_t* nrows) {
     if (pl && row_pitch_bytes < pl->row_bytes) return fail(B2F_EINVAL, "row pitch smaller than one output row");
-    if (row_pitch_bytes % 4) return fail(B2F_EINVAL, "row pitch must be a multiple of 4 bytes");
+    {
+        // kq_quantise stores 4 output elements at a time: 4 bytes for 8-bit (1 byte for 2-bit), 8 for 16-bit, 16 for float
+        const int align = !pl ? 4 : (pl->prm.out_nbit == 16 ? 8 : (pl->prm.out_nbit == -32 ? 16 : 4));
+        if (row_pitch_bytes % align || (reinterpret_cast<uintptr_t>(out) % align))
+            return fail(B2F_EINVAL, "row pitch and output pointer must be multiples of " + std::to_string(align) + " bytes for this nbit");
+    }
     return pull_impl(pl, out, max_rows, 1, row_pitch_bytes, nrows);
 }
 
@@ -1091,11 +1166,14 @@ static int pull_impl(b2f_plan* pl, void* out, int64_t max_rows, int out_on_devic
             });
             if (rc) return rc;
             pl->stats_ready = true;
+            pl->rows_this_interval = nstat;
         } else {
             return 0;
         }
     }
-    const int64_t n = std::min(pl->rows_held, max_rows);
+    const bool running = pl->prm.rescale_mode == B2F_RESCALE_RUNNING && !pl->prm.keep_bandpass && !pl->preset_stats;
+    int64_t n = std::min(pl->rows_held, max_rows);
+    if (running) n = std::min(n, pl->rows_this_interval);       // the statistics in force cover only their own interval
     if (n <= 0) return 0;
     if (!out) return fail(B2F_EINVAL, "null output buffer");
     void* dst = out;
@@ -1120,6 +1198,7 @@ static int pull_impl(b2f_plan* pl, void* out, int64_t max_rows, int out_on_devic
     kq.out_pitch_bytes = pitch_bytes > 0 ? pitch_bytes : pl->row_bytes;
     kq.nif = nif; kq.nprod = pl->nprod; kq.nchan = pl->N; kq.out_nbit = pl->prm.out_nbit;
     kq.pol_major = pl->prm.splice_pol_major;
+    kq.inv_digi_sigma = (float)(1.0 / (pl->prm.digi_sigma > 0 ? pl->prm.digi_sigma : 6.0));
     for (int i = 0; i < nif; ++i) {
         kq.if_order[i] = pl->prm.if_order[i];
         kq.flip[i] = pl->prm.bw_mhz[i] > 0 ? 1 : 0;
@@ -1143,6 +1222,10 @@ static int pull_impl(b2f_plan* pl, void* out, int64_t max_rows, int out_on_devic
     pl->rows_held -= n;
     pl->rows_emitted += n;
     pl->rows_off = pl->rows_held ? pl->rows_off + n : 0;
+    if (running) {
+        pl->rows_this_interval -= n;
+        if (pl->rows_this_interval == 0) pl->stats_ready = false;     // the next interval measures itself
+    }
     *nrows = n;
     return 0;
 }
@@ -1408,6 +1491,7 @@ int b2f_debug_copy(b2f_plan* pl, int which, void* dst, size_t nbytes, size_t* ne
         case 5: src = pl->d_colsum; n = (size_t)nbt * pl->R * sizeof(float2); break;
         case 6: src = pl->d_eps; n = (size_t)nbt * pl->N * sizeof(float2); break;
         case 7: src = pl->d_F; n = (size_t)pl->F_if_stride * nif * sizeof(float); break;
+        case 8: src = pl->d_fprof; n = (size_t)pl->f_grid * kFWarps * 8 * sizeof(unsigned long long); break;
         default: return fail(B2F_EINVAL, "which");
     }
     if (!src) return fail(B2F_EINVAL, "this buffer is not used by the plan's channeliser path");

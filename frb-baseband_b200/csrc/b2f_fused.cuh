@@ -40,7 +40,10 @@ template <> struct FShape<16>  { static constexpr int TR = 4,  PT = 4;  };
 template <> struct FShape<32>  { static constexpr int TR = 4,  PT = 8;  };
 template <> struct FShape<64>  { static constexpr int TR = 8,  PT = 8;  };
 template <> struct FShape<128> { static constexpr int TR = 8,  PT = 16; };
-template <> struct FShape<256> { static constexpr int TR = 16, PT = 16; };
+#ifndef B2F_F256_TR
+#define B2F_F256_TR 16
+#endif
+template <> struct FShape<256> { static constexpr int TR = B2F_F256_TR, PT = 256 / B2F_F256_TR; };
 template <> struct FShape<512> { static constexpr int TR = 16, PT = 32; };
 
 template <int R>
@@ -66,7 +69,7 @@ struct FGeo {
 struct FParams {
     const uint8_t* tstream;        // [if][blk][pair][half][lane][16] index bytes (k0t_transpose)
     size_t tstream_if_stride;
-    float2* ring;                  // fused: [2 * lanes][M]; split: [blocks of the launch][M]; slot layout [pair][512][2]
+    float2* ring;                  // fused: [(lag + 1) * lanes][M]; split: [blocks of the launch][M]; slot layout [R/2 column pairs][512 rows][2 columns]
     float2* colsum;                // [nif*nblk][R]
     float2* eps;                   // [nif*nblk][R/2]
     const float2 *tab_h, *tab_w, *tab_beta, *tab_r;
@@ -79,7 +82,10 @@ struct FParams {
     unsigned* sync;                // [lanes][FS_STRIDE]
     unsigned* abort_flag;
     int phase;                     // 0 fused, 1 column halves only, 2 row halves only
-    int nslot;                     // ring slots per lane (fused): 2 or 3
+    int nslot;                     // ring slots per lane (fused): lag + 1
+    int lag;                       // rounds between the column half and the row half of a block (fused): 1 or 2
+    const float4* levels;          // JA98 decode: [nif*nblk][R windows] (lo0, hi0, lo1, hi1); NULL = static levels
+    unsigned long long* prof;      // optional [warps][8] cycle counters (B2F_FUSED_PROF=1): where a warp's time goes
 };
 
 // ------------------------------------------------------------------ inter-warp ordering through L2
@@ -93,12 +99,16 @@ __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-// the whole warp calls; true when *ctr >= target was observed (acquire), false on abort / timeout
+// The whole warp calls; true when *ctr >= target was observed, false on abort / timeout.  The poll is a relaxed
+// gpu-scope load: everything a waiter reads afterwards is read with .cg loads / cp.async.cg, i.e. from L2, the point
+// of coherence, and is issued after the poll returned (control dependency), while the producer ordered its stores
+// before the counter update with a gpu-scope fence.  An acquire load here costs an L1 invalidation (CCTL.IVALL) per
+// poll: 12 % of the fused kernel's stall samples in the first version.
 __device__ __forceinline__ bool warp_wait_ge(const unsigned* ctr, unsigned target, unsigned* abort_flag, int lane) {
     int ok = 1;
     if (lane == 0) {
         unsigned spins = 0;
-        while (ld_acquire_u32(ctr) < target) {
+        while (ld_relaxed_u32(ctr) < target) {
             if (++spins > kFSpinLimit || ((spins & 63u) == 0 && ld_relaxed_u32(abort_flag) != 0)) {
                 atomicExch(abort_flag, 1u);
                 ok = 0;
@@ -110,13 +120,19 @@ __device__ __forceinline__ bool warp_wait_ge(const unsigned* ctr, unsigned targe
     ok = __shfl_sync(0xffffffffu, ok, 0);
     return ok != 0;
 }
-// all lanes have finished their global stores / loads; one release-ordered increment for the warp
+// all lanes have finished their global stores; one release-ordered increment for the warp.  The fence waits until
+// the warp's earlier stores are visible, so callers place this well after the stores (end of the round).
 __device__ __forceinline__ void warp_arrive(unsigned* ctr, int lane) {
     __syncwarp();
     if (lane == 0) {
         __threadfence();
         atomicAdd(ctr, 1u);
     }
+}
+// the warp's loads have completed (their data is in shared memory): nothing to publish, a relaxed increment is enough
+__device__ __forceinline__ void warp_arrive_relaxed(unsigned* ctr, int lane) {
+    __syncwarp();
+    if (lane == 0) asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
 }
 __device__ __forceinline__ float2 ldcg_f2(const float2* p) {
     float2 v;
@@ -133,9 +149,16 @@ __device__ __forceinline__ uint4 ldg_stream16(const void* p) {       // read-onc
 // ------------------------------------------------------------------ column half of one work item
 // lane = 2 * item + col.  xb: this warp's exchange buffer, E[a][b] of column c at float4 index a * 34 + 2 b + c.
 // dst: this warp's 8 KiB of the block slot, float2 index 2 * row + col.
+// sign and size class from the static lookup, magnitude from the window's levels (JA98 decode)
+__device__ __forceinline__ float2 f_ja98(float2 v, float4 lv) {
+    const float ax = fabsf(v.x), ay = fabsf(v.y);
+    return make_float2(ax == 0.f ? 0.f : copysignf(ax > 2.f ? lv.y : lv.x, v.x), ay == 0.f ? 0.f : copysignf(ay > 2.f ? lv.w : lv.z, v.y));
+}
+
 template <int R>
 __device__ __forceinline__ void f_col_front(const uint4 rawA, const uint4 rawB, float4* xb, const float4* s_w4,
-                                            const uint8_t* s_lut, const float4* s_h4w, const int lane, float2* colsum_n1) {
+                                            const uint8_t* s_lut, const float4* s_h4w, const int lane, float2* colsum_n1,
+                                            const float4* levels_blk) {
     const int item = lane >> 1, col = lane & 1;
     // ---- P1: decode, FFT_16 over r (n2 = 32 r + l) for l = item (A) and item + 16 (B), twiddle W_512^(l q)
     {
@@ -147,6 +170,14 @@ __device__ __forceinline__ void f_col_front(const uint4 rawA, const uint4 rawB, 
             const uint32_t ib = __byte_perm(wb[r >> 2], 0u, 0x4440 + (r & 3));
             vA[r] = *reinterpret_cast<const float2*>(s_lut + ia);
             vB[r] = *reinterpret_cast<const float2*>(s_lut + ib);
+        }
+        if (levels_blk) {           // a window of 512 time samples is 512 / R rows of the block (R <= 512)
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const int rowA = 32 * r + item;
+                vA[r] = f_ja98(vA[r], __ldg(levels_blk + ((rowA * R) >> 9)));
+                vB[r] = f_ja98(vB[r], __ldg(levels_blk + (((rowA + 16) * R) >> 9)));
+            }
         }
         fft_inreg<16, false>(vA);
         fft_inreg<16, false>(vB);
@@ -188,6 +219,10 @@ __device__ __forceinline__ void f_col_front(const uint4 rawA, const uint4 rawB, 
 }
 
 // ---- P3: * beta^q (W_M^(q n1) conj W_512^(q m1));  IFFT_16 over q -> m2;  rows m1 + 32 m2, m1 = item, item + 16
+// dst: this warp's 8 KiB of the block slot (slot layout [column pair][512 rows][2 columns] float2): every store instruction
+// of the warp writes 256 contiguous bytes.  (Measured alternative, row-pair-major [256][R/2][2][2] so that the row pass reads
+// contiguous memory: the 32-byte store granules made the column half 2.6x slower, 61 vs 23 ms per 20 s of C2.)
+template <int R>
 __device__ __forceinline__ void f_col_back(const float4* xb, const float2 (&betaS)[4], const int lane, float2* dst) {
     {
         float2 pw[16];
@@ -241,15 +276,23 @@ __device__ __forceinline__ void f_row_fft(const float2* tile, float2* myx, const
     for (int j = 0; j < QPT; ++j) fft_inreg<TR, false>(z[j]);
 }
 
-// 16-byte pieces of rows [m0, m0 + RPW) of a block slot -> this warp's row tile
+// 16-byte pieces (one column pair of one row) of rows [m0, m0 + RPW) of a block slot -> this warp's row-major tile
 template <int R>
 __device__ __forceinline__ void f_row_load(const float2* slot, const int m0, uint8_t* wbuf, const int lane) {
     using G = FGeo<R>;
+    if (G::RPW <= 32) {                                         // RPW * NPAIR = 512 pieces: lane = (pair, row), row fastest
+        constexpr int PPK = 32 / (G::RPW <= 32 ? G::RPW : 32);  // pairs per instruction
+        const int r = lane % G::RPW, pp0 = lane / G::RPW;
+        uint8_t* dst = wbuf + r * G::kPitch + pp0 * 16;
+        const float2* src = slot + ((int64_t)pp0 * kL + m0 + r) * 2;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {                              // RPW * NPAIR = 512 pieces
-        const int idx = lane + 32 * k;
-        const int r = idx % G::RPW, pp = idx / G::RPW;
-        cp_async16(wbuf + r * G::kPitch + pp * 16, slot + ((int64_t)pp * kL + m0 + r) * 2);
+        for (int k = 0; k < 16; ++k) cp_async16(dst + k * PPK * 16, src + (int64_t)k * PPK * kL * 2);
+    } else {                                                    // R = 16: 64 rows per warp, two instructions per pair
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int r = lane + 32 * (k & 1), pp = k >> 1;
+            cp_async16(wbuf + r * G::kPitch + pp * 16, slot + ((int64_t)pp * kL + m0 + r) * 2);
+        }
     }
     cp_async_commit();
 }
@@ -392,27 +435,31 @@ __global__ void __launch_bounds__(kFThreads, 1) kf_fused(const FParams p) {
     }
     for (int i = tid; i < G::PT * G::TR; i += kFThreads) s_tw[i] = p.tab_r[i];
 
-    // ---- this warp's static place: lane `lam` (one block per round), column pair `pr`
+    // ---- this warp's static place: lane `lam` (one block per round), column pair `pr`.  Consecutive warps belong to
+    // different lanes, so the 16 warps of an SM work on 16 different blocks: when one lane waits, the others keep the
+    // SM busy (with whole lanes per SM every inter-warp wait idled the SM).
     const int gw = blockIdx.x * kFWarps + warp;
     const int nl = (int)(gridDim.x * kFWarps) / G::NPAIR;
-    const int lam = gw / G::NPAIR, pr = gw % G::NPAIR;
+    const int lam = gw % nl, pr = gw / nl;
+    const bool active = pr < G::NPAIR;
     const int item = lane >> 1, col = lane & 1;
-    const int n1 = 2 * pr + col;
+    const int n1 = 2 * (active ? pr : 0) + col;
     {
         const int pp = lane >> 1;                                // 16 entries x 2 columns
-        const float2 h0 = p.tab_h[pp * R + 2 * pr + (lane & 1)], h1 = p.tab_h[(pp + 16) * R + 2 * pr + (lane & 1)];
-        s_h4w[pp * 2 + (lane & 1)] = make_float4(h0.x, h0.y, h1.x, h1.y);
+        const float2 h0 = p.tab_h[pp * R + n1], h1 = p.tab_h[(pp + 16) * R + n1];
+        s_h4w[pp * 2 + col] = make_float4(h0.x, h0.y, h1.x, h1.y);
     }
     float2 betaS[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) betaS[k] = p.tab_beta[(size_t)(item * 4 + k) * R + n1];
     __syncthreads();
-    if (lam >= nl) return;
+    if (!active) return;
 
     const int64_t nb = p.gb_end - p.gb_begin;
     const int64_t M = (int64_t)R * kL;
     unsigned* sy = p.sync + (size_t)lam * FS_STRIDE;
     const int phase = p.phase, ns = p.nslot;
+    const int lag = phase == 0 ? p.lag : 0;                  // rounds between a block's columns and its rows
 
     auto raw_ptr = [&](int64_t lb) {
         const int64_t gb = p.gb_begin + lb;
@@ -427,58 +474,108 @@ __global__ void __launch_bounds__(kFThreads, 1) kf_fused(const FParams p) {
         rawB = ldg_stream16(q + 512);
     }
 
+    unsigned long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tprev = clock64();
+    auto tick = [&](int k) {
+        if (p.prof) {
+            const long long t = clock64();
+            tacc[k] += (unsigned long long)(t - tprev);
+            tprev = t;
+        }
+    };
+    // Round i of a lane: rows of block i - lag, then (one rotating warp) eps of block i - 1, then the columns of block i.
+    // Every wait is for something the other warps of the lane did about a round earlier: the rows of block i - lag need
+    // the columns published early in round i - lag + 1 and the eps computed in the middle of it; the ring slot the
+    // columns of block i go to (lag + 1 slots per lane) was read at the start of round i - 1.  The three counters are
+    // therefore read once at the top of the round, long before they are needed; a polling loop only runs if such a value
+    // is not yet sufficient.  A round's own column result is published at the NEXT round's row stage, after a load wait,
+    // when its stores have long left the SM: the gpu-scope fence in front of the counter update is then cheap (directly
+    // after the stores it cost a store round trip per work item, 6 % of the kernel).
+    bool col_pending = false;
 #pragma unroll 1
     for (int i = 0;; ++i) {
         const int64_t lbc = (int64_t)i * nl + lam;                         // block whose columns run this round
-        const int64_t lbr = phase == 2 ? lbc : lbc - nl;                   // block whose rows run this round
+        const int64_t lbr = lbc - (int64_t)lag * nl;                       // block whose rows run this round
+        const int64_t lbe = lbc - nl;                                      // block whose eps is due this round
         const bool vc = phase != 2 && lbc < nb;
         const bool vr = phase != 1 && lbr >= 0 && lbr < nb;
-        if (!vc && !vr) break;
+        const bool ve = phase == 0 && lbe >= 0 && lbe < nb && pr == (i % G::NPAIR);
+        if (lbr >= nb || lam >= nb) break;                                 // this lane's last block has had its rows
         __syncwarp();
-        // ---- eps of last round's block, by one rotating warp, before its own column work
-        if (phase == 0 && vr && pr == (i % G::NPAIR)) {
-            if (!warp_wait_ge(sy + FS_COL, (unsigned)(G::NPAIR * i), p.abort_flag, lane)) return;
+        unsigned c_col = 0, c_row = 0, c_eps = 0;
+        if (phase == 0) {                                                  // all lanes read the same words: one transaction each
+            c_col = ld_relaxed_u32(sy + FS_COL);
+            c_eps = ld_relaxed_u32(sy + FS_EPS);
+            c_row = ld_relaxed_u32(sy + FS_ROW);
+        }
+        tick(7);
+        if (vr) {
             const int64_t gb = p.gb_begin + lbr;
+            const int64_t slot = phase == 0 ? (int64_t)lam * ns + ((i - lag) % ns) : lbr;
+            if (phase == 0) {
+                if (c_col < (unsigned)(G::NPAIR * (i - lag + 1)) &&
+                    !warp_wait_ge(sy + FS_COL, (unsigned)(G::NPAIR * (i - lag + 1)), p.abort_flag, lane)) return;
+                if (c_eps < (unsigned)(i - lag + 1) && !warp_wait_ge(sy + FS_EPS, (unsigned)(i - lag + 1), p.abort_flag, lane)) return;
+            }
+            tick(3);
+            f_row_load<R>(p.ring + slot * M, pr * G::RPW, wbuf, lane);
+            cp_async_wait<0>();
+            __syncwarp();
+            tick(4);
+        }
+        if (col_pending) { warp_arrive(sy + FS_COL, lane); col_pending = false; }     // last round's columns
+        if (vr && phase == 0) warp_arrive_relaxed(sy + FS_ROW, lane);                  // the slot has been read
+        if (vc && i > 0 && phase != 1) {                                   // input of this round's columns (round 0: loaded above)
+            const uint8_t* q = raw_ptr(lbc);
+            rawA = ldg_stream16(q);
+            rawB = ldg_stream16(q + 512);
+        }
+        tick(5);
+        if (vr) {
+            const int64_t gb = p.gb_begin + lbr;
+            f_row_compute<R, MODE>(p, wbuf, s_tw, p.eps + gb * G::N, gb, pr * G::RPW, lane);
+            __syncwarp();
+            tick(6);
+        }
+        if (ve) {
+            if (!warp_wait_ge(sy + FS_COL, (unsigned)(G::NPAIR * i), p.abort_flag, lane)) return;
+            const int64_t gb = p.gb_begin + lbe;
             f_eps<R>(p.colsum + gb * R, p.eps + gb * G::N, wbuf, s_tw, lane);
             __syncwarp();
             if (lane == 0) {
                 __threadfence();
                 atomicMax(sy + FS_EPS, (unsigned)i);
             }
+            tick(3);
         }
         if (vc) {
             const int64_t gb = p.gb_begin + lbc;
             const int64_t slot = phase == 0 ? (int64_t)lam * ns + (i % ns) : lbc;
-            f_col_front<R>(rawA, rawB, reinterpret_cast<float4*>(wbuf), s_w4, s_lut, s_h4w, lane, p.colsum + gb * R + n1);
-            // the slot written now was read by the row halves `ns` rounds ago (they ran one round later)
-            if (phase == 0 && i >= ns) {
+            f_col_front<R>(rawA, rawB, reinterpret_cast<float4*>(wbuf), s_w4, s_lut, s_h4w, lane, p.colsum + gb * R + n1,
+                           p.levels ? p.levels + gb * R : nullptr);
+            tick(0);
+            // the slot written now was read by the row halves of the block `ns` rounds back
+            if (phase == 0 && i >= ns && c_row < (unsigned)(G::NPAIR * (i - ns + 1))) {
                 if (!warp_wait_ge(sy + FS_ROW, (unsigned)(G::NPAIR * (i - ns + 1)), p.abort_flag, lane)) return;
             }
-            f_col_back(reinterpret_cast<const float4*>(wbuf), betaS, lane, p.ring + slot * M + (size_t)pr * 1024);
-            if (phase == 0) warp_arrive(sy + FS_COL, lane);
-            if (lbc + nl < nb) {
+            tick(1);
+            f_col_back<R>(reinterpret_cast<const float4*>(wbuf), betaS, lane, p.ring + slot * M + (size_t)pr * 1024);
+            col_pending = phase == 0;
+            if (phase == 1 && lbc + nl < nb) {                             // columns only: prefetch the next work item
                 const uint8_t* q = raw_ptr(lbc + nl);
                 rawA = ldg_stream16(q);
                 rawB = ldg_stream16(q + 512);
             }
+            tick(2);
         }
-        if (vr) {
-            const int64_t gb = p.gb_begin + lbr;
-            const int64_t slot = phase == 0 ? (int64_t)lam * ns + ((i - 1) % ns) : lbr;
-            if (phase == 0) {
-                if (!warp_wait_ge(sy + FS_COL, (unsigned)(G::NPAIR * i), p.abort_flag, lane)) return;
-            }
-            __syncwarp();
-            f_row_load<R>(p.ring + slot * M, pr * G::RPW, wbuf, lane);
-            if (phase == 0) {
-                if (!warp_wait_ge(sy + FS_EPS, (unsigned)i, p.abort_flag, lane)) return;
-            }
-            cp_async_wait<0>();
-            __syncwarp();
-            if (phase == 0) warp_arrive(sy + FS_ROW, lane);               // the slot has been read
-            f_row_compute<R, MODE>(p, wbuf, s_tw, p.eps + gb * G::N, gb, pr * G::RPW, lane);
-            __syncwarp();
-        }
+        if (lag < 2 && col_pending) { warp_arrive(sy + FS_COL, lane); col_pending = false; }   // lag 1: next round's rows wait for it
+    }
+    if (col_pending) warp_arrive(sy + FS_COL, lane);
+    // 0 column front, 1 wait for the ring slot, 2 column back + stores, 3 eps / publish / wait for the block's columns,
+    // 4 row load (issue, eps wait, data), 5 arrivals, 6 row compute, 7 loop overhead
+    if (p.prof && lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) atomicAdd(&p.prof[(size_t)gw * 8 + k], tacc[k]);
     }
 }
 
@@ -539,7 +636,7 @@ static __global__ void k0h_headers(const K0HParams p) {
 
 template <int SC>
 static __global__ void __launch_bounds__(256) k0t_transpose(const K0TParams p) {
-    constexpr int PB = SC / 2;                   // payload bytes per row piece
+    constexpr int PB = SC / 2;                   // payload bytes per row piece (a whole 32-byte sector for SC = 64)
     constexpr int NW = PB / 4;                   // 32-bit words per piece
     constexpr int PITCH = SC + 8;                // bytes between rows of expanded index bytes: conflict-free word reads
     __shared__ __align__(16) uint8_t s_exp[kL * PITCH];
@@ -548,72 +645,97 @@ static __global__ void __launch_bounds__(256) k0t_transpose(const K0TParams p) {
     const int64_t M = (int64_t)R * kL;
     const int64_t nunits = (int64_t)p.nif * p.nblk * nstrip;
     unsigned long long nfill_total = 0;
-    for (int64_t u = blockIdx.x; u < nunits; u += gridDim.x) {
+    uint32_t w[2][NW];
+    uint8_t dead[2];
+    int64_t fr[2];
+    int fif = 0;
+    // the pieces of the next unit are loaded into registers while this unit's transposed read-out runs
+    auto load_unit = [&](int64_t u) {
         const int strip = (int)(u % nstrip);
         const int64_t gb = u / nstrip;
         const int ifi = (int)(gb / p.nblk);
         const int64_t blk = gb % p.nblk;
         const uint8_t* frames = p.frames[ifi];
-        // ---- load, validate, expand: two rows per thread
+        fif = ifi;
 #pragma unroll
-        for (int k = 0; k < kL / 256; ++k) {
+        for (int k = 0; k < 2; ++k) {
             const int row = tid + 256 * k;
             const int64_t pb = (blk * M + (int64_t)R * row + (int64_t)strip * SC) >> 1;     // payload byte of the stream
             const int64_t f = pb / p.payload_bytes;
             const int off = (int)(pb - f * p.payload_bytes);
             const uint8_t* src = frames + f * p.frame_bytes + p.header_bytes + off;
-            uint32_t w[NW];
-            if (NW == 4) {
-                const uint4 v = ldg_stream16(src);
-                w[0] = v.x; w[1] = v.y; w[2 % NW] = v.z; w[3 % NW] = v.w;
+            if (NW >= 4) {
+#pragma unroll
+                for (int v = 0; v < NW / 4; ++v) {
+                    const uint4 x = ldg_stream16(src + 16 * v);
+                    w[k][(4 * v) % NW] = x.x; w[k][(4 * v + 1) % NW] = x.y; w[k][(4 * v + 2) % NW] = x.z; w[k][(4 * v + 3) % NW] = x.w;
+                }
             } else {
-                const uint2 v = *reinterpret_cast<const uint2*>(src);
-                w[0] = v.x; w[1] = v.y;
+                const uint2 x = *reinterpret_cast<const uint2*>(src);
+                w[k][0] = x.x; w[k][1 % NW] = x.y;
             }
-            const bool dead = p.fstat[ifi * p.fstat_stride + f] == 2;
+            dead[k] = p.fstat[ifi * p.fstat_stride + f];
+            fr[k] = f;
+        }
+    };
+    if (blockIdx.x < nunits) load_unit(blockIdx.x);
+    for (int64_t u = blockIdx.x; u < nunits; u += gridDim.x) {
+        const int strip = (int)(u % nstrip);
+        const int64_t gb = u / nstrip;
+        const int ifi = (int)(gb / p.nblk);
+        const int64_t blk = gb % p.nblk;
+        // ---- validate + expand what was loaded: two rows per thread
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int row = tid + 256 * k;
+            const bool isdead = dead[k] == 2;
             unsigned fm = 0;
 #pragma unroll
-            for (int j = 0; j < NW; ++j) fm |= (unsigned)(w[j] == kFillWord) << j;
-            if (fm && !dead) {
+            for (int j = 0; j < NW; ++j) fm |= (unsigned)(w[k][j] == kFillWord) << j;
+            if (fm && !isdead) {
                 nfill_total += __popc(fm);
-                if (p.mask_faults && atomicExch(&p.fillflag[ifi * p.fillflag_stride + f], 1) == 0) {
+                if (p.mask_faults && atomicExch(&p.fillflag[fif * p.fillflag_stride + fr[k]], 1) == 0) {
                     atomicAdd(&p.counters[C_FILLFRAMES], 1ull);
                     atomicAdd(&p.counters[C_OK], ~0ull);                    // -1: alive, but not clean
                 }
             }
-            const unsigned mask = !p.mask_faults ? 0u : (dead ? 0xFu : fm);
+            const unsigned mask = !p.mask_faults ? 0u : (isdead ? 0xFFFFu : fm);
             uint2* d = reinterpret_cast<uint2*>(s_exp + row * PITCH);
 #pragma unroll
-            for (int j = 0; j < NW; ++j) d[j] = expand_word_2bit(w[j], (mask >> j) & 1);
+            for (int j = 0; j < NW; ++j) d[j] = expand_word_2bit(w[k][j], (mask >> j) & 1);
         }
         __syncthreads();
+        if (u + gridDim.x < nunits) load_unit(u + gridDim.x);
         // ---- transposed read-out: thread = (half, column quad, item); 16 rows x 4 columns -> 4 outputs of 16 bytes
         {
             const int lane = tid & 31, wrp = tid >> 5;
             const int item = lane & 15;
-            const int cq = (wrp & 3) * 2 + (lane >> 4);
             const int half = wrp >> 2;
-            if (cq < SC / 4) {
-                uint32_t o[4][4];
+            uint8_t* tb = p.tstream + ifi * p.tstream_if_stride + blk * M;
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    uint32_t a[4];
+            for (int t = 0; t < (SC + 31) / 32; ++t) {
+                const int cq = (wrp & 3) * 2 + (lane >> 4) + 8 * t;
+                if (cq < SC / 4) {
+                    uint32_t o[4][4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        a[j] = *reinterpret_cast<const uint32_t*>(s_exp + (32 * (4 * g + j) + item + 16 * half) * PITCH + 4 * cq);
-                    const uint32_t t0 = __byte_perm(a[0], a[1], 0x5140), t1 = __byte_perm(a[2], a[3], 0x5140);
-                    const uint32_t t2 = __byte_perm(a[0], a[1], 0x7362), t3 = __byte_perm(a[2], a[3], 0x7362);
-                    o[0][g] = __byte_perm(t0, t1, 0x5410);
-                    o[1][g] = __byte_perm(t0, t1, 0x7632);
-                    o[2][g] = __byte_perm(t2, t3, 0x5410);
-                    o[3][g] = __byte_perm(t2, t3, 0x7632);
-                }
-                uint8_t* tb = p.tstream + ifi * p.tstream_if_stride + blk * M;
+                    for (int g = 0; g < 4; ++g) {
+                        uint32_t a[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int pair = strip * (SC / 2) + 2 * cq + (j >> 1), col = j & 1;
-                    *reinterpret_cast<uint4*>(tb + ((size_t)(pair * 2 + half) * 32 + 2 * item + col) * 16) =
-                        make_uint4(o[j][0], o[j][1], o[j][2], o[j][3]);
+                        for (int j = 0; j < 4; ++j)
+                            a[j] = *reinterpret_cast<const uint32_t*>(s_exp + (32 * (4 * g + j) + item + 16 * half) * PITCH + 4 * cq);
+                        const uint32_t t0 = __byte_perm(a[0], a[1], 0x5140), t1 = __byte_perm(a[2], a[3], 0x5140);
+                        const uint32_t t2 = __byte_perm(a[0], a[1], 0x7362), t3 = __byte_perm(a[2], a[3], 0x7362);
+                        o[0][g] = __byte_perm(t0, t1, 0x5410);
+                        o[1][g] = __byte_perm(t0, t1, 0x7632);
+                        o[2][g] = __byte_perm(t2, t3, 0x5410);
+                        o[3][g] = __byte_perm(t2, t3, 0x7632);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int pair = strip * (SC / 2) + 2 * cq + (j >> 1), col = j & 1;
+                        *reinterpret_cast<uint4*>(tb + ((size_t)(pair * 2 + half) * 32 + 2 * item + col) * 16) =
+                            make_uint4(o[j][0], o[j][1], o[j][2], o[j][3]);
+                    }
                 }
             }
         }
@@ -622,6 +744,57 @@ static __global__ void __launch_bounds__(256) k0t_transpose(const K0TParams p) {
     // fill words: one atomic per warp
     for (int m = 16; m; m >>= 1) nfill_total += __shfl_xor_sync(0xffffffffu, nfill_total, m);
     if ((tid & 31) == 0 && nfill_total) atomicAdd(&p.counters[C_FILLWORDS], nfill_total);
+}
+
+// JA98 decode (B2F_DECODE_JA98): one warp per window of 512 time samples of one IF counts, per polarisation, the samples
+// between the thresholds (codes 1 and 2) among the samples that are not masked, and turns the fraction into the two
+// output magnitudes (oracle: ja98_levels).  256 payload bytes per window; words never straddle a frame.
+struct KJParams {
+    const uint8_t* frames[B2F_MAX_IF];
+    const uint8_t* fstat; size_t fstat_stride;
+    float4* levels;                      // [nif*nblk][R]
+    int nblk, nif, R, frame_bytes, header_bytes, payload_bytes, mask_faults;
+};
+static __global__ void kj_ja98_levels(const KJParams p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;          // window number over all IFs
+    const int64_t nwin = (int64_t)p.nif * p.nblk * p.R;
+    if (w >= nwin) return;
+    const int ifi = (int)(w / ((int64_t)p.nblk * p.R));
+    const int64_t wi = w % ((int64_t)p.nblk * p.R);                                    // window inside this IF's push
+    unsigned lowP = 0, lowQ = 0, nval = 0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int64_t pb = wi * 256 + (lane + 32 * k) * 4;
+        const int64_t f = pb / p.payload_bytes;
+        const int off = (int)(pb - f * p.payload_bytes);
+        const uint32_t x = *reinterpret_cast<const uint32_t*>(p.frames[ifi] + f * p.frame_bytes + p.header_bytes + off);
+        const bool masked = p.mask_faults && (x == kFillWord || p.fstat[ifi * p.fstat_stride + f] == 2);
+        if (!masked) {
+            const uint32_t m = x ^ (x >> 1);                 // bit 0 of every 2-bit field: code is 1 or 2
+            lowP += __popc(m & 0x11111111u);
+            lowQ += __popc(m & 0x44444444u);
+            nval += 8;
+        }
+    }
+    for (int m = 16; m; m >>= 1) {
+        lowP += __shfl_xor_sync(0xffffffffu, lowP, m);
+        lowQ += __shfl_xor_sync(0xffffffffu, lowQ, m);
+        nval += __shfl_xor_sync(0xffffffffu, nval, m);
+    }
+    if (lane == 0) {
+        float lv[4];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            double phi = nval ? (double)(q ? lowQ : lowP) / (double)nval : 0.5;
+            phi = fmin(fmax(phi, 1.0 / 512.0), 1.0 - 1.0 / 512.0);
+            const double t = 1.4142135623730951 * erfinv(phi);
+            const double e = exp(-0.5 * t * t);
+            lv[2 * q] = (float)(0.7978845608028654 * (1.0 - e) / phi);
+            lv[2 * q + 1] = (float)(0.7978845608028654 * e / (1.0 - phi));
+        }
+        p.levels[w] = make_float4(lv[0], lv[1], lv[2], lv[3]);
+    }
 }
 
 // F[row][col] = sum of `ratio` consecutive partial rows, fixed order

@@ -422,8 +422,10 @@ static __global__ void k0b_finish_slots(const K0bParams p) {
         uint8_t* m = p.wmask + ifi * p.wmask_stride + slot * (int64_t)p.groups_per_slot;
         for (int g = 0; g < p.groups_per_slot; ++g) m[g] = 0xFF;
         if (p.in_nbit == 2) {                                   // masking lives in the index stream for 2-bit input
-            uint4* d = reinterpret_cast<uint4*>(p.compact + ifi * p.compact_stride + slot * (int64_t)p.slot_bytes);
-            for (int k = 0; k < p.slot_bytes / 16; ++k) d[k] = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
+            // 32-bit stores: a slot is a whole number of words, but with raw 64-bit input (slot_bytes = 1000) neither a
+            // multiple of 16 bytes nor 16-byte aligned
+            uint32_t* d = reinterpret_cast<uint32_t*>(p.compact + ifi * p.compact_stride + slot * (int64_t)p.slot_bytes);
+            for (int k = 0; k < p.slot_bytes / 4; ++k) d[k] = 0x80808080u;
         }
         atomicAdd(&p.counters[C_MISSING], 1ull);
     }
@@ -516,6 +518,7 @@ struct KAParams {
     int* sm_slots;           // [>= #SMs] arrival counters used to stagger co-resident CTAs
     int stagger_cycles;
     int variant;             // 0 = product kernel; else a timing ablation
+    float in8_offset;        // 8-bit samples: value = code - in8_offset (127.5, or 128: SURVEY D3)
 };
 
 template <int NBIT>
@@ -668,8 +671,8 @@ __global__ void __launch_bounds__(kKAThreads, kKACtasPerSM) ka_column_pass(const
                 } else {
                     const uint32_t a = *reinterpret_cast<const uint16_t*>(raw + rowA * 2 * C + lane16 * 2);
                     const uint32_t b = *reinterpret_cast<const uint16_t*>(raw + rowB * 2 * C + lane16 * 2);
-                    vA[r] = make_float2((float)(a & 255u) - 127.5f, (float)(a >> 8) - 127.5f);
-                    vB[r] = make_float2((float)(b & 255u) - 127.5f, (float)(b >> 8) - 127.5f);
+                    vA[r] = make_float2((float)(a & 255u) - p.in8_offset, (float)(a >> 8) - p.in8_offset);
+                    vB[r] = make_float2((float)(b & 255u) - p.in8_offset, (float)(b >> 8) - p.in8_offset);
                 }
             }
             if (NBIT == 8 && dirty) {
@@ -1113,6 +1116,188 @@ __global__ void __launch_bounds__(kKBThreads, 2) kb_row_pass(const KBParams p) {
         ++it;
     }
 }
+
+// Row pass over the block layout the round-2 column kernel writes, [R/2 column pairs][512 rows][2 columns] float2 per block
+// (b2f_fused.cuh): a row is R/2 pieces of 16 bytes, 8 KiB apart, so the per-warp ring is filled with cp.async (LDGSTS)
+// pieces -- two neighbouring rows of a pair are one 32-byte sector -- instead of one bulk copy.  From HBM that access
+// pattern costs twice the time of kb_row_pass's contiguous rows (28.8 vs 15.0 ms per 20 s of C2): this kernel exists for the
+// two-launch form of the round-2 path (B2F_PATH=split), a debugging and profiling aid.  Everything after the load is kb_row_pass: each warp owns whole integration groups, the next pass's
+// rows land while this pass is transformed, nothing synchronises the block.
+template <int TR, int PT, int MODE>
+__global__ void __launch_bounds__(kKBThreads, 2) kr_row_pass(const KBParams p) {
+    using S = KBSmem<TR, PT>;
+    constexpr int NPROD = nprod_of_mode(MODE);
+    constexpr int R = TR * PT, N = R / 2, RW = S::RW, QPT = PT / TR, HP = TR / 2;
+    extern __shared__ __align__(128) uint8_t kb_smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int s = lane % TR, rsw = lane / TR;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(kb_smem) + kKBStages * warp;
+    uint8_t* stage0 = kb_smem + S::kBarBytes + (size_t)warp * S::kWarpBytes;
+    float2* s_tw = reinterpret_cast<float2*>(kb_smem + S::kBarBytes + (size_t)S::kWarps * S::kWarpBytes);
+
+    for (int i = tid; i < PT * TR; i += kKBThreads) s_tw[i] = p.tab_r[i];
+    (void)mbar;
+    __syncthreads();
+
+    const int D = MODE == kModeSpectrum ? 1 : p.D;
+    const int GW = D > RW ? D : RW;                 // rows per group
+    const int passes = GW / RW;
+    const int nout = GW / D;                        // output samples per group (1 unless D < RW)
+    const int slots_per_out = RW / nout;
+    const int groups_per_blk = kL / GW;
+    const int64_t ngroups = (p.gb_end - p.gb_begin) * groups_per_blk;      // groups of this launch
+    const int64_t wstride = (int64_t)gridDim.x * S::kWarps;
+
+    auto issue = [&](int64_t grp, int pass, int buf) {
+        const int64_t lb = grp / groups_per_blk;                // block index inside this launch
+        const int64_t gb = p.gb_begin + lb;
+        const int row0 = (int)(grp % groups_per_blk) * GW + pass * RW;
+        uint8_t* dst = stage0 + buf * S::kStage;
+        const float2* src = p.inter + lb * (int64_t)kL * R;     // block slot [column pair][512 rows][2 columns]
+        __syncwarp();                                           // everybody is done with the tile this refills
+        constexpr int NPC = RW * (R / 2);                       // 16-byte pieces: lane -> (pair, row), row fastest
+#pragma unroll
+        for (int k = 0; k < (NPC + 31) / 32; ++k) {
+            const int idx = lane + 32 * k;
+            if (NPC % 32 == 0 || idx < NPC) {
+                const int r = idx % RW, pp = idx / RW;
+                cp_async16(dst + r * S::kPitch + pp * 16, src + ((int64_t)pp * kL + row0 + r) * 2);
+            }
+        }
+        if (pass == 0 && MODE != kModeSpectrum)
+            for (int idx = lane; idx < N / 2; idx += 32) cp_async16(dst + S::kBody + idx * 16, p.eps + gb * N + idx * 2);
+    };
+
+    int64_t grp_cur = (int64_t)blockIdx.x * S::kWarps + warp;
+    int pass_cur = 0;
+    auto advance = [&](int64_t& g, int& ps) {
+        if (++ps == passes) { ps = 0; g += wstride; }
+    };
+    // the issue pointer runs kKBStages - 1 tiles ahead of the tile being transformed
+    int64_t grp_iss = grp_cur;
+    int pass_iss = 0, iss = 0;
+    for (int k = 0; k < kKBStages - 1; ++k) {
+        if (grp_iss < ngroups) {
+            issue(grp_iss, pass_iss, iss % kKBStages);
+            ++iss;
+            advance(grp_iss, pass_iss);
+        }
+        cp_async_commit();
+    }
+
+    float acc[QPT][HP][NPROD];
+    float2 e[QPT][HP];
+    int it = 0;
+    while (grp_cur < ngroups) {
+        const int buf = it % kKBStages;
+        // the stage consumed one iteration ago (program order) is free: refill it
+        if (grp_iss < ngroups) {
+            issue(grp_iss, pass_iss, iss % kKBStages);
+            ++iss;
+            advance(grp_iss, pass_iss);
+        }
+        cp_async_commit();                              // one group per iteration (possibly empty): uniform accounting
+        cp_async_wait<kKBStages - 1>();                 // everything but the newest kKBStages - 1 groups has landed
+        __syncwarp();
+        uint8_t* st = stage0 + buf * S::kStage;
+        const float2* tile = reinterpret_cast<const float2*>(st + rsw * S::kPitch);
+        if (pass_cur == 0 && MODE != kModeSpectrum) {
+            const float2* s_eps = reinterpret_cast<const float2*>(st + S::kBody);
+#pragma unroll
+            for (int j = 0; j < QPT; ++j)
+#pragma unroll
+                for (int pp = 0; pp < HP; ++pp) {
+                    e[j][pp] = s_eps[(s + TR * j) + PT * pp];
+#pragma unroll
+                    for (int k = 0; k < NPROD; ++k) acc[j][pp][k] = 0.f;
+                }
+        }
+        float2 v[PT];
+#pragma unroll
+        for (int a = 0; a < PT; ++a) v[a] = tile[s + TR * a];
+        fft_inreg<PT, false>(v);
+#pragma unroll
+        for (int q = 1; q < PT; ++q) v[q] = cmul(v[q], s_tw[q * TR + s]);
+        // transpose PT x TR through the (now consumed) row area of this stage
+        float2* myx = reinterpret_cast<float2*>(st) + (size_t)rsw * TR * (PT + 1);
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < PT; ++q) myx[s * (PT + 1) + q] = v[q];
+        __syncwarp();
+        float2 z[QPT][TR];
+#pragma unroll
+        for (int j = 0; j < QPT; ++j)
+#pragma unroll
+            for (int t = 0; t < TR; ++t) z[j][t] = myx[t * (PT + 1) + s + TR * j];
+#pragma unroll
+        for (int j = 0; j < QPT; ++j) fft_inreg<TR, false>(z[j]);
+        if (MODE == kModeSpectrum) {
+            // z[j][pp] = Z[k2 = this row][c = (s + TR j) + PT pp]: store the whole row
+            const int64_t lb = grp_cur / groups_per_blk;
+            const int row = (int)(grp_cur % groups_per_blk) * GW + pass_cur * RW + rsw;
+            float2* dst = p.spec + (lb * (int64_t)kL + row) * R;
+#pragma unroll
+            for (int j = 0; j < QPT; ++j)
+#pragma unroll
+                for (int pp = 0; pp < TR; ++pp) dst[(s + TR * j) + PT * pp] = z[j][pp];
+            advance(grp_cur, pass_cur);
+            ++it;
+            continue;
+        }
+        // z[j][pp] = Z_c at c = (s + TR j) + PT pp.  Mirror R-1-c lives in lane s^(TR-1),
+        // register [QPT-1-j][TR-1-pp].
+#pragma unroll
+        for (int j = 0; j < QPT; ++j)
+#pragma unroll
+            for (int pp = 0; pp < HP; ++pp) {
+                const float2 a = z[j][pp];
+                const float2 bs = z[QPT - 1 - j][TR - 1 - pp];
+                const float bx = __shfl_xor_sync(0xffffffffu, bs.x, TR - 1);
+                const float by = __shfl_xor_sync(0xffffffffu, bs.y, TR - 1);
+                const float2 bp = make_float2(bx - e[j][pp].x, -by - e[j][pp].y);
+                if (MODE == B2F_POL_I) {
+                    // |yP|^2 + |yQ|^2 = (|a + b'|^2 + |a - b'|^2) / 4 = (|a|^2 + |b'|^2) / 2: no need to form P and Q
+                    float t = a.x * a.x;
+                    t = fmaf(a.y, a.y, t);
+                    t = fmaf(bp.x, bp.x, t);
+                    t = fmaf(bp.y, bp.y, t);
+                    acc[j][pp][0] = fmaf(0.5f, t, acc[j][pp][0]);
+                } else {
+                    detect_acc<MODE == kModeSpectrum ? B2F_POL_P0 : MODE>(acc[j][pp], make_float2(a.x + bp.x, a.y + bp.y), make_float2(a.x - bp.x, a.y - bp.y));
+                }
+            }
+        if (pass_cur == passes - 1) {
+            // add up the row slots that integrate into the same output sample
+            for (int m = TR; m < TR * slots_per_out; m <<= 1) {
+#pragma unroll
+                for (int j = 0; j < QPT; ++j)
+#pragma unroll
+                    for (int pp = 0; pp < HP; ++pp)
+#pragma unroll
+                        for (int k = 0; k < NPROD; ++k)
+                            acc[j][pp][k] += __shfl_xor_sync(0xffffffffu, acc[j][pp][k], m);
+            }
+            if (rsw % slots_per_out == 0) {
+                const int64_t gb = p.gb_begin + grp_cur / groups_per_blk;
+                const int ifi = (int)(gb / p.nblk);
+                const int64_t blk = gb % p.nblk;
+                const int g0 = (int)(grp_cur % groups_per_blk) * GW;
+                const int64_t t = p.row0 + (blk * kL + g0) / D + rsw / slots_per_out;
+                float* dst = p.F + ifi * p.F_if_stride + t * (int64_t)(NPROD * N);
+#pragma unroll
+                for (int k = 0; k < NPROD; ++k)
+#pragma unroll
+                    for (int j = 0; j < QPT; ++j)
+#pragma unroll
+                        for (int pp = 0; pp < HP; ++pp) dst[k * N + (s + TR * j) + PT * pp] = acc[j][pp][k];
+            }
+        }
+        advance(grp_cur, pass_cur);
+        ++it;
+    }
+    cp_async_wait<0>();
+}
+
 
 // ================================================================== kernel 2: dedispersion back end
 // Dedispersion path only (digifil -D dm -F nchan:D).  Input: the full spectrum Z[k2][k1] of one
@@ -1739,6 +1924,7 @@ struct KQParams {
     int nif, nprod, nchan, out_nbit, pol_major;
     int if_order[B2F_MAX_IF];
     int flip[B2F_MAX_IF];                          // 1: channel reversal (USB)
+    float inv_digi_sigma;                          // 1 / (sigmas spanned by half the output range): 1/6 for digifil
 };
 
 __device__ __forceinline__ float quant(float y, float dscale, float dmean, float dmax) {
@@ -1779,14 +1965,14 @@ static __global__ void kq_quantise(const KQParams p) {
     if (p.out_nbit == 8) {
         uint32_t w = 0;
 #pragma unroll
-        for (int a = 0; a < 4; ++a) w |= (uint32_t)quant(y[a], 127.5f / 6.0f, 127.5f, 255.f) << (8 * a);
+        for (int a = 0; a < 4; ++a) w |= (uint32_t)quant(y[a], 127.5f * p.inv_digi_sigma, 127.5f, 255.f) << (8 * a);
         *reinterpret_cast<uint32_t*>(orow + j) = w;
     } else if (p.out_nbit == 16) {
         ushort4 w;
-        w.x = (unsigned short)quant(y[0], 32768.0f / 6.0f, 32768.0f, 65535.f);
-        w.y = (unsigned short)quant(y[1], 32768.0f / 6.0f, 32768.0f, 65535.f);
-        w.z = (unsigned short)quant(y[2], 32768.0f / 6.0f, 32768.0f, 65535.f);
-        w.w = (unsigned short)quant(y[3], 32768.0f / 6.0f, 32768.0f, 65535.f);
+        w.x = (unsigned short)quant(y[0], 32768.0f * p.inv_digi_sigma, 32768.0f, 65535.f);
+        w.y = (unsigned short)quant(y[1], 32768.0f * p.inv_digi_sigma, 32768.0f, 65535.f);
+        w.z = (unsigned short)quant(y[2], 32768.0f * p.inv_digi_sigma, 32768.0f, 65535.f);
+        w.w = (unsigned short)quant(y[3], 32768.0f * p.inv_digi_sigma, 32768.0f, 65535.f);
         *reinterpret_cast<ushort4*>(orow + 2 * (int64_t)j) = w;
     } else if (p.out_nbit == 2) {
         uint32_t w = 0;

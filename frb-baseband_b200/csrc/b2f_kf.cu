@@ -28,13 +28,19 @@ static cudaError_t go(const FParams& p, int grid, int cooperative, cudaStream_t 
 cudaError_t B2F_CAT(b2f_launch_kf_, B2F_FR)(int mode, const FParams& p, int grid, int cooperative, cudaStream_t st,
                                             int* max_ctas_per_sm) {
     switch (mode) {
+#if !defined(B2F_KF_ONLY_I) && !defined(B2F_KF_MAIN_MODES)
         case B2F_POL_P0: return go<B2F_POL_P0>(p, grid, cooperative, st, max_ctas_per_sm);
         case B2F_POL_P1: return go<B2F_POL_P1>(p, grid, cooperative, st, max_ctas_per_sm);
+#endif
         case B2F_POL_I: return go<B2F_POL_I>(p, grid, cooperative, st, max_ctas_per_sm);
+#if !defined(B2F_KF_ONLY_I) && !defined(B2F_KF_MAIN_MODES)
         case B2F_POL_I2: return go<B2F_POL_I2>(p, grid, cooperative, st, max_ctas_per_sm);
+        case B2F_POL_PPQQ: return go<B2F_POL_PPQQ>(p, grid, cooperative, st, max_ctas_per_sm);
+#endif
+#ifndef B2F_KF_ONLY_I
         case B2F_POL_COHERENCE: return go<B2F_POL_COHERENCE>(p, grid, cooperative, st, max_ctas_per_sm);
         case B2F_POL_IQUV: return go<B2F_POL_IQUV>(p, grid, cooperative, st, max_ctas_per_sm);
-        case B2F_POL_PPQQ: return go<B2F_POL_PPQQ>(p, grid, cooperative, st, max_ctas_per_sm);
+#endif
     }
     return cudaErrorInvalidValue;
 }

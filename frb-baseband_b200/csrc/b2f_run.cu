@@ -245,6 +245,11 @@ extern "C" int b2f_run_scan(b2f_plan* pl, int nfiles, const char* const* vdif_pa
     if (rc) return rc;
     rc = b2f_get_geometry(pl, &g);
     if (rc) return rc;
+    // Placement by header time works inside one push: a frame whose header time lies beyond the push is dropped and
+    // never presented again, while this runner reads files positionally chunk by chunk -- after a gap every later
+    // chunk would lose its last frames.  Whole files are digifil's positional reader (process_vdif.py:157-161).
+    if (prm.frame_time_mode == B2F_FRAMES_BY_HEADER)
+        return failf(B2F_EUNSUPPORTED, "b2f_run_scan reads frames positionally: frame_time_mode = B2F_FRAMES_BY_HEADER is single-push only (b2f_push)");
     const int nstreams = prm.raw_word_bits ? 1 : prm.nif;
     if (nfiles != nstreams)
         return failf(B2F_EINVAL, "the plan expects " + std::to_string(nstreams) + " input file(s), got " + std::to_string(nfiles));
@@ -321,12 +326,15 @@ extern "C" int b2f_run_scan(b2f_plan* pl, int nfiles, const char* const* vdif_pa
         struct stat st;
         const bool fifo = stat(out_path, &st) == 0 && S_ISFIFO(st.st_mode);
         if (fifo && in_parts) return failf(B2F_EINVAL, "parts of a scan cannot be written to a FIFO");
-        if (fifo) ofd = open(out_path, O_WRONLY);
+        if (fifo) {
+            ofd = open(out_path, O_WRONLY);
 #ifdef F_SETPIPE_SZ
-        // what setfifo.perl does for every FIFO of the splice list (setfifo.perl:10, base2fil.sh:417-419): 1 MiB pipe
-        if (fifo && ofd >= 0) (void)fcntl(ofd, F_SETPIPE_SZ, 1048576);
+            // what setfifo.perl does for every FIFO of the splice list (setfifo.perl:10, base2fil.sh:417-419): 1 MiB pipe
+            if (ofd >= 0) (void)fcntl(ofd, F_SETPIPE_SZ, 1048576);
 #endif
-        else ofd = open(out_path, in_parts ? (O_WRONLY | O_CREAT) : (O_WRONLY | O_CREAT | O_TRUNC), 0644);
+        } else {
+            ofd = open(out_path, in_parts ? (O_WRONLY | O_CREAT) : (O_WRONLY | O_CREAT | O_TRUNC), 0644);
+        }
         if (ofd < 0) return failf(B2F_EINVAL, std::string("cannot open ") + out_path + " for writing: " + strerror(errno));
         own.fds.push_back(ofd);
         positioned = in_parts;

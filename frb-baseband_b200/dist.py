@@ -99,6 +99,14 @@ def broadcast_rescale(plan, rank: int, src: int = 0, group=None, device=None):
     return host[:n].copy(), host[n:].copy()
 
 
+def measure_first_interval(plan, paths, **scan_kw):
+    """digifil -c statistics of THIS scan: drop any preset first (it survives b2f_reset and would end the
+    stats_only pass after one chunk with the previous scan's numbers), then measure."""
+    plan.set_rescale(None)
+    plan.run_scan(paths, None, stats_only=True, **scan_kw)
+    return plan.rescale()
+
+
 def run_scan_time_sharded(plan, paths, out_path: str, world: int, rank: int, *, group=None, device=None,
                           **scan_kw) -> dict:
     """Rank `rank` of `world` processes its time segment of the scan into `out_path` (shared file system).
@@ -110,15 +118,21 @@ def run_scan_time_sharded(plan, paths, out_path: str, world: int, rank: int, *, 
     if world == 1:
         return plan.run_scan(paths, out_path, **scan_kw)
     keep_bp = bool(plan.cfg.keep_bandpass)
+    # a preset left over from an earlier scan survives b2f_reset and would make the stats_only pass stop at once
+    # and hand out the OLD scan's mean/scale: every rank returns to measuring first
+    plan.set_rescale(None)
     if rank == 0:
         if os.path.exists(out_path):
             os.remove(out_path)                 # parts never truncate: start from nothing
         if not keep_bp:
-            plan.run_scan(paths, None, stats_only=True, **scan_kw)
+            measure_first_interval(plan, paths, **scan_kw)
     if not keep_bp:
         broadcast_rescale(plan, rank, 0, group, device)
     else:
         dist.barrier(group=group)               # nobody writes before the stale file is gone
-    res = plan.run_scan(paths, out_path, part=(rank, world), **scan_kw)
+    try:
+        res = plan.run_scan(paths, out_path, part=(rank, world), **scan_kw)
+    finally:
+        plan.set_rescale(None)                  # the plan goes back to measuring: a later plain run_scan is a new scan
     dist.barrier(group=group)
     return res

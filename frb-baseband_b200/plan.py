@@ -53,6 +53,11 @@ class PlanConfig:
     coherent: bool = False                   # digifil -F nchan:D
     raw_word_bits: int = 0                   # 16/32/64: one raw multi-BBC VDIF stream, corner turn on the GPU
     raw_bits: list | None = None             # per IF: 4 source bit positions (spif2file recipe)
+    decode_mode: int = 0                     # 0 static optimal levels, 1 Jenet-Anderson dynamic levels per 512 samples
+    in8_offset_mode: int = 0                 # 8-bit input: 0 code - 127.5, 1 code - 128 (D3)
+    fft_normalised: bool = False             # D4
+    rescale_mode: int = 0                    # 0 digifil -c (first interval, frozen), 1 running (D8)
+    digi_sigma: float = 0.0                  # D9: 0 = 6 sigma
     extra: dict = field(default_factory=dict)
 
 
@@ -97,6 +102,11 @@ class Plan:
                 for k in range(4):
                     p.raw_bits[i][k] = int(cfg.raw_bits[i][k])
         p.stream = cfg.stream
+        p.decode_mode = cfg.decode_mode
+        p.in8_offset_mode = cfg.in8_offset_mode
+        p.fft_normalised = int(cfg.fft_normalised)
+        p.rescale_mode = cfg.rescale_mode
+        p.digi_sigma = cfg.digi_sigma
         self.if_order = list(order)
         self.freq_mhz = list(freq)
         self._h = C.c_void_p()

@@ -145,6 +145,7 @@ def run_digifil(hdr, fil_out_dir=None, start=1, nsecs=120, nchan=128, overwrite=
     if pol not in (0, 1, 2, 3, 4):
         raise InputError(f"pol = {pol} not implemented. Choices are 0, 1, 2, 3, 4")
     from . import _lib, sigproc, vdif
+    from .admission import GpuSlot
     from .plan import Plan, PlanConfig, pol_mode_from_reference, reference_freq_res
 
     kv = read_hdr(hdr)
@@ -161,8 +162,12 @@ def run_digifil(hdr, fil_out_dir=None, start=1, nsecs=120, nchan=128, overwrite=
         cfg = PlanConfig(nchan=nchan, bw_mhz=[bw], freq_mhz=[freq], tscrunch=max(1, tscrunch),
                          pol_mode=pol_mode_from_reference(pol), out_nbit=nbit, in_nbit=info.nbit,
                          frame_bytes=info.frame_bytes, header_bytes=info.header_bytes, keep_bandpass=keepBP,
-                         device=device, dm=float(dm), coherent=bool(coherent and dm > 0.0))
-        with Plan(cfg) as pl:
+                         device=device, dm=float(dm), coherent=bool(coherent and dm > 0.0),
+                         # the reference passes -2 (:157,160): DSPSR's dynamic 2-bit levels; this build defaults to the
+                         # static optimal levels, B2F_DECODE_MODE=ja98 selects the reference-faithful unpacker
+                         decode_mode=_lib.DECODE_JA98 if os.environ.get("B2F_DECODE_MODE", "").lower() == "ja98" else _lib.DECODE_STATIC)
+        # pwait (base2fil.sh:21-28,404-405) counts processes named digifil; B2F_MAX_CONCURRENT is the same throttle here
+        with GpuSlot(device), Plan(cfg) as pl:
             # the digifil child process (reference :191): file in, .fil (or FIFO) out, inside libb2f
             c = pl.run_scan([datafile], fil, start_s=start, nsec=nsecs, source_name=kv.get("SOURCE", "unknown"),
                             telescope_id=sigproc.TELESCOPE_IDS.get(kv.get("TELESCOPE", "").lower(), 0),

@@ -33,7 +33,11 @@ def mode_string(payload: int, datarate_mbps: int, nbbc: int, nbits: int) -> str:
 
 def parse_recipe(recipe: str):
     """'32>[16,17,24,25][0,1,8,9]...:0-7' -> (32, [[16,17,24,25],[0,1,8,9],...])"""
-    m = re.match(r"\s*(?:swap_sign_mag\+)?(\d+)>((?:\[[0-9,]+\])+):", recipe)
+    if recipe.lstrip().startswith("swap_sign_mag"):
+        # Mark5B recordings (spif2file.sh:79-93) store sign and magnitude the other way round; accepting the prefix and
+        # ignoring it would decode every sample wrongly
+        raise ValueError("swap_sign_mag (Mark5B) recipes are not implemented")
+    m = re.match(r"\s*(\d+)>((?:\[[0-9,]+\])+):", recipe)
     if not m:
         raise ValueError(f"not a spif2file recipe: {recipe!r}")
     groups = [[int(x) for x in g.split(",")] for g in re.findall(r"\[([0-9,]+)\]", m.group(2))]

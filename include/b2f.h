@@ -56,7 +56,24 @@ enum b2f_pol_mode {
 
 enum b2f_frame_time_mode {
     B2F_FRAMES_POSITIONAL = 0,     /* frame k of a push is time slot k (digifil's reader) */
-    B2F_FRAMES_BY_HEADER = 1       /* slot from header seconds/frame#; gaps zero-filled    */
+    B2F_FRAMES_BY_HEADER = 1       /* slot from header seconds/frame#; gaps zero-filled; frames whose time lies outside the
+                                      push are dropped, so this mode is for single pushes (b2f_run_scan / b2f_run_file,
+                                      which read files positionally, refuse it) */
+};
+
+/* 2-bit reconstruction levels.  The reference calls `digifil -2` (process_vdif.py:157,160); DSPSR's
+ * 2-bit unpacker then sets the two output magnitudes per polarisation and window of 512 samples from the fraction of samples
+ * between the thresholds (Jenet & Anderson 1998, excision disabled), while the north star of this build names the static VLBI
+ * optimal levels.  Both are selectable; static is the default. */
+enum b2f_decode_mode {
+    B2F_DECODE_STATIC = 0,         /* -hi, -lo, +lo, +hi with lo = 1, hi = 3.3359 */
+    B2F_DECODE_JA98 = 1            /* per window of 512 samples: lo, hi = conditional means of |x| for the observed fraction */
+};
+
+/* what `-c` freezes */
+enum b2f_rescale_mode {
+    B2F_RESCALE_CONSTANT = 0,      /* digifil -c: mean / sigma of the first interval, applied from sample 0, frozen */
+    B2F_RESCALE_RUNNING = 1        /* without -c: every interval is scaled with its own statistics */
 };
 
 typedef struct b2f_params {
@@ -93,6 +110,13 @@ typedef struct b2f_params {
                                       sample of every BBC channel; the corner turn is done on the GPU          */
     uint8_t raw_bits[B2F_MAX_IF][4]; /* spif2file recipe (spif2file.sh:31-98): source bit of output bits 0..3
                                       (pol0 lsb, pol0 msb, pol1 lsb, pol1 msb) of IF i                        */
+    /* ---- knobs for what cannot be pinned without a running digifil; 0 = this build's default */
+    int32_t decode_mode;           /* enum b2f_decode_mode; SURVEY D2                                           */
+    int32_t in8_offset_mode;       /* 8-bit VDIF samples, SURVEY D3: 0 = code - 127.5, 1 = code - 128           */
+    int32_t fft_normalised;        /* D4: 1 = detected power divided by M * freq_res (squared for -d3), i.e. the
+                                      transforms normalised; only visible with keep_bandpass (cancels under -c)  */
+    int32_t rescale_mode;          /* enum b2f_rescale_mode; SURVEY D8                                          */
+    double digi_sigma;             /* D9: half the output range spans this many sigma (digifil: 6); 0 = 6       */
 } b2f_params;
 
 typedef struct b2f_geometry {

@@ -78,9 +78,25 @@ def vdif_epoch_mjd(ref_epoch: int) -> int:
     return jdn - 2400001  # JDN at noon -> MJD at preceding midnight
 
 
+JA98_WINDOW = 512            # samples per level-setting window of DSPSR's 2-bit unpacker
+
+
+def ja98_levels(phi):
+    """Jenet & Anderson (1998) dynamic 2-bit output levels for a window in which a fraction `phi` of the samples
+    fell between the thresholds: with t = sqrt(2) erfinv(phi) (threshold in units of sigma),
+    lo = E|x|  for |x| < t = sqrt(2/pi) (1 - exp(-t^2/2)) / phi,  hi = E|x| for |x| > t = sqrt(2/pi) exp(-t^2/2) / (1 - phi),
+    in units of the window's sigma.  phi = 0.6667 (thresholds at 0.9674 sigma) gives lo 0.4473, hi 1.4991 (ratio 3.352,
+    the static optimal ratio is 3.3359).  phi is clamped to [1/512, 1 - 1/512]."""
+    from scipy.special import erfinv
+    phi = np.clip(np.asarray(phi, np.float64), 1.0 / JA98_WINDOW, 1.0 - 1.0 / JA98_WINDOW)
+    t = np.sqrt(2.0) * erfinv(phi)
+    e = np.exp(-0.5 * t * t)
+    return np.sqrt(2.0 / np.pi) * (1.0 - e) / phi, np.sqrt(2.0 / np.pi) * e / (1.0 - phi)
+
+
 def decode_vdif(buf: np.ndarray, *, nbit: int = 2, header_bytes: int = 32,
                 frame_bytes: int | None = None, mask_invalid: bool = True,
-                offset8: float = 127.5, return_flags: bool = False):
+                offset8: float = 127.5, return_flags: bool = False, mode: str = "static"):
     """VDIF byte stream (2 channels, real) -> x[2, nsamp] float64.
 
     Follows digifil's VDIF reader + unpacker as restated in SURVEY.md Appendix A1/A2:
@@ -122,6 +138,24 @@ def decode_vdif(buf: np.ndarray, *, nbit: int = 2, header_bytes: int = 32,
         fm = np.repeat(fill, samp_per_word, axis=1)               # [nframes, t]
         x[fm] = 0.0
     out = np.ascontiguousarray(x.reshape(-1, 2).T)
+    if mode == "ja98":
+        # SURVEY.md Appendix A2 / D2, the mode DSPSR's unpacker runs in behind `digifil -2` (excision off): per
+        # polarisation and window of 512 consecutive samples the two output magnitudes follow the fraction of samples
+        # between the thresholds.  Masked samples (0.0) are left out of the count and stay 0.0.
+        assert nbit == 2
+        n = out.shape[1] // JA98_WINDOW * JA98_WINDOW
+        w = out[:, :n].reshape(2, -1, JA98_WINDOW)
+        a = np.abs(w)
+        valid = a > 0
+        nlow = (valid & (a < 2.0)).sum(axis=2)
+        nval = valid.sum(axis=2)
+        lo, hi = ja98_levels(np.where(nval > 0, nlow / np.maximum(nval, 1), 0.5))
+        mag = np.where(a < 2.0, lo[..., None], hi[..., None])
+        out = out.copy()
+        out[:, :n] = (np.sign(w) * np.where(valid, mag, 0.0)).reshape(2, n)
+        # a tail shorter than one window keeps the static levels (never reached: blocks are multiples of 512)
+    elif mode != "static":
+        raise ValueError(mode)
     if return_flags:
         return out, {"invalid_frames": int(invalid.sum()), "fill_words": int(fill.sum())}
     return out
@@ -206,14 +240,14 @@ def rescale_stats(d: np.ndarray, nsamp_interval: int):
     return mean, scale
 
 
-def digitise(y: np.ndarray, nbit: int) -> np.ndarray:
-    """SigProcDigitizer (Appendix A8)."""
+def digitise(y: np.ndarray, nbit: int, digi_sigma: float = 6.0) -> np.ndarray:
+    """SigProcDigitizer (Appendix A8): half the output range spans `digi_sigma` standard deviations (D9)."""
     if nbit == -32:
         return y.astype(np.float32)
     if nbit == 8:
-        return np.clip(np.floor(y * (127.5 / 6.0) + 127.5 + 0.5), 0, 255).astype(np.uint8)
+        return np.clip(np.floor(y * (127.5 / digi_sigma) + 127.5 + 0.5), 0, 255).astype(np.uint8)
     if nbit == 16:
-        return np.clip(np.floor(y * (32768.0 / 6.0) + 32768.0 + 0.5), 0, 65535).astype(np.uint16)
+        return np.clip(np.floor(y * (32768.0 / digi_sigma) + 32768.0 + 0.5), 0, 65535).astype(np.uint16)
     if nbit == 2:
         q = np.clip(np.floor(y + 1.5 + 0.5), 0, 3).astype(np.uint8)
         flat = q.reshape(q.shape[0], -1)
@@ -283,7 +317,9 @@ def digifil(vdif: np.ndarray, *, freq_mhz: float, bw_mhz: float, nchan: int,
             rescale_interval_s: float = 10.0, keep_bandpass: bool = False,
             frame_bytes: int | None = None, header_bytes: int = 32,
             dtype=np.float64, return_float: bool = False, dm: float = 0.0, coherent: bool = False,
-            nfilt: tuple[int, int] | None = None, x: np.ndarray | None = None) -> dict:
+            nfilt: tuple[int, int] | None = None, x: np.ndarray | None = None,
+            decode_mode: str = "static", offset8: float = 127.5, digi_sigma: float = 6.0,
+            fft_normalised: bool = False, rescale_mode: str = "constant") -> dict:
     """One IF: VDIF bytes -> SIGPROC samples, as `digifil -cont -c -b<nbit> -S<start> -T<nsec>
     -2 -D 0.0 [-t D] -d<..> -F<nchan>:<freq_res> [-I0]` (/root/reference/process_vdif.py:157-182).
 
@@ -307,7 +343,7 @@ def digifil(vdif: np.ndarray, *, freq_mhz: float, bw_mhz: float, nchan: int,
         nfr = min(nfr, int(round(nsec * fps)))
     if x is None:
         x = decode_vdif(vdif[f0 * frame_bytes: (f0 + nfr) * frame_bytes], nbit=in_nbit,
-                        header_bytes=header_bytes, frame_bytes=frame_bytes)
+                        header_bytes=header_bytes, frame_bytes=frame_bytes, mode=decode_mode, offset8=offset8)
     # (x given: samples already decoded, e.g. by corner_turn(); vdif is then only read for its header time)
     if coherent and dm > 0:                                  # digifil -D dm -F nchan:D (process_vdif.py:177-180)
         H = chirp(nchan, freq_res, freq_mhz, bw_mhz, dm)
@@ -317,18 +353,30 @@ def digifil(vdif: np.ndarray, *, freq_mhz: float, bw_mhz: float, nchan: int,
         yP = filterbank(x[0], nchan, freq_res, dtype)
         yQ = filterbank(x[1], nchan, freq_res, dtype)
     d = tscrunch(detect(yP, yQ, pol_mode), tscrunch_factor)
+    if fft_normalised:
+        # D4: the unnormalised forward (M) and backward (freq_res) transforms leave detected power M * freq_res times the
+        # input's; "normalised" divides that out (squared for the squared-intensity product).  Cancels under rescaling.
+        norm = 1.0 / (2.0 * nchan * freq_res * freq_res)
+        d = d * (norm * norm if pol_mode == "I2" else norm)
     tsamp = tscrunch_factor * nchan / (abs(bw_mhz) * 1e6)
+    nint = int(np.floor(rescale_interval_s / tsamp + 0.5))
     if keep_bandpass:
         y = d.astype(np.float64)
         mean = np.zeros(d.shape[1:]); scale = np.ones(d.shape[1:])
+    elif rescale_mode == "running" and nint > 0:
+        # D8 alternative: without -c every interval is scaled with its own statistics
+        y = np.empty(d.shape, np.float64)
+        for r0 in range(0, d.shape[0], nint):
+            mean, scale = rescale_stats(d[r0:r0 + nint], nint)
+            y[r0:r0 + nint] = (d[r0:r0 + nint] - mean) * scale
     else:
-        mean, scale = rescale_stats(d, int(np.floor(rescale_interval_s / tsamp + 0.5)))
+        mean, scale = rescale_stats(d, nint)
         y = (d - mean) * scale
     if bw_mhz > 0:                                           # USB: flip so that foff < 0
         yo = y[:, :, ::-1]
     else:
         yo = y
-    data = digitise(yo, out_nbit)
+    data = digitise(yo, out_nbit, digi_sigma)
     h_first = parse_vdif_header(vdif[f0 * frame_bytes: f0 * frame_bytes + 16].view("<u4"))
     tstart = (vdif_epoch_mjd(h_first["ref_epoch"]) + (h_first["seconds"] + h_first["frame_nr"] / fps) / 86400.0)
     out = {

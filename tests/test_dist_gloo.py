@@ -66,8 +66,11 @@ class _FakePlan:
         m = np.arange(8, dtype=np.float32).reshape(2, 1, 4) + 0.5
         return m, 1.0 / (m + 1.0)
 
-    def set_rescale(self, mean, scale):
-        self.preset = (np.array(mean), np.array(scale))
+    def set_rescale(self, mean, scale=None):
+        if mean is None:                          # back to measuring
+            self.preset = None
+            return
+        self.preset = self.last_preset = (np.array(mean), np.array(scale))
 
     def run_scan(self, paths, out_path, **kw):
         self.calls.append((out_path, kw.get("part"), kw.get("stats_only", False), self.preset is not None))
@@ -83,8 +86,10 @@ def _worker_time(rank, world, port, q, out_path):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     pl = _FakePlan(rank)
+    pl.preset = (np.zeros(8), np.ones(8))         # left over from an earlier scan: must not reach the stats pass
     run_scan_time_sharded(pl, ["a.vdif", "b.vdif"], out_path, world, rank, nsec=3600.0)
-    q.put((rank, pl.calls, pl.preset[0].tolist(), pl.preset[1].tolist()))
+    assert pl.preset is None                      # and the plan is handed back measuring
+    q.put((rank, pl.calls, pl.last_preset[0].tolist(), pl.last_preset[1].tolist()))
     dist.barrier()
     dist.destroy_process_group()
 

@@ -177,6 +177,29 @@ def test_scan_in_time_parts_is_bit_identical(gpu, tmp_path, kind):
         assert open(out, "rb").read() == ref, f"{kind}: {n} parts differ from the single run"
 
 
+def test_one_plan_two_scans_measures_each_scan(gpu, tmp_path):
+    """A plan reused for a second, different scan through the time-sharded entry re-measures the rescale: a preset left
+    from the first scan survives b2f_reset, and without clearing it the stats_only pass would stop after one chunk and
+    hand out the first scan's mean/scale (dist.measure_first_interval is what run_scan_time_sharded calls on rank 0)."""
+    from frb_baseband_b200 import dist
+    from frb_baseband_b200.plan import Plan, PlanConfig
+    bw, nfr = 32.0, 2 * 1024
+    kw = dict(nchan=128, bw_mhz=[-bw], tscrunch=16, rescale_interval_s=0.2)
+    pa, pb = tmp_path / "a.vdif", tmp_path / "b.vdif"
+    _write_vdif(str(pa), nfr, 301, bw, tone_frac=0.2)
+    _write_vdif(str(pb), nfr, 302, bw, tone_frac=0.7, tone_amp=1.5)
+    with Plan(PlanConfig(**kw)) as fresh:
+        want_b = dist.measure_first_interval(fresh, [str(pb)])
+    with Plan(PlanConfig(**kw)) as pl:
+        got_a = dist.measure_first_interval(pl, [str(pa)])
+        pl.set_rescale(*got_a)                                   # what broadcast_rescale leaves behind on every rank
+        pl.run_scan([str(pa)], str(tmp_path / "a.fil"), part=(0, 2))
+        got_b = dist.measure_first_interval(pl, [str(pb)])       # second scan, same plan
+        assert pl.counters()["rescale_preset"] == 0
+    assert not np.allclose(got_a[0], got_b[0])
+    assert np.array_equal(got_b[0], want_b[0]) and np.array_equal(got_b[1], want_b[1])
+
+
 def test_edge_inputs_empty_short_and_widest(gpu, tmp_path):
     """Inputs at the edges of what base2fil can hand over: an empty split file (base2fil.sh:391-394 writes an
     empty .fil for it; the runner writes a header-only one), a file shorter than one FFT block (no samples), a

@@ -39,7 +39,7 @@ def test_column_pass_stages(gpu):
         nblk = int(pl.geometry.unit_blocks * (pl.chunk_frames // pl.geometry.unit_frames))
         if pl.path == 2:                                   # fused kernel: the intermediate only exists as a ring in L2
             inter = None
-        elif pl.path == 1:                                 # block slots are [pair][row][2]
+        elif pl.path == 1:                                 # block slots are [column pair][row][2 columns]
             inter = pl.debug(4, np.complex64).reshape(nblk, R // 2, L, 2).transpose(0, 2, 1, 3).reshape(nblk, L, R)
         else:
             inter = pl.debug(4, np.complex64).reshape(nblk, L, R)
@@ -107,6 +107,51 @@ def test_requantised_output(gpu, out_nbit):
         assert (d != 0).mean() < (1e-3 if out_nbit == 8 else 2e-2)
     mean, scale = info["rescale"]
     assert np.allclose(mean[0, 0], ref["mean"][0], rtol=1e-5) and np.allclose(scale[0, 0], ref["scale"][0], rtol=1e-4)
+
+
+@pytest.mark.parametrize("interval,chunk_units,npieces", [(0.7, 1, 5), (10.0, 0, 44)])
+def test_rescale_boundary_inside_a_late_push(gpu, interval, chunk_units, npieces):
+    """digifil -c: mean / sigma of the first `interval` seconds, frozen, applied from sample 0 (process_vdif.py:157-161).
+    The streaming plan holds the float rows of several pushes until the interval is full; here the boundary falls inside
+    push 3 of 5 (0.7 s, 1024-frame pushes) and, for the reference's default 10 s with the C2 geometry of one IF, inside
+    push 20 of 22.  Four distinct 1024-frame pieces (= 125 whole FFT blocks each) are tiled in time, so the oracle's float
+    rows are computed once per piece; its own rescale_stats / digitise then give the expected 8-bit rows."""
+    nchan, bw, D, fb = 128, 32.0, 16, 8032
+    pieces = [synth.make_vdif(1024, seed=880 + k, bw_mhz=bw, tone_frac=0.05 + 0.2 * k, tone_amp=0.3 + 0.2 * k) for k in range(4)]
+    order = [(3 * k + k // 4) % 4 for k in range(npieces)]
+    floats = []
+    for v in pieces:
+        x = o.decode_vdif(v)
+        d = o.tscrunch(o.detect(o.filterbank(x[0], nchan, 512), o.filterbank(x[1], nchan, 512), "I"), D)
+        floats.append(d)
+    d_all = np.concatenate([floats[k] for k in order])
+    tsamp = D * nchan / (bw * 1e6)
+    mean, scale = o.rescale_stats(d_all, int(np.floor(interval / tsamp + 0.5)))
+    ref = o.digitise((d_all - mean) * scale, 8).reshape(d_all.shape[0], -1)
+    cfg = PlanConfig(nchan=nchan, bw_mhz=[-bw], tscrunch=D, rescale_interval_s=interval, chunk_units=chunk_units)
+    out = []
+    with Plan(cfg) as pl:
+        cf = int(pl.chunk_frames)
+        per = cf // 1024
+        assert cf % 1024 == 0
+        pushes_before_rows = 0
+        for k0 in range(0, npieces, per):
+            chunk = np.concatenate([pieces[order[k]] for k in range(k0, min(k0 + per, npieces))])
+            pl.push([chunk])
+            r = pl.pull()
+            if len(r):
+                out.append(r.copy())
+            elif not out:
+                pushes_before_rows += 1
+        pl.flush()
+        r = pl.pull()
+        if len(r):
+            out.append(r.copy())
+    rows = np.concatenate(out)
+    assert pushes_before_rows >= 2, "the rescale interval must span several pushes for this test to mean anything"
+    assert rows.shape == ref.shape
+    dd = np.abs(rows.astype(int) - ref.astype(int))
+    assert dd.max() <= 1 and (dd != 0).mean() < 1e-3, (dd.max(), (dd != 0).mean())
 
 
 def test_multi_if_splice_and_flip(gpu):

@@ -227,3 +227,27 @@ def test_oracle_reproduces_committed_small_scans():
         assert r["fch1"] == pytest.approx(c["fch1"]) and r["tsamp_s"] == pytest.approx(c["tsamp_s"])
         n += 1
     assert n == 3
+
+
+def test_ja98_levels_known_answer():
+    """with the thresholds at 0.9674 sigma two thirds of the samples fall between them, and the
+    conditional means of |x| are 0.4473 sigma (inner) and 1.4991 sigma (outer): ratio 3.352 against the static 3.3359."""
+    lo, hi = o.ja98_levels(0.6667)
+    assert abs(lo - 0.4473) < 2e-4 and abs(hi - 1.4991) < 2e-4
+    v = synth.make_vdif(64, seed=12, bw_mhz=32.0)
+    x = o.decode_vdif(v, mode="ja98")
+    assert abs(x.std() - 0.94) < 0.02                       # quantisation keeps 88 % of the power: sigma 0.94
+    xs = o.decode_vdif(v)
+    assert np.array_equal(np.sign(x), np.sign(xs)) and np.array_equal(np.abs(x) > 1.0, np.abs(xs) > 2.0)
+
+
+def test_knob_alternatives_change_only_what_they_name():
+    v = synth.make_vdif(300, seed=13, bw_mhz=32.0, tone_frac=0.2)
+    kw = dict(freq_mhz=1400.0, bw_mhz=-32.0, nchan=128, tscrunch_factor=16, rescale_interval_s=0.02)
+    base = o.digifil(v, **kw)
+    assert np.array_equal(o.digifil(v, fft_normalised=True, **kw)["data"], base["data"])       # cancels under -c
+    wide = o.digifil(v, digi_sigma=3.0, **kw)["data"].astype(float)
+    assert abs((wide - 127.5).std() / (base["data"].astype(float) - 127.5).std() - 2.0) < 0.1
+    run = o.digifil(v, rescale_mode="running", **kw)["data"]
+    nint = int(np.floor(0.02 / base["tsamp_s"] + 0.5))
+    assert np.array_equal(run[:nint], base["data"][:nint]) and not np.array_equal(run[nint:], base["data"][nint:])
