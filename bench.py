@@ -209,11 +209,12 @@ def parity_check(torch, vd0, cfg: dict, bw_signed: float, freq: float, device: i
     with Plan(PlanConfig(nchan=cfg["nchan"], bw_mhz=[bw_signed], freq_mhz=[freq], tscrunch=cfg["tscrunch"], pol_mode=mode,
                          out_nbit=-32, keep_bandpass=True, dm=dm, coherent=dm > 0, device=device)) as pl:
         path = pl.path
+        nfilt = (int(pl.geometry.nfilt_pos), int(pl.geometry.nfilt_neg))
         pl.push([v])
         pl.flush()
         rows = pl.pull().view(np.float32).astype(np.float64)
     ref = o.digifil(v, freq_mhz=freq, bw_mhz=bw_signed, nchan=cfg["nchan"], tscrunch_factor=cfg["tscrunch"], pol_mode=cfg["pol"],
-                    out_nbit=-32, keep_bandpass=True, dm=dm, coherent=dm > 0)["data"].astype(np.float64)
+                    out_nbit=-32, keep_bandpass=True, dm=dm, coherent=dm > 0, nfilt=nfilt if dm > 0 else None)["data"].astype(np.float64)
     n = min(rows.shape[0], ref.shape[0])
     ref = ref[:n]
     got = rows[:n].reshape(ref.shape)

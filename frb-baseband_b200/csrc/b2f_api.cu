@@ -752,16 +752,21 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
         if (pl->path) {
             int occ = 0;
             FParams dummy{};
+            if (prm->decode_mode == B2F_DECODE_JA98) dummy.levels = reinterpret_cast<const float4*>(&dummy);   // selects the instantiation
             if (b2f_launch_kf(R, prm->pol_mode, dummy, 0, 0, nullptr, &occ) != cudaSuccess || occ < 1) {
                 cudaGetLastError();
                 pl->path = 0;
+                if (prm->decode_mode == B2F_DECODE_JA98) {
+                    delete pl;
+                    return fail(B2F_EUNSUPPORTED, "decode_mode JA98 is built for the detection products I, coherence and IQUV");
+                }
             } else {
                 const int npair = R / 2;                                   // warps per lane (one block per lane and round)
                 pl->f_grid = pl->num_sms;                                  // one 16-warp CTA per SM
                 pl->f_lanes = pl->f_grid * kFWarps / npair;
                 if (pl->f_lanes < 1) pl->path = 0;
                 const char* lg = getenv("B2F_ROW_LAG");
-                pl->f_lag = lg ? std::max(1, std::min(3, atoi(lg))) : 2;
+                pl->f_lag = lg ? std::max(2, std::min(3, atoi(lg))) : 2;
                 { const char* e2 = getenv("B2F_RING_SLOTS"); pl->f_nslot = e2 ? std::max(pl->f_lag + 1, std::min(6, atoi(e2))) : pl->f_lag + 1; }
                 pl->Dp = std::min(D, 1024 / R);
             }

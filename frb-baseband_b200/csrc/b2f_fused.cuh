@@ -155,7 +155,7 @@ __device__ __forceinline__ float2 f_ja98(float2 v, float4 lv) {
     return make_float2(ax == 0.f ? 0.f : copysignf(ax > 2.f ? lv.y : lv.x, v.x), ay == 0.f ? 0.f : copysignf(ay > 2.f ? lv.w : lv.z, v.y));
 }
 
-template <int R>
+template <int R, bool JA98>
 __device__ __forceinline__ void f_col_front(const uint4 rawA, const uint4 rawB, float4* xb, const float4* s_w4,
                                             const uint8_t* s_lut, const float4* s_h4w, const int lane, float2* colsum_n1,
                                             const float4* levels_blk) {
@@ -171,7 +171,7 @@ __device__ __forceinline__ void f_col_front(const uint4 rawA, const uint4 rawB, 
             vA[r] = *reinterpret_cast<const float2*>(s_lut + ia);
             vB[r] = *reinterpret_cast<const float2*>(s_lut + ib);
         }
-        if (levels_blk) {           // a window of 512 time samples is 512 / R rows of the block (R <= 512)
+        if (JA98) {                 // a window of 512 time samples is 512 / R rows of the block (R <= 512)
 #pragma unroll
             for (int r = 0; r < 16; ++r) {
                 const int rowA = 32 * r + item;
@@ -409,7 +409,9 @@ __device__ __forceinline__ void f_eps(const float2* colsum_blk, float2* eps_blk,
     __syncwarp();
 }
 
-template <int R, int MODE>
+// JA98 is a template parameter: as a run-time branch it cost the default decode 324 bytes of spills in the hot loop and
+// 20 % of the column half's speed.
+template <int R, int MODE, bool JA98>
 __global__ void __launch_bounds__(kFThreads, 1) kf_fused(const FParams p) {
     using G = FGeo<R>;
     extern __shared__ __align__(128) uint8_t kf_smem[];
@@ -474,6 +476,9 @@ __global__ void __launch_bounds__(kFThreads, 1) kf_fused(const FParams p) {
         rawB = ldg_stream16(q + 512);
     }
 
+    // per-section cycle counters: compiled in only with -DB2F_KF_PROF (16 live registers otherwise spill in the hot loop:
+    // the first instrumented build made the column half 20 % slower)
+#ifdef B2F_KF_PROF
     unsigned long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tprev = clock64();
     auto tick = [&](int k) {
@@ -483,6 +488,9 @@ __global__ void __launch_bounds__(kFThreads, 1) kf_fused(const FParams p) {
             tprev = t;
         }
     };
+#else
+    auto tick = [](int) {};
+#endif
     // Round i of a lane: rows of block i - lag, then (one rotating warp) eps of block i - 1, then the columns of block i.
     // Every wait is for something the other warps of the lane did about a round earlier: the rows of block i - lag need
     // the columns published early in round i - lag + 1 and the eps computed in the middle of it; the ring slot the
@@ -551,8 +559,8 @@ __global__ void __launch_bounds__(kFThreads, 1) kf_fused(const FParams p) {
         if (vc) {
             const int64_t gb = p.gb_begin + lbc;
             const int64_t slot = phase == 0 ? (int64_t)lam * ns + (i % ns) : lbc;
-            f_col_front<R>(rawA, rawB, reinterpret_cast<float4*>(wbuf), s_w4, s_lut, s_h4w, lane, p.colsum + gb * R + n1,
-                           p.levels ? p.levels + gb * R : nullptr);
+            f_col_front<R, JA98>(rawA, rawB, reinterpret_cast<float4*>(wbuf), s_w4, s_lut, s_h4w, lane, p.colsum + gb * R + n1,
+                                 JA98 ? p.levels + gb * R : nullptr);
             tick(0);
             // the slot written now was read by the row halves of the block `ns` rounds back
             if (phase == 0 && i >= ns && c_row < (unsigned)(G::NPAIR * (i - ns + 1))) {
@@ -573,10 +581,12 @@ __global__ void __launch_bounds__(kFThreads, 1) kf_fused(const FParams p) {
     if (col_pending) warp_arrive(sy + FS_COL, lane);
     // 0 column front, 1 wait for the ring slot, 2 column back + stores, 3 eps / publish / wait for the block's columns,
     // 4 row load (issue, eps wait, data), 5 arrivals, 6 row compute, 7 loop overhead
+#ifdef B2F_KF_PROF
     if (p.prof && lane == 0) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) atomicAdd(&p.prof[(size_t)gw * 8 + k], tacc[k]);
     }
+#endif
 }
 
 // ================================================================== front end of the fused path

@@ -27,13 +27,15 @@ static cudaError_t go_r(const KBParams& p, int grid, cudaStream_t st) {
 template <int TR, int PT>
 static cudaError_t by_mode_r(int mode, const KBParams& p, int grid, cudaStream_t st) {
     switch (mode) {
+#ifndef B2F_KF_MAIN_MODES
         case B2F_POL_P0: return go_r<TR, PT, B2F_POL_P0>(p, grid, st);
         case B2F_POL_P1: return go_r<TR, PT, B2F_POL_P1>(p, grid, st);
-        case B2F_POL_I: return go_r<TR, PT, B2F_POL_I>(p, grid, st);
         case B2F_POL_I2: return go_r<TR, PT, B2F_POL_I2>(p, grid, st);
+        case B2F_POL_PPQQ: return go_r<TR, PT, B2F_POL_PPQQ>(p, grid, st);
+#endif
+        case B2F_POL_I: return go_r<TR, PT, B2F_POL_I>(p, grid, st);
         case B2F_POL_COHERENCE: return go_r<TR, PT, B2F_POL_COHERENCE>(p, grid, st);
         case B2F_POL_IQUV: return go_r<TR, PT, B2F_POL_IQUV>(p, grid, st);
-        case B2F_POL_PPQQ: return go_r<TR, PT, B2F_POL_PPQQ>(p, grid, st);
     }
     return cudaErrorInvalidValue;
 }

@@ -7,9 +7,9 @@ using namespace b2f;
 #define B2F_CAT2(a, b) a##b
 #define B2F_CAT(a, b) B2F_CAT2(a, b)
 
-template <int MODE>
-static cudaError_t go(const FParams& p, int grid, int cooperative, cudaStream_t st, int* max_ctas_per_sm) {
-    auto kern = kf_fused<B2F_FR, MODE>;
+template <int MODE, bool JA98>
+static cudaError_t go2(const FParams& p, int grid, int cooperative, cudaStream_t st, int* max_ctas_per_sm) {
+    auto kern = kf_fused<B2F_FR, MODE, JA98>;
     const size_t smem = FGeo<B2F_FR>::kBytes;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -23,6 +23,17 @@ static cudaError_t go(const FParams& p, int grid, int cooperative, cudaStream_t 
     }
     kern<<<grid, kFThreads, smem, st>>>(p);
     return cudaGetLastError();
+}
+
+// the dynamic-level decode is instantiated for the products the north star names (I, coherence, IQUV)
+template <int MODE>
+static cudaError_t go(const FParams& p, int grid, int cooperative, cudaStream_t st, int* max_ctas_per_sm) {
+    if (p.levels) {
+        if (MODE == B2F_POL_I || MODE == B2F_POL_COHERENCE || MODE == B2F_POL_IQUV)
+            return go2<(MODE == B2F_POL_I || MODE == B2F_POL_COHERENCE || MODE == B2F_POL_IQUV) ? MODE : B2F_POL_I, true>(p, grid, cooperative, st, max_ctas_per_sm);
+        return cudaErrorInvalidValue;
+    }
+    return go2<MODE, false>(p, grid, cooperative, st, max_ctas_per_sm);
 }
 
 cudaError_t B2F_CAT(b2f_launch_kf_, B2F_FR)(int mode, const FParams& p, int grid, int cooperative, cudaStream_t st,

@@ -307,3 +307,20 @@ def test_mode_a_concurrent_processes_share_the_gpu(gpu, tmp_path):
     rows = np.concatenate(tiles, axis=1)
     assert rows.shape == ref["data"].shape
     assert np.abs(rows.astype(int) - ref["data"].astype(int)).max() <= 1
+
+
+def test_peer_splice_equals_nccl_gather_on_two_gpus(gpu):
+    """the one exchange of the path is the frequency splice (base2fil.sh:422).  Across GPUs it is done by peer
+    stores over NVLink from the requantise kernel (PeerSplice + b2f_pull_strided); the rows must equal an NCCL gather of
+    every rank's tile laid out highest frequency first.  Needs two GPUs on the box; skipped (not failed) on one."""
+    import subprocess
+    import sys
+    from frb_baseband_b200 import _lib
+    if _lib.lib().b2f_device_count() < 2:
+        pytest.skip("one GPU on this box: the peer-store splice needs two")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29641", os.path.join(root, "tools", "check_peer_splice.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "equal=True" in r.stdout

@@ -37,15 +37,22 @@ def test_paths_match_oracle_float(gpu, monkeypatch, nchan, bw, D, nfr):
         assert c["frames_ok"] + c["frames_invalid"] + c["frames_with_fill"] == nfr, (name, c)
 
 
-@pytest.mark.parametrize("mode,name", [(_lib.POL_P0, "P0"), (_lib.POL_P1, "P1"), (_lib.POL_I2, "I2"), (_lib.POL_PPQQ, "PPQQ"),
-                                       (_lib.POL_COHERENCE, "coherence"), (_lib.POL_IQUV, "IQUV")])
-def test_fused_pol_modes_equal_legacy(gpu, monkeypatch, mode, name):
-    """Every detection product of the fused kernel against the round-1 kernels (which test_pol_modes pins to the oracle)."""
+@pytest.mark.parametrize("path", ["fused", "split"])
+@pytest.mark.parametrize("mode,name", [(_lib.POL_COHERENCE, "coherence"), (_lib.POL_IQUV, "IQUV")])
+def test_round2_pol_modes_equal_round1(gpu, monkeypatch, mode, name, path):
+    """The four-product modes of the round-2 kernels against the round-1 kernels (which test_pol_modes pins to the oracle).
+    The round-2 kernels are built for Stokes I, coherence products and IQUV; the other products run on the round-1 kernels
+    whatever B2F_PATH says."""
     nchan, bw, D = 128, 32.0, 16
+    monkeypatch.setenv("B2F_PATH", path)
+    with Plan(PlanConfig(nchan=nchan, bw_mhz=[bw], pol_mode=mode)) as probe:
+        assert probe.path == PATHS[path]
+    with Plan(PlanConfig(nchan=nchan, bw_mhz=[bw], pol_mode=_lib.POL_PPQQ)) as probe:
+        assert probe.path in (0, PATHS[path])
     v = synth.make_vdif(1024, seed=77, bw_mhz=bw, tone_frac=0.2, rho=0.4)
     kw = dict(nchan=nchan, bw=[bw], tscrunch=D, pol_mode=mode, out_nbit=-32, keep_bandpass=True)
     leg, _ = _rows(monkeypatch, "legacy", [v], **kw)
-    fus, info = _rows(monkeypatch, "fused", [v], **kw)
+    fus, info = _rows(monkeypatch, path, [v], **kw)
     nprod = info["nprod"]
     assert_rel(fus.reshape(-1, nprod, nchan), leg.reshape(-1, nprod, nchan).astype(np.float64), 2e-6, name)
 

@@ -14,16 +14,13 @@ import torch.distributed as dist
 
 
 def numa_of_gpu(idx: int):
+    """(pci bus id, NUMA node) of CUDA device idx; node None when sysfs does not say"""
     try:
-        bus = torch.cuda.get_device_properties(idx).pci_bus_id if hasattr(torch.cuda.get_device_properties(idx), "pci_bus_id") else None
+        import subprocess
+        uuid_or_idx = os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")[idx] if os.environ.get("CUDA_VISIBLE_DEVICES") else str(idx)
+        bus = subprocess.check_output(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", uuid_or_idx], text=True).strip()
     except Exception:
-        bus = None
-    if bus is None:
-        try:
-            import subprocess
-            bus = subprocess.check_output(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(idx)], text=True).strip()
-        except Exception:
-            return None, None
+        return None, None
     b = bus.lower()
     if len(b.split(":")[0]) == 8:
         b = b[4:]
