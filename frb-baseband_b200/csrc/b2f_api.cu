@@ -557,7 +557,19 @@ int push_fused(b2f_plan* pl, const K0Params& k0, int64_t nframes, int64_t nblk) 
             ke_eps<<<(unsigned)nbt, std::min(pl->R / 2, 512), pl->R * sizeof(float2), pl->stream>>>(pl->d_colsum, pl->d_eps, pl->R);
         });
         if (rc) return rc;
-        // row pass over the [pair][row][2] blocks: per-warp cp.async ring, whole integration groups per warp -> F directly
+        if (pl->R == 256 && !getenv("B2F_NO_TILE_ROWS")) {
+            // 16-row tiles are 32 KiB contiguous in the block layout: one bulk copy per tile, block-wide second FFT stage
+            KTParams kt{};
+            kt.inter = pl->d_inter; kt.eps = pl->d_eps; kt.tab_r = pl->d_tab_r;
+            kt.F = pl->d_F; kt.F_if_stride = pl->F_if_stride; kt.row0 = pl->rows_off + pl->rows_held;
+            kt.nblk = (int)nblk; kt.nif = nif; kt.D = pl->D; kt.nb = nbt;
+            const int64_t units = nbt * (32 / std::max(1, pl->D / 16));
+            rc = timed(pl, B2F_K_ROW, [&] { e = b2f_launch_kt(pl->prm.pol_mode, kt, (int)std::min<int64_t>(units, (int64_t)pl->num_sms * 2), pl->stream); });
+            if (rc) return rc;
+            if (e != cudaSuccess) return fail(B2F_ECUDA, std::string("tile row pass launch: ") + cudaGetErrorString(e));
+            return 0;
+        }
+        // other row lengths: per-warp cp.async ring over the same blocks, whole integration groups per warp -> F directly
         int TR, PT;
         kb_shape(pl->R, &TR, &PT);
         const int RW = 32 / TR, GW = std::max(pl->D, RW);

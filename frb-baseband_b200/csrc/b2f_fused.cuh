@@ -69,7 +69,7 @@ struct FGeo {
 struct FParams {
     const uint8_t* tstream;        // [if][blk][pair][half][lane][16] index bytes (k0t_transpose)
     size_t tstream_if_stride;
-    float2* ring;                  // fused: [(lag + 1) * lanes][M]; split: [blocks of the launch][M]; slot layout [R/2 column pairs][512 rows][2 columns]
+    float2* ring;                  // fused: [(lag + 1) * lanes][M]; split: [blocks of the launch][M]; slot layout [32 row tiles][R/2 column pairs][16 rows][2 columns]
     float2* colsum;                // [nif*nblk][R]
     float2* eps;                   // [nif*nblk][R/2]
     const float2 *tab_h, *tab_w, *tab_beta, *tab_r;
@@ -219,9 +219,11 @@ __device__ __forceinline__ void f_col_front(const uint4 rawA, const uint4 rawB, 
 }
 
 // ---- P3: * beta^q (W_M^(q n1) conj W_512^(q m1));  IFFT_16 over q -> m2;  rows m1 + 32 m2, m1 = item, item + 16
-// dst: this warp's 8 KiB of the block slot (slot layout [column pair][512 rows][2 columns] float2): every store instruction
-// of the warp writes 256 contiguous bytes.  (Measured alternative, row-pair-major [256][R/2][2][2] so that the row pass reads
-// contiguous memory: the 32-byte store granules made the column half 2.6x slower, 61 vs 23 ms per 20 s of C2.)
+// Block slot layout: [32 row tiles][R/2 column pairs][16 rows][2 columns] float2.  A store instruction of the warp covers rows
+// item + 32 m2 (item = 0..15) of its two columns = one 256-byte (tile, pair) chunk, fully coalesced; and a tile of 16 rows of
+// ALL columns is 16 R contiguous bytes for the row pass (one bulk copy).  dst = slot + 32 * pair.
+// (Measured alternatives: [pair][512 rows][2]: same store efficiency, but a row is R/2 pieces 8 KiB apart and a row pass that
+// streams it from HBM takes twice the time; row-pair-major [256][R/2][2][2]: 32-byte store granules, column half 2.6x slower.)
 template <int R>
 __device__ __forceinline__ void f_col_back(const float4* xb, const float2 (&betaS)[4], const int lane, float2* dst) {
     {
@@ -242,10 +244,11 @@ __device__ __forceinline__ void f_col_back(const float4* xb, const float2 (&beta
         }
         fft_inreg<16, true>(yA);
         fft_inreg<16, true>(yB);
+        constexpr int TS = (R / 2) * 32;                        // float2 per row tile
 #pragma unroll
         for (int m2 = 0; m2 < 16; ++m2) {
-            dst[64 * m2 + lane] = yA[m2];                       // row item + 32 m2
-            dst[64 * m2 + 32 + lane] = yB[m2];                  // row item + 16 + 32 m2
+            dst[(2 * m2) * TS + lane] = yA[m2];                 // row item + 32 m2      -> tile 2 m2
+            dst[(2 * m2 + 1) * TS + lane] = yB[m2];             // row item + 16 + 32 m2 -> tile 2 m2 + 1
         }
     }
 }
@@ -280,19 +283,13 @@ __device__ __forceinline__ void f_row_fft(const float2* tile, float2* myx, const
 template <int R>
 __device__ __forceinline__ void f_row_load(const float2* slot, const int m0, uint8_t* wbuf, const int lane) {
     using G = FGeo<R>;
-    if (G::RPW <= 32) {                                         // RPW * NPAIR = 512 pieces: lane = (pair, row), row fastest
-        constexpr int PPK = 32 / (G::RPW <= 32 ? G::RPW : 32);  // pairs per instruction
-        const int r = lane % G::RPW, pp0 = lane / G::RPW;
-        uint8_t* dst = wbuf + r * G::kPitch + pp0 * 16;
-        const float2* src = slot + ((int64_t)pp0 * kL + m0 + r) * 2;
+    constexpr int NP = G::NPAIR;
 #pragma unroll
-        for (int k = 0; k < 16; ++k) cp_async16(dst + k * PPK * 16, src + (int64_t)k * PPK * kL * 2);
-    } else {                                                    // R = 16: 64 rows per warp, two instructions per pair
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const int r = lane + 32 * (k & 1), pp = k >> 1;
-            cp_async16(wbuf + r * G::kPitch + pp * 16, slot + ((int64_t)pp * kL + m0 + r) * 2);
-        }
+    for (int k = 0; k < 16; ++k) {                              // RPW * NPAIR = 512 pieces: lane -> (pair, row), row fastest
+        const int idx = lane + 32 * k;
+        const int r = idx % G::RPW, pp = idx / G::RPW;
+        const int m = m0 + r;
+        cp_async16(wbuf + r * G::kPitch + pp * 16, slot + ((((m >> 4) * NP + pp) * 16 + (m & 15)) * 2));
     }
     cp_async_commit();
 }
@@ -567,7 +564,7 @@ __global__ void __launch_bounds__(kFThreads, 1) kf_fused(const FParams p) {
                 if (!warp_wait_ge(sy + FS_ROW, (unsigned)(G::NPAIR * (i - ns + 1)), p.abort_flag, lane)) return;
             }
             tick(1);
-            f_col_back<R>(reinterpret_cast<const float4*>(wbuf), betaS, lane, p.ring + slot * M + (size_t)pr * 1024);
+            f_col_back<R>(reinterpret_cast<const float4*>(wbuf), betaS, lane, p.ring + slot * M + (size_t)pr * 32);
             col_pending = phase == 0;
             if (phase == 1 && lbc + nl < nb) {                             // columns only: prefetch the next work item
                 const uint8_t* q = raw_ptr(lbc + nl);
@@ -587,6 +584,173 @@ __global__ void __launch_bounds__(kFThreads, 1) kf_fused(const FParams p) {
         for (int k = 0; k < 8; ++k) atomicAdd(&p.prof[(size_t)gw * 8 + k], tacc[k]);
     }
 #endif
+}
+
+// ================================================================== row pass over 16-row tiles (R = 256)
+// Consumer of the round-2 column kernel when the intermediate goes through HBM (B2F_PATH=split): a CTA streams whole 16-row
+// tiles -- 32 KiB contiguous in the [tile][pair][16 rows][2] block layout, ONE bulk copy (TMA, mbarrier) per tile, double
+// buffered -- so DRAM sees nothing but long sequential reads.  The tile arrives pair-major; instead of re-laying it out, the
+// first radix-16 stage is spread so that the layout is conflict-free as it is: warp w, lane (row r, column c) takes the points
+// n1 = (2w + c) + 16a, a = 0..15 (pairs w + 8a), i.e. the 32 lanes of a load instruction differ in (r, c) only: 32 different
+// 8-byte bank slots.  The exchange between the two radix-16 stages is block-wide, X[q][s][r ^ 8 (s & 1)] (both sides
+// conflict-free without padding).  Second stage: warp w owns q = w and 15 - w -- a channel and its mirror, one lane-xor-16
+// shuffle apart -- for all 16 rows (lane = r + 16 j): FFT over s, detection, and the time integration over the rows of the
+// tile is a butterfly of shuffles inside the warp; sums over several tiles (tscrunch > 16) stay in registers.  A tile buffer is
+// dead after the first stage, so it is refilled right after the barrier: two bulk copies in flight per CTA.  One block
+// barrier per tile (exchange written -> read); "everybody has read the exchange buffer" is a split mbarrier: arrive after the
+// reads, wait only before the next tile's writes, with that tile's loads and first FFT stage in between.  tscrunch 1..512.
+struct KTParams {
+    const float2* inter;        // [blocks][32 tiles][128 pairs][16 rows][2 columns]
+    const float2* eps;          // [blocks][128]
+    const float2* tab_r;        // [16][16] W_256^(s q), q-major
+    float* F; int64_t F_if_stride; int64_t row0;
+    int nblk, nif, D;
+    int64_t nb;                 // blocks of this launch
+};
+constexpr int kKTThreads = 256;
+constexpr int kKTTile = 16 * 256 * (int)sizeof(float2);          // 32 KiB
+constexpr int kKTEps = 128 * (int)sizeof(float2);
+struct KTSmem {
+    static constexpr int kOffTile = 128;
+    static constexpr int kOffX = kOffTile + 2 * (kKTTile + kKTEps);
+    static constexpr int kOffTw = kOffX + 16 * 256 * (int)sizeof(float2);
+    static constexpr size_t kBytes = (size_t)kOffTw + 256 * sizeof(float2);
+};
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kKTThreads, 2) kt_row_tiles(const KTParams p) {
+    constexpr int NPROD = nprod_of_mode(MODE), N = 128;
+    using S = KTSmem;
+    extern __shared__ __align__(128) uint8_t kt_smem[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(kt_smem);            // [0], [1]: tile landed; [2]: exchange buffer read
+    float2* X = reinterpret_cast<float2*>(kt_smem + S::kOffX);
+    float2* s_tw = reinterpret_cast<float2*>(kt_smem + S::kOffTw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rA = lane >> 1, cA = lane & 1, sA = 2 * warp + cA;     // first stage: row, column of the pair, s
+    const int rB = lane & 15, qB = (lane >> 4) ? 15 - warp : warp;   // second stage: row, q
+    s_tw[tid] = p.tab_r[tid];
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        mbar_init(&bar[2], kKTThreads);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int D = p.D;
+    const int lgG = D > 16 ? 31 - __clz(D / 16) : 0;         // 2^lgG tiles per integration unit
+    const int G = 1 << lgG, lgU = 5 - lgG;                   // 2^lgU units per block
+    const int Dt = D < 16 ? D : 16;                          // rows of one tile that add up to one output row
+    const int nunits_cta = (int)((p.nb * (32 >> lgG) - blockIdx.x + gridDim.x - 1) / gridDim.x);   // units this CTA owns
+    const int nseq = nunits_cta > 0 ? nunits_cta << lgG : 0;
+    auto locate = [&](int seq, int& lb, int& rt) {
+        const int64_t u = blockIdx.x + (int64_t)(seq >> lgG) * gridDim.x;
+        lb = (int)(u >> lgU);
+        rt = ((int)(u & ((1 << lgU) - 1)) << lgG) + (seq & (G - 1));
+    };
+    auto issue = [&](int lb, int rt, int buf) {              // thread 0 only
+        uint8_t* dst = kt_smem + S::kOffTile + buf * (kKTTile + kKTEps);
+        mbar_expect_tx(&bar[buf], kKTTile + kKTEps);
+        bulk_g2s(dst, p.inter + ((int64_t)lb * 32 + rt) * (128 * 32), kKTTile, &bar[buf]);
+        bulk_g2s(dst + kKTTile, p.eps + (int64_t)lb * N, kKTEps, &bar[buf]);
+    };
+    int lb, rt, lbn, rtn;
+    if (tid == 0) {                                          // two tiles in flight per CTA
+        for (int k = 0; k < 2 && k < nseq; ++k) {
+            locate(k, lb, rt);
+            issue(lb, rt, k);
+        }
+    }
+    float acc[8][NPROD];
+#pragma unroll
+    for (int pp = 0; pp < 8; ++pp)
+#pragma unroll
+        for (int c = 0; c < NPROD; ++c) acc[pp][c] = 0.f;
+    float2* xw = X + sA * 16 + (rA ^ (cA << 3));             // + 256 q
+    const float2* xr0 = X + qB * 256 + rB;                   // + 16 t, even t
+    const float2* xr1 = X + qB * 256 + (rB ^ 8);             //         odd t
+#pragma unroll 1
+    for (int seq = 0; seq < nseq; ++seq) {
+        const int buf = seq & 1;
+        locate(seq, lb, rt);
+        mbar_wait(&bar[buf], (uint32_t)((seq >> 1) & 1));
+        const float2* T = reinterpret_cast<const float2*>(kt_smem + S::kOffTile + buf * (kKTTile + kKTEps));
+        const float2* s_eps = T + 16 * 256;
+        // ---- first stage: FFT_16 over a of x[s + 16 a], twiddle W_256^(s q)
+        {
+            float2 v[16];
+#pragma unroll
+            for (int a = 0; a < 16; ++a) v[a] = T[((warp + 8 * a) * 16 + rA) * 2 + cA];
+            fft_inreg<16, false>(v);
+#pragma unroll
+            for (int q = 1; q < 16; ++q) v[q] = cmul(v[q], s_tw[q * 16 + sA]);
+            if (seq > 0) mbar_wait(&bar[2], (uint32_t)((seq - 1) & 1));      // the previous tile's exchange values have been read
+#pragma unroll
+            for (int q = 0; q < 16; ++q) xw[q * 256] = v[q];
+        }
+        float2 e[8];                                         // eps of this tile's block, before the buffer is given away
+#pragma unroll
+        for (int pp = 0; pp < 8; ++pp) e[pp] = s_eps[qB + 16 * pp];
+        __syncthreads();
+        // the tile has been consumed (rows in the first stage, eps just now): refill its buffer with the tile after next,
+        // so that two bulk copies are in flight per CTA with two buffers
+        if (tid == 0 && seq + 2 < nseq) {
+            locate(seq + 2, lbn, rtn);
+            fence_proxy_async();
+            issue(lbn, rtn, buf);
+        }
+        // ---- second stage: FFT_16 over s -> channels c = q + 16 pp; mirror R-1-c in lane ^ 16, register 15 - pp
+        {
+            float2 z[16];
+#pragma unroll
+            for (int t = 0; t < 16; ++t) z[t] = (t & 1) ? xr1[t * 16] : xr0[t * 16];
+            mbar_arrive(&bar[2]);                            // this thread is done with the exchange buffer
+            fft_inreg<16, false>(z);
+#pragma unroll
+            for (int pp = 0; pp < 8; ++pp) {
+                const float2 a = z[pp];
+                const float2 bs = z[15 - pp];
+                const float bx = __shfl_xor_sync(0xffffffffu, bs.x, 16);
+                const float by = __shfl_xor_sync(0xffffffffu, bs.y, 16);
+                const float2 bp = make_float2(bx - e[pp].x, -by - e[pp].y);
+                if (MODE == B2F_POL_I) {
+                    float t = a.x * a.x;
+                    t = fmaf(a.y, a.y, t);
+                    t = fmaf(bp.x, bp.x, t);
+                    t = fmaf(bp.y, bp.y, t);
+                    acc[pp][0] = fmaf(0.5f, t, acc[pp][0]);
+                } else {
+                    detect_acc<MODE>(acc[pp], make_float2(a.x + bp.x, a.y + bp.y), make_float2(a.x - bp.x, a.y - bp.y));
+                }
+            }
+        }
+        // ---- an output row is complete: add up its rows (lanes differ in r) and store
+        if ((rt & (G - 1)) == G - 1) {
+            for (int m = 1; m < Dt; m <<= 1) {
+#pragma unroll
+                for (int pp = 0; pp < 8; ++pp)
+#pragma unroll
+                    for (int c = 0; c < NPROD; ++c) acc[pp][c] += __shfl_xor_sync(0xffffffffu, acc[pp][c], m);
+            }
+            if ((rB & (Dt - 1)) == 0) {
+                const int ifi = lb / p.nblk;
+                const int blk = lb - ifi * p.nblk;
+                const int64_t t = p.row0 + ((int64_t)blk * kL + ((rt >> lgG) << lgG) * 16 + rB) / D;
+                float* dst = p.F + ifi * p.F_if_stride + t * (int64_t)(NPROD * N) + qB;
+#pragma unroll
+                for (int c = 0; c < NPROD; ++c)
+#pragma unroll
+                    for (int pp = 0; pp < 8; ++pp) dst[c * N + 16 * pp] = acc[pp][c];
+            }
+#pragma unroll
+            for (int pp = 0; pp < 8; ++pp)
+#pragma unroll
+                for (int c = 0; c < NPROD; ++c) acc[pp][c] = 0.f;
+        }
+    }
 }
 
 // ================================================================== front end of the fused path

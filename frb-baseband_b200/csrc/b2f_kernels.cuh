@@ -1153,7 +1153,7 @@ __global__ void __launch_bounds__(kKBThreads, 2) kr_row_pass(const KBParams p) {
         const int64_t gb = p.gb_begin + lb;
         const int row0 = (int)(grp % groups_per_blk) * GW + pass * RW;
         uint8_t* dst = stage0 + buf * S::kStage;
-        const float2* src = p.inter + lb * (int64_t)kL * R;     // block slot [column pair][512 rows][2 columns]
+        const float2* src = p.inter + lb * (int64_t)kL * R;     // block slot [32 row tiles][column pair][16 rows][2 columns]
         __syncwarp();                                           // everybody is done with the tile this refills
         constexpr int NPC = RW * (R / 2);                       // 16-byte pieces: lane -> (pair, row), row fastest
 #pragma unroll
@@ -1161,7 +1161,8 @@ __global__ void __launch_bounds__(kKBThreads, 2) kr_row_pass(const KBParams p) {
             const int idx = lane + 32 * k;
             if (NPC % 32 == 0 || idx < NPC) {
                 const int r = idx % RW, pp = idx / RW;
-                cp_async16(dst + r * S::kPitch + pp * 16, src + ((int64_t)pp * kL + row0 + r) * 2);
+                const int m = row0 + r;
+                cp_async16(dst + r * S::kPitch + pp * 16, src + ((((m >> 4) * (R / 2) + pp) * 16 + (m & 15)) * 2));
             }
         }
         if (pass == 0 && MODE != kModeSpectrum)

@@ -26,3 +26,5 @@ cudaError_t b2f_launch_kf_64(int mode, const b2f::FParams& p, int grid, int coop
 cudaError_t b2f_launch_kf_128(int mode, const b2f::FParams& p, int grid, int cooperative, cudaStream_t st, int* max_ctas_per_sm);
 cudaError_t b2f_launch_kf_256(int mode, const b2f::FParams& p, int grid, int cooperative, cudaStream_t st, int* max_ctas_per_sm);
 cudaError_t b2f_launch_kf_512(int mode, const b2f::FParams& p, int grid, int cooperative, cudaStream_t st, int* max_ctas_per_sm);
+namespace b2f { struct KTParams; }
+cudaError_t b2f_launch_kt(int mode, const b2f::KTParams& p, int grid, cudaStream_t st);      // tile row pass, R = 256

@@ -296,7 +296,7 @@ int b2f_fp32_peak(int device, double* tflops);
 
 /* Test hooks: copy an internal device buffer of the most recent push to the host.
  * which: 0 compact payload, 1 word mask, 2 frame status, 3 block dirty flags,
- *        4 column-pass output [blk][L][R] float2 (paths 1, 2: slots of [R/2][L][2] float2; path 2: only the ring),
+ *        4 column-pass output [blk][L][R] float2 (paths 1, 2: slots of [32][R/2][16][2] float2; path 2: only the ring),
  *        5 column sums [blk][R] float2,
  *        6 eps [blk][nchan] float2, 7 detected floats of held rows [if][row][prod][chan]. */
 int b2f_debug_copy(struct b2f_plan* plan, int which, void* dst, size_t nbytes, size_t* needed);

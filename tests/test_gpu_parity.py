@@ -39,8 +39,8 @@ def test_column_pass_stages(gpu):
         nblk = int(pl.geometry.unit_blocks * (pl.chunk_frames // pl.geometry.unit_frames))
         if pl.path == 2:                                   # fused kernel: the intermediate only exists as a ring in L2
             inter = None
-        elif pl.path == 1:                                 # block slots are [column pair][row][2 columns]
-            inter = pl.debug(4, np.complex64).reshape(nblk, R // 2, L, 2).transpose(0, 2, 1, 3).reshape(nblk, L, R)
+        elif pl.path == 1:                                 # block slots are [32 row tiles][column pair][16 rows][2 columns]
+            inter = pl.debug(4, np.complex64).reshape(nblk, 32, R // 2, 16, 2).transpose(0, 1, 3, 2, 4).reshape(nblk, L, R)
         else:
             inter = pl.debug(4, np.complex64).reshape(nblk, L, R)
         colsum = pl.debug(5, np.complex64).reshape(nblk, R)

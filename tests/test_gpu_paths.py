@@ -21,7 +21,8 @@ def _rows(monkeypatch, path, vdifs, **kw):
 
 @pytest.mark.parametrize("nchan,bw,D,nfr", [(128, 32.0, 16, 2048 + 512), (32, 16.0, 32, 700), (64, 32.0, 1, 600),
                                             (128, 32.0, 512, 2048), (8, 16.0, 4, 200), (256, 32.0, 8, 1024),
-                                            (16, 16.0, 64, 400)])
+                                            (16, 16.0, 64, 400), (128, 32.0, 4, 1024), (128, 32.0, 2, 600),
+                                            (128, 32.0, 64, 1024), (128, 32.0, 1, 600)])
 def test_paths_match_oracle_float(gpu, monkeypatch, nchan, bw, D, nfr):
     """-b-32 -I0 rows of every path within 1e-5 of the oracle (faulty frames included)."""
     v = synth.make_vdif(nfr, seed=900 + nchan, bw_mhz=bw, tone_frac=0.27, invalid_frac=0.004, fill_frac=0.004)

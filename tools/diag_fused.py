@@ -36,8 +36,8 @@ def run(path, v, nchan, bw, D, mode=_lib.POL_I, stages=False):
                 out["colsum"] = pl.debug(5, np.complex64)[: nblk * R].reshape(nblk, R).copy()
                 out["eps"] = pl.debug(6, np.complex64)[: nblk * nchan].reshape(nblk, nchan).copy()
                 if pl.path == 1:
-                    it = pl.debug(4, np.complex64)[: nblk * L * R].reshape(nblk, R // 2, L, 2)
-                    out["inter"] = it.transpose(0, 2, 1, 3).reshape(nblk, L, R).copy()
+                    it = pl.debug(4, np.complex64)[: nblk * L * R].reshape(nblk, 32, R // 2, 16, 2)
+                    out["inter"] = it.transpose(0, 1, 3, 2, 4).reshape(nblk, L, R).copy()
                 elif pl.path == 0:
                     out["inter"] = pl.debug(4, np.complex64)[: nblk * L * R].reshape(nblk, L, R).copy()
                 out["tstream"] = pl.debug(0, np.uint8).copy() if pl.path else None
