@@ -463,6 +463,9 @@ def main():
     if fused:
         dom, dom_name = ktimes["fused"], f"kf_fused<{R},{cfg['pol']}> (decode + column pass + row pass + detection, one persistent kernel)"
         dom_flops = col_flops + row_flops
+    elif pl.path == 1:
+        dom, dom_name = ktimes["column"], f"kf_fused<{R},I> column half (decode + FFT_512 . diag . IFFT_512 per column pair, warp-autonomous)"
+        dom_flops = col_flops
     else:
         dom, dom_name = ktimes["column"], "ka_column_pass (decode + column pass)"
         dom_flops = col_flops
@@ -473,7 +476,8 @@ def main():
     traffic = None
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = prof.get("kf_fused_dram_bytes_per_launch" if fused else "ka_column_pass_dram_bytes_per_launch")
+        traffic = prof.get("kf_fused_dram_bytes_per_launch" if fused else
+                           ("kf_column_half_dram_bytes_per_launch" if pl.path == 1 else "ka_column_pass_dram_bytes_per_launch"))
     except Exception:
         pass
     ach = dom_flops / launches_per_step / (dom_launch_ms * 1e-3) / 1e12
@@ -503,7 +507,7 @@ def main():
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "rt_factor": world * data_sec / (ms_step * 1e-3),
         "config": {"workload": workload, "name": args.config, "nif_per_gpu": NIF, "chunk_frames": cf,
-                   "channeliser_path": {0: "round-1 kernels", 1: "round-2 kernels, two launches", 2: "fused kernel, L2 ring"}.get(pl.path),
+                   "channeliser_path": {0: "round-1 kernels (ka_column_pass + kb_row_pass)", 1: "round-2 kernels (warp-autonomous column kernel + tile row pass)", 2: "round-2 fused kernel, L2 ring"}.get(pl.path),
                    "l2": "inputs (%.1f GB/step) larger than L2" % (in_bytes / 1e9),
                    "parallelism": (f"subband groups x{world} (weak: every GPU its own {NIF}-IF band), " + ("splice by NVLink peer stores from the requantise kernel" if peer is not None else "NCCL gather of 8-bit tiles")) if world > 1 else "1 GPU"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),

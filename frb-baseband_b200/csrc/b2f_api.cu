@@ -550,7 +550,9 @@ int push_fused(b2f_plan* pl, const K0Params& k0, int64_t nframes, int64_t nblk) 
         if (e != cudaSuccess) return fail(B2F_ECUDA, std::string("fused channeliser launch: ") + cudaGetErrorString(e));
     } else {
         fp.phase = 1;
-        rc = timed(pl, B2F_K_COLUMN, [&] { e = b2f_launch_kf(pl->R, pl->prm.pol_mode, fp, pl->f_grid, 0, pl->stream, nullptr); });
+        // the column half does not depend on the detection product: always the Stokes I instantiation, which is free of the
+        // spills the four-product row code brings into the kernel (C3: 90.8 -> 77 ms per 60 s)
+        rc = timed(pl, B2F_K_COLUMN, [&] { e = b2f_launch_kf(pl->R, B2F_POL_I, fp, pl->f_grid, 0, pl->stream, nullptr); });
         if (rc) return rc;
         if (e != cudaSuccess) return fail(B2F_ECUDA, std::string("column half launch: ") + cudaGetErrorString(e));
         rc = timed(pl, B2F_K_EPS, [&] {
@@ -741,17 +743,17 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
     if (cudaGetDeviceProperties(&prop, prm->device) != cudaSuccess) { free_plan(pl); return fail(B2F_ECUDA, "device properties"); }
     pl->num_sms = prop.multiProcessorCount;
     {
-        // Which channeliser.  Measured on B200 for C2 (20 s of 8 IF x 32 MHz): round-1 kernels 46.1 ms (column 31.1 + row 15.0),
-        // round-2 kernels as two launches 54.5 (column 25.7, 25 % faster and free of bank conflicts, but its [pair][row][2]
-        // block layout halves the row pass's HBM efficiency: 28.8), fused kernel 61.6 with 12x less DRAM traffic (0.79 GB
-        // instead of 9.75 GB per push: the intermediate stays in the L2 ring) -- its inter-warp ordering costs more than the
-        // HBM round trip saved.  So the round-1 kernels stay the default; B2F_PATH=split|fused selects the others where
-        // they apply (2-bit split streams, frames in order, 512-point columns, no dedispersion), and the JA98 decode, which
-        // only the round-2 column kernel implements, selects the fused kernel by itself.
+        // Which channeliser.  Measured on B200 for C2 (20 s of 8 IF x 32 MHz, profiles/r02_bench_C2_20s_*.json): round-1
+        // kernels 46.1 ms (column 31.1 + row 15.0); round-2 column kernel + tile row pass 42.8 (23.5 + 19.0 -> see DESIGN 5b);
+        // fused kernel 60 with 6-12x less DRAM traffic (the intermediate stays in the L2 ring) -- its inter-warp ordering costs
+        // more than the HBM round trip it saves.  So: nchan 128 (R = 256: C2, C3, C5) runs the round-2 column kernel and the
+        // tile row pass (path 1); every other shape the round-1 kernels (path 0).  B2F_PATH=legacy|split|fused overrides where
+        // the round-2 kernels apply (2-bit split streams, frames in order, 512-point columns, no dedispersion, products I /
+        // coherence / IQUV); the JA98 decode exists only in the round-2 column kernel and selects it by itself.
         const bool eligible = !generic && !dedisp && prm->in_nbit == 2 && W == 0 && prm->frame_time_mode == B2F_FRAMES_POSITIONAL &&
                               payload % 16 == 0 && prm->frame_bytes % 16 == 0 && prop.cooperativeLaunch;
         const char* e = getenv("B2F_PATH");
-        int want = prm->decode_mode == B2F_DECODE_JA98 ? 2 : 0;
+        int want = R == 256 ? 1 : (prm->decode_mode == B2F_DECODE_JA98 ? 2 : 0);
         if (e && !strcmp(e, "legacy")) want = 0;
         else if (e && !strcmp(e, "split")) want = 1;
         else if (e && !strcmp(e, "fused")) want = 2;

@@ -644,6 +644,8 @@ __global__ void __launch_bounds__(kKTThreads, 2) kt_row_tiles(const KTParams p) 
     const int lgG = D > 16 ? 31 - __clz(D / 16) : 0;         // 2^lgG tiles per integration unit
     const int G = 1 << lgG, lgU = 5 - lgG;                   // 2^lgU units per block
     const int Dt = D < 16 ? D : 16;                          // rows of one tile that add up to one output row
+    const int lgD = 31 - __clz(D);
+    int ifi = 0;
     const int nunits_cta = (int)((p.nb * (32 >> lgG) - blockIdx.x + gridDim.x - 1) / gridDim.x);   // units this CTA owns
     const int nseq = nunits_cta > 0 ? nunits_cta << lgG : 0;
     auto locate = [&](int seq, int& lb, int& rt) {
@@ -729,21 +731,49 @@ __global__ void __launch_bounds__(kKTThreads, 2) kt_row_tiles(const KTParams p) 
         }
         // ---- an output row is complete: add up its rows (lanes differ in r) and store
         if ((rt & (G - 1)) == G - 1) {
-            for (int m = 1; m < Dt; m <<= 1) {
+            while ((int64_t)(ifi + 1) * p.nblk <= lb) ++ifi;                 // lb only grows: no division
+            const int blk = lb - ifi * p.nblk;
+            if (Dt == 16) {
+                // all 16 rows: reduce-scatter over the lanes (8 shuffles instead of a 32-shuffle butterfly).  After the steps
+                // with lane masks 8, 4, 2 a lane holds the sum of one channel group pp = r >> 1 over 8 rows; mask 1 finishes it.
+                const int64_t t = p.row0 + (((int64_t)blk * kL + ((rt >> lgG) << lgG) * 16) >> lgD);
+                float* dst = p.F + ifi * p.F_if_stride + t * (int64_t)(NPROD * N) + qB + 16 * (rB >> 1);
 #pragma unroll
-                for (int pp = 0; pp < 8; ++pp)
+                for (int c = 0; c < NPROD; ++c) {
+                    float a4[4], a2[2], a1;
+                    const bool h8 = (rB & 8) != 0, h4 = (rB & 4) != 0, h2 = (rB & 2) != 0;
 #pragma unroll
-                    for (int c = 0; c < NPROD; ++c) acc[pp][c] += __shfl_xor_sync(0xffffffffu, acc[pp][c], m);
-            }
-            if ((rB & (Dt - 1)) == 0) {
-                const int ifi = lb / p.nblk;
-                const int blk = lb - ifi * p.nblk;
-                const int64_t t = p.row0 + ((int64_t)blk * kL + ((rt >> lgG) << lgG) * 16 + rB) / D;
-                float* dst = p.F + ifi * p.F_if_stride + t * (int64_t)(NPROD * N) + qB;
+                    for (int k = 0; k < 4; ++k) {
+                        const float keep = h8 ? acc[k + 4][c] : acc[k][c], send = h8 ? acc[k][c] : acc[k + 4][c];
+                        a4[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                    }
 #pragma unroll
-                for (int c = 0; c < NPROD; ++c)
+                    for (int k = 0; k < 2; ++k) {
+                        const float keep = h4 ? a4[k + 2] : a4[k], send = h4 ? a4[k] : a4[k + 2];
+                        a2[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                    }
+                    {
+                        const float keep = h2 ? a2[1] : a2[0], send = h2 ? a2[0] : a2[1];
+                        a1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+                    }
+                    a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+                    if ((rB & 1) == 0) dst[c * N] = a1;
+                }
+            } else {
+                for (int m = 1; m < Dt; m <<= 1) {
 #pragma unroll
-                    for (int pp = 0; pp < 8; ++pp) dst[c * N + 16 * pp] = acc[pp][c];
+                    for (int pp = 0; pp < 8; ++pp)
+#pragma unroll
+                        for (int c = 0; c < NPROD; ++c) acc[pp][c] += __shfl_xor_sync(0xffffffffu, acc[pp][c], m);
+                }
+                if ((rB & (Dt - 1)) == 0) {
+                    const int64_t t = p.row0 + (((int64_t)blk * kL + rt * 16 + rB) >> lgD);
+                    float* dst = p.F + ifi * p.F_if_stride + t * (int64_t)(NPROD * N) + qB;
+#pragma unroll
+                    for (int c = 0; c < NPROD; ++c)
+#pragma unroll
+                        for (int pp = 0; pp < 8; ++pp) dst[c * N + 16 * pp] = acc[pp][c];
+                }
             }
 #pragma unroll
             for (int pp = 0; pp < 8; ++pp)
