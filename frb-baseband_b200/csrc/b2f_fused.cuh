@@ -564,13 +564,13 @@ __global__ void __launch_bounds__(kFThreads, 1) kf_fused(const FParams p) {
                 if (!warp_wait_ge(sy + FS_ROW, (unsigned)(G::NPAIR * (i - ns + 1)), p.abort_flag, lane)) return;
             }
             tick(1);
-            f_col_back<R>(reinterpret_cast<const float4*>(wbuf), betaS, lane, p.ring + slot * M + (size_t)pr * 32);
-            col_pending = phase == 0;
-            if (phase == 1 && lbc + nl < nb) {                             // columns only: prefetch the next work item
+            if (phase == 1 && lbc + nl < nb) {      // columns only: the next work item's input, in flight during the back half
                 const uint8_t* q = raw_ptr(lbc + nl);
                 rawA = ldg_stream16(q);
                 rawB = ldg_stream16(q + 512);
             }
+            f_col_back<R>(reinterpret_cast<const float4*>(wbuf), betaS, lane, p.ring + slot * M + (size_t)pr * 32);
+            col_pending = phase == 0;
             tick(2);
         }
         if (lag < 2 && col_pending) { warp_arrive(sy + FS_COL, lane); col_pending = false; }   // lag 1: next round's rows wait for it
@@ -910,36 +910,44 @@ static __global__ void __launch_bounds__(256) k0t_transpose(const K0TParams p) {
         }
         __syncthreads();
         if (u + gridDim.x < nunits) load_unit(u + gridDim.x);
-        // ---- transposed read-out: thread = (half, column quad, item); 16 rows x 4 columns -> 4 outputs of 16 bytes
+        // ---- transposed read-out: thread = (half, group of 8 columns, item); 16 rows x 8 columns (64-bit shared loads,
+        // conflict-free at a row pitch of 9 x 8 bytes) -> 8 outputs of 16 bytes
         {
             const int lane = tid & 31, wrp = tid >> 5;
             const int item = lane & 15;
             const int half = wrp >> 2;
+            const int c8 = (wrp & 3) * 2 + (lane >> 4);
             uint8_t* tb = p.tstream + ifi * p.tstream_if_stride + blk * M;
+            if (c8 < SC / 8) {
+                uint32_t o[8][4];
 #pragma unroll
-            for (int t = 0; t < (SC + 31) / 32; ++t) {
-                const int cq = (wrp & 3) * 2 + (lane >> 4) + 8 * t;
-                if (cq < SC / 4) {
-                    uint32_t o[4][4];
+                for (int g = 0; g < 4; ++g) {
+                    uint2 a[4];
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        uint32_t a[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            a[j] = *reinterpret_cast<const uint32_t*>(s_exp + (32 * (4 * g + j) + item + 16 * half) * PITCH + 4 * cq);
-                        const uint32_t t0 = __byte_perm(a[0], a[1], 0x5140), t1 = __byte_perm(a[2], a[3], 0x5140);
-                        const uint32_t t2 = __byte_perm(a[0], a[1], 0x7362), t3 = __byte_perm(a[2], a[3], 0x7362);
+                    for (int j = 0; j < 4; ++j)
+                        a[j] = *reinterpret_cast<const uint2*>(s_exp + (32 * (4 * g + j) + item + 16 * half) * PITCH + 8 * c8);
+                    {
+                        const uint32_t t0 = __byte_perm(a[0].x, a[1].x, 0x5140), t1 = __byte_perm(a[2].x, a[3].x, 0x5140);
+                        const uint32_t t2 = __byte_perm(a[0].x, a[1].x, 0x7362), t3 = __byte_perm(a[2].x, a[3].x, 0x7362);
                         o[0][g] = __byte_perm(t0, t1, 0x5410);
                         o[1][g] = __byte_perm(t0, t1, 0x7632);
                         o[2][g] = __byte_perm(t2, t3, 0x5410);
                         o[3][g] = __byte_perm(t2, t3, 0x7632);
                     }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int pair = strip * (SC / 2) + 2 * cq + (j >> 1), col = j & 1;
-                        *reinterpret_cast<uint4*>(tb + ((size_t)(pair * 2 + half) * 32 + 2 * item + col) * 16) =
-                            make_uint4(o[j][0], o[j][1], o[j][2], o[j][3]);
+                    {
+                        const uint32_t t0 = __byte_perm(a[0].y, a[1].y, 0x5140), t1 = __byte_perm(a[2].y, a[3].y, 0x5140);
+                        const uint32_t t2 = __byte_perm(a[0].y, a[1].y, 0x7362), t3 = __byte_perm(a[2].y, a[3].y, 0x7362);
+                        o[4][g] = __byte_perm(t0, t1, 0x5410);
+                        o[5][g] = __byte_perm(t0, t1, 0x7632);
+                        o[6][g] = __byte_perm(t2, t3, 0x5410);
+                        o[7][g] = __byte_perm(t2, t3, 0x7632);
                     }
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int pair = strip * (SC / 2) + 4 * c8 + (j >> 1), col = j & 1;
+                    *reinterpret_cast<uint4*>(tb + ((size_t)(pair * 2 + half) * 32 + 2 * item + col) * 16) =
+                        make_uint4(o[j][0], o[j][1], o[j][2], o[j][3]);
                 }
             }
         }
