@@ -14,6 +14,7 @@
 
 #define B2F_API_TU
 #include "b2f_fused.cuh"
+#include "b2f_generic.cuh"
 #include "b2f_launch.h"
 
 using namespace b2f;
@@ -86,6 +87,13 @@ struct b2f_plan {
     // coherent dedispersion (digifil -D dm -F nchan:D): overlap-save geometry and halo carry
     bool dedisp = false;
     bool generic = false;          // freq_res / nchan outside the tuned 512-point kernels
+    // tscrunch that is not a power of two, or longer than freq_res (process_vdif.py:156-158 passes any -t): the kernels
+    // integrate D = the largest power of two dividing it (<= freq_res), d_Fk holds their rows and kd_sum_rows adds tsq of them
+    int tsq = 1;
+    float* d_Fk = nullptr;
+    int64_t Fk_if_stride = 0, fk_pending = 0;
+    int kgt_lg = 0;                // generic kernels with compile-time geometry (L = R = 2^kgt_lg), 0 = run-time kernels
+    int kgt_cols = 0, kgt_rb = 0, kgt_col_ctas = 0, kgt_row_ctas = 0;
     bool carry_mode = false;       // pushes need not hold whole blocks: unconsumed samples are carried over
     float2 *d_tw_col = nullptr, *d_tw_row = nullptr;
     int nfilt_pos = 0, nfilt_neg = 0, keep = 0;
@@ -130,6 +138,11 @@ struct b2f_plan {
 namespace {
 
 static const int kStatSplit = 64;
+
+// where the row kernels put their rows: straight into F, or behind the rows still waiting in the staging buffer
+inline float* row_dst(const b2f_plan* pl) { return pl->tsq > 1 ? pl->d_Fk : pl->d_F; }
+inline int64_t row_dst_stride(const b2f_plan* pl) { return pl->tsq > 1 ? pl->Fk_if_stride : pl->F_if_stride; }
+inline int64_t row_dst_row0(const b2f_plan* pl) { return pl->tsq > 1 ? pl->fk_pending : pl->rows_off + pl->rows_held; }
 
 template <class Fn>
 int timed(b2f_plan* pl, int kid, Fn&& fn) {
@@ -301,6 +314,7 @@ void free_plan(b2f_plan* pl) {
                     pl->d_tstream, pl->d_fillflag, pl->d_part, pl->d_fsync, pl->d_fprof, pl->d_levels};
     for (void* b : bufs)
         if (b) cudaFree(b);
+    if (pl->d_Fk) cudaFree(pl->d_Fk);
     for (auto& t : pl->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     for (auto& e : pl->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     if (pl->copy_stream) cudaStreamDestroy(pl->copy_stream);
@@ -316,6 +330,7 @@ int init_state(b2f_plan* pl) {
     pl->have_base = false;
     pl->frames_pushed = 0;
     pl->carry_len = 0;
+    pl->fk_pending = 0;
     pl->blocks_dirty = 0;
     pl->last_nblk = pl->last_nframes = 0;
     pl->rows_this_interval = 0;
@@ -353,7 +368,7 @@ int push_dedisp(b2f_plan* pl, int64_t nblk, int64_t T) {
         kg.compact = pl->d_compact; kg.compact_stride = pl->compact_stride;
         kg.inter = pl->d_inter; kg.colsum = pl->d_colsum; kg.eps = pl->d_eps;
         kg.tw_col = pl->d_tw_col; kg.tw_row = pl->d_tw_row;
-        kg.F = pl->d_F; kg.F_if_stride = pl->F_if_stride; kg.row0 = pl->rows_off + pl->rows_held;
+        kg.F = row_dst(pl); kg.F_if_stride = row_dst_stride(pl); kg.row0 = row_dst_row0(pl);
         kg.L = pl->L; kg.lgL = 31 - __builtin_clz(pl->L); kg.R = pl->R; kg.lgR = 31 - __builtin_clz(pl->R);
         kg.C = std::min(16, 8192 / pl->L);                    // 64 KiB of column data per CTA, two CTAs per SM
         kg.lgC = 31 - __builtin_clz(kg.C);
@@ -361,28 +376,46 @@ int push_dedisp(b2f_plan* pl, int64_t nblk, int64_t T) {
         const int RB = std::max(1, std::min(16, 4096 / pl->R));
         const size_t smem_col = ((size_t)pl->L + 32 + kg_padded((size_t)pl->L * kg.C)) * sizeof(float2);
         const size_t smem_row = ((size_t)pl->R + kg_padded((size_t)RB * pl->R) + 2 * (size_t)RB * pl->R) * sizeof(float2);
-        CU(cudaFuncSetAttribute(kg_column_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_col));
-        CU(cudaFuncSetAttribute(kg_row_pass<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row));
-        CU(cudaFuncSetAttribute(kg_row_pass<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row));
+        if (!pl->kgt_lg) {
+            CU(cudaFuncSetAttribute(kg_column_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_col));
+            CU(cudaFuncSetAttribute(kg_row_pass<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row));
+            CU(cudaFuncSetAttribute(kg_row_pass<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row));
+        }
+        if (pl->R * sizeof(float2) > 48 * 1024)
+            CU(cudaFuncSetAttribute(ke_eps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(pl->R * sizeof(float2))));
         for (int64_t b0 = 0; b0 < nbt; b0 += NB) {
             const int64_t nb = std::min(NB, nbt - b0);
             kg.gb_begin = b0; kg.gb_end = b0 + nb;
-            const int64_t work = nb * (pl->R / kg.C);
+            cudaError_t le = cudaSuccess;
             rc = timed(pl, B2F_K_COLUMN, [&] {
-                kg_column_pass<<<(unsigned)std::min<int64_t>(work, 2 * (int64_t)pl->num_sms), 256, smem_col, pl->stream>>>(kg);
+                if (pl->kgt_lg) {                           // compile-time geometry (b2f_generic.cuh): L = R = 2^kgt_lg
+                    const int64_t work = nb * (pl->R / pl->kgt_cols);
+                    le = b2f_launch_kgt_col(pl->kgt_lg, kg, (int)std::min<int64_t>(work, (int64_t)pl->kgt_col_ctas * pl->num_sms), pl->stream, nullptr);
+                } else {
+                    const int64_t work = nb * (pl->R / kg.C);
+                    kg_column_pass<<<(unsigned)std::min<int64_t>(work, 2 * (int64_t)pl->num_sms), 256, smem_col, pl->stream>>>(kg);
+                }
             });
             if (rc) return rc;
+            if (le != cudaSuccess) return fail(B2F_ECUDA, std::string("generic column pass: ") + cudaGetErrorString(le));
             rc = timed(pl, B2F_K_EPS, [&] {
                 ke_eps<<<(unsigned)nb, std::min(pl->R / 2, 512), pl->R * sizeof(float2), pl->stream>>>(pl->d_colsum + b0 * pl->R,
                                                                                        pl->d_eps + b0 * pl->N, pl->R);
             });
             if (rc) return rc;
-            const int64_t nunits = nb * (pl->L / std::max(pl->D, RB));
             rc = timed(pl, B2F_K_ROW, [&] {
-                if (pl->N > 1024) kg_row_pass<8><<<(unsigned)std::min<int64_t>(nunits, (int64_t)pl->num_sms * 2), 256, smem_row, pl->stream>>>(kg);
-                else kg_row_pass<4><<<(unsigned)std::min<int64_t>(nunits, (int64_t)pl->num_sms * 2), 256, smem_row, pl->stream>>>(kg);
+                if (pl->kgt_lg) {
+                    const int64_t nunits = nb * (pl->L / std::max(pl->D, pl->kgt_rb));
+                    le = b2f_launch_kgt_row(pl->kgt_lg, pl->prm.pol_mode, kg, (int)std::min<int64_t>(nunits, (int64_t)pl->kgt_row_ctas * pl->num_sms),
+                                            pl->stream, nullptr);
+                } else {
+                    const int64_t nunits = nb * (pl->L / std::max(pl->D, RB));
+                    if (pl->N > 1024) kg_row_pass<8><<<(unsigned)std::min<int64_t>(nunits, (int64_t)pl->num_sms * 2), 256, smem_row, pl->stream>>>(kg);
+                    else kg_row_pass<4><<<(unsigned)std::min<int64_t>(nunits, (int64_t)pl->num_sms * 2), 256, smem_row, pl->stream>>>(kg);
+                }
             });
             if (rc) return rc;
+            if (le != cudaSuccess) return fail(B2F_ECUDA, std::string("generic row pass: ") + cudaGetErrorString(le));
         }
     } else if (nblk > 0) {
         const int64_t cap = pl->batch_blocks > 0 ? pl->batch_blocks : (int64_t)nif * pl->chunk_blocks;
@@ -401,7 +434,7 @@ int push_dedisp(b2f_plan* pl, int64_t nblk, int64_t T) {
         kb.F = nullptr; kb.nblk = (int)nblk; kb.nif = nif; kb.D = 1;
         KCParams kc{};
         kc.spec = pl->d_spec; kc.chirp = pl->d_chirp; kc.tab_w = pl->d_tab_w;
-        kc.F = pl->d_F; kc.F_if_stride = pl->F_if_stride; kc.row0 = pl->rows_off + pl->rows_held;
+        kc.F = row_dst(pl); kc.F_if_stride = row_dst_stride(pl); kc.row0 = row_dst_row0(pl);
         kc.nblk = (int)nblk; kc.nif = nif; kc.D = pl->D; kc.mode = pl->prm.pol_mode;
         kc.nfilt_pos = pl->nfilt_pos; kc.keep = pl->keep;
         int TR, PT;
@@ -463,6 +496,35 @@ cudaError_t b2f_launch_kf(int R, int mode, const FParams& p, int grid, int coope
         case 512: return b2f_launch_kf_512(mode, p, grid, cooperative, st, occ);
     }
     return cudaErrorInvalidValue;
+}
+
+cudaError_t b2f_launch_kgt_col(int lg, const KGParams& p, int grid, cudaStream_t st, int* ctas) {
+    switch (lg) {
+        case 10: return b2f_launch_kgt_col_10(p, grid, st, ctas);
+        case 11: return b2f_launch_kgt_col_11(p, grid, st, ctas);
+        case 12: return b2f_launch_kgt_col_12(p, grid, st, ctas);
+        case 13: return b2f_launch_kgt_col_13(p, grid, st, ctas);
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t b2f_launch_kgt_row(int lg, int mode, const KGParams& p, int grid, cudaStream_t st, int* ctas) {
+    switch (lg) {
+        case 10: return b2f_launch_kgt_row_10(mode, p, grid, st, ctas);
+        case 11: return b2f_launch_kgt_row_11(mode, p, grid, st, ctas);
+        case 12: return b2f_launch_kgt_row_12(mode, p, grid, st, ctas);
+        case 13: return b2f_launch_kgt_row_13(mode, p, grid, st, ctas);
+    }
+    return cudaErrorInvalidValue;
+}
+
+void b2f_kgt_geometry(int lg, int* cols, int* rb) {
+    switch (lg) {
+        case 10: *cols = KGT<10>::C; *rb = KGT<10>::RB; break;
+        case 11: *cols = KGT<11>::C; *rb = KGT<11>::RB; break;
+        case 12: *cols = KGT<12>::C; *rb = KGT<12>::RB; break;
+        default: *cols = KGT<13>::C; *rb = KGT<13>::RB; break;
+    }
 }
 
 namespace {
@@ -534,9 +596,9 @@ int push_fused(b2f_plan* pl, const K0Params& k0, int64_t nframes, int64_t nblk) 
     fp.ring = pl->d_inter; fp.colsum = pl->d_colsum; fp.eps = pl->d_eps;
     fp.tab_h = pl->d_tab_h; fp.tab_w = pl->d_tab_w; fp.tab_beta = pl->d_tab_beta; fp.tab_r = pl->d_tab_r;
     const bool direct = pl->Dp == pl->D || pl->path == 1;
-    fp.out = direct ? pl->d_F : pl->d_part;
-    fp.out_if_stride = direct ? pl->F_if_stride : pl->part_if_stride;
-    fp.out_row0 = direct ? pl->rows_off + pl->rows_held : 0;
+    fp.out = direct ? row_dst(pl) : pl->d_part;
+    fp.out_if_stride = direct ? row_dst_stride(pl) : pl->part_if_stride;
+    fp.out_row0 = direct ? row_dst_row0(pl) : 0;
     fp.Dp = pl->Dp; fp.nblk = (int)nblk; fp.nif = nif;
     fp.gb_begin = 0; fp.gb_end = nbt;
     fp.sync = pl->d_fsync; fp.abort_flag = pl->d_fsync + (size_t)pl->f_lanes * FS_STRIDE;
@@ -563,7 +625,7 @@ int push_fused(b2f_plan* pl, const K0Params& k0, int64_t nframes, int64_t nblk) 
             // 16-row tiles are 32 KiB contiguous in the block layout: one bulk copy per tile, block-wide second FFT stage
             KTParams kt{};
             kt.inter = pl->d_inter; kt.eps = pl->d_eps; kt.tab_r = pl->d_tab_r;
-            kt.F = pl->d_F; kt.F_if_stride = pl->F_if_stride; kt.row0 = pl->rows_off + pl->rows_held;
+            kt.F = row_dst(pl); kt.F_if_stride = row_dst_stride(pl); kt.row0 = row_dst_row0(pl);
             kt.nblk = (int)nblk; kt.nif = nif; kt.D = pl->D; kt.nb = nbt;
             const int64_t units = nbt * (32 / std::max(1, pl->D / 16));
             rc = timed(pl, B2F_K_ROW, [&] { e = b2f_launch_kt(pl->prm.pol_mode, kt, (int)std::min<int64_t>(units, (int64_t)pl->num_sms * 2), pl->stream); });
@@ -577,7 +639,7 @@ int push_fused(b2f_plan* pl, const K0Params& k0, int64_t nframes, int64_t nblk) 
         const int RW = 32 / TR, GW = std::max(pl->D, RW);
         KBParams kb{};
         kb.inter = pl->d_inter; kb.eps = pl->d_eps; kb.tab_r = pl->d_tab_r;
-        kb.F = pl->d_F; kb.F_if_stride = pl->F_if_stride; kb.row0 = pl->rows_off + pl->rows_held;
+        kb.F = row_dst(pl); kb.F_if_stride = row_dst_stride(pl); kb.row0 = row_dst_row0(pl);
         kb.nblk = (int)nblk; kb.nif = nif; kb.D = pl->D; kb.gb_begin = 0; kb.gb_end = nbt;
         const int64_t ngroups = nbt * (kL / GW);
         const int64_t ctas = (ngroups + kKBThreads / 32 - 1) / (kKBThreads / 32);
@@ -592,13 +654,48 @@ int push_fused(b2f_plan* pl, const K0Params& k0, int64_t nframes, int64_t nblk) 
         const int64_t n4 = rows * (ncol / 4);
         rc = timed(pl, B2F_K_TSUM, [&] {
             kt_sum_partials<<<dim3((unsigned)((n4 + 255) / 256), nif), 256, 0, pl->stream>>>(
-                pl->d_part, pl->part_if_stride, pl->d_F, pl->F_if_stride, pl->rows_off + pl->rows_held, rows, ncol, pl->D / pl->Dp);
+                pl->d_part, pl->part_if_stride, row_dst(pl), row_dst_stride(pl), row_dst_row0(pl), rows, ncol, pl->D / pl->Dp);
         });
         if (rc) return rc;
     }
     return 0;
 }
 
+}  // namespace
+
+// tscrunch beyond what the row kernels integrate: output row r = sum of tsq consecutive kernel rows, in a fixed order
+static __global__ void kd_sum_rows(const float* __restrict__ Fk, int64_t Fk_if_stride, float* __restrict__ F, int64_t F_if_stride,
+                                   int64_t row0, int64_t nrows, int ncol, int q) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= nrows * ncol) return;
+    const int64_t r = i / ncol;
+    const int c = (int)(i - r * ncol);
+    const float* src = Fk + blockIdx.y * Fk_if_stride + r * q * (int64_t)ncol + c;
+    float acc = 0.f;
+    for (int k = 0; k < q; ++k) acc += src[(int64_t)k * ncol];
+    F[blockIdx.y * F_if_stride + (row0 + r) * ncol + c] = acc;
+}
+
+namespace {
+int sum_rows(b2f_plan* pl, int64_t krows, int64_t rows) {
+    if (pl->tsq <= 1) return 0;
+    const int ncol = pl->nprod * pl->N, nif = pl->prm.nif;
+    const int64_t total = pl->fk_pending + krows, left = total - rows * pl->tsq;
+    if (rows > 0) {
+        const int64_t n = rows * ncol;
+        int rc = timed(pl, B2F_K_TSUM, [&] {
+            kd_sum_rows<<<dim3((unsigned)((n + 255) / 256), nif), 256, 0, pl->stream>>>(pl->d_Fk, pl->Fk_if_stride, pl->d_F, pl->F_if_stride,
+                                                                                      pl->rows_off + pl->rows_held, rows, ncol, pl->tsq);
+        });
+        if (rc) return rc;
+        // the kernel rows of the unfinished sample (fewer than tsq, so they cannot overlap their destination) move to the front
+        for (int i = 0; i < nif && left > 0; ++i)
+            CU(cudaMemcpyAsync(pl->d_Fk + i * pl->Fk_if_stride, pl->d_Fk + i * pl->Fk_if_stride + rows * pl->tsq * (int64_t)ncol,
+                               (size_t)left * ncol * sizeof(float), cudaMemcpyDeviceToDevice, pl->stream));
+    }
+    pl->fk_pending = left;
+    return 0;
+}
 }  // namespace
 
 extern "C" {
@@ -628,18 +725,23 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
     if (prm->nchan < 1) return fail(B2F_EINVAL, "nchan");
     const int L = prm->freq_res > 0 ? prm->freq_res : (prm->nchan <= 128 ? 512 : 2 * prm->nchan);
     const int R = 2 * prm->nchan;
-    if (!is_pow2(R) || R < 16 || R > 4096) return fail(B2F_EUNSUPPORTED, "nchan must be a power of two in 8..2048");
-    if (!is_pow2(L) || L < 16 || L > 4096) return fail(B2F_EUNSUPPORTED, "freq_res must be a power of two in 16..4096");
+    if (!is_pow2(R) || R < 16 || R > 8192) return fail(B2F_EUNSUPPORTED, "nchan must be a power of two in 8..4096");
+    if (!is_pow2(L) || L < 16 || L > 8192) return fail(B2F_EUNSUPPORTED, "freq_res must be a power of two in 16..8192");
+    if ((R > 4096 || L > 4096) && L != R)
+        return fail(B2F_EUNSUPPORTED, "nchan 4096 needs freq_res = 2 nchan (digifil -F nchan:2*nchan, process_vdif.py:162)");
     const bool generic = !(L == kL && R <= 512);        // tuned kernels: 512-point columns, rows up to 512
     if (generic && prm->in_nbit != 2) return fail(B2F_EUNSUPPORTED, "freq_res != 512 or nchan > 256 needs 2-bit input in this build");
-    const int D = prm->tscrunch < 1 ? 1 : prm->tscrunch;
-    if (!is_pow2(D) || D > L) return fail(B2F_EUNSUPPORTED, "tscrunch must be a power of two <= freq_res");
+    const int D_user = prm->tscrunch < 1 ? 1 : prm->tscrunch;
+    if (D_user > (1 << 20)) return fail(B2F_EUNSUPPORTED, "tscrunch above 2^20");
+    int D = D_user & -D_user;                       // what the kernels integrate; kd_sum_rows adds tsq = D_user / D of their rows
+    while (D > L) D >>= 1;
+    if (prm->coherent && prm->dm > 0.0) while (D > 128) D >>= 1;
+    const int tsq = D_user / D;
     if (prm->header_bytes != 32 && prm->header_bytes != 16) return fail(B2F_EINVAL, "header_bytes must be 32 or 16");
     const int payload = prm->frame_bytes - prm->header_bytes;
     if (payload <= 0 || payload % 8) return fail(B2F_EINVAL, "frame_bytes");
     const bool dedisp = prm->coherent && prm->dm > 0.0;
     if (dedisp && prm->in_nbit != 2) return fail(B2F_EUNSUPPORTED, "coherent dedispersion needs 2-bit input in this build");
-    if (dedisp && D > 128) return fail(B2F_EUNSUPPORTED, "coherent dedispersion needs tscrunch <= 128");
     if (dedisp && generic) return fail(B2F_EUNSUPPORTED, "coherent dedispersion needs freq_res 512 and nchan <= 256 in this build");
     const double abw = std::fabs(prm->bw_mhz[0]);
     if (abw <= 0) return fail(B2F_EINVAL, "bw_mhz");
@@ -675,7 +777,8 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
     b2f_plan* pl = new b2f_plan();
     pl->prm = *prm;
     pl->prm.freq_res = L;
-    pl->prm.tscrunch = D;
+    pl->prm.tscrunch = D_user;
+    pl->tsq = tsq;
     pl->R = R; pl->N = prm->nchan; pl->L = L; pl->D = D; pl->nprod = nprod;
     pl->nstrips = R / kStripCols;
     pl->M = (int64_t)R * L;
@@ -723,7 +826,8 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
     if (generic) pl->chunk_blocks = pl->chunk_frames * pl->spf / pl->M;
     if (pl->carry_mode) pl->chunk_blocks += 1;                 // carried samples can complete one more block
     pl->chunk_rows = pl->chunk_blocks * pl->keep / D;
-    const double tsamp = (double)D * prm->nchan / (abw * 1e6);
+    if (tsq > 1) pl->chunk_rows = pl->chunk_rows / tsq + 1;       // a push can complete one more output sample than its share
+    const double tsamp = (double)D_user * prm->nchan / (abw * 1e6);
     const double interval = prm->rescale_interval_s > 0 ? prm->rescale_interval_s : 10.0;
     pl->interval_rows = prm->keep_bandpass ? 0 : (int64_t)llround(interval / tsamp);
     pl->F_cap_rows = pl->interval_rows + 2 * pl->chunk_rows;
@@ -846,12 +950,33 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
     CUB(cudaMalloc(&pl->d_eps, (size_t)nbt * pl->N * sizeof(float2)));
     pl->F_if_stride = pl->F_cap_rows * nprod * pl->N;
     CUB(cudaMalloc(&pl->d_F, (size_t)pl->F_if_stride * nif * sizeof(float)));
+    if (tsq > 1) {
+        pl->Fk_if_stride = (pl->chunk_blocks * pl->keep / D + tsq) * nprod * pl->N;
+        CUB(cudaMalloc(&pl->d_Fk, (size_t)pl->Fk_if_stride * nif * sizeof(float)));
+    }
     CUB(cudaMalloc(&pl->d_mean, (size_t)nif * nprod * pl->N * sizeof(float)));
     CUB(cudaMalloc(&pl->d_scale, (size_t)nif * nprod * pl->N * sizeof(float)));
     CUB(cudaMalloc(&pl->d_partial, (size_t)nif * kStatSplit * nprod * pl->N * sizeof(double2)));
     CUB(cudaMalloc(&pl->d_counters, C_COUNT * sizeof(unsigned long long)));
     CUB(cudaMalloc(&pl->d_sm_slots, 1024 * sizeof(int)));
     if (pl->carry_mode) CUB(cudaMalloc(&pl->d_carry, (size_t)pl->M * nif));
+    if (generic && L == R && L >= 1024) {
+        // the shapes process_vdif.py:162 produces (-F nchan:2*nchan): kernels with compile-time geometry
+        const char* e = getenv("B2F_GENERIC");
+        const int lg = 31 - __builtin_clz(L);
+        if (!(e && !strcmp(e, "runtime") && L <= 4096)) {
+            int cc = 0, rc2 = 0;
+            if (b2f_launch_kgt_col(lg, KGParams{}, 0, nullptr, &cc) != cudaSuccess || cc < 1 ||
+                b2f_launch_kgt_row(lg, prm->pol_mode, KGParams{}, 0, nullptr, &rc2) != cudaSuccess || rc2 < 1) {
+                cudaGetLastError();
+                if (L > 4096) { g_err = "generic kernels for nchan 4096 do not fit this device"; return bail(B2F_EUNSUPPORTED); }
+            } else {
+                pl->kgt_lg = lg;
+                pl->kgt_col_ctas = cc; pl->kgt_row_ctas = rc2;
+                b2f_kgt_geometry(lg, &pl->kgt_cols, &pl->kgt_rb);
+            }
+        }
+    }
     if (generic) {
         auto pass_tables = [](int len) {                 // layout of kg_tw_offset: per outer pass, [q - 1][lo]
             std::vector<float2> t((size_t)len, make_float2(1.f, 0.f));
@@ -921,7 +1046,7 @@ int b2f_get_geometry(const b2f_plan* pl, b2f_geometry* g) {
     g->row_bytes = pl->row_bytes;
     g->nprod = pl->nprod;
     g->freq_res = pl->L;
-    g->tsamp_s = (double)pl->D * pl->N / (std::fabs(pl->prm.bw_mhz[0]) * 1e6);
+    g->tsamp_s = (double)pl->D * pl->tsq * pl->N / (std::fabs(pl->prm.bw_mhz[0]) * 1e6);
     g->unit_blocks = pl->unit_blocks;
     g->interval_rows = pl->interval_rows;
     g->nfilt_pos = pl->nfilt_pos;
@@ -946,7 +1071,8 @@ int b2f_push(b2f_plan* pl, const void* const* frames, int64_t nframes, int on_de
     const int nif = pl->prm.nif;
     const int64_t T = pl->carry_len + nframes * pl->spf;          // samples available per IF (carry + new)
     const int64_t nblk = pl->carry_mode ? (T >= pl->M ? (T - pl->M) / pl->step + 1 : 0) : nframes * pl->spf / pl->M;
-    const int64_t rows = nblk * pl->keep / pl->D;
+    const int64_t krows = nblk * pl->keep / pl->D;                     // rows the kernels write
+    const int64_t rows = pl->tsq > 1 ? (pl->fk_pending + krows) / pl->tsq : krows;
     if (nblk == 0 && !pl->carry_mode) return 0;
     if (pl->rows_off + pl->rows_held + rows > pl->F_cap_rows && pl->rows_off > 0 && pl->rows_held + rows <= pl->F_cap_rows) {
         // running rescale keeps the rows of an unfinished interval: move them to the front of the buffer, in pieces no
@@ -1025,6 +1151,8 @@ int b2f_push(b2f_plan* pl, const void* const* frames, int64_t nframes, int on_de
             CU(cudaEventRecord(pl->ev_stage_free[pl->stage_idx], pl->stream));
             pl->stage_idx ^= 1;
         }
+        rc = sum_rows(pl, krows, rows);
+        if (rc) return rc;
         pl->rows_held += rows;
         pl->rows_produced += rows;
         pl->frames_pushed += nframes;
@@ -1114,8 +1242,8 @@ int b2f_push(b2f_plan* pl, const void* const* frames, int64_t nframes, int on_de
         }
         KBParams kb{};
         kb.inter = pl->d_inter; kb.eps = pl->d_eps; kb.tab_r = pl->d_tab_r;
-        kb.F = pl->d_F; kb.F_if_stride = pl->F_if_stride;
-        kb.row0 = pl->rows_off + pl->rows_held;
+        kb.F = row_dst(pl); kb.F_if_stride = row_dst_stride(pl);
+        kb.row0 = row_dst_row0(pl);
         kb.nblk = (int)nblk; kb.nif = nif; kb.D = pl->D;
         for (int64_t b0 = 0; b0 < nbt; b0 += NB) {
             const int64_t nb = std::min(NB, nbt - b0);
@@ -1137,6 +1265,8 @@ int b2f_push(b2f_plan* pl, const void* const* frames, int64_t nframes, int on_de
             if (rc) return rc;
         }
     }
+    rc = sum_rows(pl, krows, rows);
+    if (rc) return rc;
     pl->rows_held += rows;
     pl->rows_produced += rows;
     pl->frames_pushed += nframes;

@@ -304,6 +304,9 @@ extern "C" int b2f_run_scan(b2f_plan* pl, int nfiles, const char* const* vdif_pa
         if (!prm.keep_bandpass && !c0.rescale_preset)
             return failf(B2F_ESTATE, "a scan processed in parts needs the statistics of its first interval: call b2f_set_rescale first");
         const int64_t D = std::max(1, prm.tscrunch), spf = g.samples_per_frame, M = g.block_samples;
+        if ((D & (D - 1)) || D > g.freq_res)
+            return failf(B2F_EUNSUPPORTED, "a scan in time parts needs a power-of-two tscrunch <= freq_res (parts are cut where FFT blocks and "
+                                           "output samples coincide)");
         const int64_t keep = g.freq_res - g.nfilt_pos - g.nfilt_neg, step = keep * 2 * prm.nchan;
         const int64_t T = nfr * spf, NB = T >= M ? (T - M) / step + 1 : 0;
         const int64_t gg = std::gcd(spf, step), ub = spf / gg;           // blocks between aligned boundaries

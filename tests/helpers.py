@@ -9,15 +9,20 @@ from frb_baseband_b200.plan import Plan, PlanConfig
 REL_TOL = 1e-5
 
 
-def assert_rel(gpu, ref, tol=REL_TOL, what=""):
+def assert_rel(gpu, ref, tol=REL_TOL, what="", power=None):
     """|gpu-ref| <= tol * max(|ref|, rms(ref) per product).  Detected powers are sums of
     squares so |ref| is the natural scale; cross products may pass through zero, where the rms
-    of the same product is used instead."""
+    of the same product is used instead.  `power` (same shape as one product, [row][chan]): the
+    total power PP + QQ of every sample -- the scale of a difference or cross product (Q = PP - QQ,
+    Re/Im PQ*) in a channel that holds a strong line, where the product is a small difference of
+    two large numbers and its rms over all channels says nothing about the rounding to expect."""
     gpu = np.asarray(gpu, np.float64)
     ref = np.asarray(ref, np.float64)
     assert gpu.shape == ref.shape, (gpu.shape, ref.shape)
     rms = np.sqrt((ref ** 2).mean(axis=(0, 2), keepdims=True)) if ref.ndim == 3 else np.sqrt((ref ** 2).mean())
     den = np.maximum(np.abs(ref), rms)
+    if power is not None:
+        den = np.maximum(den, np.asarray(power, np.float64)[:, None, :] if ref.ndim == 3 else power)
     err = np.abs(gpu - ref) / np.where(den > 0, den, 1.0)
     assert err.max() <= tol, f"{what}: max rel err {err.max():.3e} > {tol} at {np.unravel_index(err.argmax(), err.shape)}"
     return err.max()

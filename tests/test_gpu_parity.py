@@ -292,7 +292,7 @@ def test_other_row_lengths(gpu, nchan, bw, D):
 
 
 def test_unsupported_requests_fail_loudly(gpu):
-    for kw in (dict(nchan=4096), dict(nchan=128, tscrunch=3), dict(nchan=128, tscrunch=1024), dict(nchan=4),
+    for kw in (dict(nchan=8192), dict(nchan=4096, freq_res=4096), dict(nchan=128, tscrunch=1 << 21), dict(nchan=4),
                dict(nchan=512, in_nbit=8), dict(nchan=512, dm=100.0, coherent=True)):
         with pytest.raises(_lib.B2FError) as e:
             Plan(PlanConfig(bw_mhz=[-32.0], **kw))
@@ -301,7 +301,7 @@ def test_unsupported_requests_fail_loudly(gpu):
 
 @pytest.mark.parametrize("nchan,freq_res,D,nframes", [(512, 0, 4, 1500), (1024, 0, 2, 1100), (128, 64, 16, 300), (32, 2048, 32, 700),
                                                         (8, 16, 1, 40), (16, 32, 2, 60), (512, 512, 4, 500), (64, 256, 256, 200),
-                                                        (2048, 0, 1, 2300)])
+                                                        (2048, 0, 1, 2300), (4096, 0, 2, 4300)])
 def test_generic_channeliser(gpu, nchan, freq_res, D, nframes):
     """freq_res / nchan outside the tuned kernels, e.g. process_vdif's default --nchan 512 ->
     digifil -F512:1024 (process_vdif.py:46,162).  Pushes are 1024-frame pieces that do not align
@@ -326,6 +326,69 @@ def test_generic_channeliser(gpu, nchan, freq_res, D, nframes):
                     keep_bandpass=True)["data"]
     assert rows.shape[0] == ref.shape[0] and ref.shape[0] > 0
     assert_rel(rows.reshape(ref.shape), ref.astype(np.float64), REL_TOL, f"generic nchan {nchan} L {L}")
+
+
+@pytest.mark.parametrize("nchan,D,dm,interval", [(128, 3, 0.0, 0.05), (128, 24, 0.0, 0.05), (128, 1024, 0.0, 0.0), (128, 1536, 0.0, 0.0),
+                                                  (32, 100, 0.0, 0.05), (512, 6, 0.0, 0.0), (128, 12, 300.0, 0.0), (64, 1000, 0.0, 0.0)])
+def test_any_tscrunch(gpu, nchan, D, dm, interval):
+    """process_vdif.py:156-158 hands digifil whatever --tscrunch it was given (submit_job.py:109-111: int(t_res / t_samp)):
+    factors that are not a power of two or exceed freq_res.  The kernels integrate the largest power of two dividing the
+    factor, kd_sum_rows the rest; output samples straddle pushes and FFT blocks, the incomplete tail is dropped."""
+    bw = 32.0
+    nframes = 2300 if nchan == 512 else 1200
+    v = synth.make_vdif(nframes, seed=900 + D, bw_mhz=bw, tone_frac=0.21, rho=0.2)
+    kb = interval == 0.0
+    cfg = PlanConfig(nchan=nchan, bw_mhz=[-bw], freq_mhz=[1400.0], tscrunch=D, out_nbit=-32 if kb else 8, keep_bandpass=kb,
+                     rescale_interval_s=interval or 10.0, dm=dm, coherent=dm > 0, chunk_units=400 if nchan == 512 else 0)
+    out = []
+    with Plan(cfg) as pl:
+        cf, fb = int(pl.chunk_frames), cfg.frame_bytes
+        assert abs(pl.tsamp_s - D * nchan / (bw * 1e6)) < 1e-15
+        for f0 in range(0, nframes, cf):
+            n = min(cf, nframes - f0)
+            pl.push([v[f0 * fb:(f0 + n) * fb]])
+            out.append(pl.pull().copy())
+        pl.flush()
+        out.append(pl.pull().copy())
+        rows = pl.view_rows(np.concatenate(out))
+        nf = pl.geometry.nfilt_pos
+    ref = o.digifil(v, freq_mhz=1400.0, bw_mhz=-bw, nchan=nchan, tscrunch_factor=D, out_nbit=-32 if kb else 8, keep_bandpass=kb,
+                    rescale_interval_s=interval or 10.0, dm=dm, coherent=dm > 0, nfilt=(nf, nf) if dm > 0 else (0, 0))["data"]
+    # whole FFT blocks only: the GPU path stops at the last complete block of the scan, the oracle at the last complete sample
+    assert 0 < rows.shape[0] <= ref.shape[0] and ref.shape[0] - rows.shape[0] <= max(1, 2 * 512 // D + 1)
+    ref = ref[:rows.shape[0]]
+    if kb:
+        assert_rel(rows.reshape(ref.shape), ref.astype(np.float64), REL_TOL, f"tscrunch {D}")
+    else:
+        d = np.abs(rows.reshape(ref.shape).astype(int) - ref.astype(int))
+        assert d.max() <= 1 and (d != 0).mean() < 2e-3
+
+
+@pytest.mark.parametrize("nchan", [512, 1024])
+@pytest.mark.parametrize("mode,name", [(_lib.POL_P0, "P0"), (_lib.POL_P1, "P1"), (_lib.POL_I, "I"), (_lib.POL_I2, "I2"),
+                                       (_lib.POL_COHERENCE, "coherence"), (_lib.POL_IQUV, "IQUV"), (_lib.POL_PPQQ, "PPQQ")])
+def test_generic_compile_time_geometry(gpu, monkeypatch, nchan, mode, name):
+    """The shapes process_vdif.py:162 produces for nchan > 128 (-F nchan:2*nchan) run kernels whose geometry is a template
+    parameter (b2f_generic.cuh): every detection product against the oracle, and against the run-time kernels (B2F_GENERIC=runtime)."""
+    bw, D = 32.0, 4
+    nframes = (2 * nchan * 2 * nchan * 2) // 16000 + 40               # two FFT blocks
+    v = synth.make_vdif(nframes, seed=77 + nchan, bw_mhz=bw, tone_frac=0.37, rho=0.3)
+    kw = dict(nchan=nchan, bw=[-bw], tscrunch=D, pol_mode=mode, out_nbit=-32, keep_bandpass=True)
+    rows, _ = run_plan([v], **kw)
+    ref = o.digifil(v, freq_mhz=1400.0, bw_mhz=-bw, nchan=nchan, tscrunch_factor=D, pol_mode=name, out_nbit=-32,
+                    keep_bandpass=True)["data"]
+    assert rows.shape[0] == ref.shape[0] > 0
+    # total power per sample: the scale of the difference / cross products in the channel of the test tone
+    power = ref[:, 0] + ref[:, 1] if name == "coherence" else (ref[:, 0] if name == "IQUV" else None)
+    assert_rel(rows.reshape(ref.shape), ref.astype(np.float64), REL_TOL, f"{name} nchan {nchan}", power=power)
+    monkeypatch.setenv("B2F_GENERIC", "runtime")
+    rows_rt, _ = run_plan([v], **kw)
+    # two fp32 implementations, each within REL_TOL of the fp64 oracle
+    assert_rel(rows.reshape(ref.shape), rows_rt.reshape(ref.shape).astype(np.float64), 2 * REL_TOL, f"{name} nchan {nchan} vs run-time kernels",
+               power=power)
+    # the run-time kernels (now only the fall-back for shapes with freq_res != 2 nchan, which the reference never asks for) reach
+    # 1.2e-5 on the cross-polarisation products of a 4 Mi-sample block where the compile-time kernels stay below 1e-5
+    assert_rel(rows_rt.reshape(ref.shape), ref.astype(np.float64), 1.5 * REL_TOL, f"{name} nchan {nchan}, run-time kernels", power=power)
 
 
 def test_property_random_configurations(gpu):
