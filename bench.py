@@ -160,11 +160,16 @@ def _cpu_worker(args):
         pool = scipy.fft.set_workers(nthr)
     except Exception:
         pool = contextlib.nullcontext()
+    dm, nfilt = cfg.get("dm", 0.0), None
+    if dm > 0:             # overlap-save discard, the library's rule: 0.55 x the smearing of the lowest channel, whole output samples
+        D = cfg["tscrunch"]
+        nf = int(np.ceil(0.55 * o.smearing_samples(fc, sbw, cfg["nchan"], dm)))
+        nf = max(D, (nf + D - 1) // D * D)
+        nfilt = (nf, nf)
     t0 = time.perf_counter()
     with pool:
         r = o.digifil(v, freq_mhz=fc, bw_mhz=sbw, nchan=cfg["nchan"], freq_res=FREQ_RES, tscrunch_factor=cfg["tscrunch"],
-                      pol_mode=cfg["pol"], out_nbit=cfg["out_nbit"], dm=cfg.get("dm", 0.0), coherent=cfg.get("dm", 0.0) > 0,
-                      dtype=np.float32)
+                      pol_mode=cfg["pol"], out_nbit=cfg["out_nbit"], dm=dm, coherent=dm > 0, nfilt=nfilt, dtype=np.float32)
     return time.perf_counter() - t0, r["data"].shape[0]
 
 

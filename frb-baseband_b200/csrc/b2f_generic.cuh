@@ -48,12 +48,21 @@ __device__ __forceinline__ int kgt_rev16(int seg) {
 }
 
 // One radix-16 column pass over segments of 2^LGN points, two neighbouring columns per thread (see kg_pass16_pair).
-template <int LG, int LGN, bool INV, int SRC, int DST>
+// WM (warp-major): warp W works on the thread-iterations [W CNT/8, (W+1) CNT/8) -- the points [W N/8, (W+1) N/8) of every
+// column of the strip, i.e. two whole segments of the second pass.  Every stage between the outermost forward and the
+// outermost inverse pass stays inside those points, so with this mapping a warp only reads what it wrote itself and
+// the stages are separated by __syncwarp instead of a block barrier: 3 block barriers per strip instead of 6 (8 for
+// N = 8192), and the warps of a CTA drift into different stages (load burst / butterflies / store burst overlap).
+template <int LG, int LGN, bool INV, int SRC, int DST, bool WM = false>
 __device__ __forceinline__ void kgt_col_pass16(float2* sm, const float2* tw, const uint8_t* gsrc_b, float2* gdst, const float2* lut) {
     using G = KGT<LG>;
     constexpr int LGM = LGN - 4, M1 = 1 << LGM, LGP = G::LGC - 1, CNT = (G::N >> 4) << LGP;
+    constexpr int NW = G::kColThreads / 32, PER = WM ? CNT / NW : CNT, STEP = WM ? 32 : G::kColThreads;
+    static_assert(!WM || (CNT % (NW * 32) == 0), "whole warp iterations");
+    const int t0 = WM ? (threadIdx.x >> 5) * PER : 0;
 #pragma unroll 1
-    for (int t = threadIdx.x; t < CNT; t += G::kColThreads) {
+    for (int tl = WM ? (threadIdx.x & 31) : threadIdx.x; tl < PER; tl += STEP) {
+        const int t = t0 + tl;
         const int c2 = (t & ((1 << LGP) - 1)) * 2, w = t >> LGP;
         const int lo = w & (M1 - 1), seg = w >> LGM;
         const int base = (seg << LGN) + lo;
@@ -138,8 +147,12 @@ template <int LG>
 __device__ __forceinline__ void kgt_col_inner(float2* sm, int n1_0, float2* colsum) {
     using G = KGT<LG>;
     constexpr int RM = G::RM, LGP = G::LGC - 1, CNT = (G::N >> G::LGI) << LGP, LGM = 2 * LG;
+    constexpr int NW = G::kColThreads / 32, PER = CNT / NW;                 // warp-major, see kgt_col_pass16
+    static_assert(CNT % (NW * 32) == 0, "whole warp iterations");
+    const int t0 = (threadIdx.x >> 5) * PER;
 #pragma unroll 1
-    for (int t = threadIdx.x; t < CNT; t += G::kColThreads) {
+    for (int tl = threadIdx.x & 31; tl < PER; tl += 32) {
+        const int t = t0 + tl;
         const int c2 = (t & ((1 << LGP) - 1)) * 2, seg = t >> LGP;
         float2 a[RM], b[RM];
 #pragma unroll
@@ -203,20 +216,20 @@ __global__ void __launch_bounds__(KGT<LG>::kColThreads, KGT<LG>::kColCtas) kgt_c
         // forward, outermost first
         kgt_col_pass16<LG, LG, false, 1, 0>(data, tw, src, nullptr, lut);
         __syncthreads();
-        kgt_col_pass16<LG, LG - 4, false, 0, 0>(data, tw + kg_tw_offset(LG, 1), nullptr, nullptr, lut);
-        __syncthreads();
+        kgt_col_pass16<LG, LG - 4, false, 0, 0, true>(data, tw + kg_tw_offset(LG, 1), nullptr, nullptr, lut);
+        __syncwarp();
         if constexpr (NF == 3) {
-            kgt_col_pass16<LG, LG - 8, false, 0, 0>(data, tw + kg_tw_offset(LG, 2), nullptr, nullptr, lut);
-            __syncthreads();
+            kgt_col_pass16<LG, LG - 8, false, 0, 0, true>(data, tw + kg_tw_offset(LG, 2), nullptr, nullptr, lut);
+            __syncwarp();
         }
         kgt_col_inner<LG>(data, strip * C, colsum);
-        __syncthreads();
+        __syncwarp();
         // inverse, innermost first
         if constexpr (NF == 3) {
-            kgt_col_pass16<LG, LG - 8, true, 0, 0>(data, tw + kg_tw_offset(LG, 2), nullptr, nullptr, lut);
-            __syncthreads();
+            kgt_col_pass16<LG, LG - 8, true, 0, 0, true>(data, tw + kg_tw_offset(LG, 2), nullptr, nullptr, lut);
+            __syncwarp();
         }
-        kgt_col_pass16<LG, LG - 4, true, 0, 0>(data, tw + kg_tw_offset(LG, 1), nullptr, nullptr, lut);
+        kgt_col_pass16<LG, LG - 4, true, 0, 0, true>(data, tw + kg_tw_offset(LG, 1), nullptr, nullptr, lut);
         __syncthreads();
         kgt_col_pass16<LG, LG, true, 0, 1>(data, tw, nullptr, dst, lut);
         __syncthreads();

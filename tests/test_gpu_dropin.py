@@ -47,8 +47,11 @@ def test_process_vdif_writes_into_existing_fifo(gpu, tmp_path):
     got = {}
 
     def reader():
+        import fcntl
         with open(fifo, "rb") as f:
-            got["raw"] = f.read()
+            first = f.read(1)                       # the writer has opened (and resized) the pipe by now
+            got["pipe_size"] = fcntl.fcntl(f.fileno(), getattr(fcntl, "F_GETPIPE_SZ", 1032))
+            got["raw"] = first + f.read()
 
     t = threading.Thread(target=reader)
     t.start()
@@ -56,6 +59,7 @@ def test_process_vdif_writes_into_existing_fifo(gpu, tmp_path):
                        "--nsec", "10", "--start", "0", "--force", "--tscrunch", "32", "--fil_out_dir", str(tmp_path)])
     t.join(60)
     assert not t.is_alive() and os.path.exists(fifo)
+    assert got["pipe_size"] == 1048576              # setfifo.perl:10 (F_SETPIPE_SZ, 1 MiB) for every FIFO of the splice list
     h, off = sigproc.read_header(got["raw"])
     d = np.frombuffer(got["raw"], np.uint8, offset=off).reshape(-1, 32)
     ref = o.digifil(v, freq_mhz=1400.0, bw_mhz=16.0, nchan=32, tscrunch_factor=32)
