@@ -49,6 +49,11 @@ CONFIGS = {
     "C5": dict(nif=16, bw=32.0, nchan=128, tscrunch=16, seconds=3600.0, sample_seconds=30.0, pol="I", out_nbit=8,
                what="C5: 16 IF x 32 MHz 2-bit (4 Gbps) streaming Stokes I; bounded sample of {sec:.0f} s of the 3600 s scan "
                     "(the scan is 120 such stretches; nothing carries over between them but the frozen rescale)"),
+    # not a BASELINE.json configuration: the shape the reference's own job policy asks for at DM 560 (submit_job.py:58-76 ->
+    # 8192 band channels over 8 IFs, DownSamp int(64 us / 32 us) = 2) -- the generic path with compile-time geometry
+    "P1": dict(nif=8, bw=32.0, nchan=1024, tscrunch=2, seconds=20.0, pol="I", out_nbit=8,
+               what="P1: the C2 input at the reference policy's channelisation for DM 560: nchan 1024 per IF, freq_res 2048 "
+                    "(digifil -F1024:2048, process_vdif.py:162), tscrunch 2, 8-bit Stokes I spliced to 8192 channels, {sec:.0f} s"),
 }
 # module-level geometry of the selected configuration (set by select_config; tools/ import these)
 NIF, BW, NCHAN, FREQ_RES, TSCRUNCH = 8, 32.0, 128, 512, 16
@@ -57,9 +62,10 @@ BYTES_PER_DATA_SEC = NIF * FPS * FRAME_BYTES   # 257.024 MB of VDIF per second o
 
 
 def select_config(name: str) -> dict:
-    global NIF, BW, NCHAN, TSCRUNCH, FPS, BYTES_PER_DATA_SEC
+    global NIF, BW, NCHAN, FREQ_RES, TSCRUNCH, FPS, BYTES_PER_DATA_SEC
     c = CONFIGS[name]
     NIF, BW, NCHAN, TSCRUNCH = c["nif"], c["bw"], c["nchan"], c["tscrunch"]
+    FREQ_RES = 512 if NCHAN <= 128 else 2 * NCHAN          # process_vdif.py:162
     FPS = int(round(2 * BW * 1e6 / 16000))
     BYTES_PER_DATA_SEC = NIF * FPS * FRAME_BYTES
     return c
@@ -295,7 +301,8 @@ def main():
                                pol_mode=mode, dm=dm, coherent=dm > 0, device=local_rank, profile=True, stream=stream.cuda_stream,
                                chunk_units=chunk_units))
 
-    pl = make_plan(bws, freqs, 0 if dm > 0 else args.chunk_units)
+    generic = FREQ_RES != 512             # pushes of the generic path are plain frame counts (library default 1024), not block units
+    pl = make_plan(bws, freqs, 0 if (dm > 0 or generic) else args.chunk_units)
     cf = int(pl.chunk_frames)
     row_bytes = int(pl.row_bytes)
     rows_total = int(seconds / pl.tsamp_s) + 8          # only an upper bound
@@ -384,7 +391,7 @@ def main():
         per = NIF // world
         sl = slice(rank * per, (rank + 1) * per)
         _, bws1, freqs1 = rank_if_plan(NIF, 1, 0, FREQ_LSB0, BW)
-        pls = make_plan(bws1[sl], freqs1[sl], 0 if dm > 0 else args.chunk_units * world)
+        pls = make_plan(bws1[sl], freqs1[sl], 0 if (dm > 0 or generic) else args.chunk_units * world)
         outs = torch.empty((cap_rows, int(pls.row_bytes)), dtype=torch.uint8, device=dev)
         peers = None
         if peer is not None:
@@ -463,13 +470,16 @@ def main():
     fused = ktimes.get("fused", (0.0, 0))[1] > 0
     R, L = 2 * NCHAN, FREQ_RES
     blocks_per_step = NIF * (nframes * 16000 // (R * L))
-    col_flops = blocks_per_step * 2.0 * R * 5 * L * 9            # FFT_512 + IFFT_512 per column, 5 N log2 N
+    col_flops = blocks_per_step * 2.0 * R * 5 * L * np.log2(L)   # FFT_L + IFFT_L per column, 5 N log2 N
     row_flops = blocks_per_step * L * 5.0 * R * np.log2(R)
     if fused:
         dom, dom_name = ktimes["fused"], f"kf_fused<{R},{cfg['pol']}> (decode + column pass + row pass + detection, one persistent kernel)"
         dom_flops = col_flops + row_flops
     elif pl.path == 1:
         dom, dom_name = ktimes["column"], f"kf_fused<{R},I> column half (decode + FFT_512 . diag . IFFT_512 per column pair, warp-autonomous)"
+        dom_flops = col_flops
+    elif generic:
+        dom, dom_name = ktimes["column"], f"kgt_column_pass<{int(np.log2(L))}> (decode + FFT_{L} . diag . IFFT_{L} per column, compile-time geometry)"
         dom_flops = col_flops
     else:
         dom, dom_name = ktimes["column"], "ka_column_pass (decode + column pass)"
@@ -481,7 +491,7 @@ def main():
     traffic = None
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = prof.get("kf_fused_dram_bytes_per_launch" if fused else
+        traffic = None if generic else prof.get("kf_fused_dram_bytes_per_launch" if fused else
                            ("kf_column_half_dram_bytes_per_launch" if pl.path == 1 else "ka_column_pass_dram_bytes_per_launch"))
     except Exception:
         pass
@@ -512,7 +522,7 @@ def main():
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "rt_factor": world * data_sec / (ms_step * 1e-3),
         "config": {"workload": workload, "name": args.config, "nif_per_gpu": NIF, "chunk_frames": cf,
-                   "channeliser_path": {0: "round-1 kernels (ka_column_pass + kb_row_pass)", 1: "round-2 kernels (warp-autonomous column kernel + tile row pass)", 2: "round-2 fused kernel, L2 ring"}.get(pl.path),
+                   "channeliser_path": "generic kernels with compile-time geometry (kgt_column_pass + kgt_row_pass)" if generic else {0: "round-1 kernels (ka_column_pass + kb_row_pass)", 1: "round-2 kernels (warp-autonomous column kernel + tile row pass)", 2: "round-2 fused kernel, L2 ring"}.get(pl.path),
                    "l2": "inputs (%.1f GB/step) larger than L2" % (in_bytes / 1e9),
                    "parallelism": (f"subband groups x{world} (weak: every GPU its own {NIF}-IF band), " + ("splice by NVLink peer stores from the requantise kernel" if peer is not None else "NCCL gather of 8-bit tiles")) if world > 1 else "1 GPU"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),

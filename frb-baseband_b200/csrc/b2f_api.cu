@@ -815,7 +815,15 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
         const int64_t unit_bytes = (int64_t)prm->nif * pl->unit_blocks * L * R * (int64_t)sizeof(float2);
         cu = (int)std::max<int64_t>(1, std::min<int64_t>(cu, (4ll << 30) / std::max<int64_t>(unit_bytes, 1)));
     }
-    if (dedisp && prm->chunk_units <= 0) cu = (int)std::max<int64_t>(1, 1024 / pl->unit_frames);
+    if (dedisp && prm->chunk_units <= 0) {
+        // the three-kernel dedispersion path holds two [blocks][512][R] buffers: pushes of about 4096 frames per IF (C4, 20 s:
+        // 139.8 ms at 1024 frames, 134.9 at 2048, 134.0 at 4096; profiles/r02_c4_push_size_sweep.jsonl) as long as each buffer
+        // stays under 8 GiB.  B2F_DEDISP_CHUNK_FRAMES overrides.
+        const char* e = getenv("B2F_DEDISP_CHUNK_FRAMES");
+        const int64_t want = e ? std::max<int64_t>(256, atoll(e)) : 4096;
+        const int64_t unit_bytes = (int64_t)prm->nif * (pl->unit_blocks + 1) * L * R * (int64_t)sizeof(float2);
+        cu = (int)std::max<int64_t>(1, std::min<int64_t>(want / pl->unit_frames, (8ll << 30) / std::max<int64_t>(unit_bytes, 1)));
+    }
     if (generic) {                 // blocks span seconds: pushes are plain 1024-frame pieces, the carry does the rest
         pl->unit_frames = 1;
         pl->unit_blocks = 0;

@@ -943,11 +943,21 @@ static __global__ void __launch_bounds__(256) k0t_transpose(const K0TParams p) {
                         o[7][g] = __byte_perm(t2, t3, 0x7632);
                     }
                 }
+                // A lane holds both columns of its item for four pairs; written as they are, a store instruction would touch
+                // 32 half sectors (lanes 32 bytes apart).  Neighbouring lanes (items 2i, 2i + 1) swap one column each, so that
+                // a lane pair writes the 32 contiguous bytes (item, col 0 | col 1) of one sector: 16 whole sectors per store.
+                const bool odd = lane & 1;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int pair = strip * (SC / 2) + 4 * c8 + (j >> 1), col = j & 1;
-                    *reinterpret_cast<uint4*>(tb + ((size_t)(pair * 2 + half) * 32 + 2 * item + col) * 16) =
-                        make_uint4(o[j][0], o[j][1], o[j][2], o[j][3]);
+                for (int pp = 0; pp < 4; ++pp) {
+                    uint32_t rcv[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) rcv[k] = __shfl_xor_sync(0xffffffffu, odd ? o[2 * pp][k] : o[2 * pp + 1][k], 1);
+                    const int pair = strip * (SC / 2) + 4 * c8 + pp;
+                    uint8_t* pb = tb + (size_t)(pair * 2 + half) * 32 * 16;
+                    *reinterpret_cast<uint4*>(pb + (2 * (item & ~1) + (int)odd) * 16) =
+                        odd ? make_uint4(rcv[0], rcv[1], rcv[2], rcv[3]) : make_uint4(o[2 * pp][0], o[2 * pp][1], o[2 * pp][2], o[2 * pp][3]);
+                    *reinterpret_cast<uint4*>(pb + (2 * (item | 1) + (int)odd) * 16) =
+                        odd ? make_uint4(o[2 * pp + 1][0], o[2 * pp + 1][1], o[2 * pp + 1][2], o[2 * pp + 1][3]) : make_uint4(rcv[0], rcv[1], rcv[2], rcv[3]);
                 }
             }
         }
