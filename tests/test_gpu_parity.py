@@ -231,7 +231,7 @@ def test_coherent_dedispersion(gpu, usb, mode, name):
     nchan, bw, D, dm, fc = 128, 32.0, 16, 560.0, 1254.0
     sbw = bw if usb else -bw
     cfg = PlanConfig(nchan=nchan, bw_mhz=[sbw], freq_mhz=[fc], tscrunch=D, pol_mode=mode, out_nbit=-32, keep_bandpass=True,
-                     dm=dm, coherent=True)
+                     dm=dm, coherent=True, chunk_units=8)          # pushes of 1024 frames (the default is 4096): three pushes
     v = synth.make_vdif(2048 + 300, seed=91, bw_mhz=bw, rho=0.3, tone_frac=0.37)
     out = []
     with Plan(cfg) as pl:
@@ -239,6 +239,7 @@ def test_coherent_dedispersion(gpu, usb, mode, name):
         nf = (int(g.nfilt_pos), int(g.nfilt_neg))
         assert nf[0] == nf[1] and nf[0] % D == 0 and 64 <= nf[0] < 256
         cf, fb = int(pl.chunk_frames), cfg.frame_bytes
+        assert cf == 1024
         for f0 in range(0, 2348, cf):
             n = min(cf, 2348 - f0)
             pl.push([v[f0 * fb:(f0 + n) * fb]])
@@ -339,7 +340,8 @@ def test_any_tscrunch(gpu, nchan, D, dm, interval):
     v = synth.make_vdif(nframes, seed=900 + D, bw_mhz=bw, tone_frac=0.21, rho=0.2)
     kb = interval == 0.0
     cfg = PlanConfig(nchan=nchan, bw_mhz=[-bw], freq_mhz=[1400.0], tscrunch=D, out_nbit=-32 if kb else 8, keep_bandpass=kb,
-                     rescale_interval_s=interval or 10.0, dm=dm, coherent=dm > 0, chunk_units=400 if nchan == 512 else 0)
+                     rescale_interval_s=interval or 10.0, dm=dm, coherent=dm > 0,
+                     chunk_units=400 if nchan == 512 else (4 if dm > 0 else 0))     # generic: 400 frames; dedispersion: 512 frames per push
     out = []
     with Plan(cfg) as pl:
         cf, fb = int(pl.chunk_frames), cfg.frame_bytes
