@@ -100,6 +100,12 @@ struct b2f_plan {
     int64_t step = 0;              // samples between block starts = keep * R
     int64_t carry_len = 0;         // samples of the previous push still needed (per IF)
     uint8_t* d_carry = nullptr;
+    // 8-bit input in carry mode: the stream holds bps = 2 bytes per time sample and no code decodes to 0.0, so the word
+    // masks travel with the samples: d_wmask is indexed by stream position (one byte per 32 stream bytes, carried part
+    // in front) instead of by frame slot, and the masks of the carried samples wait in d_carry_mask.
+    int bps = 1;
+    bool smask = false;
+    uint8_t* d_carry_mask = nullptr;
     float2* d_spec = nullptr;
     float2* d_chirp = nullptr;
     uint8_t* d_out_stage[2]{};
@@ -311,7 +317,7 @@ void free_plan(b2f_plan* pl) {
     void* bufs[] = {pl->d_compact, pl->d_wmask, pl->d_fstat, pl->d_blkdirty, pl->d_inter, pl->d_colsum,
                     pl->d_eps, pl->d_F, pl->d_mean, pl->d_scale, pl->d_partial, pl->d_tab_g, pl->d_tab_h,
                     pl->d_tab_w, pl->d_tab_r, pl->d_tab_beta, pl->d_counters, pl->d_sm_slots, pl->d_carry, pl->d_spec, pl->d_chirp, pl->d_tw_col, pl->d_tw_row,
-                    pl->d_tstream, pl->d_fillflag, pl->d_part, pl->d_fsync, pl->d_fprof, pl->d_levels};
+                    pl->d_tstream, pl->d_fillflag, pl->d_part, pl->d_fsync, pl->d_fprof, pl->d_levels, pl->d_carry_mask};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (pl->d_Fk) cudaFree(pl->d_Fk);
@@ -362,10 +368,19 @@ int push_dedisp(b2f_plan* pl, int64_t nblk, int64_t T) {
     const int nif = pl->prm.nif;
     const int64_t nbt = (int64_t)nif * nblk;
     int rc = 0;
+    if (nblk > 0 && pl->smask) {                              // which blocks hold a masked word (stream-coordinate masks)
+        k8_blkdirty<<<dim3((unsigned)nblk, (unsigned)nif), 256, 0, pl->stream>>>(pl->d_wmask, pl->wmask_stride, pl->d_blkdirty, (int)nblk,
+                                                                                pl->step * pl->bps / 32, pl->M * pl->bps / 32);
+        pl->launches++;
+        CU(cudaGetLastError());
+    }
     if (nblk > 0 && pl->generic) {
         const int64_t NB = pl->batch_blocks > 0 ? std::min<int64_t>(pl->batch_blocks, nbt) : nbt;
         KGParams kg{};
         kg.compact = pl->d_compact; kg.compact_stride = pl->compact_stride;
+        kg.wmask = pl->d_wmask; kg.wmask_stride = pl->wmask_stride; kg.blkdirty = pl->d_blkdirty;
+        kg.in8_offset = pl->prm.in8_offset_mode ? 128.0f : 127.5f;
+        const int nbit = pl->prm.in_nbit;
         kg.inter = pl->d_inter; kg.colsum = pl->d_colsum; kg.eps = pl->d_eps;
         kg.tw_col = pl->d_tw_col; kg.tw_row = pl->d_tw_row;
         kg.F = row_dst(pl); kg.F_if_stride = row_dst_stride(pl); kg.row0 = row_dst_row0(pl);
@@ -377,7 +392,8 @@ int push_dedisp(b2f_plan* pl, int64_t nblk, int64_t T) {
         const size_t smem_col = ((size_t)pl->L + 32 + kg_padded((size_t)pl->L * kg.C)) * sizeof(float2);
         const size_t smem_row = ((size_t)pl->R + kg_padded((size_t)RB * pl->R) + 2 * (size_t)RB * pl->R) * sizeof(float2);
         if (!pl->kgt_lg) {
-            CU(cudaFuncSetAttribute(kg_column_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_col));
+            CU(cudaFuncSetAttribute(kg_column_pass<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_col));
+            CU(cudaFuncSetAttribute(kg_column_pass<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_col));
             CU(cudaFuncSetAttribute(kg_row_pass<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row));
             CU(cudaFuncSetAttribute(kg_row_pass<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row));
         }
@@ -390,10 +406,12 @@ int push_dedisp(b2f_plan* pl, int64_t nblk, int64_t T) {
             rc = timed(pl, B2F_K_COLUMN, [&] {
                 if (pl->kgt_lg) {                           // compile-time geometry (b2f_generic.cuh): L = R = 2^kgt_lg
                     const int64_t work = nb * (pl->R / pl->kgt_cols);
-                    le = b2f_launch_kgt_col(pl->kgt_lg, kg, (int)std::min<int64_t>(work, (int64_t)pl->kgt_col_ctas * pl->num_sms), pl->stream, nullptr);
+                    le = b2f_launch_kgt_col(pl->kgt_lg, nbit, kg, (int)std::min<int64_t>(work, (int64_t)pl->kgt_col_ctas * pl->num_sms), pl->stream, nullptr);
                 } else {
                     const int64_t work = nb * (pl->R / kg.C);
-                    kg_column_pass<<<(unsigned)std::min<int64_t>(work, 2 * (int64_t)pl->num_sms), 256, smem_col, pl->stream>>>(kg);
+                    const unsigned grid = (unsigned)std::min<int64_t>(work, 2 * (int64_t)pl->num_sms);
+                    if (nbit == 8) kg_column_pass<8><<<grid, 256, smem_col, pl->stream>>>(kg);
+                    else kg_column_pass<2><<<grid, 256, smem_col, pl->stream>>>(kg);
                 }
             });
             if (rc) return rc;
@@ -427,7 +445,8 @@ int push_dedisp(b2f_plan* pl, int64_t nblk, int64_t T) {
         ka.tab_g = pl->d_tab_g; ka.tab_h = pl->d_tab_h; ka.tab_w = pl->d_tab_w; ka.tab_beta = pl->d_tab_beta;
         ka.R = pl->R; ka.nstrips = pl->nstrips; ka.nblk = (int)nblk; ka.nif = nif;
         ka.payload_bytes = (int)pl->payload; ka.groups_per_slot = (int)pl->groups_per_slot;
-        ka.blk_step_bytes = pl->step;                             // 1 index byte per sample
+        ka.blk_step_bytes = pl->step * pl->bps;                   // 2-bit: 1 index byte per sample; 8-bit: 2 bytes, masks by stream position
+        ka.in8_offset = pl->prm.in8_offset_mode ? 128.0f : 127.5f;
         ka.sm_slots = pl->d_sm_slots; ka.stagger_cycles = 0; ka.variant = 32;      // forward only
         KBParams kb{};
         kb.inter = pl->d_inter; kb.eps = nullptr; kb.tab_r = pl->d_tab_r; kb.spec = pl->d_spec;
@@ -466,8 +485,12 @@ int push_dedisp(b2f_plan* pl, int64_t nblk, int64_t T) {
     const int64_t tail = T - used;
     if (tail > pl->M) return fail(B2F_ESTATE, "internal: dedispersion carry larger than one block");
     for (int i = 0; i < nif; ++i)
-        CU(cudaMemcpyAsync(pl->d_carry + (size_t)i * pl->M, pl->d_compact + i * pl->compact_stride + used, (size_t)tail,
-                           cudaMemcpyDeviceToDevice, pl->stream));
+        CU(cudaMemcpyAsync(pl->d_carry + (size_t)i * pl->M * pl->bps, pl->d_compact + i * pl->compact_stride + used * pl->bps,
+                           (size_t)tail * pl->bps, cudaMemcpyDeviceToDevice, pl->stream));
+    if (pl->smask)
+        for (int i = 0; i < nif; ++i)
+            CU(cudaMemcpyAsync(pl->d_carry_mask + (size_t)i * (pl->M * pl->bps / 32), pl->d_wmask + i * pl->wmask_stride + used * pl->bps / 32,
+                               (size_t)(tail * pl->bps / 32), cudaMemcpyDeviceToDevice, pl->stream));
     pl->carry_len = tail;
     return 0;
 }
@@ -498,12 +521,12 @@ cudaError_t b2f_launch_kf(int R, int mode, const FParams& p, int grid, int coope
     return cudaErrorInvalidValue;
 }
 
-cudaError_t b2f_launch_kgt_col(int lg, const KGParams& p, int grid, cudaStream_t st, int* ctas) {
+cudaError_t b2f_launch_kgt_col(int lg, int in_nbit, const KGParams& p, int grid, cudaStream_t st, int* ctas) {
     switch (lg) {
-        case 10: return b2f_launch_kgt_col_10(p, grid, st, ctas);
-        case 11: return b2f_launch_kgt_col_11(p, grid, st, ctas);
-        case 12: return b2f_launch_kgt_col_12(p, grid, st, ctas);
-        case 13: return b2f_launch_kgt_col_13(p, grid, st, ctas);
+        case 10: return b2f_launch_kgt_col_10(in_nbit, p, grid, st, ctas);
+        case 11: return b2f_launch_kgt_col_11(in_nbit, p, grid, st, ctas);
+        case 12: return b2f_launch_kgt_col_12(in_nbit, p, grid, st, ctas);
+        case 13: return b2f_launch_kgt_col_13(in_nbit, p, grid, st, ctas);
     }
     return cudaErrorInvalidValue;
 }
@@ -730,7 +753,6 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
     if ((R > 4096 || L > 4096) && L != R)
         return fail(B2F_EUNSUPPORTED, "nchan 4096 needs freq_res = 2 nchan (digifil -F nchan:2*nchan, process_vdif.py:162)");
     const bool generic = !(L == kL && R <= 512);        // tuned kernels: 512-point columns, rows up to 512
-    if (generic && prm->in_nbit != 2) return fail(B2F_EUNSUPPORTED, "freq_res != 512 or nchan > 256 needs 2-bit input in this build");
     const int D_user = prm->tscrunch < 1 ? 1 : prm->tscrunch;
     if (D_user > (1 << 20)) return fail(B2F_EUNSUPPORTED, "tscrunch above 2^20");
     int D = D_user & -D_user;                       // what the kernels integrate; kd_sum_rows adds tsq = D_user / D of their rows
@@ -741,7 +763,8 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
     const int payload = prm->frame_bytes - prm->header_bytes;
     if (payload <= 0 || payload % 8) return fail(B2F_EINVAL, "frame_bytes");
     const bool dedisp = prm->coherent && prm->dm > 0.0;
-    if (dedisp && prm->in_nbit != 2) return fail(B2F_EUNSUPPORTED, "coherent dedispersion needs 2-bit input in this build");
+    if ((dedisp || generic) && prm->in_nbit == 8 && payload % 32)
+        return fail(B2F_EUNSUPPORTED, "8-bit input with coherent dedispersion, freq_res != 512 or nchan > 256 needs a payload that is a multiple of 32 bytes");
     if (dedisp && generic) return fail(B2F_EUNSUPPORTED, "coherent dedispersion needs freq_res 512 and nchan <= 256 in this build");
     const double abw = std::fabs(prm->bw_mhz[0]);
     if (abw <= 0) return fail(B2F_EINVAL, "bw_mhz");
@@ -787,6 +810,8 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
     pl->dedisp = dedisp;
     pl->generic = generic;
     pl->carry_mode = dedisp || generic;
+    pl->bps = (!W && prm->in_nbit == 8) ? 2 : 1;
+    pl->smask = pl->carry_mode && pl->bps == 2;
     pl->step = pl->M;
     pl->keep = L;
     if (dedisp) {
@@ -926,8 +951,8 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
     const int nif = prm->nif;
     const int64_t nbt = (int64_t)nif * pl->chunk_blocks;
     pl->slot_bytes = W ? (int)spf : (prm->in_nbit == 2 ? 2 * payload : payload);      // 2-bit: one index byte per time sample
-    pl->compact_stride = (size_t)((pl->chunk_frames * (int64_t)pl->slot_bytes + (pl->carry_mode ? pl->M : 0) + 255) / 256 * 256);
-    pl->wmask_stride = (size_t)((pl->chunk_frames * pl->groups_per_slot + 255) / 256 * 256);
+    pl->compact_stride = (size_t)((pl->chunk_frames * (int64_t)pl->slot_bytes + (pl->carry_mode ? pl->M * pl->bps : 0) + 255) / 256 * 256);
+    pl->wmask_stride = (size_t)((pl->chunk_frames * pl->groups_per_slot + (pl->smask ? pl->M * pl->bps / 32 : 0) + 255) / 256 * 256);
     pl->fstat_stride = (size_t)((pl->chunk_frames + 255) / 256 * 256);
     if (!pl->path) {
         CUB(cudaMalloc(&pl->d_compact, pl->compact_stride * nif));
@@ -967,14 +992,15 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
     CUB(cudaMalloc(&pl->d_partial, (size_t)nif * kStatSplit * nprod * pl->N * sizeof(double2)));
     CUB(cudaMalloc(&pl->d_counters, C_COUNT * sizeof(unsigned long long)));
     CUB(cudaMalloc(&pl->d_sm_slots, 1024 * sizeof(int)));
-    if (pl->carry_mode) CUB(cudaMalloc(&pl->d_carry, (size_t)pl->M * nif));
+    if (pl->carry_mode) CUB(cudaMalloc(&pl->d_carry, (size_t)pl->M * pl->bps * nif));
+    if (pl->smask) CUB(cudaMalloc(&pl->d_carry_mask, (size_t)pl->M * pl->bps / 32 * nif));
     if (generic && L == R && L >= 1024) {
         // the shapes process_vdif.py:162 produces (-F nchan:2*nchan): kernels with compile-time geometry
         const char* e = getenv("B2F_GENERIC");
         const int lg = 31 - __builtin_clz(L);
         if (!(e && !strcmp(e, "runtime") && L <= 4096)) {
             int cc = 0, rc2 = 0;
-            if (b2f_launch_kgt_col(lg, KGParams{}, 0, nullptr, &cc) != cudaSuccess || cc < 1 ||
+            if (b2f_launch_kgt_col(lg, prm->in_nbit, KGParams{}, 0, nullptr, &cc) != cudaSuccess || cc < 1 ||
                 b2f_launch_kgt_row(lg, prm->pol_mode, KGParams{}, 0, nullptr, &rc2) != cudaSuccess || rc2 < 1) {
                 cudaGetLastError();
                 if (L > 4096) { g_err = "generic kernels for nchan 4096 do not fit this device"; return bail(B2F_EUNSUPPORTED); }
@@ -1131,8 +1157,8 @@ int b2f_push(b2f_plan* pl, const void* const* frames, int64_t nframes, int on_de
     }
 
     // ---- kernel 1: validate + de-frame
-    k0.compact = pl->d_compact + pl->carry_len; k0.compact_stride = pl->compact_stride;   // carried halo sits in front
-    k0.wmask = pl->d_wmask; k0.wmask_stride = pl->wmask_stride;
+    k0.compact = pl->d_compact + pl->carry_len * pl->bps; k0.compact_stride = pl->compact_stride;   // carried halo sits in front
+    k0.wmask = pl->d_wmask + (pl->smask ? pl->carry_len * pl->bps / 32 : 0); k0.wmask_stride = pl->wmask_stride;
     k0.fstat = pl->d_fstat; k0.fstat_stride = pl->fstat_stride;
     k0.counters = pl->d_counters;
     k0.nframes = nframes; k0.nslots = nframes;
@@ -1148,8 +1174,12 @@ int b2f_push(b2f_plan* pl, const void* const* frames, int64_t nframes, int on_de
     }
     if (pl->carry_mode && pl->carry_len) {
         for (int i = 0; i < nif; ++i)
-            CU(cudaMemcpyAsync(pl->d_compact + i * pl->compact_stride, pl->d_carry + (size_t)i * pl->M, (size_t)pl->carry_len,
+            CU(cudaMemcpyAsync(pl->d_compact + i * pl->compact_stride, pl->d_carry + (size_t)i * pl->M * pl->bps, (size_t)pl->carry_len * pl->bps,
                                cudaMemcpyDeviceToDevice, pl->stream));
+        if (pl->smask)
+            for (int i = 0; i < nif; ++i)
+                CU(cudaMemcpyAsync(pl->d_wmask + i * pl->wmask_stride, pl->d_carry_mask + (size_t)i * (pl->M * pl->bps / 32),
+                                   (size_t)(pl->carry_len * pl->bps / 32), cudaMemcpyDeviceToDevice, pl->stream));
     }
     int rc = 0;
     if (pl->path) {
@@ -1207,13 +1237,13 @@ int b2f_push(b2f_plan* pl, const void* const* frames, int64_t nframes, int on_de
     }
     {
         K0bParams kb{};
-        kb.wmask = pl->d_wmask; kb.wmask_stride = pl->wmask_stride;
+        kb.wmask = k0.wmask; kb.wmask_stride = pl->wmask_stride;
         kb.fstat = pl->d_fstat; kb.fstat_stride = pl->fstat_stride;
         kb.blkdirty = pl->d_blkdirty; kb.counters = pl->d_counters;
         kb.nslots = nframes; kb.nif = nif; kb.nblk = pl->carry_mode ? 0 : (int)nblk;
         kb.groups_per_slot = (int)pl->groups_per_slot; kb.samples_per_frame = (int)pl->spf;
         kb.block_samples = pl->M;
-        kb.compact = pl->d_compact + pl->carry_len; kb.compact_stride = pl->compact_stride;
+        kb.compact = k0.compact; kb.compact_stride = pl->compact_stride;
         kb.slot_bytes = pl->slot_bytes; kb.in_nbit = pl->prm.in_nbit;
         const int64_t n = nframes * nif;
         k0b_finish_slots<<<(unsigned)((n + 255) / 256), 256, 0, pl->stream>>>(kb);

@@ -53,8 +53,10 @@ __device__ __forceinline__ int kgt_rev16(int seg) {
 // outermost inverse pass stays inside those points, so with this mapping a warp only reads what it wrote itself and
 // the stages are separated by __syncwarp instead of a block barrier: 3 block barriers per strip instead of 6 (8 for
 // N = 8192), and the warps of a CTA drift into different stages (load burst / butterflies / store burst overlap).
+// SRC: 0 shared, 1 index bytes of the 2-bit decode, 2 8-bit sample pairs (KG8: offset and stream-coordinate word masks).
 template <int LG, int LGN, bool INV, int SRC, int DST, bool WM = false>
-__device__ __forceinline__ void kgt_col_pass16(float2* sm, const float2* tw, const uint8_t* gsrc_b, float2* gdst, const float2* lut) {
+__device__ __forceinline__ void kgt_col_pass16(float2* sm, const float2* tw, const uint8_t* gsrc_b, float2* gdst, const float2* lut,
+                                               const KG8* s8 = nullptr) {
     using G = KGT<LG>;
     constexpr int LGM = LGN - 4, M1 = 1 << LGM, LGP = G::LGC - 1, CNT = (G::N >> 4) << LGP;
     constexpr int NW = G::kColThreads / 32, PER = WM ? CNT / NW : CNT, STEP = WM ? 32 : G::kColThreads;
@@ -75,6 +77,9 @@ __device__ __forceinline__ void kgt_col_pass16(float2* sm, const float2* tw, con
                 const uint32_t two = *reinterpret_cast<const uint16_t*>(gsrc_b + (int64_t)idx * G::N + c2);
                 a[j] = *reinterpret_cast<const float2*>(reinterpret_cast<const uint8_t*>(lut) + (two & 255u));
                 b[j] = *reinterpret_cast<const float2*>(reinterpret_cast<const uint8_t*>(lut) + (two >> 8));
+            } else if (SRC == 2) {
+                const int64_t o = ((int64_t)idx * G::N + c2) * 2;
+                kg_decode8(*reinterpret_cast<const uint32_t*>(gsrc_b + o), *s8, o, a[j], b[j]);
             } else {
                 const float4 v4 = *reinterpret_cast<const float4*>(&sm[kg_phys<false>((idx << G::LGC) + c2)]);
                 a[j] = make_float2(v4.x, v4.y);
@@ -185,7 +190,7 @@ __device__ __forceinline__ void kgt_col_inner(float2* sm, int n1_0, float2* cols
     }
 }
 
-template <int LG>
+template <int LG, int NBIT>
 __global__ void __launch_bounds__(KGT<LG>::kColThreads, KGT<LG>::kColCtas) kgt_column_pass(const KGParams p) {
     using G = KGT<LG>;
     constexpr int N = G::N, C = G::C, NF = G::NF, NSTRIPS = N / C, LGS = LG - G::LGC;
@@ -210,11 +215,14 @@ __global__ void __launch_bounds__(KGT<LG>::kColThreads, KGT<LG>::kColCtas) kgt_c
         const int strip = (int)(w & (NSTRIPS - 1));
         const int ifi = (int)(gb / p.nblk);
         const int64_t blk = gb - (int64_t)ifi * p.nblk;
-        const uint8_t* src = p.compact + ifi * p.compact_stride + (blk << (2 * LG)) + (int64_t)strip * C;
+        constexpr int BPS = NBIT == 8 ? 2 : 1;                            // stream bytes per time sample
+        const int64_t off = ((blk << (2 * LG)) + (int64_t)strip * C) * BPS;
+        const uint8_t* src = p.compact + ifi * p.compact_stride + off;
+        const KG8 s8{p.wmask + ifi * p.wmask_stride, off, p.in8_offset, NBIT == 8 && p.blkdirty[gb] != 0};
         float2* dst = p.inter + (lb << (2 * LG)) + strip * C;
         float2* colsum = p.colsum + gb * N + strip * C;
         // forward, outermost first
-        kgt_col_pass16<LG, LG, false, 1, 0>(data, tw, src, nullptr, lut);
+        kgt_col_pass16<LG, LG, false, NBIT == 8 ? 2 : 1, 0>(data, tw, src, nullptr, lut, &s8);
         __syncthreads();
         kgt_col_pass16<LG, LG - 4, false, 0, 0, true>(data, tw + kg_tw_offset(LG, 1), nullptr, nullptr, lut);
         __syncwarp();

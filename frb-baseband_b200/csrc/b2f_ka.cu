@@ -31,7 +31,6 @@ cudaError_t B2F_CAT(b2f_launch_ka_, B2F_NBIT)(int R, const KAParams& p, unsigned
         }
     }
 #endif
-#if B2F_NBIT == 2
     if (p.variant == 32) {                     // forward-only product mode of the dedispersion path
         switch (R) {
             case 16: return go<16, 32>(p, grid, st);
@@ -43,7 +42,6 @@ cudaError_t B2F_CAT(b2f_launch_ka_, B2F_NBIT)(int R, const KAParams& p, unsigned
         }
         return cudaErrorInvalidValue;
     }
-#endif
     switch (R) {
         case 16: return go<16>(p, grid, st);
         case 32: return go<32>(p, grid, st);

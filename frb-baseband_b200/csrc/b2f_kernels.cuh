@@ -435,6 +435,19 @@ static __global__ void k0b_finish_slots(const K0bParams p) {
 }
 #endif
 
+#ifdef B2F_API_TU
+// 8-bit input in carry mode keeps its word masks by stream position (b2f_plan::smask): a block is dirty when any mask
+// byte of its M samples is set.  step32 / blk32: block stride and block length in mask bytes.
+static __global__ void k8_blkdirty(const uint8_t* wmask, size_t wmask_stride, uint8_t* blkdirty, int nblk, int64_t step32, int64_t blk32) {
+    const int b = blockIdx.x, ifi = blockIdx.y;
+    const uint8_t* m = wmask + ifi * wmask_stride + b * step32;
+    int any = 0;
+    for (int64_t i = threadIdx.x; i < blk32; i += blockDim.x) any |= m[i];
+    any = __syncthreads_or(any);
+    if (threadIdx.x == 0) blkdirty[ifi * (int64_t)nblk + b] = any ? 1 : 0;
+}
+#endif
+
 // ================================================================== stand-alone decode
 // compact payload (+ word mask) -> planar float samples out[2][nsamp].  HBM-bound expansion
 // (2 bit -> 32 bit); the production path never runs it, the column pass decodes on the fly.
@@ -1459,7 +1472,24 @@ struct KGParams {
     float* F; int64_t F_if_stride; int64_t row0;
     int L, lgL, R, lgR, C, lgC, nblk, nif, D, mode;
     int64_t M, gb_begin, gb_end;
+    // 8-bit input: word masks in stream coordinates (one byte per 32 bytes of the de-framed stream, carried over with the
+    // samples), blocks that hold a masked word, the offset of the code -> value map (127.5 or 128)
+    const uint8_t* wmask; size_t wmask_stride;
+    const uint8_t* blkdirty;
+    float in8_offset;
 };
+
+// One 32-bit word of an 8-bit stream = two time samples x (pol 0, pol 1).  `o` = byte offset of the word from s.byte0,
+// which in turn counts from the start of the IF's de-framed stream of this push (carried samples included).
+struct KG8 { const uint8_t* wm; int64_t byte0; float off; bool dirty; };
+__device__ __forceinline__ void kg_decode8(uint32_t four, const KG8& s, int64_t o, float2& a, float2& b) {
+    a = make_float2((float)(four & 255u) - s.off, (float)((four >> 8) & 255u) - s.off);
+    b = make_float2((float)((four >> 16) & 255u) - s.off, (float)(four >> 24) - s.off);
+    if (s.dirty) {
+        const int64_t w = (s.byte0 + o) >> 2;
+        if ((s.wm[w >> 3] >> (w & 7)) & 1) a = b = make_float2(0.f, 0.f);
+    }
+}
 
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
@@ -1553,7 +1583,8 @@ __device__ __forceinline__ void kg_pass16(float2* sm, const float2* tw, int lgLe
 // independent 16-point transforms interleave.  SRC: 0 shared, 1 index bytes.  DST: 0 shared, 1 global.
 template <bool INV, int SRC, int DST>
 __device__ __forceinline__ void kg_pass16_pair(float2* sm, const float2* tw, int lgLen, int lgn, int lgC, int cnt,
-                                               const uint8_t* gsrc_b, float2* gdst, int64_t gstride, const float2* lut) {
+                                               const uint8_t* gsrc_b, float2* gdst, int64_t gstride, const float2* lut,
+                                               const KG8* s8 = nullptr) {
     const int lgm = lgn - 4, m = 1 << lgm, lgP = lgC - 1;           // 2^lgP column pairs per strip
     for (int t = threadIdx.x; t < cnt; t += blockDim.x) {
         const int c2 = (t & ((1 << lgP) - 1)) * 2, w = t >> lgP;
@@ -1568,6 +1599,9 @@ __device__ __forceinline__ void kg_pass16_pair(float2* sm, const float2* tw, int
                 const uint32_t two = *reinterpret_cast<const uint16_t*>(gsrc_b + (int64_t)idx * gstride + c2);
                 a[j] = *reinterpret_cast<const float2*>(reinterpret_cast<const uint8_t*>(lut) + (two & 255u));
                 b[j] = *reinterpret_cast<const float2*>(reinterpret_cast<const uint8_t*>(lut) + (two >> 8));
+            } else if (SRC == 2) {                                   // 8-bit sample pairs
+                const int64_t o = ((int64_t)idx * gstride + c2) * 2;
+                kg_decode8(*reinterpret_cast<const uint32_t*>(gsrc_b + o), *s8, o, a[j], b[j]);
             } else {
                 const float4 v4 = *reinterpret_cast<const float4*>(&sm[kg_phys<false>((idx << lgC) + c2)]);
                 a[j] = make_float2(v4.x, v4.y);
@@ -1648,7 +1682,7 @@ __device__ __forceinline__ void kg_column_inner_pair(float2* sm, const KGParams&
 // innermost step of the column pass: FFT_RM, diagonal, IFFT_RM on the RM values of one segment
 template <int RM, bool GLOBAL>
 __device__ __forceinline__ void kg_column_inner(float2* sm, const KGParams& p, int n1_0, float2* colsum, const uint8_t* gsrc_b,
-                                                float2* gdst, const float2* lut) {
+                                                float2* gdst, const float2* lut, const KG8* s8 = nullptr) {
     constexpr int LGI = ilog2(RM);
     const int lgC = p.lgC, cnt = (p.L >> LGI) << lgC;
     const int nf = kg_outer_passes(p.lgL);
@@ -1659,7 +1693,12 @@ __device__ __forceinline__ void kg_column_inner(float2* sm, const KGParams& p, i
 #pragma unroll
         for (int q = 0; q < RM; ++q) {
             const int idx = seg * RM + q;
-            if (GLOBAL) v[q] = *reinterpret_cast<const float2*>(reinterpret_cast<const uint8_t*>(lut) + gsrc_b[(int64_t)idx * p.R + cl]);
+            if (GLOBAL && s8) {                                     // 8-bit: one (pol 0, pol 1) pair = half a stream word
+                const int64_t o = ((int64_t)idx * p.R + cl) * 2;
+                float2 lo, hi;
+                kg_decode8(*reinterpret_cast<const uint32_t*>(gsrc_b + (o & ~(int64_t)3)), *s8, o & ~(int64_t)3, lo, hi);
+                v[q] = (o & 2) ? hi : lo;
+            } else if (GLOBAL) v[q] = *reinterpret_cast<const float2*>(reinterpret_cast<const uint8_t*>(lut) + gsrc_b[(int64_t)idx * p.R + cl]);
             else v[q] = sm[kg_phys<false>((idx << lgC) + cl)];
         }
         fft_inreg<RM, false>(v);
@@ -1686,6 +1725,7 @@ __device__ __forceinline__ void kg_column_inner(float2* sm, const KGParams& p, i
 }
 
 #ifdef B2F_API_TU        // non-template kernels are launched from b2f_api.cu only: compile them once
+template <int NBIT>
 static __global__ void __launch_bounds__(256, 2) kg_column_pass(const KGParams p) {
     extern __shared__ __align__(16) uint8_t kg_smem[];
     float2* tw = reinterpret_cast<float2*>(kg_smem);                     // [L]
@@ -1708,16 +1748,18 @@ static __global__ void __launch_bounds__(256, 2) kg_column_pass(const KGParams p
         const int strip = (int)(w % nstrips);
         const int ifi = (int)(gb / p.nblk);
         const int64_t blk = gb % p.nblk;
-        const uint8_t* src = p.compact + ifi * p.compact_stride + blk * p.M + (int64_t)strip * C;
+        const int64_t off = (blk * p.M + (int64_t)strip * C) * (NBIT == 8 ? 2 : 1);
+        const uint8_t* src = p.compact + ifi * p.compact_stride + off;
+        const KG8 s8{p.wmask + ifi * p.wmask_stride, off, p.in8_offset, NBIT == 8 && p.blkdirty[gb] != 0};
         float2* dst = p.inter + lb * (int64_t)L * R + strip * C;
         float2* colsum = p.colsum + gb * R + strip * C;
         if (nf == 0) {                                       // L = 16: one register-resident step, no shared memory
-            kg_column_inner<16, true>(data, p, strip * C, colsum, src, dst, lut);
+            kg_column_inner<16, true>(data, p, strip * C, colsum, src, dst, lut, NBIT == 8 ? &s8 : nullptr);
             continue;
         }
         const int cnt2 = cnt16 >> 1;                         // two neighbouring columns per thread
         for (int f = 0; f < nf; ++f) {                       // forward, outermost first
-            if (f == 0) kg_pass16_pair<false, 1, 0>(data, tw, lgL, lgL, lgC, cnt2, src, nullptr, R, lut);
+            if (f == 0) kg_pass16_pair<false, NBIT == 8 ? 2 : 1, 0>(data, tw, lgL, lgL, lgC, cnt2, src, nullptr, R, lut, &s8);
             else kg_pass16_pair<false, 0, 0>(data, tw + kg_tw_offset(lgL, f), lgL, lgL - 4 * f, lgC, cnt2, nullptr, nullptr, 0, lut);
             __syncthreads();
         }

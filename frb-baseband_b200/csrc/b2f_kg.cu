@@ -23,14 +23,19 @@ static cudaError_t row_go(const KGParams& p, int grid, cudaStream_t st, int* cta
 }
 
 // grid <= 0: only report how many CTAs fit on one SM (*ctas)
-cudaError_t KG_CAT(b2f_launch_kgt_col_, B2F_KG_LG)(const KGParams& p, int grid, cudaStream_t st, int* ctas) {
+template <int NBIT>
+static cudaError_t col_go(const KGParams& p, int grid, cudaStream_t st, int* ctas) {
     using G = KGT<B2F_KG_LG>;
-    auto kern = kgt_column_pass<B2F_KG_LG>;
+    auto kern = kgt_column_pass<B2F_KG_LG, NBIT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::kColSmem);
     if (e != cudaSuccess) return e;
     if (ctas) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, kern, G::kColThreads, G::kColSmem);
     kern<<<grid, G::kColThreads, G::kColSmem, st>>>(p);
     return cudaGetLastError();
+}
+
+cudaError_t KG_CAT(b2f_launch_kgt_col_, B2F_KG_LG)(int in_nbit, const KGParams& p, int grid, cudaStream_t st, int* ctas) {
+    return in_nbit == 8 ? col_go<8>(p, grid, st, ctas) : col_go<2>(p, grid, st, ctas);
 }
 
 cudaError_t KG_CAT(b2f_launch_kgt_row_, B2F_KG_LG)(int mode, const KGParams& p, int grid, cudaStream_t st, int* ctas) {

@@ -32,11 +32,11 @@ cudaError_t b2f_launch_kt(int mode, const b2f::KTParams& p, int grid, cudaStream
 // generic channeliser with compile-time geometry (b2f_generic.cuh), one translation unit per size L = R = 2^lg, lg = 10..13.
 // With ctas != NULL the call only reports how many CTAs of the kernel fit on one SM.
 namespace b2f { struct KGParams; }
-cudaError_t b2f_launch_kgt_col(int lg, const b2f::KGParams& p, int grid, cudaStream_t st, int* ctas);
+cudaError_t b2f_launch_kgt_col(int lg, int in_nbit, const b2f::KGParams& p, int grid, cudaStream_t st, int* ctas);
 cudaError_t b2f_launch_kgt_row(int lg, int mode, const b2f::KGParams& p, int grid, cudaStream_t st, int* ctas);
 void b2f_kgt_geometry(int lg, int* cols_per_cta, int* rows_per_batch);
 #define B2F_KGT_DECL(LG)                                                                                         \
-    cudaError_t b2f_launch_kgt_col_##LG(const b2f::KGParams& p, int grid, cudaStream_t st, int* ctas);           \
+    cudaError_t b2f_launch_kgt_col_##LG(int in_nbit, const b2f::KGParams& p, int grid, cudaStream_t st, int* ctas);           \
     cudaError_t b2f_launch_kgt_row_##LG(int mode, const b2f::KGParams& p, int grid, cudaStream_t st, int* ctas);
 B2F_KGT_DECL(10) B2F_KGT_DECL(11) B2F_KGT_DECL(12) B2F_KGT_DECL(13)
 #undef B2F_KGT_DECL

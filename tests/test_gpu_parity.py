@@ -204,6 +204,62 @@ def test_8bit_input(gpu):
     assert_rel(rows.reshape(-1, 1, nchan), ref["data"].astype(np.float64), REL_TOL, "8-bit input")
 
 
+@pytest.mark.parametrize("nchan,freq_res,D,nframes,chunk", [(512, 0, 4, 1300, 400), (1024, 0, 2, 2200, 1000), (128, 64, 16, 300, 100),
+                                                             (8, 16, 1, 60, 40), (64, 256, 8, 500, 200), (32, 2048, 32, 700, 300)])
+def test_8bit_input_generic(gpu, nchan, freq_res, D, nframes, chunk):
+    """8-bit VDIF (base2fil.sh:230,251 `nbits`) through the generic channeliser, e.g. the CLI default --nchan 512.  No 8-bit
+    code decodes to 0.0, so the word masks of invalid frames and fill words travel with the carried samples."""
+    bw = 32.0
+    L = freq_res or (512 if nchan <= 128 else 2 * nchan)
+    v = synth.make_vdif(nframes, seed=171 + nchan, bw_mhz=bw, nbit=8, tone_frac=0.43, rho=0.2, invalid_frac=0.01, fill_frac=0.02)
+    cfg = PlanConfig(nchan=nchan, bw_mhz=[bw], freq_res=freq_res, tscrunch=D, in_nbit=8, out_nbit=-32, keep_bandpass=True, chunk_units=chunk)
+    out = []
+    with Plan(cfg) as pl:
+        cf, fb = int(pl.chunk_frames), cfg.frame_bytes
+        assert cf == chunk and int(pl.geometry.freq_res) == L
+        for f0 in range(0, nframes, cf):
+            n = min(cf, nframes - f0)
+            pl.push([v[f0 * fb:(f0 + n) * fb]])
+            out.append(pl.pull().copy())
+        pl.flush()
+        out.append(pl.pull().copy())
+        rows = pl.view_rows(np.concatenate(out))
+        c = pl.counters()
+    assert c["frames_invalid"] > 0 and c["frames_with_fill"] > 0
+    ref = o.digifil(v, freq_mhz=1400.0, bw_mhz=bw, nchan=nchan, freq_res=L, tscrunch_factor=D, in_nbit=8, out_nbit=-32,
+                    keep_bandpass=True)["data"]
+    assert rows.shape[0] == ref.shape[0] and ref.shape[0] > 0
+    assert_rel(rows.reshape(ref.shape), ref.astype(np.float64), REL_TOL, f"8-bit generic nchan {nchan} L {L}")
+
+
+def test_8bit_input_coherent_dedispersion(gpu):
+    """8-bit VDIF with digifil -D: overlapping blocks, the halo and its word masks carried across pushes."""
+    nchan, bw, D, dm, fc = 128, 32.0, 16, 560.0, 1254.0
+    cfg = PlanConfig(nchan=nchan, bw_mhz=[-bw], freq_mhz=[fc], tscrunch=D, in_nbit=8, out_nbit=-32, keep_bandpass=True,
+                     dm=dm, coherent=True, chunk_units=1)
+    out = []
+    with Plan(cfg) as pl:
+        g = pl.geometry
+        nf = (int(g.nfilt_pos), int(g.nfilt_neg))
+        cf, fb = int(pl.chunk_frames), cfg.frame_bytes
+        nframes = 2 * cf + 301
+        assert nframes * 4000 < 40e6
+        v = synth.make_vdif(nframes, seed=93, bw_mhz=bw, nbit=8, rho=0.3, tone_frac=0.37, invalid_frac=0.003, fill_frac=0.005)
+        for f0 in range(0, nframes, cf):
+            n = min(cf, nframes - f0)
+            pl.push([v[f0 * fb:(f0 + n) * fb]])
+            out.append(pl.pull().copy())
+        pl.flush()
+        out.append(pl.pull().copy())
+        rows = pl.view_rows(np.concatenate(out))
+        c = pl.counters()
+    assert c["frames_invalid"] > 0 and c["frames_with_fill"] > 0
+    ref = o.digifil(v, freq_mhz=fc, bw_mhz=-bw, nchan=nchan, tscrunch_factor=D, in_nbit=8, out_nbit=-32,
+                    keep_bandpass=True, dm=dm, coherent=True, nfilt=nf)["data"]
+    assert rows.shape[0] == ref.shape[0] and rows.shape[0] > 0
+    assert_rel(rows.reshape(ref.shape), ref.astype(np.float64), REL_TOL, "8-bit dedispersed")
+
+
 def test_linearity_full_size_property(gpu):
     """Size-independent property at the full C2 block geometry: an all-zero payload (every word
     the fill pattern) yields exactly zero power, and Parseval holds per block."""
@@ -294,7 +350,7 @@ def test_other_row_lengths(gpu, nchan, bw, D):
 
 def test_unsupported_requests_fail_loudly(gpu):
     for kw in (dict(nchan=8192), dict(nchan=4096, freq_res=4096), dict(nchan=128, tscrunch=1 << 21), dict(nchan=4),
-               dict(nchan=512, in_nbit=8), dict(nchan=512, dm=100.0, coherent=True)):
+               dict(nchan=512, dm=100.0, coherent=True), dict(nchan=512, in_nbit=8, frame_bytes=8032 + 8)):
         with pytest.raises(_lib.B2FError) as e:
             Plan(PlanConfig(bw_mhz=[-32.0], **kw))
         assert e.value.code == _lib.EUNSUPPORTED
