@@ -16,6 +16,7 @@ KERNEL_NAMES = ["validate", "column", "eps", "row", "stats", "quant", "decode", 
 EINVAL, ECUDA, ENOMEM, ESTATE, EUNSUPPORTED = -1, -2, -3, -4, -5
 DECODE_STATIC, DECODE_JA98 = 0, 1
 RESCALE_CONSTANT, RESCALE_RUNNING = 0, 1
+RAW_VDIF, RAW_MARK5B = 0, 1
 
 
 class Params(C.Structure):
@@ -31,6 +32,7 @@ class Params(C.Structure):
         ("raw_word_bits", C.c_int32), ("raw_bits", (C.c_uint8 * 4) * B2F_MAX_IF),
         ("decode_mode", C.c_int32), ("in8_offset_mode", C.c_int32), ("fft_normalised", C.c_int32),
         ("rescale_mode", C.c_int32), ("digi_sigma", C.c_double),
+        ("raw_format", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 

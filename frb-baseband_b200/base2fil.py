@@ -151,12 +151,15 @@ def run_scan_raw(raw_path: str, out_path: str, *, mode: str, nif: int, bw: float
     ifs = list(range(1, nif + 1))
     freqs = [freq_lsb0 + (i - 1) * bw for i in ifs]
     bws = [bw if i % 2 == 0 else -bw for i in ifs]
-    with open(raw_path, "rb") as f:
-        info = vdif.parse_header(f.read(32))
+    frame_bytes, header_bytes, raw_format = spif.frame_geometry(mode)
+    if not raw_format:                                        # VDIF says what it is (legacy headers are 16 bytes)
+        with open(raw_path, "rb") as f:
+            info = vdif.parse_header(f.read(32))
+        frame_bytes, header_bytes = info.frame_bytes, info.header_bytes
     cfg = PlanConfig(nchan=nchan, bw_mhz=bws, freq_mhz=freqs, tscrunch=max(1, tscrunch),
-                     pol_mode=pol_mode_from_reference(pol), out_nbit=nbit, in_nbit=2, frame_bytes=info.frame_bytes,
-                     header_bytes=info.header_bytes, keep_bandpass=keep_bandpass, device=device,
-                     raw_word_bits=W, raw_bits=bits)
+                     pol_mode=pol_mode_from_reference(pol), out_nbit=nbit, in_nbit=2, frame_bytes=frame_bytes,
+                     header_bytes=header_bytes, keep_bandpass=keep_bandpass, device=device,
+                     raw_word_bits=W, raw_bits=bits, raw_format=raw_format)
     with Plan(cfg) as pl:
         r = pl.run_scan([raw_path], out_path, start_s=start, nsec=nsec, source_name=source,
                         telescope_id=sigproc.TELESCOPE_IDS.get(telescope.lower(), 0),

@@ -779,6 +779,9 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
     const int W = prm->raw_word_bits;
     if (W != 0 && W != 16 && W != 32 && W != 64) return fail(B2F_EINVAL, "raw_word_bits must be 0, 16, 32 or 64");
     if (W && prm->in_nbit != 2) return fail(B2F_EUNSUPPORTED, "raw multi-BBC input must be 2-bit");
+    if (prm->reserved0) return fail(B2F_EINVAL, "reserved0 must be 0");
+    if (prm->raw_format != B2F_RAW_VDIF && prm->raw_format != B2F_RAW_MARK5B) return fail(B2F_EINVAL, "raw_format");
+    if (W && prm->raw_format == B2F_RAW_MARK5B && prm->header_bytes != 16) return fail(B2F_EINVAL, "Mark5B frames have a 16-byte header");
     if (W && (prm->frame_bytes % 16 || payload % (W / 2))) return fail(B2F_EUNSUPPORTED, "raw frame size");
     if (W) for (int i = 0; i < prm->nif; ++i) for (int k = 0; k < 4; ++k)
         if (prm->raw_bits[i][k] >= W) return fail(B2F_EINVAL, "raw_bits entry outside the word");
@@ -1127,11 +1130,16 @@ int b2f_push(b2f_plan* pl, const void* const* frames, int64_t nframes, int on_de
 
     if (!pl->have_base) {
         for (int i = 0; i < (pl->prm.raw_word_bits ? 1 : nif); ++i) {
-            uint32_t w[2];
-            if (on_device) CU(cudaMemcpy(w, frames[i], 8, cudaMemcpyDeviceToHost));
-            else memcpy(w, frames[i], 8);
-            pl->base_sec0[i] = w[0] & 0x3FFFFFFFu;
-            pl->base_fnum0[i] = w[1] & 0xFFFFFFu;
+            uint32_t w[4];
+            if (on_device) CU(cudaMemcpy(w, frames[i], 16, cudaMemcpyDeviceToHost));
+            else memcpy(w, frames[i], 16);
+            if (pl->prm.raw_word_bits && pl->prm.raw_format == B2F_RAW_MARK5B) {
+                pl->base_sec0[i] = mark5b_seconds(w[2]);
+                pl->base_fnum0[i] = w[1] & 0x7FFFu;
+            } else {
+                pl->base_sec0[i] = w[0] & 0x3FFFFFFFu;
+                pl->base_fnum0[i] = w[1] & 0xFFFFFFu;
+            }
         }
         pl->have_base = true;
     }
@@ -1209,7 +1217,7 @@ int b2f_push(b2f_plan* pl, const void* const* frames, int64_t nframes, int on_de
         kr.frame_bytes = pl->prm.frame_bytes; kr.header_bytes = pl->prm.header_bytes; kr.payload_bytes = (int)pl->payload;
         kr.word_bits = pl->prm.raw_word_bits; kr.nif = nif; kr.time_mode = pl->prm.frame_time_mode;
         kr.mask_faults = pl->prm.mask_faults; kr.fps = (int)pl->fps; kr.slot_bytes = pl->slot_bytes;
-        kr.base_sec = k0.base_sec[0]; kr.base_fnum = k0.base_fnum[0];
+        kr.base_sec = k0.base_sec[0]; kr.base_fnum = k0.base_fnum[0]; kr.format = pl->prm.raw_format;
         for (int i = 0; i < nif; ++i) for (int k = 0; k < 4; ++k) kr.bit[i][k] = pl->prm.raw_bits[i][k];
         if (reinterpret_cast<uintptr_t>(kr.frames) & 15) return fail(B2F_EINVAL, "raw frames must be 16-byte aligned");
         const int stage_bytes = (kr.frame_bytes + 127) & ~127;

@@ -280,7 +280,17 @@ struct K0RParams {
     int frame_bytes, header_bytes, payload_bytes, word_bits, nif, time_mode, mask_faults, fps, slot_bytes;
     uint32_t base_sec, base_fnum;
     uint8_t bit[B2F_MAX_IF][4];
+    int format;                 // enum b2f_raw_format
 };
+
+// Mark5B time code word (BCD JJJSSSSS: MJD mod 1000, second of day) -> JJJ * 86400 + SSSSS
+__host__ __device__ inline uint32_t mark5b_seconds(uint32_t w2) {
+    uint32_t sss = 0, jjj = 0;
+    for (int d = 4; d >= 0; --d) sss = sss * 10 + ((w2 >> (4 * d)) & 15u);
+    for (int d = 7; d >= 5; --d) jjj = jjj * 10 + ((w2 >> (4 * d)) & 15u);
+    return jjj * 86400u + sss;
+}
+constexpr uint32_t kMark5BSync = 0xABADDEEDu;
 
 template <typename WORD>
 __device__ __forceinline__ uint32_t gather_nibble_index(WORD w, const uint8_t (&b)[4]) {
@@ -319,11 +329,15 @@ __global__ void __launch_bounds__(kK0Threads) k0r_corner_turn(const K0RParams p)
         mbar_wait(&mbar[stage], (it / kK0Stages) & 1);
         const uint32_t* hw = reinterpret_cast<const uint32_t*>(buf);
         const uint32_t w0 = hw[0], w1 = hw[1], w2 = hw[2], w3 = hw[3];
-        const bool invalid = (w0 >> 31) != 0;
-        const bool bad = ((w2 & 0xFFFFFFu) * 8u != (uint32_t)p.frame_bytes) || ((int)((w3 >> 26) & 31u) + 1 != 2) ||
-                         ((int)((w0 >> 30) & 1u) != (p.header_bytes == 16 ? 1 : 0));
-        const int64_t tslot = ((int64_t)(w0 & 0x3FFFFFFFu) - (int64_t)p.base_sec) * p.fps +
-                              ((int64_t)(w1 & 0xFFFFFFu) - (int64_t)p.base_fnum);
+        const bool mk5 = p.format == B2F_RAW_MARK5B;
+        // Mark5B: no invalid bit and no length field; the sync word pins the framing, test-vector frames carry no sky data
+        const bool invalid = mk5 ? ((w1 >> 15) & 1u) != 0 : (w0 >> 31) != 0;
+        const bool bad = mk5 ? w0 != kMark5BSync
+                             : ((w2 & 0xFFFFFFu) * 8u != (uint32_t)p.frame_bytes) || ((int)((w3 >> 26) & 31u) + 1 != 2) ||
+                                   ((int)((w0 >> 30) & 1u) != (p.header_bytes == 16 ? 1 : 0));
+        const int64_t tslot = mk5 ? ((int64_t)mark5b_seconds(w2) - (int64_t)p.base_sec) * p.fps + ((int64_t)(w1 & 0x7FFFu) - (int64_t)p.base_fnum)
+                                  : ((int64_t)(w0 & 0x3FFFFFFFu) - (int64_t)p.base_sec) * p.fps +
+                                        ((int64_t)(w1 & 0xFFFFFFu) - (int64_t)p.base_fnum);
         const int64_t slot = p.time_mode ? tslot : f;
         const bool in_range = (slot >= 0 && slot < p.nslots);
         const bool dead = invalid || bad;

@@ -20,6 +20,7 @@
 #include <condition_variable>
 #include <cstdio>
 #include <cstring>
+#include <ctime>
 #include <mutex>
 #include <numeric>
 #include <string>
@@ -51,6 +52,22 @@ FrameHead parse_head(const uint8_t* b) {
     h.nchan = 1u << ((w[2] >> 24) & 0x1Fu);
     h.nbit = ((w[3] >> 26) & 0x1Fu) + 1u;
     return h;
+}
+
+// Mark5B disk frame header: sync word, frame number within the second (bits 0..14 of word 1), BCD time code
+// JJJSSSSS (MJD mod 1000, second of day).  The thousands of the MJD are not recorded: the latest day that is not in the
+// future is taken, as jive5ab does with the system clock.
+bool mark5b_head(const uint8_t* b, double fps, double* tstart) {
+    uint32_t w[4];
+    memcpy(w, b, 16);
+    if (w[0] != 0xABADDEEDu) return false;
+    uint32_t sss = 0, jjj = 0;
+    for (int d = 4; d >= 0; --d) sss = sss * 10 + ((w[2] >> (4 * d)) & 15u);
+    for (int d = 7; d >= 5; --d) jjj = jjj * 10 + ((w[2] >> (4 * d)) & 15u);
+    const int64_t mjd_now = 40587 + (int64_t)(time(nullptr) / 86400);
+    int64_t mjd = (int64_t)jjj + (mjd_now - (int64_t)jjj) / 1000 * 1000;
+    if (tstart) *tstart = (double)mjd + ((double)sss + (double)(w[1] & 0x7FFFu) / fps) / 86400.0;
+    return true;
 }
 
 // MJD of 00:00 UTC on the first day of a VDIF reference epoch (six-month steps from 2000-01-01)
@@ -274,7 +291,11 @@ extern "C" int b2f_run_scan(b2f_plan* pl, int nfiles, const char* const* vdif_pa
         nfr = std::min<int64_t>(nfr, (int64_t)(st.st_size / (off_t)fb) - f0);
         uint8_t head[32];
         size_t got = 0;
-        if (read_fully(fd, head, 32, 0, &got) && got == 32) {
+        const bool mk5 = prm.raw_word_bits && prm.raw_format == B2F_RAW_MARK5B;
+        if (mk5) {
+            if (read_fully(fd, head, 16, 0, &got) && got == 16 && !mark5b_head(head, (double)fps, nullptr))
+                return failf(B2F_EINVAL, std::string(vdif_paths[i]) + ": no Mark5B sync word at the start of the file");
+        } else if (read_fully(fd, head, 32, 0, &got) && got == 32) {
             const FrameHead h = parse_head(head);
             if (h.frame_bytes != fb || (int)(h.legacy ? 16 : 32) != prm.header_bytes ||
                 (!prm.raw_word_bits && (int)h.nbit != prm.in_nbit))
@@ -289,7 +310,9 @@ extern "C" int b2f_run_scan(b2f_plan* pl, int nfiles, const char* const* vdif_pa
     {
         uint8_t head[32];
         size_t got = 0;
-        if (read_fully(own.fds[0], head, 32, (off_t)(f0 * (int64_t)fb), &got) && got == 32) {
+        if (prm.raw_word_bits && prm.raw_format == B2F_RAW_MARK5B) {
+            if (read_fully(own.fds[0], head, 16, (off_t)(f0 * (int64_t)fb), &got) && got == 16) mark5b_head(head, (double)fps, &tstart);
+        } else if (read_fully(own.fds[0], head, 32, (off_t)(f0 * (int64_t)fb), &got) && got == 32) {
             const FrameHead h = parse_head(head);
             tstart = (double)epoch_mjd(h.epoch) + ((double)h.seconds + (double)h.frame_nr / (double)fps) / 86400.0;
         }

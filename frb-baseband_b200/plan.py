@@ -53,6 +53,7 @@ class PlanConfig:
     coherent: bool = False                   # digifil -F nchan:D
     raw_word_bits: int = 0                   # 16/32/64: one raw multi-BBC VDIF stream, corner turn on the GPU
     raw_bits: list | None = None             # per IF: 4 source bit positions (spif2file recipe)
+    raw_format: int = 0                      # 0 VDIF frames, 1 Mark5B disk frames (16 B header, 10000 B payload)
     decode_mode: int = 0                     # 0 static optimal levels, 1 Jenet-Anderson dynamic levels per 512 samples
     in8_offset_mode: int = 0                 # 8-bit input: 0 code - 127.5, 1 code - 128 (D3)
     fft_normalised: bool = False             # D4
@@ -97,6 +98,7 @@ class Plan:
         p.coherent = int(cfg.coherent)
         p.profile = int(cfg.profile)
         p.raw_word_bits = cfg.raw_word_bits
+        p.raw_format = cfg.raw_format
         if cfg.raw_word_bits:
             for i in range(nif):
                 for k in range(4):

@@ -32,22 +32,49 @@ def mode_string(payload: int, datarate_mbps: int, nbbc: int, nbits: int) -> str:
 
 
 def parse_recipe(recipe: str):
-    """'32>[16,17,24,25][0,1,8,9]...:0-7' -> (32, [[16,17,24,25],[0,1,8,9],...])"""
-    if recipe.lstrip().startswith("swap_sign_mag"):
-        # Mark5B recordings (spif2file.sh:79-93) store sign and magnitude the other way round; accepting the prefix and
-        # ignoring it would decode every sample wrongly
-        raise ValueError("swap_sign_mag (Mark5B) recipes are not implemented")
+    """'32>[16,17,24,25][0,1,8,9]...:0-7' -> (32, [[16,17,24,25],[0,1,8,9],...]).
+
+    Mark5B recordings store sign and magnitude the other way round, so their recipes (spif2file.sh:79-93) start with
+    the step `swap_sign_mag+`: the two bits of every 2-bit field change places before the extraction.  Extracting bit b
+    of the swapped word is extracting bit b ^ 1 of the recorded word, which is what is returned for such a recipe."""
+    recipe = recipe.strip()
+    swap = recipe.startswith("swap_sign_mag+")
+    if swap:
+        recipe = recipe[len("swap_sign_mag+"):]
     m = re.match(r"\s*(\d+)>((?:\[[0-9,]+\])+):", recipe)
     if not m:
         raise ValueError(f"not a spif2file recipe: {recipe!r}")
     groups = [[int(x) for x in g.split(",")] for g in re.findall(r"\[([0-9,]+)\]", m.group(2))]
     if any(len(g) != 4 for g in groups):
         raise ValueError("only 2-bit dual-polarisation recipes (4 bits per IF) are supported")
+    if swap:
+        groups = [[b ^ 1 for b in g] for g in groups]
     return int(m.group(1)), groups
+
+
+def frame_geometry(mode: str):
+    """(frame_bytes, header_bytes, raw_format) of a mode string: VDIF_<payload>-... has 32-byte headers,
+    MARK5B-... 16-byte headers and 10000-byte payloads (spif2file.sh:99-113)."""
+    if mode.startswith("MARK5B"):
+        return 10016, 16, 1
+    m = re.match(r"VDIF_(\d+)-", mode)
+    if not m:
+        raise ValueError(f"Cannot determine frame sizes from {mode}")
+    return int(m.group(1)) + 32, 32, 0
 
 
 def recipe_for_mode(mode: str, nif: int, flip_if: bool = False):
     """(word_bits, bits per IF 1..nif) for a base2fil mode string; flip_if swaps neighbouring IFs."""
+    m5 = re.match(r"MARK5B-(\d+)-(\d+)-(\d+)$", mode)
+    if m5:                                                          # spif2file.sh:79-93
+        rate, nbbc, nbits = (int(x) for x in m5.groups())
+        if (rate, nbbc, nbits) not in ((1024, 16, 2), (1024, 8, 2), (2048, 16, 2), (2048, 32, 2)):
+            raise ValueError(f"mode {mode} not implemented")
+        if nbbc == 32:
+            # 10000-byte payloads hold 1250 64-bit words: not a whole number of the 4-sample groups the kernel writes
+            raise ValueError(f"mode {mode}: Mark5B with 64-bit words is not implemented")
+        W, groups = parse_recipe("swap_sign_mag+" + _RECIPES[(nbbc, nbits)])
+        return W, _flip(groups[:nif], flip_if)
     m = re.match(r"VDIF_(\d+)-(\d+)-(\d+)-(\d+)$", mode)
     if not m:
         raise ValueError(f"mode {mode} not implemented")
@@ -59,8 +86,12 @@ def recipe_for_mode(mode: str, nif: int, flip_if: bool = False):
     else:
         raise ValueError(f"mode {mode} not implemented")
     W, groups = parse_recipe(rec)
-    groups = groups[:nif]
+    return W, _flip(groups[:nif], flip_if)
+
+
+def _flip(groups, flip_if: bool):
+    """spif2file.sh:117-131: with flipIF neighbouring IFs swap recipes"""
     if flip_if:
         groups = [groups[i + 1] if i % 2 == 0 and i + 1 < len(groups) else groups[i - 1] if i % 2 else groups[i]
                   for i in range(len(groups))]
-    return W, groups
+    return groups

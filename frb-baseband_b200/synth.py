@@ -97,6 +97,27 @@ def if_file_name(exp: str, st: str, scan: str, i: int) -> str:
     return f"{exp}_{st}_no0{scan}_IF{i}.vdif"
 
 
+def make_raw_mark5b(codes: np.ndarray, word_bits: int, bits, *, bw_mhz: float, mjd: int = 60000, sec0: int = 0) -> np.ndarray:
+    """Raw multi-BBC Mark5B stream: like make_raw_vdif with 16-byte Mark5B headers and 10000-byte payloads.  `bits` are the
+    source bits in the recorded word, i.e. what spif.parse_recipe returns for a swap_sign_mag recipe."""
+    nif, _, nsamp = codes.shape
+    dt = {16: np.uint16, 32: np.uint32}[word_bits]
+    w = np.zeros(nsamp, dtype=dt)
+    for i in range(nif):
+        nib = (codes[i, 0].astype(np.uint64) | (codes[i, 1].astype(np.uint64) << np.uint64(2)))
+        for k in range(4):
+            w |= (((nib >> np.uint64(k)) & np.uint64(1)) << np.uint64(bits[i][k])).astype(dt)
+    pb, hb = vdif.MARK5B_PAYLOAD_BYTES, vdif.MARK5B_HEADER_BYTES
+    spf = pb * 8 // word_bits
+    nframes = nsamp // spf
+    fps = int(round(2 * abs(bw_mhz) * 1e6 / spf))
+    hdr = vdif.make_mark5b_headers(nframes, frames_per_sec=fps, mjd=mjd, sec0=sec0)
+    out = np.empty((nframes, hb + pb), dtype=np.uint8)
+    out[:, :hb] = hdr.view(np.uint8).reshape(nframes, hb)
+    out[:, hb:] = w[: nframes * spf].view(np.uint8).reshape(nframes, pb)
+    return out.reshape(-1)
+
+
 def make_raw_vdif(codes: np.ndarray, word_bits: int, bits, *, bw_mhz: float, payload_bytes: int = 8000,
                   ref_epoch: int = 40, sec0: int = 0) -> np.ndarray:
     """Raw multi-BBC VDIF stream (what the recorder holds): codes[if, pol, t] in 0..3 are scattered to

@@ -71,6 +71,34 @@ def make_headers(nframes: int, *, frames_per_sec: int, payload_bytes: int = 8000
     return h
 
 
+MARK5B_SYNC = 0xABADDEED
+MARK5B_HEADER_BYTES = 16
+MARK5B_PAYLOAD_BYTES = 10000
+
+
+def _bcd(v: np.ndarray, ndigits: int) -> np.ndarray:
+    out = np.zeros_like(v, dtype=np.uint32)
+    for d in range(ndigits):
+        out |= ((v // 10 ** d) % 10).astype(np.uint32) << np.uint32(4 * d)
+    return out
+
+
+def make_mark5b_headers(nframes: int, *, frames_per_sec: int, mjd: int = 60000, sec0: int = 0, frame0: int = 0) -> np.ndarray:
+    """[nframes, 4] uint32 Mark5B disk frame headers: sync word, frame number within the second (bits 0..14), BCD
+    time code JJJSSSSS (MJD mod 1000, second of day), BCD fraction of the second .SSSS (the CRC half is left 0).
+    /root/reference/spif2file.sh:105-108: 16-byte header, 10000-byte payload."""
+    idx = np.arange(nframes, dtype=np.int64) + frame0
+    sec = sec0 + idx // frames_per_sec
+    fnr = idx % frames_per_sec
+    day = (mjd + sec // 86400) % 1000
+    h = np.zeros((nframes, 4), dtype="<u4")
+    h[:, 0] = MARK5B_SYNC
+    h[:, 1] = fnr & 0x7FFF
+    h[:, 2] = (_bcd(day, 3) << np.uint32(20)) | _bcd(sec % 86400, 5)
+    h[:, 3] = _bcd(fnr * 10000 // frames_per_sec, 4) << np.uint32(16)
+    return h
+
+
 def epoch_mjd(ref_epoch: int) -> int:
     """MJD at 00:00 UTC of the start of a VDIF reference epoch."""
     year = 2000 + ref_epoch // 2

@@ -76,6 +76,14 @@ enum b2f_rescale_mode {
     B2F_RESCALE_RUNNING = 1        /* without -c: every interval is scaled with its own statistics */
 };
 
+/* framing of the raw multi-BBC stream (raw_word_bits != 0) */
+enum b2f_raw_format {
+    B2F_RAW_VDIF = 0,              /* VDIF frames (spif2file.sh:31-77)                                                    */
+    B2F_RAW_MARK5B = 1             /* Mark5B disk frames: 16-byte header (sync 0xABADDEED, frame# in second, BCD JJJSSSSS time
+                                      code), 10000-byte payload (spif2file.sh:79-93,105-108).  The recipes of these modes start
+                                      with swap_sign_mag: fold that into raw_bits (source bit b -> b ^ 1, spif.parse_recipe) */
+};
+
 typedef struct b2f_params {
     uint32_t struct_size;          /* = sizeof(b2f_params) */
     int32_t device;                /* CUDA device ordinal */
@@ -117,6 +125,8 @@ typedef struct b2f_params {
                                       transforms normalised; only visible with keep_bandpass (cancels under -c)  */
     int32_t rescale_mode;          /* enum b2f_rescale_mode; SURVEY D8                                          */
     double digi_sigma;             /* D9: half the output range spans this many sigma (digifil: 6); 0 = 6       */
+    int32_t raw_format;            /* enum b2f_raw_format; only read when raw_word_bits != 0                    */
+    int32_t reserved0;             /* must be 0                                                                 */
 } b2f_params;
 
 typedef struct b2f_geometry {

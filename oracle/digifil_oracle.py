@@ -391,17 +391,27 @@ def digifil(vdif: np.ndarray, *, freq_mhz: float, bw_mhz: float, nchan: int,
 
 
 def corner_turn(raw: np.ndarray, word_bits: int, bits, *, frame_bytes: int = 8032, header_bytes: int = 32,
-                mask_invalid: bool = True) -> np.ndarray:
+                mask_invalid: bool = True, mark5b: bool = False, swap_sign_mag: bool = False) -> np.ndarray:
     """jive5ab spif2file as arithmetic (/root/reference/spif2file.sh:31-98,178-186): raw multi-BBC VDIF ->
     x[if, pol, t] decoded samples.  bits[if] = the 4 source bits of that IF's (pol0 lsb, pol0 msb, pol1 lsb,
-    pol1 msb).  Samples of invalid frames and of 32-bit payload words equal to the fill pattern are 0.0."""
+    pol1 msb).  Samples of invalid frames and of 32-bit payload words equal to the fill pattern are 0.0.
+    mark5b: Mark5B disk frames (spif2file.sh:79-93,105-108; pass frame_bytes 10016, header_bytes 16): frames without the
+    sync word or with the test-vector bit carry no data.  swap_sign_mag: the first step of those modes' recipes,
+    done literally -- the two bits of every 2-bit field change places before `bits` (the recipe as written) is applied."""
     raw = np.ascontiguousarray(raw, dtype=np.uint8)
     nframes = raw.size // frame_bytes
     fr = raw[: nframes * frame_bytes].reshape(nframes, frame_bytes)
-    invalid = (fr[:, 0:4].copy().view("<u4")[:, 0] >> 31).astype(bool)
+    hw = fr[:, 0:8].copy().view("<u4")
+    if mark5b:
+        invalid = (hw[:, 0] != 0xABADDEED) | ((hw[:, 1] >> 15) & 1).astype(bool)
+    else:
+        invalid = (hw[:, 0] >> 31).astype(bool)
     pay = np.ascontiguousarray(fr[:, header_bytes:])
     dt = {16: "<u2", 32: "<u4", 64: "<u8"}[word_bits]
     w = pay.view(dt).astype(np.uint64)                                   # [frame, sample]
+    if swap_sign_mag:
+        even = np.uint64(0x5555555555555555)
+        w = ((w & even) << np.uint64(1)) | ((w >> np.uint64(1)) & even)
     fill32 = pay.view("<u4") == VDIF_FILL_WORD
     if word_bits == 32:
         bad = fill32

@@ -45,6 +45,112 @@ def test_oracle_corner_turn_inverts_synthetic_raw(mode, nif):
     assert np.all(x2[:, :, 1] == 0) and np.array_equal(x2[:, :, 0], x.reshape(nif, 2, 3, spf)[:, :, 0])
 
 
+def test_mark5b_recipes_fold_swap_sign_mag():
+    """spif2file.sh:79-93: `swap_sign_mag+<recipe>`.  The host folds the swap into the bit positions (b -> b ^ 1); the
+    oracle does the swap literally on the words and then applies the recipe as written."""
+    W, g = spif.recipe_for_mode("MARK5B-1024-16-2", 8)                        # :79-81
+    Wv, gv = spif.recipe_for_mode("VDIF_8000-2048-16-2", 8)
+    assert W == Wv == 32 and g == [[b ^ 1 for b in grp] for grp in gv] and g[0] == [17, 16, 25, 24]
+    W16, g16 = spif.recipe_for_mode("MARK5B-1024-8-2", 4)                     # :83-85
+    assert W16 == 16 and g16[0] == [9, 8, 13, 12]
+    assert spif.parse_recipe("swap_sign_mag+16>[8,9,12,13][0,1,4,5][10,11,14,15][2,3,6,7]:0-3") == (16, g16)
+    assert spif.frame_geometry("MARK5B-2048-16-2") == (10016, 16, 1)          # :105-108
+    assert spif.frame_geometry("VDIF_8000-2048-16-2") == (8032, 32, 0) and spif.frame_geometry("VDIF_1000-1024-16-2")[0] == 1032
+    _, f = spif.recipe_for_mode("MARK5B-2048-16-2", 8, flip_if=True)
+    assert f[0] == g[1] and f[1] == g[0]
+    with pytest.raises(ValueError):
+        spif.recipe_for_mode("MARK5B-2048-32-2", 16)                          # 64-bit words: stated as not implemented
+    with pytest.raises(ValueError):
+        spif.recipe_for_mode("MARK5B-512-16-2", 8)
+    rng = np.random.default_rng(6)
+    spf = 10000 * 8 // W
+    codes = rng.integers(0, 4, size=(8, 2, 3 * spf), dtype=np.uint8)
+    raw = synth.make_raw_mark5b(codes, W, g, bw_mhz=16.0, sec0=86399)
+    assert raw.size == 3 * 10016
+    hw = raw.reshape(3, 10016)[:, :16].copy().view("<u4")
+    assert np.all(hw[:, 0] == 0xABADDEED) and list(hw[:, 1]) == [0, 1, 2] and hw[0, 2] == 0x00086399   # BCD JJJSSSSS
+    x = o.corner_turn(raw, W, g, frame_bytes=10016, header_bytes=16, mark5b=True)
+    assert np.array_equal(x, o.LEVELS_2BIT[codes])
+    x_lit = o.corner_turn(raw, W, gv, frame_bytes=10016, header_bytes=16, mark5b=True, swap_sign_mag=True)
+    assert np.array_equal(x_lit, x)
+    raw2 = raw.copy().reshape(3, 10016)
+    raw2[1, 0] ^= 1                                                          # broken sync word
+    raw2[2, 5] |= 0x80                                                       # test-vector bit (bit 15 of word 1)
+    x2 = o.corner_turn(raw2.reshape(-1), W, g, frame_bytes=10016, header_bytes=16, mark5b=True).reshape(8, 2, 3, spf)
+    assert np.all(x2[:, :, 1:] == 0) and np.array_equal(x2[:, :, 0], x.reshape(8, 2, 3, spf)[:, :, 0])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode,nif,bw", [("MARK5B-1024-16-2", 8, 16.0), ("MARK5B-1024-8-2", 4, 32.0)])
+def test_gpu_mark5b_corner_turn(gpu, mode, nif, bw):
+    """Mark5B disk frames in, spliced filterbank out == oracle(swap_sign_mag -> recipe as written -> digifil per IF -> splice)."""
+    nchan, D, nfr = 32, 32, 1024
+    W, bits = spif.recipe_for_mode(mode, nif)
+    _, written = spif.recipe_for_mode({16: "VDIF_8000-2048-16-2", 8: "VDIF_8000-1024-8-2"}[2 * nif], nif)
+    fb, hb, fmt = spif.frame_geometry(mode)
+    bws = [bw if i % 2 == 0 else -bw for i in range(1, nif + 1)]
+    freqs = [1300.0 + (i - 1) * bw for i in range(1, nif + 1)]
+    cfg = PlanConfig(nchan=nchan, bw_mhz=bws, freq_mhz=freqs, tscrunch=D, out_nbit=-32, keep_bandpass=True,
+                     raw_word_bits=W, raw_bits=bits, raw_format=fmt, frame_bytes=fb, header_bytes=hb)
+    spf = 10000 * 8 // W
+    rng = np.random.default_rng(19)
+    codes = synth.quantise_2bit(rng.standard_normal((nif, 2, nfr * spf)) + 0.4 * np.cos(0.9 * np.arange(nfr * spf)))
+    raw = synth.make_raw_mark5b(codes, W, bits, bw_mhz=bw, sec0=100).reshape(nfr, fb)
+    raw[5, 0] ^= 1                                                           # a frame without the sync word
+    raw[7, 5] |= 0x80                                                        # a test-vector frame
+    raw[9, hb + 400:hb + 440].view("<u4")[:] = 0x11223344                    # a run of fill words
+    with Plan(cfg) as pl:
+        assert int(pl.chunk_frames) >= nfr and int(pl.geometry.samples_per_frame) == spf
+        pl.push([raw.reshape(-1)])
+        rows = pl.view_rows(pl.pull())
+        c = pl.counters()
+    assert c["frames_badhdr"] == 1 and c["frames_invalid"] == 1 and c["frames_with_fill"] == 1 and c["frames_ok"] == nfr - 3
+    x = o.corner_turn(raw.reshape(-1), W, written, frame_bytes=fb, header_bytes=hb, mark5b=True, swap_sign_mag=True)
+    parts = []
+    for i in sorted(range(nif), key=lambda k: -freqs[k]):
+        parts.append(o.digifil(np.zeros(8032, np.uint8), freq_mhz=freqs[i], bw_mhz=bws[i], nchan=nchan, tscrunch_factor=D,
+                               out_nbit=-32, keep_bandpass=True, x=x[i], frame_bytes=8032))   # x given: the bytes are not decoded
+    ref = o.splice(parts)["data"]
+    assert rows.shape == ref.shape and rows.shape[0] > 0
+    assert_rel(rows.reshape(rows.shape[0], 1, -1), ref.reshape(ref.shape[0], 1, -1).astype(np.float64), REL_TOL, "corner turn " + mode)
+
+
+@pytest.mark.gpu
+def test_gpu_mark5b_file_to_filterbank(gpu, tmp_path):
+    """base2fil.run_scan_raw on a Mark5B recording: same rows as the streaming calls, start time from the BCD time code."""
+    from frb_baseband_b200 import base2fil, sigproc
+    mode, nif, bw, nchan, D = "MARK5B-1024-16-2", 8, 16.0, 8, 32
+    W, bits = spif.recipe_for_mode(mode, nif)
+    fb, hb, fmt = spif.frame_geometry(mode)
+    bws = [bw if i % 2 == 0 else -bw for i in range(1, nif + 1)]
+    freqs = [1300.0 + (i - 1) * bw for i in range(1, nif + 1)]
+    cfg = PlanConfig(nchan=nchan, bw_mhz=bws, freq_mhz=freqs, tscrunch=D, out_nbit=-32, keep_bandpass=True,
+                     raw_word_bits=W, raw_bits=bits, raw_format=fmt, frame_bytes=fb, header_bytes=hb)
+    with Plan(cfg) as pl:
+        nfr = int(pl.geometry.unit_frames)
+        assert nfr * fb < 64e6
+        rng = np.random.default_rng(23)
+        codes = rng.integers(0, 4, size=(nif, 2, nfr * 2500), dtype=np.uint8)
+        raw = synth.make_raw_mark5b(codes, W, bits, bw_mhz=bw, mjd=60123, sec0=3600)
+        rows = []
+        cf = int(pl.chunk_frames)
+        for f0 in range(0, nfr, cf):
+            pl.push([raw[f0 * fb:(f0 + min(cf, nfr - f0)) * fb]])
+            rows.append(pl.pull().copy())
+        pl.flush()
+        rows.append(pl.pull().copy())
+        rows = np.concatenate(rows)
+    path, out = tmp_path / "scan.m5b", tmp_path / "scan.fil"
+    raw.tofile(path)
+    base2fil.run_scan_raw(str(path), str(out), mode=mode, nif=nif, bw=bw, freq_lsb0=1300.0, nchan=nchan, tscrunch=D,
+                          nbit=-32, keep_bandpass=True, verbose=False)
+    hdr, data = sigproc.read_fil(str(out))
+    assert hdr.nchans == nif * nchan and hdr.nbits == 32
+    # JJJ = 123: the thousands come from the clock (latest such day that is not in the future)
+    assert abs(hdr.tstart % 1000 - (123 + 3600 / 86400.0)) < 1e-9 and hdr.tstart > 1000
+    assert np.array_equal(np.asarray(data).reshape(-1).view(np.uint8), rows.reshape(-1).view(np.uint8))
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("mode,nif,bw", [("VDIF_8000-2048-16-2", 8, 32.0), ("VDIF_8000-4096-32-2", 16, 32.0),
                                          ("VDIF_8000-1024-8-2", 4, 32.0)])
