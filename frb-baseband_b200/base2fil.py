@@ -157,7 +157,7 @@ def run_scan_raw(raw_path: str, out_path: str, *, mode: str, nif: int, bw: float
             info = vdif.parse_header(f.read(32))
         frame_bytes, header_bytes = info.frame_bytes, info.header_bytes
     cfg = PlanConfig(nchan=nchan, bw_mhz=bws, freq_mhz=freqs, tscrunch=max(1, tscrunch),
-                     pol_mode=pol_mode_from_reference(pol), out_nbit=nbit, in_nbit=2, frame_bytes=frame_bytes,
+                     pol_mode=pol_mode_from_reference(pol), out_nbit=nbit, in_nbit=len(bits[0]) // 2, frame_bytes=frame_bytes,
                      header_bytes=header_bytes, keep_bandpass=keep_bandpass, device=device,
                      raw_word_bits=W, raw_bits=bits, raw_format=raw_format)
     with Plan(cfg) as pl:

@@ -496,7 +496,7 @@ int push_dedisp(b2f_plan* pl, int64_t nblk, int64_t T) {
 }
 
 cudaError_t b2f_launch_ka(int in_nbit, int R, const KAParams& p, unsigned grid, cudaStream_t st) {
-    return in_nbit == 2 ? b2f_launch_ka_2(R, p, grid, st) : b2f_launch_ka_8(R, p, grid, st);
+    return in_nbit == 8 ? b2f_launch_ka_8(R, p, grid, st) : b2f_launch_ka_2(R, p, grid, st);   // 1- and 2-bit: index-byte stream
 }
 cudaError_t b2f_launch_kr(int R, int mode, const KBParams& p, int grid, cudaStream_t st) {
     if (R <= 64) return b2f_launch_kr_part0(R, mode, p, grid, st);
@@ -744,7 +744,7 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
     if (!nprod) return fail(B2F_EINVAL, "pol_mode not in 0..6 (process_vdif --pol choices map to 0,1,2,3,4)");
     if (!(prm->out_nbit == 2 || prm->out_nbit == 8 || prm->out_nbit == 16 || prm->out_nbit == -32))
         return fail(B2F_EINVAL, "nbit not in supported values of [2, 8, 16, -32]");
-    if (!(prm->in_nbit == 2 || prm->in_nbit == 8)) return fail(B2F_EUNSUPPORTED, "VDIF bits/sample must be 2 or 8");
+    if (!(prm->in_nbit == 1 || prm->in_nbit == 2 || prm->in_nbit == 8)) return fail(B2F_EUNSUPPORTED, "VDIF bits/sample must be 1, 2 or 8");
     if (prm->nchan < 1) return fail(B2F_EINVAL, "nchan");
     const int L = prm->freq_res > 0 ? prm->freq_res : (prm->nchan <= 128 ? 512 : 2 * prm->nchan);
     const int R = 2 * prm->nchan;
@@ -778,7 +778,7 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
     if (prm->digi_sigma < 0) return fail(B2F_EINVAL, "digi_sigma");
     const int W = prm->raw_word_bits;
     if (W != 0 && W != 16 && W != 32 && W != 64) return fail(B2F_EINVAL, "raw_word_bits must be 0, 16, 32 or 64");
-    if (W && prm->in_nbit != 2) return fail(B2F_EUNSUPPORTED, "raw multi-BBC input must be 2-bit");
+    if (W && prm->in_nbit != 2 && prm->in_nbit != 1) return fail(B2F_EUNSUPPORTED, "raw multi-BBC input must be 1- or 2-bit");
     if (prm->reserved0) return fail(B2F_EINVAL, "reserved0 must be 0");
     if (prm->raw_format != B2F_RAW_VDIF && prm->raw_format != B2F_RAW_MARK5B) return fail(B2F_EINVAL, "raw_format");
     if (W && prm->raw_format == B2F_RAW_MARK5B && prm->header_bytes != 16) return fail(B2F_EINVAL, "Mark5B frames have a 16-byte header");
@@ -953,7 +953,7 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
     }
     const int nif = prm->nif;
     const int64_t nbt = (int64_t)nif * pl->chunk_blocks;
-    pl->slot_bytes = W ? (int)spf : (prm->in_nbit == 2 ? 2 * payload : payload);      // 2-bit: one index byte per time sample
+    pl->slot_bytes = W ? (int)spf : (prm->in_nbit == 8 ? payload : (int)spf);         // 1- and 2-bit: one index byte per time sample
     pl->compact_stride = (size_t)((pl->chunk_frames * (int64_t)pl->slot_bytes + (pl->carry_mode ? pl->M * pl->bps : 0) + 255) / 256 * 256);
     pl->wmask_stride = (size_t)((pl->chunk_frames * pl->groups_per_slot + (pl->smask ? pl->M * pl->bps / 32 : 0) + 255) / 256 * 256);
     pl->fstat_stride = (size_t)((pl->chunk_frames + 255) / 256 * 256);
@@ -1217,7 +1217,7 @@ int b2f_push(b2f_plan* pl, const void* const* frames, int64_t nframes, int on_de
         kr.frame_bytes = pl->prm.frame_bytes; kr.header_bytes = pl->prm.header_bytes; kr.payload_bytes = (int)pl->payload;
         kr.word_bits = pl->prm.raw_word_bits; kr.nif = nif; kr.time_mode = pl->prm.frame_time_mode;
         kr.mask_faults = pl->prm.mask_faults; kr.fps = (int)pl->fps; kr.slot_bytes = pl->slot_bytes;
-        kr.base_sec = k0.base_sec[0]; kr.base_fnum = k0.base_fnum[0]; kr.format = pl->prm.raw_format;
+        kr.base_sec = k0.base_sec[0]; kr.base_fnum = k0.base_fnum[0]; kr.format = pl->prm.raw_format; kr.sample_bits = pl->prm.in_nbit;
         for (int i = 0; i < nif; ++i) for (int k = 0; k < 4; ++k) kr.bit[i][k] = pl->prm.raw_bits[i][k];
         if (reinterpret_cast<uintptr_t>(kr.frames) & 15) return fail(B2F_EINVAL, "raw frames must be 16-byte aligned");
         const int stage_bytes = (kr.frame_bytes + 127) & ~127;
@@ -1279,7 +1279,7 @@ int b2f_push(b2f_plan* pl, const void* const* frames, int64_t nframes, int on_de
         ka.tab_g = pl->d_tab_g; ka.tab_h = pl->d_tab_h; ka.tab_w = pl->d_tab_w; ka.tab_beta = pl->d_tab_beta;
         ka.R = pl->R; ka.nstrips = pl->nstrips; ka.nblk = (int)nblk; ka.nif = nif;
         ka.payload_bytes = (int)pl->payload; ka.groups_per_slot = (int)pl->groups_per_slot;
-        ka.blk_step_bytes = pl->M * (pl->prm.in_nbit == 2 ? 1 : 2);
+        ka.blk_step_bytes = pl->M * pl->bps;
         ka.sm_slots = pl->d_sm_slots; ka.stagger_cycles = pl->stagger_cycles;
         ka.in8_offset = pl->prm.in8_offset_mode ? 128.0f : 127.5f;
         {
@@ -1534,7 +1534,7 @@ int b2f_reset_timers(b2f_plan* pl) {
 int b2f_decode(const void* frames, int64_t nframes, int frame_bytes, int header_bytes, int in_nbit, int mask_faults,
                int in_on_device, float* out, int out_on_device, int device, b2f_counters* counters) {
     if (!frames || !out || nframes <= 0) return fail(B2F_EINVAL, "null argument");
-    if (!(in_nbit == 2 || in_nbit == 8)) return fail(B2F_EUNSUPPORTED, "VDIF bits/sample must be 2 or 8");
+    if (!(in_nbit == 1 || in_nbit == 2 || in_nbit == 8)) return fail(B2F_EUNSUPPORTED, "VDIF bits/sample must be 1, 2 or 8");
     const int payload = frame_bytes - header_bytes;
     if (payload <= 0 || payload % 8 || (header_bytes != 32 && header_bytes != 16)) return fail(B2F_EINVAL, "frame geometry");
     int ndev = 0;
@@ -1573,7 +1573,7 @@ int b2f_decode(const void* frames, int64_t nframes, int frame_bytes, int header_
         CUD(cudaMemcpy(d_in, frames, (size_t)nframes * frame_bytes, cudaMemcpyHostToDevice));
         src = d_in;
     }
-    const int slot_bytes = in_nbit == 2 ? 2 * payload : payload;
+    const int slot_bytes = in_nbit == 8 ? payload : (int)spf;             // 1- and 2-bit: one index byte per time sample
     CUD(cudaMalloc(&d_compact, (size_t)nframes * slot_bytes));
     CUD(cudaMalloc(&d_wmask, (size_t)nframes * gps));
     CUD(cudaMalloc(&d_fstat, (size_t)nframes));
@@ -1593,7 +1593,7 @@ int b2f_decode(const void* frames, int64_t nframes, int frame_bytes, int header_
     rc = launch_k0(nullptr, k0, 0, false);
     if (rc) { cleanup(); return rc; }
     const int64_t nwords = nframes * (int64_t)(slot_bytes / 4);      // 2-bit: index words of 4 time samples
-    if (in_nbit == 2)
+    if (in_nbit != 8)
         k_decode<2><<<(unsigned)((nwords + 255) / 256), 256>>>(d_compact, d_wmask, payload, gps, nwords, d_out, nsamp);
     else
         k_decode<8><<<(unsigned)((nwords + 255) / 256), 256>>>(d_compact, d_wmask, payload, gps, nwords, d_out, nsamp);

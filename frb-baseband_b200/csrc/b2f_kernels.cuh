@@ -126,6 +126,18 @@ __device__ __forceinline__ uint2 expand_word_2bit(uint32_t w, bool masked) {
     return make_uint2(lo << 3, hi << 3);
 }
 
+// 1-bit payload word (16 time samples x 2 channels, bit 2t = ch0, bit 2t+1 = ch1) -> 16 index bytes.  A 1-bit sample decodes
+// to -1.0 / +1.0 = the inner levels of the 2-bit table (codes 1 and 2): index = ((s0 ? 2 : 1) | (s1 ? 8 : 4)) << 3
+// = 0x28 + 8 s0 + 32 s1, so everything behind this kernel sees the same index-byte stream as for 2-bit input.
+__device__ __forceinline__ uint4 expand_word_1bit(uint32_t w, bool masked) {
+    if (masked) return make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
+    auto four = [](uint32_t x) {                             // 4 (s0, s1) pairs in the low byte -> 4 index bytes
+        const uint32_t t = (x | (x << 6) | (x << 12) | (x << 18)) & 0x03030303u;
+        return 0x28282828u + ((t & 0x01010101u) << 3) + ((t & 0x02020202u) << 4);
+    };
+    return make_uint4(four(w & 255u), four((w >> 8) & 255u), four((w >> 16) & 255u), four(w >> 24));
+}
+
 constexpr int kK0Threads = 256;
 constexpr int kK0Stages = 4;
 
@@ -188,7 +200,7 @@ __global__ void __launch_bounds__(kK0Threads) k0_validate_compact(const K0Params
             const int ngroups = p.groups_per_slot;
             uint8_t* dst = compact + slot * (int64_t)p.slot_bytes;
             const uint8_t* pay = buf + p.header_bytes;
-            const bool two = p.in_nbit == 2;
+            const bool two = p.in_nbit == 2, one = p.in_nbit == 1;
             for (int g = tid; g < ngroups; g += kK0Threads) {
                 uint32_t m = 0;
                 uint32_t w[8];
@@ -209,7 +221,17 @@ __global__ void __launch_bounds__(kK0Threads) k0_validate_compact(const K0Params
                 else if (dead) m = 0xFF;
                 wmask[slot * (int64_t)ngroups + g] = (uint8_t)m;
                 any_fill |= (m != 0);
-                if (two) {               // 8 words -> 64 index bytes
+                if (one) {               // 8 words -> 128 index bytes
+                    for (int k = 0; k < nw; ++k) {
+                        const uint4 e = expand_word_1bit(w[k], (m >> k) & 1);
+                        if (VEC) {
+                            reinterpret_cast<uint4*>(dst + 128 * g)[k] = e;
+                        } else {
+                            reinterpret_cast<uint2*>(dst + 128 * g)[2 * k] = make_uint2(e.x, e.y);
+                            reinterpret_cast<uint2*>(dst + 128 * g)[2 * k + 1] = make_uint2(e.z, e.w);
+                        }
+                    }
+                } else if (two) {        // 8 words -> 64 index bytes
                     uint2 e[8];
 #pragma unroll
                     for (int k = 0; k < 8; ++k) e[k] = expand_word_2bit(w[k], (m >> k) & 1);
@@ -281,6 +303,7 @@ struct K0RParams {
     uint32_t base_sec, base_fnum;
     uint8_t bit[B2F_MAX_IF][4];
     int format;                 // enum b2f_raw_format
+    int sample_bits;            // 2, or 1: bit[i][0] / bit[i][2] are the source bits of pol 0 / pol 1 (spif2file.sh:58-61)
 };
 
 // Mark5B time code word (BCD JJJSSSSS: MJD mod 1000, second of day) -> JJJ * 86400 + SSSSS
@@ -295,6 +318,12 @@ constexpr uint32_t kMark5BSync = 0xABADDEEDu;
 template <typename WORD>
 __device__ __forceinline__ uint32_t gather_nibble_index(WORD w, const uint8_t (&b)[4]) {
     return (uint32_t)(((w >> b[0]) & 1) << 3 | ((w >> b[1]) & 1) << 4 | ((w >> b[2]) & 1) << 5 | ((w >> b[3]) & 1) << 6);
+}
+// 1-bit samples: 0 -> -1.0, 1 -> +1.0 = the inner levels of the 2-bit table (codes 1 and 2), so the same decode LUT serves
+template <typename WORD>
+__device__ __forceinline__ uint32_t gather_1bit_index(WORD w, const uint8_t (&b)[4]) {
+    const uint32_t s0 = (uint32_t)((w >> b[0]) & 1), s1 = (uint32_t)((w >> b[2]) & 1);
+    return ((s0 ? 2u : 1u) | (s1 ? 8u : 4u)) << 3;
 }
 
 template <int WBITS>
@@ -320,6 +349,7 @@ __global__ void __launch_bounds__(kK0Threads) k0r_corner_turn(const K0RParams p)
         }
     }
     constexpr int SPW = WBITS == 16 ? 2 : 1;                  // time samples per 32-bit payload unit (16-bit words: 2)
+    const bool one_bit = p.sample_bits == 1;
     const int nquads = p.slot_bytes / 4;                      // groups of 4 consecutive time samples per frame
     unsigned long long c_ok = 0, c_inv = 0, c_fillf = 0, c_drop = 0, c_mis = 0, c_bad = 0;
     int it = 0;
@@ -333,7 +363,7 @@ __global__ void __launch_bounds__(kK0Threads) k0r_corner_turn(const K0RParams p)
         // Mark5B: no invalid bit and no length field; the sync word pins the framing, test-vector frames carry no sky data
         const bool invalid = mk5 ? ((w1 >> 15) & 1u) != 0 : (w0 >> 31) != 0;
         const bool bad = mk5 ? w0 != kMark5BSync
-                             : ((w2 & 0xFFFFFFu) * 8u != (uint32_t)p.frame_bytes) || ((int)((w3 >> 26) & 31u) + 1 != 2) ||
+                             : ((w2 & 0xFFFFFFu) * 8u != (uint32_t)p.frame_bytes) || ((int)((w3 >> 26) & 31u) + 1 != p.sample_bits) ||
                                    ((int)((w0 >> 30) & 1u) != (p.header_bytes == 16 ? 1 : 0));
         const int64_t tslot = mk5 ? ((int64_t)mark5b_seconds(w2) - (int64_t)p.base_sec) * p.fps + ((int64_t)(w1 & 0x7FFFu) - (int64_t)p.base_fnum)
                                   : ((int64_t)(w0 & 0x3FFFFFFFu) - (int64_t)p.base_sec) * p.fps +
@@ -379,7 +409,8 @@ __global__ void __launch_bounds__(kK0Threads) k0r_corner_turn(const K0RParams p)
                 for (int i = 0; i < p.nif; ++i) {
                     uint32_t o = 0;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) o |= (masked[k] ? 0x80u : gather_nibble_index<WORD>(w[k], p.bit[i])) << (8 * k);
+                    for (int k = 0; k < 4; ++k)
+                        o |= (masked[k] ? 0x80u : one_bit ? gather_1bit_index<WORD>(w[k], p.bit[i]) : gather_nibble_index<WORD>(w[k], p.bit[i])) << (8 * k);
                     *reinterpret_cast<uint32_t*>(p.compact + i * p.compact_stride + slot * (int64_t)p.slot_bytes + 4 * g) = o;
                 }
             }
@@ -435,7 +466,7 @@ static __global__ void k0b_finish_slots(const K0bParams p) {
     if (st == 0) {
         uint8_t* m = p.wmask + ifi * p.wmask_stride + slot * (int64_t)p.groups_per_slot;
         for (int g = 0; g < p.groups_per_slot; ++g) m[g] = 0xFF;
-        if (p.in_nbit == 2) {                                   // masking lives in the index stream for 2-bit input
+        if (p.in_nbit != 8) {                                   // masking lives in the index stream for 1- and 2-bit input
             // 32-bit stores: a slot is a whole number of words, but with raw 64-bit input (slot_bytes = 1000) neither a
             // multiple of 16 bytes nor 16-byte aligned
             uint32_t* d = reinterpret_cast<uint32_t*>(p.compact + ifi * p.compact_stride + slot * (int64_t)p.slot_bytes);

@@ -101,8 +101,11 @@ class Plan:
         p.raw_format = cfg.raw_format
         if cfg.raw_word_bits:
             for i in range(nif):
+                b = list(cfg.raw_bits[i])
+                if len(b) == 2:                                   # 1-bit samples: (pol 0, pol 1) -> entries 0 and 2
+                    b = [b[0], b[0], b[1], b[1]]
                 for k in range(4):
-                    p.raw_bits[i][k] = int(cfg.raw_bits[i][k])
+                    p.raw_bits[i][k] = int(b[k])
         p.stream = cfg.stream
         p.decode_mode = cfg.decode_mode
         p.in8_offset_mode = cfg.in8_offset_mode

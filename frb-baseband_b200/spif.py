@@ -21,6 +21,7 @@ _RECIPES = {
              "[24,25,56,57][8,9,40,41][26,27,58,59][10,11,42,43][28,29,60,61][12,13,44,45][30,31,62,63][14,15,46,47]:0-15",
     (16, 2): "32>[16,17,24,25][0,1,8,9][18,19,26,27][2,3,10,11][20,21,28,29][4,5,12,13][22,23,30,31][6,7,14,15]:0-7",
     (8, 2): "16>[8,9,12,13][0,1,4,5][10,11,14,15][2,3,6,7]:0-3",
+    (16, 1): "16>[8,12][0,4][9,13][1,5][10,14][2,6][11,15][3,7]:0-7",        # 1-bit samples: (pol A, pol B) per IF, :58-61
 }
 #: the 1024 Mbps 16-BBC modes use the mirrored pairing (spif2file.sh:44-52)
 _RECIPE_16_1024 = "32>[24,25,16,17][8,9,0,1][26,27,18,19][10,11,2,3][28,29,20,21][12,13,4,5][30,31,22,23][14,15,6,7]:0-7"
@@ -45,8 +46,8 @@ def parse_recipe(recipe: str):
     if not m:
         raise ValueError(f"not a spif2file recipe: {recipe!r}")
     groups = [[int(x) for x in g.split(",")] for g in re.findall(r"\[([0-9,]+)\]", m.group(2))]
-    if any(len(g) != 4 for g in groups):
-        raise ValueError("only 2-bit dual-polarisation recipes (4 bits per IF) are supported")
+    if any(len(g) != len(groups[0]) for g in groups) or len(groups[0]) not in (2, 4):
+        raise ValueError("only dual-polarisation recipes with 1-bit (2 bits per IF) or 2-bit samples (4 bits per IF) are supported")
     if swap:
         groups = [[b ^ 1 for b in g] for g in groups]
     return int(m.group(1)), groups
@@ -64,7 +65,8 @@ def frame_geometry(mode: str):
 
 
 def recipe_for_mode(mode: str, nif: int, flip_if: bool = False):
-    """(word_bits, bits per IF 1..nif) for a base2fil mode string; flip_if swaps neighbouring IFs."""
+    """(word_bits, bits per IF 1..nif) for a base2fil mode string; flip_if swaps neighbouring IFs.  Two bits per IF
+    mean 1-bit samples (in_nbit = 1), four mean 2-bit samples."""
     m5 = re.match(r"MARK5B-(\d+)-(\d+)-(\d+)$", mode)
     if m5:                                                          # spif2file.sh:79-93
         rate, nbbc, nbits = (int(x) for x in m5.groups())

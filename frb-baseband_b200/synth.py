@@ -68,6 +68,8 @@ def make_vdif(nframes: int, *, seed: int, bw_mhz: float = 32.0, nbit: int = 2,
     elif nbit == 8:
         q = np.clip(np.floor(x * 20.0 + 128.0), 0, 255).astype(np.uint8)   # sigma = 20 counts
         payload = np.ascontiguousarray(q.T).reshape(-1)
+    elif nbit == 1:                                                         # sign bits, ch0 / ch1 interleaved from bit 0 up
+        payload = np.packbits(np.ascontiguousarray((x > 0).T).reshape(-1), bitorder="little")
     else:
         raise ValueError(nbit)
     payload = payload.reshape(nframes, payload_bytes)
@@ -97,7 +99,8 @@ def if_file_name(exp: str, st: str, scan: str, i: int) -> str:
     return f"{exp}_{st}_no0{scan}_IF{i}.vdif"
 
 
-def make_raw_mark5b(codes: np.ndarray, word_bits: int, bits, *, bw_mhz: float, mjd: int = 60000, sec0: int = 0) -> np.ndarray:
+def make_raw_mark5b(codes: np.ndarray, word_bits: int, bits, *, bw_mhz: float, mjd: int = 60000, sec0: int = 0,
+                    frame0: int = 0) -> np.ndarray:
     """Raw multi-BBC Mark5B stream: like make_raw_vdif with 16-byte Mark5B headers and 10000-byte payloads.  `bits` are the
     source bits in the recorded word, i.e. what spif.parse_recipe returns for a swap_sign_mag recipe."""
     nif, _, nsamp = codes.shape
@@ -111,7 +114,7 @@ def make_raw_mark5b(codes: np.ndarray, word_bits: int, bits, *, bw_mhz: float, m
     spf = pb * 8 // word_bits
     nframes = nsamp // spf
     fps = int(round(2 * abs(bw_mhz) * 1e6 / spf))
-    hdr = vdif.make_mark5b_headers(nframes, frames_per_sec=fps, mjd=mjd, sec0=sec0)
+    hdr = vdif.make_mark5b_headers(nframes, frames_per_sec=fps, mjd=mjd, sec0=sec0, frame0=frame0)
     out = np.empty((nframes, hb + pb), dtype=np.uint8)
     out[:, :hb] = hdr.view(np.uint8).reshape(nframes, hb)
     out[:, hb:] = w[: nframes * spf].view(np.uint8).reshape(nframes, pb)
@@ -126,16 +129,16 @@ def make_raw_vdif(codes: np.ndarray, word_bits: int, bits, *, bw_mhz: float, pay
     nif, _, nsamp = codes.shape
     dt = {16: np.uint16, 32: np.uint32, 64: np.uint64}[word_bits]
     w = np.zeros(nsamp, dtype=dt)
+    sample_bits = len(bits[0]) // 2                 # two recipe entries per IF: 1-bit samples, codes in 0..1
     for i in range(nif):
-        nib = (codes[i, 0].astype(np.uint64) | (codes[i, 1].astype(np.uint64) << np.uint64(2)))
-        for k in range(4):
+        nib = (codes[i, 0].astype(np.uint64) | (codes[i, 1].astype(np.uint64) << np.uint64(sample_bits)))
+        for k in range(2 * sample_bits):
             w |= (((nib >> np.uint64(k)) & np.uint64(1)) << np.uint64(bits[i][k])).astype(dt)
     spf = payload_bytes * 8 // word_bits
     nframes = nsamp // spf
     fps = int(round(2 * abs(bw_mhz) * 1e6 / spf))
-    nbbc = 2 * nif
-    hdr = vdif.make_headers(nframes, frames_per_sec=fps, payload_bytes=payload_bytes, nbit=2,
-                            log2_nchan=int(np.log2(max(1, word_bits // 2))), ref_epoch=ref_epoch, sec0=sec0)
+    hdr = vdif.make_headers(nframes, frames_per_sec=fps, payload_bytes=payload_bytes, nbit=sample_bits,
+                            log2_nchan=int(np.log2(max(1, word_bits // sample_bits))), ref_epoch=ref_epoch, sec0=sec0)
     out = np.empty((nframes, vdif.HEADER_BYTES + payload_bytes), dtype=np.uint8)
     out[:, : vdif.HEADER_BYTES] = hdr.view(np.uint8).reshape(nframes, vdif.HEADER_BYTES)
     out[:, vdif.HEADER_BYTES:] = w[: nframes * spf].view(np.uint8).reshape(nframes, payload_bytes)

@@ -131,6 +131,12 @@ def decode_vdif(buf: np.ndarray, *, nbit: int = 2, header_bytes: int = 32,
     elif nbit == 8:
         x = payload.astype(np.float64).reshape(nframes, pbytes // 2, 2) - offset8
         samp_per_word = 2
+    elif nbit == 1:
+        # what jive5ab writes for the 1-bit modes (/root/reference/spif2file.sh:58-61): bit 2t = ch0, bit 2t+1 = ch1 of time
+        # sample t; 0 -> -1.0, 1 -> +1.0
+        bits = np.unpackbits(np.ascontiguousarray(payload), axis=1, bitorder="little")     # [nframes, pbytes * 8]
+        x = 2.0 * bits.reshape(nframes, pbytes * 4, 2).astype(np.float64) - 1.0
+        samp_per_word = 16
     else:
         raise ValueError(f"unsupported VDIF nbit={nbit}")
     if mask_invalid:
@@ -422,9 +428,13 @@ def corner_turn(raw: np.ndarray, word_bits: int, bits, *, frame_bytes: int = 803
     bad = bad | invalid[:, None]
     out = np.empty((len(bits), 2, w.size), dtype=np.float64)
     for i, b in enumerate(bits):
-        c0 = ((w >> np.uint64(b[0])) & np.uint64(1)) | (((w >> np.uint64(b[1])) & np.uint64(1)) << np.uint64(1))
-        c1 = ((w >> np.uint64(b[2])) & np.uint64(1)) | (((w >> np.uint64(b[3])) & np.uint64(1)) << np.uint64(1))
-        x0, x1 = LEVELS_2BIT[c0.astype(np.int64)], LEVELS_2BIT[c1.astype(np.int64)]
+        if len(b) == 2:                                                  # 1-bit samples (spif2file.sh:58-61): 0 -> -1, 1 -> +1
+            x0 = 2.0 * ((w >> np.uint64(b[0])) & np.uint64(1)).astype(np.float64) - 1.0
+            x1 = 2.0 * ((w >> np.uint64(b[1])) & np.uint64(1)).astype(np.float64) - 1.0
+        else:
+            c0 = ((w >> np.uint64(b[0])) & np.uint64(1)) | (((w >> np.uint64(b[1])) & np.uint64(1)) << np.uint64(1))
+            c1 = ((w >> np.uint64(b[2])) & np.uint64(1)) | (((w >> np.uint64(b[3])) & np.uint64(1)) << np.uint64(1))
+            x0, x1 = LEVELS_2BIT[c0.astype(np.int64)], LEVELS_2BIT[c1.astype(np.int64)]
         if mask_invalid:
             x0 = np.where(bad, 0.0, x0)
             x1 = np.where(bad, 0.0, x1)

@@ -81,9 +81,12 @@ def test_mark5b_recipes_fold_swap_sign_mag():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode,nif,bw", [("MARK5B-1024-16-2", 8, 16.0), ("MARK5B-1024-8-2", 4, 32.0)])
-def test_gpu_mark5b_corner_turn(gpu, mode, nif, bw):
-    """Mark5B disk frames in, spliced filterbank out == oracle(swap_sign_mag -> recipe as written -> digifil per IF -> splice)."""
+@pytest.mark.parametrize("mode,nif,bw,by_header", [("MARK5B-1024-16-2", 8, 16.0, False), ("MARK5B-1024-8-2", 4, 32.0, False),
+                                                   ("MARK5B-2048-16-2", 8, 32.0, True)])
+def test_gpu_mark5b_corner_turn(gpu, mode, nif, bw, by_header):
+    """Mark5B disk frames in, spliced filterbank out == oracle(swap_sign_mag -> recipe as written -> digifil per IF -> splice).
+    by_header: 17 frames are missing from the recording and the push crosses a second boundary; frames are placed by the BCD
+    time code and the frame number within the second, the gap is zero-filled."""
     nchan, D, nfr = 32, 32, 1024
     W, bits = spif.recipe_for_mode(mode, nif)
     _, written = spif.recipe_for_mode({16: "VDIF_8000-2048-16-2", 8: "VDIF_8000-1024-8-2"}[2 * nif], nif)
@@ -91,20 +94,30 @@ def test_gpu_mark5b_corner_turn(gpu, mode, nif, bw):
     bws = [bw if i % 2 == 0 else -bw for i in range(1, nif + 1)]
     freqs = [1300.0 + (i - 1) * bw for i in range(1, nif + 1)]
     cfg = PlanConfig(nchan=nchan, bw_mhz=bws, freq_mhz=freqs, tscrunch=D, out_nbit=-32, keep_bandpass=True,
-                     raw_word_bits=W, raw_bits=bits, raw_format=fmt, frame_bytes=fb, header_bytes=hb)
+                     raw_word_bits=W, raw_bits=bits, raw_format=fmt, frame_bytes=fb, header_bytes=hb, frame_time_mode=int(by_header))
     spf = 10000 * 8 // W
+    fps = int(round(2 * bw * 1e6 / spf))
     rng = np.random.default_rng(19)
     codes = synth.quantise_2bit(rng.standard_normal((nif, 2, nfr * spf)) + 0.4 * np.cos(0.9 * np.arange(nfr * spf)))
-    raw = synth.make_raw_mark5b(codes, W, bits, bw_mhz=bw, sec0=100).reshape(nfr, fb)
+    raw = synth.make_raw_mark5b(codes, W, bits, bw_mhz=bw, sec0=86399, frame0=fps - 500).reshape(nfr, fb)   # crosses midnight too
     raw[5, 0] ^= 1                                                           # a frame without the sync word
     raw[7, 5] |= 0x80                                                        # a test-vector frame
     raw[9, hb + 400:hb + 440].view("<u4")[:] = 0x11223344                    # a run of fill words
+    sent = raw
+    if by_header:
+        lost = np.arange(600, 617)
+        filler = np.repeat(raw[:1], lost.size, axis=0)
+        filler[:, 8:12] = np.frombuffer(np.uint32(0x50000000).tobytes(), np.uint8)       # day 500: far outside the push -> dropped
+        sent = np.concatenate([np.delete(raw, lost, axis=0), filler])
+        raw[lost, 5] |= 0x80                                                 # oracle: the missing frames carry no data
     with Plan(cfg) as pl:
         assert int(pl.chunk_frames) >= nfr and int(pl.geometry.samples_per_frame) == spf
-        pl.push([raw.reshape(-1)])
+        pl.push([sent.reshape(-1)])
         rows = pl.view_rows(pl.pull())
         c = pl.counters()
-    assert c["frames_badhdr"] == 1 and c["frames_invalid"] == 1 and c["frames_with_fill"] == 1 and c["frames_ok"] == nfr - 3
+    assert c["frames_badhdr"] == 1 and c["frames_invalid"] == 1 and c["frames_with_fill"] == 1
+    assert c["frames_ok"] == nfr - 3 - (17 if by_header else 0) and c["slots_missing"] == (17 if by_header else 0)
+    assert c["frames_dropped"] == (17 if by_header else 0)
     x = o.corner_turn(raw.reshape(-1), W, written, frame_bytes=fb, header_bytes=hb, mark5b=True, swap_sign_mag=True)
     parts = []
     for i in sorted(range(nif), key=lambda k: -freqs[k]):
@@ -151,9 +164,23 @@ def test_gpu_mark5b_file_to_filterbank(gpu, tmp_path):
     assert np.array_equal(np.asarray(data).reshape(-1).view(np.uint8), rows.reshape(-1).view(np.uint8))
 
 
+def test_one_bit_recipe_and_oracle():
+    """VDIF_8000-1024-16-1 (spif2file.sh:58-61): 16 BBC channels of 1-bit samples, two recipe bits per IF."""
+    W, g = spif.recipe_for_mode("VDIF_8000-1024-16-1", 8)
+    assert W == 16 and g[0] == [8, 12] and g[7] == [3, 7] and sorted(b for grp in g for b in grp) == list(range(16))
+    _, f = spif.recipe_for_mode("VDIF_8000-1024-16-1", 8, flip_if=True)
+    assert f[0] == [0, 4] and f[1] == [8, 12]
+    rng = np.random.default_rng(8)
+    codes = rng.integers(0, 2, size=(8, 2, 2 * 4000), dtype=np.uint8)
+    raw = synth.make_raw_vdif(codes, W, g, bw_mhz=32.0)
+    assert raw.size == 2 * 8032 and (int(raw[15]) >> 2) & 31 == 0             # header: bits per sample - 1 = 0
+    x = o.corner_turn(raw, W, g)
+    assert np.array_equal(x, 2.0 * codes - 1.0)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("mode,nif,bw", [("VDIF_8000-2048-16-2", 8, 32.0), ("VDIF_8000-4096-32-2", 16, 32.0),
-                                         ("VDIF_8000-1024-8-2", 4, 32.0)])
+                                         ("VDIF_8000-1024-8-2", 4, 32.0), ("VDIF_8000-1024-16-1", 8, 32.0)])
 def test_gpu_corner_turn_equals_split_path(gpu, mode, nif, bw):
     """One raw stream in, spliced filterbank out == oracle(corner turn -> digifil per IF -> splice)."""
     nchan, D = 32, 32
@@ -161,12 +188,13 @@ def test_gpu_corner_turn_equals_split_path(gpu, mode, nif, bw):
     bws = [bw if i % 2 == 0 else -bw for i in range(1, nif + 1)]
     freqs = [1300.0 + (i - 1) * bw for i in range(1, nif + 1)]
     cfg = PlanConfig(nchan=nchan, bw_mhz=bws, freq_mhz=freqs, tscrunch=D, out_nbit=-32, keep_bandpass=True,
-                     raw_word_bits=W, raw_bits=bits, frame_bytes=8032)
+                     raw_word_bits=W, raw_bits=bits, frame_bytes=8032, in_nbit=len(bits[0]) // 2)
     with Plan(cfg) as pl:
         nfr = int(pl.chunk_frames)
         spf = 8000 * 8 // W
         rng = np.random.default_rng(17)
-        codes = synth.quantise_2bit(rng.standard_normal((nif, 2, nfr * spf)) + 0.4 * np.cos(0.9 * np.arange(nfr * spf)))
+        sig = rng.standard_normal((nif, 2, nfr * spf)) + 0.4 * np.cos(0.9 * np.arange(nfr * spf))
+        codes = synth.quantise_2bit(sig) if len(bits[0]) == 4 else (sig > 0).astype(np.uint8)
         raw = synth.make_raw_vdif(codes, W, bits, bw_mhz=bw).reshape(nfr, 8032)
         raw[5, 3] |= 0x80                                                    # an invalid frame
         raw[9, 32 + 400:32 + 440].view("<u4")[:] = 0x11223344                # a run of fill words

@@ -28,6 +28,47 @@ def test_decode_8bit_bit_exact(gpu):
     assert np.array_equal(x, o.decode_vdif(v, nbit=8).astype(np.float32))
 
 
+def test_decode_1bit_bit_exact(gpu):
+    """1-bit split streams (what jive5ab writes for VDIF_8000-1024-16-1, spif2file.sh:58-61): 0 -> -1.0, 1 -> +1.0."""
+    v = synth.make_vdif(64, seed=13, nbit=1, invalid_frac=0.05, fill_frac=0.05)
+    x, c = decode(v, in_nbit=1)
+    ref = o.decode_vdif(v, nbit=1).astype(np.float32)
+    assert x.shape == (2, 64 * 32000) and np.array_equal(x, ref)
+    assert set(np.unique(x)) == {-1.0, 0.0, 1.0} and c["frames_invalid"] > 0 and c["frames_with_fill"] > 0
+    v2 = synth.make_vdif(5, seed=14, nbit=1, payload_bytes=1000)     # payload not a multiple of 32: the scalar front end
+    x2, _ = decode(v2, in_nbit=1, frame_bytes=1032)
+    assert np.array_equal(x2, o.decode_vdif(v2, nbit=1).astype(np.float32))
+
+
+@pytest.mark.parametrize("nchan,D,nframes,chunk,dm", [(128, 16, 0, 0, 0.0), (512, 4, 170, 60, 0.0), (64, 16, 0, 0, 300.0)])
+def test_1bit_input(gpu, nchan, D, nframes, chunk, dm):
+    """1-bit VDIF through the tuned channeliser (one full push), the generic one (nchan 512, carried samples) and the
+    dedispersion path: the front end turns the sign bits into the same index-byte stream the 2-bit decode uses."""
+    bw, fc = 32.0, 1400.0
+    cfg = PlanConfig(nchan=nchan, bw_mhz=[-bw], freq_mhz=[fc], tscrunch=D, in_nbit=1, out_nbit=-32, keep_bandpass=True, chunk_units=chunk,
+                     dm=dm, coherent=dm > 0)
+    out = []
+    with Plan(cfg) as pl:
+        nf = (int(pl.geometry.nfilt_pos), int(pl.geometry.nfilt_neg))
+        cf, fb = int(pl.chunk_frames), cfg.frame_bytes
+        assert int(pl.geometry.samples_per_frame) == 32000
+        nframes = nframes or min(cf, 160)
+        v = synth.make_vdif(nframes, seed=181 + nchan, bw_mhz=bw, nbit=1, tone_frac=0.43, rho=0.2, invalid_frac=0.03, fill_frac=0.04)
+        for f0 in range(0, nframes, cf):
+            n = min(cf, nframes - f0)
+            pl.push([v[f0 * fb:(f0 + n) * fb]])
+            out.append(pl.pull().copy())
+        pl.flush()
+        out.append(pl.pull().copy())
+        rows = pl.view_rows(np.concatenate(out))
+        c = pl.counters()
+    assert c["frames_invalid"] > 0 and c["frames_with_fill"] > 0
+    ref = o.digifil(v, freq_mhz=fc, bw_mhz=-bw, nchan=nchan, tscrunch_factor=D, in_nbit=1, out_nbit=-32, keep_bandpass=True,
+                    dm=dm, coherent=dm > 0, nfilt=nf)["data"]
+    assert rows.shape[0] == ref.shape[0] and ref.shape[0] > 0
+    assert_rel(rows.reshape(ref.shape), ref.astype(np.float64), REL_TOL, f"1-bit input nchan {nchan}")
+
+
 def test_column_pass_stages(gpu):
     """Intermediates of one push against the NumPy model of the same decomposition."""
     nchan, bw = 32, 16.0
@@ -211,7 +252,8 @@ def test_8bit_input_generic(gpu, nchan, freq_res, D, nframes, chunk):
     code decodes to 0.0, so the word masks of invalid frames and fill words travel with the carried samples."""
     bw = 32.0
     L = freq_res or (512 if nchan <= 128 else 2 * nchan)
-    v = synth.make_vdif(nframes, seed=171 + nchan, bw_mhz=bw, nbit=8, tone_frac=0.43, rho=0.2, invalid_frac=0.01, fill_frac=0.02)
+    v = synth.make_vdif(nframes, seed=171 + nchan, bw_mhz=bw, nbit=8, tone_frac=0.43, rho=0.2, invalid_frac=max(0.01, 6.0 / nframes),
+                        fill_frac=max(0.02, 6.0 / nframes))
     cfg = PlanConfig(nchan=nchan, bw_mhz=[bw], freq_res=freq_res, tscrunch=D, in_nbit=8, out_nbit=-32, keep_bandpass=True, chunk_units=chunk)
     out = []
     with Plan(cfg) as pl:
