@@ -782,7 +782,8 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
     if (prm->reserved0) return fail(B2F_EINVAL, "reserved0 must be 0");
     if (prm->raw_format != B2F_RAW_VDIF && prm->raw_format != B2F_RAW_MARK5B) return fail(B2F_EINVAL, "raw_format");
     if (W && prm->raw_format == B2F_RAW_MARK5B && prm->header_bytes != 16) return fail(B2F_EINVAL, "Mark5B frames have a 16-byte header");
-    if (W && (prm->frame_bytes % 16 || payload % (W / 2))) return fail(B2F_EUNSUPPORTED, "raw frame size");
+    // whole groups of 4 words per payload; 64-bit words may end on a group of 2 (Mark5B: 1250 words in 10000 bytes)
+    if (W && (prm->frame_bytes % 16 || payload % (W == 64 ? 16 : W / 2))) return fail(B2F_EUNSUPPORTED, "raw frame size");
     if (W) for (int i = 0; i < prm->nif; ++i) for (int k = 0; k < 4; ++k)
         if (prm->raw_bits[i][k] >= W) return fail(B2F_EINVAL, "raw_bits entry outside the word");
     const int64_t spf = W ? (int64_t)payload * 8 / W : (int64_t)payload * 8 / (prm->in_nbit * 2);

@@ -351,6 +351,9 @@ __global__ void __launch_bounds__(kK0Threads) k0r_corner_turn(const K0RParams p)
     constexpr int SPW = WBITS == 16 ? 2 : 1;                  // time samples per 32-bit payload unit (16-bit words: 2)
     const bool one_bit = p.sample_bits == 1;
     const int nquads = p.slot_bytes / 4;                      // groups of 4 consecutive time samples per frame
+    // Mark5B payloads of 64-bit words hold 1250 samples: a last group of 2, and slots that start on odd 16-bit boundaries
+    const bool half = WBITS == 64 && (p.slot_bytes & 2) != 0;
+    const int ngroups = nquads + (half ? 1 : 0);
     unsigned long long c_ok = 0, c_inv = 0, c_fillf = 0, c_drop = 0, c_mis = 0, c_bad = 0;
     int it = 0;
     for (int64_t f = blockIdx.x; f < p.nframes; f += gridDim.x, ++it) {
@@ -375,7 +378,8 @@ __global__ void __launch_bounds__(kK0Threads) k0r_corner_turn(const K0RParams p)
         unsigned nfill = 0;
         if (in_range) {
             const uint8_t* pay = buf + p.header_bytes;
-            for (int g = tid; g < nquads; g += kK0Threads) {
+            for (int g = tid; g < ngroups; g += kK0Threads) {
+                const int ns = (half && g == nquads) ? 2 : 4;           // samples in this group
                 WORD w[4];
                 bool masked[4];
                 if (WBITS == 16) {
@@ -392,6 +396,11 @@ __global__ void __launch_bounds__(kK0Threads) k0r_corner_turn(const K0RParams p)
                 } else {
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {
+                        if (2 * k >= ns) {                               // beyond the payload
+                            w[2 * k] = w[2 * k + 1] = 0;
+                            masked[2 * k] = masked[2 * k + 1] = false;
+                            continue;
+                        }
                         const uint4 v = *reinterpret_cast<const uint4*>(pay + 32 * g + 16 * k);
                         w[2 * k] = (WORD)v.x | ((WORD)v.y << 32);
                         w[2 * k + 1] = (WORD)v.z | ((WORD)v.w << 32);
@@ -411,7 +420,13 @@ __global__ void __launch_bounds__(kK0Threads) k0r_corner_turn(const K0RParams p)
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         o |= (masked[k] ? 0x80u : one_bit ? gather_1bit_index<WORD>(w[k], p.bit[i]) : gather_nibble_index<WORD>(w[k], p.bit[i])) << (8 * k);
-                    *reinterpret_cast<uint32_t*>(p.compact + i * p.compact_stride + slot * (int64_t)p.slot_bytes + 4 * g) = o;
+                    uint8_t* d = p.compact + i * p.compact_stride + slot * (int64_t)p.slot_bytes + 4 * g;
+                    if (half) {
+                        reinterpret_cast<uint16_t*>(d)[0] = (uint16_t)(o & 0xFFFFu);
+                        if (ns == 4) reinterpret_cast<uint16_t*>(d)[1] = (uint16_t)(o >> 16);
+                    } else {
+                        *reinterpret_cast<uint32_t*>(d) = o;
+                    }
                 }
             }
         }
@@ -469,8 +484,14 @@ static __global__ void k0b_finish_slots(const K0bParams p) {
         if (p.in_nbit != 8) {                                   // masking lives in the index stream for 1- and 2-bit input
             // 32-bit stores: a slot is a whole number of words, but with raw 64-bit input (slot_bytes = 1000) neither a
             // multiple of 16 bytes nor 16-byte aligned
-            uint32_t* d = reinterpret_cast<uint32_t*>(p.compact + ifi * p.compact_stride + slot * (int64_t)p.slot_bytes);
-            for (int k = 0; k < p.slot_bytes / 4; ++k) d[k] = 0x80808080u;
+            uint8_t* d8 = p.compact + ifi * p.compact_stride + slot * (int64_t)p.slot_bytes;
+            if (p.slot_bytes & 2) {                              // Mark5B, 64-bit words: 1250 samples per frame
+                uint16_t* d = reinterpret_cast<uint16_t*>(d8);
+                for (int k = 0; k < p.slot_bytes / 2; ++k) d[k] = 0x8080u;
+            } else {
+                uint32_t* d = reinterpret_cast<uint32_t*>(d8);
+                for (int k = 0; k < p.slot_bytes / 4; ++k) d[k] = 0x80808080u;
+            }
         }
         atomicAdd(&p.counters[C_MISSING], 1ull);
     }

@@ -72,9 +72,6 @@ def recipe_for_mode(mode: str, nif: int, flip_if: bool = False):
         rate, nbbc, nbits = (int(x) for x in m5.groups())
         if (rate, nbbc, nbits) not in ((1024, 16, 2), (1024, 8, 2), (2048, 16, 2), (2048, 32, 2)):
             raise ValueError(f"mode {mode} not implemented")
-        if nbbc == 32:
-            # 10000-byte payloads hold 1250 64-bit words: not a whole number of the 4-sample groups the kernel writes
-            raise ValueError(f"mode {mode}: Mark5B with 64-bit words is not implemented")
         W, groups = parse_recipe("swap_sign_mag+" + _RECIPES[(nbbc, nbits)])
         return W, _flip(groups[:nif], flip_if)
     m = re.match(r"VDIF_(\d+)-(\d+)-(\d+)-(\d+)$", mode)

@@ -104,7 +104,7 @@ def make_raw_mark5b(codes: np.ndarray, word_bits: int, bits, *, bw_mhz: float, m
     """Raw multi-BBC Mark5B stream: like make_raw_vdif with 16-byte Mark5B headers and 10000-byte payloads.  `bits` are the
     source bits in the recorded word, i.e. what spif.parse_recipe returns for a swap_sign_mag recipe."""
     nif, _, nsamp = codes.shape
-    dt = {16: np.uint16, 32: np.uint32}[word_bits]
+    dt = {16: np.uint16, 32: np.uint32, 64: np.uint64}[word_bits]
     w = np.zeros(nsamp, dtype=dt)
     for i in range(nif):
         nib = (codes[i, 0].astype(np.uint64) | (codes[i, 1].astype(np.uint64) << np.uint64(2)))

@@ -58,8 +58,8 @@ def test_mark5b_recipes_fold_swap_sign_mag():
     assert spif.frame_geometry("VDIF_8000-2048-16-2") == (8032, 32, 0) and spif.frame_geometry("VDIF_1000-1024-16-2")[0] == 1032
     _, f = spif.recipe_for_mode("MARK5B-2048-16-2", 8, flip_if=True)
     assert f[0] == g[1] and f[1] == g[0]
-    with pytest.raises(ValueError):
-        spif.recipe_for_mode("MARK5B-2048-32-2", 16)                          # 64-bit words: stated as not implemented
+    W64, g64 = spif.recipe_for_mode("MARK5B-2048-32-2", 16)                   # :91-93
+    assert W64 == 64 and g64[0] == [17, 16, 49, 48] and sorted(b for grp in g64 for b in grp) == list(range(64))
     with pytest.raises(ValueError):
         spif.recipe_for_mode("MARK5B-512-16-2", 8)
     rng = np.random.default_rng(6)
@@ -82,14 +82,15 @@ def test_mark5b_recipes_fold_swap_sign_mag():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("mode,nif,bw,by_header", [("MARK5B-1024-16-2", 8, 16.0, False), ("MARK5B-1024-8-2", 4, 32.0, False),
-                                                   ("MARK5B-2048-16-2", 8, 32.0, True)])
+                                                   ("MARK5B-2048-16-2", 8, 32.0, True), ("MARK5B-2048-32-2", 16, 16.0, False),
+                                                   ("MARK5B-2048-32-2", 16, 16.0, True)])
 def test_gpu_mark5b_corner_turn(gpu, mode, nif, bw, by_header):
     """Mark5B disk frames in, spliced filterbank out == oracle(swap_sign_mag -> recipe as written -> digifil per IF -> splice).
     by_header: 17 frames are missing from the recording and the push crosses a second boundary; frames are placed by the BCD
     time code and the frame number within the second, the gap is zero-filled."""
     nchan, D, nfr = 32, 32, 1024
     W, bits = spif.recipe_for_mode(mode, nif)
-    _, written = spif.recipe_for_mode({16: "VDIF_8000-2048-16-2", 8: "VDIF_8000-1024-8-2"}[2 * nif], nif)
+    _, written = spif.recipe_for_mode({32: "VDIF_8000-4096-32-2", 16: "VDIF_8000-2048-16-2", 8: "VDIF_8000-1024-8-2"}[2 * nif], nif)
     fb, hb, fmt = spif.frame_geometry(mode)
     bws = [bw if i % 2 == 0 else -bw for i in range(1, nif + 1)]
     freqs = [1300.0 + (i - 1) * bw for i in range(1, nif + 1)]
@@ -116,7 +117,7 @@ def test_gpu_mark5b_corner_turn(gpu, mode, nif, bw, by_header):
         rows = pl.view_rows(pl.pull())
         c = pl.counters()
     assert c["frames_badhdr"] == 1 and c["frames_invalid"] == 1 and c["frames_with_fill"] == 1
-    assert c["frames_ok"] == nfr - 3 - (17 if by_header else 0) and c["slots_missing"] == (17 if by_header else 0)
+    assert c["frames_ok"] == nfr - 3 - (17 if by_header else 0) and c["slots_missing"] == (17 * nif if by_header else 0)      # counted per IF stream
     assert c["frames_dropped"] == (17 if by_header else 0)
     x = o.corner_turn(raw.reshape(-1), W, written, frame_bytes=fb, header_bytes=hb, mark5b=True, swap_sign_mag=True)
     parts = []
