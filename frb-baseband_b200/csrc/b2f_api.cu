@@ -380,6 +380,7 @@ int push_dedisp(b2f_plan* pl, int64_t nblk, int64_t T) {
         kg.compact = pl->d_compact; kg.compact_stride = pl->compact_stride;
         kg.wmask = pl->d_wmask; kg.wmask_stride = pl->wmask_stride; kg.blkdirty = pl->d_blkdirty;
         kg.in8_offset = pl->prm.in8_offset_mode ? 128.0f : 127.5f;
+        kg.step = pl->step;
         const int nbit = pl->prm.in_nbit;
         kg.inter = pl->d_inter; kg.colsum = pl->d_colsum; kg.eps = pl->d_eps;
         kg.tw_col = pl->d_tw_col; kg.tw_row = pl->d_tw_row;
@@ -394,8 +395,22 @@ int push_dedisp(b2f_plan* pl, int64_t nblk, int64_t T) {
         if (!pl->kgt_lg) {
             CU(cudaFuncSetAttribute(kg_column_pass<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_col));
             CU(cudaFuncSetAttribute(kg_column_pass<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_col));
+        }
+        if (!pl->kgt_lg || pl->dedisp) {
             CU(cudaFuncSetAttribute(kg_row_pass<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row));
             CU(cudaFuncSetAttribute(kg_row_pass<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row));
+        }
+        // dedispersion behind the generic kernels (kx_dedisp_generic): the row pass leaves un-detected channel samples
+        KXParams kx{};
+        size_t smem_kx = 0;
+        if (pl->dedisp) {
+            kx.volt = pl->d_spec; kx.chirp = pl->d_chirp;
+            kx.F = kg.F; kx.F_if_stride = kg.F_if_stride; kx.row0 = kg.row0;
+            kx.L = pl->L; kx.lgL = kg.lgL; kx.N = pl->N; kx.CH = std::max(1, std::min(4, 8192 / pl->L));
+            kx.nblk = (int)nblk; kx.nif = nif; kx.D = pl->D; kx.mode = pl->prm.pol_mode;
+            kx.nfilt_pos = pl->nfilt_pos; kx.keep = pl->keep;
+            smem_kx = ((size_t)pl->L / 2 + (size_t)kx.CH * 2 * pl->L) * sizeof(float2);
+            CU(cudaFuncSetAttribute(kx_dedisp_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kx));
         }
         if (pl->R * sizeof(float2) > 48 * 1024)
             CU(cudaFuncSetAttribute(ke_eps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(pl->R * sizeof(float2))));
@@ -422,7 +437,14 @@ int push_dedisp(b2f_plan* pl, int64_t nblk, int64_t T) {
             });
             if (rc) return rc;
             rc = timed(pl, B2F_K_ROW, [&] {
-                if (pl->kgt_lg) {
+                if (pl->dedisp) {
+                    KGParams kv = kg;
+                    kv.mode = kModeVolt; kv.D = 1; kv.volt = pl->d_spec;
+                    const int64_t nunits = nb * (pl->L / RB);
+                    const unsigned grid = (unsigned)std::min<int64_t>(nunits, (int64_t)pl->num_sms * 2);
+                    if (pl->N > 1024) kg_row_pass<8><<<grid, 256, smem_row, pl->stream>>>(kv);
+                    else kg_row_pass<4><<<grid, 256, smem_row, pl->stream>>>(kv);
+                } else if (pl->kgt_lg) {
                     const int64_t nunits = nb * (pl->L / std::max(pl->D, pl->kgt_rb));
                     le = b2f_launch_kgt_row(pl->kgt_lg, pl->prm.pol_mode, kg, (int)std::min<int64_t>(nunits, (int64_t)pl->kgt_row_ctas * pl->num_sms),
                                             pl->stream, nullptr);
@@ -434,6 +456,14 @@ int push_dedisp(b2f_plan* pl, int64_t nblk, int64_t T) {
             });
             if (rc) return rc;
             if (le != cudaSuccess) return fail(B2F_ECUDA, std::string("generic row pass: ") + cudaGetErrorString(le));
+            if (pl->dedisp) {
+                kx.gb_begin = b0; kx.gb_end = b0 + nb;
+                const int64_t work = nb * (pl->N / kx.CH);
+                rc = timed(pl, B2F_K_DEDISP, [&] {
+                    kx_dedisp_generic<<<(unsigned)std::min<int64_t>(work, (int64_t)pl->num_sms), 256, smem_kx, pl->stream>>>(kx);
+                });
+                if (rc) return rc;
+            }
         }
     } else if (nblk > 0) {
         const int64_t cap = pl->batch_blocks > 0 ? pl->batch_blocks : (int64_t)nif * pl->chunk_blocks;
@@ -746,9 +776,31 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
         return fail(B2F_EINVAL, "nbit not in supported values of [2, 8, 16, -32]");
     if (!(prm->in_nbit == 1 || prm->in_nbit == 2 || prm->in_nbit == 8)) return fail(B2F_EUNSUPPORTED, "VDIF bits/sample must be 1, 2 or 8");
     if (prm->nchan < 1) return fail(B2F_EINVAL, "nchan");
-    const int L = prm->freq_res > 0 ? prm->freq_res : (prm->nchan <= 128 ? 512 : 2 * prm->nchan);
+    int L = prm->freq_res > 0 ? prm->freq_res : (prm->nchan <= 128 ? 512 : 2 * prm->nchan);
     const int R = 2 * prm->nchan;
     if (!is_pow2(R) || R < 16 || R > 8192) return fail(B2F_EUNSUPPORTED, "nchan must be a power of two in 8..4096");
+    const bool dedisp = prm->coherent && prm->dm > 0.0;
+    // overlap-save samples discarded at each end of a block and channel: half the smearing across the lowest channel of
+    // the lowest subband (8.3 us DM dnu/nu_GHz^3, the rule of submit_job.py:62) plus 10 %, rounded up to a multiple of the
+    // integration factor so that every block yields whole output samples
+    auto nfilt_half = [&](int Dint) {
+        const double bw0 = std::fabs(prm->bw_mhz[0]);
+        double fmin = 1e30;
+        for (int i = 0; i < prm->nif; ++i) fmin = std::min(fmin, prm->freq_mhz[i] - bw0 / 2 + bw0 / prm->nchan / 2);
+        const double ns = 8.3 * prm->dm * (bw0 / prm->nchan) / std::pow(fmin / 1000.0, 3) / ((double)prm->nchan / bw0);
+        int nf = (int)std::ceil(0.55 * ns);
+        nf = (nf + Dint - 1) / Dint * Dint;
+        return nf < Dint ? Dint : nf;
+    };
+    if (dedisp && prm->freq_res <= 0 && std::fabs(prm->bw_mhz[0]) > 0 && prm->nif >= 1 && prm->nif <= B2F_MAX_IF) {
+        // digifil -F nchan:D lets the dedispersion kernel choose the transform length (the next power of two
+        // >= 4 nfilt, at least the reference rule's length).  The rule's length is kept whenever the smearing fits it.
+        int D0 = (prm->tscrunch < 1 ? 1 : prm->tscrunch) & -(prm->tscrunch < 1 ? 1 : prm->tscrunch);
+        while (D0 > 128) D0 >>= 1;
+        const int nf = nfilt_half(D0);
+        if (2 * nf >= L)
+            while (L < 8 * nf && L < 8192) L *= 2;
+    }
     if (!is_pow2(L) || L < 16 || L > 8192) return fail(B2F_EUNSUPPORTED, "freq_res must be a power of two in 16..8192");
     if ((R > 4096 || L > 4096) && L != R)
         return fail(B2F_EUNSUPPORTED, "nchan 4096 needs freq_res = 2 nchan (digifil -F nchan:2*nchan, process_vdif.py:162)");
@@ -762,10 +814,10 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
     if (prm->header_bytes != 32 && prm->header_bytes != 16) return fail(B2F_EINVAL, "header_bytes must be 32 or 16");
     const int payload = prm->frame_bytes - prm->header_bytes;
     if (payload <= 0 || payload % 8) return fail(B2F_EINVAL, "frame_bytes");
-    const bool dedisp = prm->coherent && prm->dm > 0.0;
     if ((dedisp || generic) && prm->in_nbit == 8 && payload % 32)
         return fail(B2F_EUNSUPPORTED, "8-bit input with coherent dedispersion, freq_res != 512 or nchan > 256 needs a payload that is a multiple of 32 bytes");
-    if (dedisp && generic) return fail(B2F_EUNSUPPORTED, "coherent dedispersion needs freq_res 512 and nchan <= 256 in this build");
+    if (dedisp && generic && (R > 4096 || L > 4096))
+        return fail(B2F_EUNSUPPORTED, "coherent dedispersion needs nchan <= 2048 and freq_res <= 4096 in this build");
     const double abw = std::fabs(prm->bw_mhz[0]);
     if (abw <= 0) return fail(B2F_EINVAL, "bw_mhz");
     for (int i = 0; i < prm->nif; ++i) {
@@ -822,14 +874,8 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
         // smearing across the lowest channel of the lowest subband (8.3 us DM dnu/nu_GHz^3, the rule of
         // submit_job.py:62), half of it on each side plus 10 %, rounded up to a multiple of tscrunch so
         // that every block yields whole output samples
-        double fmin = 1e30;
-        for (int i = 0; i < prm->nif; ++i) fmin = std::min(fmin, prm->freq_mhz[i] - abw / 2 + abw / prm->nchan / 2);
-        const double chbw = abw / prm->nchan;
-        const double ns = 8.3 * prm->dm * chbw / std::pow(fmin / 1000.0, 3) / ((double)prm->nchan / abw);
-        int nf = (int)std::ceil(0.55 * ns);
-        nf = (nf + D - 1) / D * D;
-        if (nf < D) nf = D;
-        if (2 * nf >= L) { delete pl; return fail(B2F_EUNSUPPORTED, "dispersion smearing exceeds half of freq_res = 512 channel samples"); }
+        const int nf = nfilt_half(D);
+        if (2 * nf >= L) { delete pl; return fail(B2F_EUNSUPPORTED, "dispersion smearing exceeds freq_res channel samples (freq_res up to 4096)"); }
         pl->nfilt_pos = pl->nfilt_neg = nf;
         pl->keep = L - 2 * nf;
         pl->step = (int64_t)pl->keep * R;
@@ -860,7 +906,7 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
     }
     pl->chunk_frames = pl->unit_frames * cu;
     pl->chunk_blocks = pl->unit_blocks * cu;
-    if (generic) pl->chunk_blocks = pl->chunk_frames * pl->spf / pl->M;
+    if (generic) pl->chunk_blocks = pl->chunk_frames * pl->spf / pl->step;
     if (pl->carry_mode) pl->chunk_blocks += 1;                 // carried samples can complete one more block
     pl->chunk_rows = pl->chunk_blocks * pl->keep / D;
     if (tsq > 1) pl->chunk_rows = pl->chunk_rows / tsq + 1;       // a push can complete one more output sample than its share

@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(KGT<LG>::kColThreads, KGT<LG>::kColCtas) kgt_c
         const int ifi = (int)(gb / p.nblk);
         const int64_t blk = gb - (int64_t)ifi * p.nblk;
         constexpr int BPS = NBIT == 8 ? 2 : 1;                            // stream bytes per time sample
-        const int64_t off = ((blk << (2 * LG)) + (int64_t)strip * C) * BPS;
+        const int64_t off = (blk * p.step + (int64_t)strip * C) * BPS;           // step = M without overlap-save
         const uint8_t* src = p.compact + ifi * p.compact_stride + off;
         const KG8 s8{p.wmask + ifi * p.wmask_stride, off, p.in8_offset, NBIT == 8 && p.blkdirty[gb] != 0};
         float2* dst = p.inter + (lb << (2 * LG)) + strip * C;

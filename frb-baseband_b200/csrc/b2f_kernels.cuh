@@ -1543,7 +1543,11 @@ struct KGParams {
     const uint8_t* wmask; size_t wmask_stride;
     const uint8_t* blkdirty;
     float in8_offset;
+    int64_t step;                // samples between the starts of consecutive blocks (M, or less with overlap-save)
+    float2* volt;                // mode kModeVolt: [gb - gb_begin][L][2][R/2] un-detected channel samples (P, Q)
 };
+// kg_row_pass mode: no detection, the two polarisations of every channel sample go to KGParams::volt (dedispersion)
+constexpr int kModeVolt = 101;
 
 // One 32-bit word of an 8-bit stream = two time samples x (pol 0, pol 1).  `o` = byte offset of the word from s.byte0,
 // which in turn counts from the start of the IF's de-framed stream of this push (carried samples included).
@@ -1814,7 +1818,7 @@ static __global__ void __launch_bounds__(256, 2) kg_column_pass(const KGParams p
         const int strip = (int)(w % nstrips);
         const int ifi = (int)(gb / p.nblk);
         const int64_t blk = gb % p.nblk;
-        const int64_t off = (blk * p.M + (int64_t)strip * C) * (NBIT == 8 ? 2 : 1);
+        const int64_t off = (blk * p.step + (int64_t)strip * C) * (NBIT == 8 ? 2 : 1);
         const uint8_t* src = p.compact + ifi * p.compact_stride + off;
         const KG8 s8{p.wmask + ifi * p.wmask_stride, off, p.in8_offset, NBIT == 8 && p.blkdirty[gb] != 0};
         float2* dst = p.inter + lb * (int64_t)L * R + strip * C;
@@ -1948,6 +1952,12 @@ __global__ void __launch_bounds__(256, 2) kg_row_pass(const KGParams p) {
                         const float2 e = epsr[k];
                         const float2 bp = make_float2(b.x - e.x, -b.y - e.y);
                         const float2 P = cadd(a, bp), Q = csub(a, bp);
+                        if (p.mode == kModeVolt) {
+                            float2* v = p.volt + ((lb * (int64_t)L + (r0 + b0 + r)) * 2) * N;
+                            v[c] = P;
+                            v[N + c] = Q;
+                            continue;
+                        }
                         const float pp = 0.25f * (P.x * P.x + P.y * P.y), qq = 0.25f * (Q.x * Q.x + Q.y * Q.y);
                         const float xr = P.x * Q.x + P.y * Q.y, xi = P.y * Q.x - P.x * Q.y;
                         const float re = -0.25f * xi, im = 0.25f * xr;
@@ -1963,7 +1973,7 @@ __global__ void __launch_bounds__(256, 2) kg_row_pass(const KGParams p) {
                     }
                 }
                 const int rr = r0 + b0 + r;                  // row of the block
-                if (((rr + 1) & (D - 1)) == 0) {             // an output sample is complete
+                if (p.mode != kModeVolt && ((rr + 1) & (D - 1)) == 0) {             // an output sample is complete
                     const int64_t t = p.row0 + (blk * L + rr) / D;
                     float* dst = p.F + ifi * p.F_if_stride + t * (int64_t)(nprod * N);
 #pragma unroll
@@ -1981,6 +1991,111 @@ __global__ void __launch_bounds__(256, 2) kg_row_pass(const KGParams p) {
     }
     cp_async_wait<0>();
 }
+
+// ================================================================== dedispersion behind the generic channeliser
+// digifil -D dm -F nchan:D for the shapes the tuned 512-point path does not take (nchan > 256, or smearing that needs
+// freq_res > 512: SURVEY D5).  The generic column and row kernels run unchanged up to the detector and leave the channel
+// samples y_c[m], m = 0..L-1 of every overlap-save block in `volt` (kg_row_pass, mode kModeVolt).  Multiplying the L bins
+// of channel c by the chirp before the backward transform is the circular convolution of y_c with the chirp's impulse
+// response, so this kernel does FFT_L, * H[c][k] / L, IFFT_L per channel and polarisation, keeps the samples
+// [nfilt_pos, nfilt_pos + keep), detects and integrates D of them.  In-place radix-2 in shared memory: decimation in
+// frequency forward (output bit-reversed), the chirp is read at the bit-reversed index, decimation in time backward
+// (input bit-reversed, output in order) -- no reordering pass.  A fallback for rare shapes: two extra transforms per
+// channel and one more HBM round trip than the tuned path, not tuned further.
+struct KXParams {
+    const float2* volt;         // [gb - gb_begin][L][2][N]: (P, Q) = (2 yP, 2i yQ) as the detector takes them
+    const float2* chirp;        // [nif][L][N]  H[c][k] stored k-major
+    float* F; int64_t F_if_stride; int64_t row0;
+    int L, lgL, N, CH, nblk, nif, D, mode, nfilt_pos, keep;
+    int64_t gb_begin, gb_end;
+};
+#ifdef B2F_API_TU
+static __global__ void __launch_bounds__(256) kx_dedisp_generic(const KXParams p) {
+    extern __shared__ __align__(16) uint8_t kx_smem[];
+    const int tid = threadIdx.x, L = p.L, lgL = p.lgL, N = p.N, CH = p.CH, nseq = 2 * CH, H2 = L >> 1;
+    float2* tw = reinterpret_cast<float2*>(kx_smem);                // [L / 2]  W_L^t
+    float2* data = tw + H2;                                         // [CH][2][L]
+    for (int t = tid; t < H2; t += 256) {
+        float sn, cs;
+        sincospif(-(float)(2 * t) / (float)L, &sn, &cs);
+        tw[t] = make_float2(cs, sn);
+    }
+    __syncthreads();
+    const int ngroups = N / CH, nprod = nprod_of_mode(p.mode), nout = p.keep / p.D;
+    const float inv_l = 1.0f / (float)L;
+    const int64_t nwork = (p.gb_end - p.gb_begin) * ngroups;
+    for (int64_t w = blockIdx.x; w < nwork; w += gridDim.x) {
+        const int64_t lb = w / ngroups, gb = p.gb_begin + lb;
+        const int c0 = (int)(w % ngroups) * CH;
+        const int ifi = (int)(gb / p.nblk);
+        const int64_t blk = gb % p.nblk;
+        const float2* V = p.volt + lb * (int64_t)L * 2 * N;
+        for (int e = tid; e < L * nseq; e += 256) {                 // channel fastest: CH neighbouring float2 per access
+            const int ch = e % CH, pol = (e / CH) & 1, m = e / nseq;
+            data[(ch * 2 + pol) * L + m] = V[((int64_t)m * 2 + pol) * N + c0 + ch];
+        }
+        __syncthreads();
+        for (int lgh = lgL - 1; lgh >= 0; --lgh) {                  // forward, decimation in frequency
+            const int half = 1 << lgh;
+            for (int b = tid; b < nseq * H2; b += 256) {
+                const int seq = b >> (lgL - 1), i = b & (H2 - 1);
+                const int j = i & (half - 1), pos = ((i >> lgh) << (lgh + 1)) + j;
+                float2* x = data + seq * L;
+                const float2 u = x[pos], v = x[pos + half];
+                x[pos] = cadd(u, v);
+                x[pos + half] = cmul(csub(u, v), tw[j << (lgL - 1 - lgh)]);
+            }
+            __syncthreads();
+        }
+        const float2* H = p.chirp + (int64_t)ifi * L * N;
+        for (int e = tid; e < nseq * L; e += 256) {                 // bin k sits at the bit-reversed position
+            const int seq = e >> lgL, pos = e & (L - 1);
+            const int k = (int)(__brev((unsigned)pos) >> (32 - lgL));
+            const float2 h = H[(int64_t)k * N + c0 + (seq >> 1)];
+            const float2 y = cmul(data[e], h);
+            data[e] = make_float2(y.x * inv_l, y.y * inv_l);
+        }
+        __syncthreads();
+        for (int lgh = 0; lgh < lgL; ++lgh) {                       // backward, decimation in time
+            const int half = 1 << lgh;
+            for (int b = tid; b < nseq * H2; b += 256) {
+                const int seq = b >> (lgL - 1), i = b & (H2 - 1);
+                const int j = i & (half - 1), pos = ((i >> lgh) << (lgh + 1)) + j;
+                float2* x = data + seq * L;
+                const float2 u = x[pos], v = cmul_conj(x[pos + half], tw[j << (lgL - 1 - lgh)]);
+                x[pos] = cadd(u, v);
+                x[pos + half] = csub(u, v);
+            }
+            __syncthreads();
+        }
+        for (int o = tid; o < CH * nout; o += 256) {                // detect + integrate D samples
+            const int ch = o % CH, sidx = o / CH;
+            const float2* xp = data + (ch * 2) * L + p.nfilt_pos + sidx * p.D;
+            const float2* xq = xp + L;
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int d = 0; d < p.D; ++d) {
+                const float2 P = xp[d], Q = xq[d];
+                const float pp = 0.25f * (P.x * P.x + P.y * P.y), qq = 0.25f * (Q.x * Q.x + Q.y * Q.y);
+                const float xr = P.x * Q.x + P.y * Q.y, xi = P.y * Q.x - P.x * Q.y;
+                const float re = -0.25f * xi, im = 0.25f * xr;
+                switch (p.mode) {
+                    case B2F_POL_P0: acc[0] += pp; break;
+                    case B2F_POL_P1: acc[0] += qq; break;
+                    case B2F_POL_I: acc[0] += pp + qq; break;
+                    case B2F_POL_I2: acc[0] += (pp + qq) * (pp + qq); break;
+                    case B2F_POL_PPQQ: acc[0] += pp; acc[1] += qq; break;
+                    case B2F_POL_COHERENCE: acc[0] += pp; acc[1] += qq; acc[2] += re; acc[3] += im; break;
+                    default: acc[0] += pp + qq; acc[1] += 2.f * re; acc[2] += 2.f * im; acc[3] += pp - qq; break;
+                }
+            }
+            const int64_t t = p.row0 + blk * nout + sidx;
+            float* dst = p.F + ifi * p.F_if_stride + t * (int64_t)(nprod * N) + c0 + ch;
+            for (int q = 0; q < nprod; ++q) dst[q * N] = acc[q];
+        }
+        __syncthreads();
+    }
+}
+#endif
 
 // ================================================================== kernel 5a: statistics
 // mean / sigma per (IF, product, channel) over the first rescale interval, fp64 accumulators,
