@@ -25,6 +25,8 @@ CONFIGS = {
     "C5 (16 IF x 32 MHz = 4096 Mbps, nchan 128, D 16, 8-bit I, 10 s sample of the 3600 s scan)": dict(nif=16, bw=32.0, nchan=128, D=16, seconds=10.0),
     "generic (1 IF x 32 MHz, nchan 512 -> -F512:1024, D 4, 10 s)": dict(nif=1, bw=32.0, nchan=512, D=4, seconds=10.0),
     "generic policy (8 IF x 32 MHz, nchan 1024 -> -F1024:2048, D 2: submit_job.py at DM 560, 10 s)": dict(nif=8, bw=32.0, nchan=1024, D=2, seconds=10.0),
+    "C4g (C4 at DM 2000: freq_res 4096 chosen from the smearing, generic kernels + kx_dedisp_generic, 10 s)": dict(nif=8, bw=32.0, nchan=128, D=16, seconds=10.0, dm=2000.0),
+    "P1d (policy nchan 1024 -> -F1024:2048 with coherent dedispersion at DM 560, generic kernels + kx_dedisp_generic, 10 s)": dict(nif=8, bw=32.0, nchan=1024, D=2, seconds=10.0, dm=560.0),
 }
 only = sys.argv[1:] or None
 for name, c in CONFIGS.items():
