@@ -460,7 +460,7 @@ int push_dedisp(b2f_plan* pl, int64_t nblk, int64_t T) {
                 kx.gb_begin = b0; kx.gb_end = b0 + nb;
                 const int64_t work = nb * (pl->N / kx.CH);
                 rc = timed(pl, B2F_K_DEDISP, [&] {
-                    kx_dedisp_generic<<<(unsigned)std::min<int64_t>(work, (int64_t)pl->num_sms), 256, smem_kx, pl->stream>>>(kx);
+                    kx_dedisp_generic<<<(unsigned)std::min<int64_t>(work, (int64_t)pl->num_sms), kKXThreads, smem_kx, pl->stream>>>(kx);
                 });
                 if (rc) return rc;
             }

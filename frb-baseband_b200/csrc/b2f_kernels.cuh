@@ -2000,7 +2000,8 @@ __global__ void __launch_bounds__(256, 2) kg_row_pass(const KGParams p) {
 // response, so this kernel does FFT_L, * H[c][k] / L, IFFT_L per channel and polarisation, keeps the samples
 // [nfilt_pos, nfilt_pos + keep), detects and integrates D of them.  In-place radix-2 in shared memory: decimation in
 // frequency forward (output bit-reversed), the chirp is read at the bit-reversed index, decimation in time backward
-// (input bit-reversed, output in order) -- no reordering pass.  A fallback for rare shapes: two extra transforms per
+// (input bit-reversed, output in order) -- no reordering pass; two stages per pass over the data (points base +
+// {0, q, 2q, 3q} in registers).  A fallback for rare shapes: two extra transforms per
 // channel and one more HBM round trip than the tuned path, not tuned further.
 struct KXParams {
     const float2* volt;         // [gb - gb_begin][L][2][N]: (P, Q) = (2 yP, 2i yQ) as the detector takes them
@@ -2010,12 +2011,13 @@ struct KXParams {
     int64_t gb_begin, gb_end;
 };
 #ifdef B2F_API_TU
-static __global__ void __launch_bounds__(256) kx_dedisp_generic(const KXParams p) {
+constexpr int kKXThreads = 1024;              // one CTA per SM (up to 147 KiB of shared memory): 32 warps hide the shared-memory latency
+static __global__ void __launch_bounds__(kKXThreads) kx_dedisp_generic(const KXParams p) {
     extern __shared__ __align__(16) uint8_t kx_smem[];
-    const int tid = threadIdx.x, L = p.L, lgL = p.lgL, N = p.N, CH = p.CH, nseq = 2 * CH, H2 = L >> 1;
+    const int tid = threadIdx.x, NT = kKXThreads, L = p.L, lgL = p.lgL, N = p.N, CH = p.CH, nseq = 2 * CH, H2 = L >> 1, Q4 = L >> 2;
     float2* tw = reinterpret_cast<float2*>(kx_smem);                // [L / 2]  W_L^t
     float2* data = tw + H2;                                         // [CH][2][L]
-    for (int t = tid; t < H2; t += 256) {
+    for (int t = tid; t < H2; t += NT) {
         float sn, cs;
         sincospif(-(float)(2 * t) / (float)L, &sn, &cs);
         tw[t] = make_float2(cs, sn);
@@ -2024,31 +2026,52 @@ static __global__ void __launch_bounds__(256) kx_dedisp_generic(const KXParams p
     const int ngroups = N / CH, nprod = nprod_of_mode(p.mode), nout = p.keep / p.D;
     const float inv_l = 1.0f / (float)L;
     const int64_t nwork = (p.gb_end - p.gb_begin) * ngroups;
+    // two radix-2 stages (spans 2q and q) per pass over the data: points base + {0, q, 2q, 3q} of one sequence
+    auto quad = [&](int b, int lgq, float2*& x, int& j) {
+        const int seq = b >> (lgL - 2), i = b & (Q4 - 1);
+        j = i & ((1 << lgq) - 1);
+        x = data + seq * L + ((i >> lgq) << (lgq + 2)) + j;
+    };
+    auto span1 = [&]() {                                            // the stage of span 1 (odd log2 L): no twiddle
+        for (int b = tid; b < nseq * H2; b += NT) {
+            const float2 u = data[2 * b], v = data[2 * b + 1];
+            data[2 * b] = cadd(u, v);
+            data[2 * b + 1] = csub(u, v);
+        }
+        __syncthreads();
+    };
     for (int64_t w = blockIdx.x; w < nwork; w += gridDim.x) {
         const int64_t lb = w / ngroups, gb = p.gb_begin + lb;
         const int c0 = (int)(w % ngroups) * CH;
         const int ifi = (int)(gb / p.nblk);
         const int64_t blk = gb % p.nblk;
         const float2* V = p.volt + lb * (int64_t)L * 2 * N;
-        for (int e = tid; e < L * nseq; e += 256) {                 // channel fastest: CH neighbouring float2 per access
+        for (int e = tid; e < L * nseq; e += NT) {                  // channel fastest: CH neighbouring float2 per access
             const int ch = e % CH, pol = (e / CH) & 1, m = e / nseq;
             data[(ch * 2 + pol) * L + m] = V[((int64_t)m * 2 + pol) * N + c0 + ch];
         }
         __syncthreads();
-        for (int lgh = lgL - 1; lgh >= 0; --lgh) {                  // forward, decimation in frequency
-            const int half = 1 << lgh;
-            for (int b = tid; b < nseq * H2; b += 256) {
-                const int seq = b >> (lgL - 1), i = b & (H2 - 1);
-                const int j = i & (half - 1), pos = ((i >> lgh) << (lgh + 1)) + j;
-                float2* x = data + seq * L;
-                const float2 u = x[pos], v = x[pos + half];
-                x[pos] = cadd(u, v);
-                x[pos + half] = cmul(csub(u, v), tw[j << (lgL - 1 - lgh)]);
+        int lgh = lgL - 1;
+        for (; lgh >= 1; lgh -= 2) {                                // forward, decimation in frequency
+            const int lgq = lgh - 1, q = 1 << lgq, sh = lgL - 1 - lgh;       // W_4q^t = tw[t << sh], W_2q^t = tw[t << (sh + 1)]
+            for (int b = tid; b < nseq * Q4; b += NT) {
+                float2* x;
+                int j;
+                quad(b, lgq, x, j);
+                const float2 x0 = x[0], x1 = x[q], x2 = x[2 * q], x3 = x[3 * q];
+                const float2 u0 = cadd(x0, x2), u2 = cmul(csub(x0, x2), tw[j << sh]);
+                const float2 u1 = cadd(x1, x3), u3 = cmul(csub(x1, x3), tw[(j + q) << sh]);
+                const float2 wq = tw[j << (sh + 1)];
+                x[0] = cadd(u0, u1);
+                x[q] = cmul(csub(u0, u1), wq);
+                x[2 * q] = cadd(u2, u3);
+                x[3 * q] = cmul(csub(u2, u3), wq);
             }
             __syncthreads();
         }
+        if (lgh == 0) span1();
         const float2* H = p.chirp + (int64_t)ifi * L * N;
-        for (int e = tid; e < nseq * L; e += 256) {                 // bin k sits at the bit-reversed position
+        for (int e = tid; e < nseq * L; e += NT) {                  // bin k sits at the bit-reversed position
             const int seq = e >> lgL, pos = e & (L - 1);
             const int k = (int)(__brev((unsigned)pos) >> (32 - lgL));
             const float2 h = H[(int64_t)k * N + c0 + (seq >> 1)];
@@ -2056,19 +2079,27 @@ static __global__ void __launch_bounds__(256) kx_dedisp_generic(const KXParams p
             data[e] = make_float2(y.x * inv_l, y.y * inv_l);
         }
         __syncthreads();
-        for (int lgh = 0; lgh < lgL; ++lgh) {                       // backward, decimation in time
-            const int half = 1 << lgh;
-            for (int b = tid; b < nseq * H2; b += 256) {
-                const int seq = b >> (lgL - 1), i = b & (H2 - 1);
-                const int j = i & (half - 1), pos = ((i >> lgh) << (lgh + 1)) + j;
-                float2* x = data + seq * L;
-                const float2 u = x[pos], v = cmul_conj(x[pos + half], tw[j << (lgL - 1 - lgh)]);
-                x[pos] = cadd(u, v);
-                x[pos + half] = csub(u, v);
+        int lgq = 0;
+        if (lgL & 1) { span1(); lgq = 1; }
+        for (; lgq <= lgL - 2; lgq += 2) {                          // backward, decimation in time
+            const int q = 1 << lgq, sh = lgL - 2 - lgq;
+            for (int b = tid; b < nseq * Q4; b += NT) {
+                float2* x;
+                int j;
+                quad(b, lgq, x, j);
+                const float2 x0 = x[0], x1 = x[q], x2 = x[2 * q], x3 = x[3 * q];
+                const float2 wq = tw[j << (sh + 1)];
+                const float2 v1 = cmul_conj(x1, wq), v3 = cmul_conj(x3, wq);
+                const float2 y0 = cadd(x0, v1), y1 = csub(x0, v1), y2 = cadd(x2, v3), y3 = csub(x2, v3);
+                const float2 w2 = cmul_conj(y2, tw[j << sh]), w3 = cmul_conj(y3, tw[(j + q) << sh]);
+                x[0] = cadd(y0, w2);
+                x[2 * q] = csub(y0, w2);
+                x[q] = cadd(y1, w3);
+                x[3 * q] = csub(y1, w3);
             }
             __syncthreads();
         }
-        for (int o = tid; o < CH * nout; o += 256) {                // detect + integrate D samples
+        for (int o = tid; o < CH * nout; o += NT) {                 // detect + integrate D samples
             const int ch = o % CH, sidx = o / CH;
             const float2* xp = data + (ch * 2) * L + p.nfilt_pos + sidx * p.D;
             const float2* xq = xp + L;
