@@ -798,8 +798,10 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
         int D0 = (prm->tscrunch < 1 ? 1 : prm->tscrunch) & -(prm->tscrunch < 1 ? 1 : prm->tscrunch);
         while (D0 > 128) D0 >>= 1;
         const int nf = nfilt_half(D0);
-        if (2 * nf >= L)
-            while (L < 8 * nf && L < 8192) L *= 2;
+        if (2 * nf >= L) {
+            while (L < 8 * nf && L < 4096) L *= 2;
+            if (2 * nf >= L) return fail(B2F_EUNSUPPORTED, "dispersion smearing exceeds freq_res 4096 channel samples: use more channels");
+        }
     }
     if (!is_pow2(L) || L < 16 || L > 8192) return fail(B2F_EUNSUPPORTED, "freq_res must be a power of two in 16..8192");
     if ((R > 4096 || L > 4096) && L != R)

@@ -428,7 +428,7 @@ def test_other_row_lengths(gpu, nchan, bw, D):
 def test_unsupported_requests_fail_loudly(gpu):
     for kw in (dict(nchan=8192), dict(nchan=4096, freq_res=4096), dict(nchan=128, tscrunch=1 << 21), dict(nchan=4),
                dict(nchan=4096, dm=100.0, coherent=True), dict(nchan=512, in_nbit=8, frame_bytes=8032 + 8),
-               dict(nchan=128, dm=9000.0, coherent=True)):
+               dict(nchan=128, dm=30000.0, coherent=True)):
         with pytest.raises(_lib.B2FError) as e:
             Plan(PlanConfig(bw_mhz=[-32.0], **kw))
         assert e.value.code == _lib.EUNSUPPORTED

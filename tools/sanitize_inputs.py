@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
-"""Small scans through the input-format paths added late in round 2, for compute-sanitizer (memcheck): 8-bit input on the
+"""Small scans through the input-format paths added late in round 2 (written for compute-sanitizer's memcheck; the tool is
+closed on this GPU pool, so it runs as a plain smoke check of every new kernel variant on minimal inputs): 8-bit input on the
 generic and dedispersion paths (stream-coordinate word masks, carried), 1-bit split and raw input, Mark5B frames (32- and
 64-bit words, the latter with a gap placed by time code), dedispersion behind the generic kernels.  Faulty frames included;
 prints a checksum per case.
@@ -40,7 +41,7 @@ for nchan, L, nfr, chunk in ((64, 256, 130, 50), (8, 16, 60, 25), (512, 0, 560, 
     v = synth.make_vdif(nfr, seed=3, bw_mhz=32.0, nbit=8, **faults)
     run(f"8-bit generic nchan {nchan} L {L}", PlanConfig(nchan=nchan, bw_mhz=[32.0], freq_res=L, tscrunch=4, in_nbit=8, chunk_units=chunk, **common), v, nfr)
 v = synth.make_vdif(300, seed=4, bw_mhz=32.0, nbit=8, **faults)
-run("8-bit dedispersion nchan 8", PlanConfig(nchan=8, bw_mhz=[-32.0], freq_mhz=[1400.0], tscrunch=4, in_nbit=8, dm=30.0, coherent=True, **common), v, 300)
+run("8-bit dedispersion nchan 8", PlanConfig(nchan=8, bw_mhz=[-32.0], freq_mhz=[1400.0], tscrunch=4, in_nbit=8, dm=5.0, coherent=True, **common), v, 300)
 # 1-bit split streams: tuned path, generic path; payload that is not a multiple of 32 bytes (scalar front end)
 v = synth.make_vdif(40, seed=5, bw_mhz=32.0, nbit=1, **faults)
 run("1-bit tuned nchan 32", PlanConfig(nchan=32, bw_mhz=[-32.0], tscrunch=8, in_nbit=1, **common), v, 40)
