@@ -51,7 +51,7 @@ run("1-bit payload 1000", PlanConfig(nchan=8, bw_mhz=[-32.0], tscrunch=4, in_nbi
 # dedispersion behind the generic kernels: even and odd log2(freq_res), compile-time column kernel
 v = synth.make_vdif(200, seed=7, bw_mhz=32.0, **faults)
 for nchan, L, chunk in ((16, 64, 60), (16, 128, 60), (512, 0, 90)):
-    run(f"generic dedispersion nchan {nchan} L {L}", PlanConfig(nchan=nchan, bw_mhz=[-32.0], freq_mhz=[1300.0], freq_res=L, tscrunch=2, dm=60.0,
+    run(f"generic dedispersion nchan {nchan} L {L}", PlanConfig(nchan=nchan, bw_mhz=[-32.0], freq_mhz=[1300.0], freq_res=L, tscrunch=2, dm=1.5,
                                                                   coherent=True, chunk_units=chunk, **common), v, 200)
 # raw recordings: 1-bit VDIF, Mark5B with 32- and 64-bit words (the latter by time code, with a gap)
 rng = np.random.default_rng(9)
