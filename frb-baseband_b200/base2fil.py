@@ -133,11 +133,6 @@ def base2fil(conf_path: str, *, device: int = 0, workdir_odd: str | None = None,
     return done
 
 
-if __name__ == "__main__":
-    for p in base2fil(sys.argv[1]):
-        print(p)
-
-
 def run_scan_raw(raw_path: str, out_path: str, *, mode: str, nif: int, bw: float, freq_lsb0: float, nchan: int,
                  tscrunch: int = 1, pol: int = 2, nbit: int = 8, start: float = 0.0, nsec: float | None = None,
                  keep_bandpass: bool = False, flip_if: bool = False, source: str = "unknown", ra: str | None = None,
@@ -166,3 +161,82 @@ def run_scan_raw(raw_path: str, out_path: str, *, mode: str, nif: int, bw: float
                         src_raj=sigproc.sexagesimal_to_sigproc(ra), src_dej=sigproc.sexagesimal_to_sigproc(dec))
         tsamp = pl.tsamp_s
     return _report(r, f"raw {mode}", out_path, nif * nchan, tsamp, verbose)
+
+
+def raw_mode(cfg: FrbConf, raw_path: str | None = None) -> str:
+    """The mode string base2fil hands to spif2file (base2fil.sh:308-318): `VDIF_<payload>-<Mbps>-<nbbc>-<nbits>` with the
+    payload read from the recording's first header, or `MARK5B-<Mbps>-<nbbc>-<nbits>` when the config sets isMark5b."""
+    from . import spif
+
+    nbbc = 2 * int(cfg.nif)
+    if int(cfg.isMark5b):
+        return f"MARK5B-{cfg.datarate}-{nbbc}-{int(cfg.nbits)}"
+    with open(raw_path, "rb") as f:
+        info = vdif.parse_header(f.read(32))
+    return spif.mode_string(info.payload_bytes, cfg.datarate, nbbc, int(cfg.nbits))
+
+
+def raw_window(cfg: FrbConf, k: int, raw_path: str, mode: str) -> tuple[float, float]:
+    """(start_s, nsec) of scan k inside its raw recording.  spif2file.sh:144-151 skips to one frame before the first whole
+    second (`fps - start_frame - 1` frames; start_frame is 0 for Mark5B) plus `skips[k]` seconds and splits `lengths[k]`
+    seconds; process_vdif then runs digifil with -S `start` over what is left (base2fil.sh:61-64,395-402)."""
+    from . import spif
+
+    fb, hb, fmt = spif.frame_geometry(mode)
+    W, _ = spif.recipe_for_mode(mode, int(cfg.nif))
+    start_frame = 0
+    if not fmt:
+        with open(raw_path, "rb") as f:
+            info = vdif.parse_header(f.read(32))
+        fb, hb, start_frame = info.frame_bytes, info.header_bytes, info.frame_nr
+    fps = round(2 * float(cfg.bw) * 1e6 / ((fb - hb) * 8 // W))
+    lead = (fps - start_frame - 1) / fps
+    start = float(cfg.start)
+    return lead + float(cfg.skips[k]) + start, float(cfg.lengths[k]) - start
+
+
+def base2fil_raw(conf_path: str, *, vbsdir: str | None = None, outdir: str | None = None, device: int = 0,
+                 verbose: bool = True, send=None) -> list[str]:
+    """Mode C from a frb.conf: for every scan, the raw recording
+    `${vbsdir}/${experiment}_${st}_no0${scan}` (spif2file.sh:142) goes through the GPU corner turn straight into
+    `${outdir}/${experiment}_${st}_no0${scanname}_IFall_vdif_pol${pol}.fil` -- no jive5ab split, no split files, no FIFOs.
+    The mode (VDIF or Mark5B, word size, bits per sample), flipIF, the skip / length window and everything process_vdif is
+    told come from the same keys base2fil.sh reads."""
+    cfg = read_conf(conf_path)
+    st = station_code(cfg.station)
+    vbsdir = vbsdir or os.path.join(os.path.expandvars(cfg.vbsdir_base), cfg.experiment)
+    outdir = outdir or os.path.join(os.path.expandvars(cfg.outdir_base), cfg.experiment)
+    os.makedirs(outdir, exist_ok=True)
+    targ = cfg.target_args()
+    source = targ[0] if targ else "unknown"
+    ra = dec = None
+    for k, tok in enumerate(targ):
+        if tok == "--ra" and k + 1 < len(targ):
+            ra = targ[k + 1]
+        elif tok.startswith("--ra="):
+            ra = tok[5:]
+        elif tok == "--dec" and k + 1 < len(targ):
+            dec = targ[k + 1]
+        elif tok.startswith("--dec="):
+            dec = tok[6:]
+    done = []
+    for k, scanname in enumerate(cfg.scannames):
+        raw_path = os.path.join(vbsdir, f"{cfg.experiment}_{st}_no0{cfg.scans[k]}")
+        mode = raw_mode(cfg, raw_path)
+        start_s, nsec = raw_window(cfg, k, raw_path, mode)
+        out_path = os.path.join(outdir, spliced_name(cfg, scanname))
+        run_scan_raw(raw_path, out_path, mode=mode, nif=int(cfg.nif), bw=float(cfg.bw), freq_lsb0=float(cfg.freqLSB_0),
+                     nchan=int(cfg.nchan), tscrunch=int(cfg.tscrunch), pol=int(cfg.pol), nbit=int(cfg.nbit), start=start_s, nsec=nsec,
+                     keep_bandpass=int(cfg.keepBP) > 0, flip_if=int(cfg.flipIF) != 0, source=source, ra=ra, dec=dec,
+                     telescope=cfg.station, device=device, verbose=verbose)
+        handoff.after_scan(out_path, flag_file=str(cfg.flagFile), submit2fetch=int(cfg.submit2fetch) != 0, keep_vdif=True, send=send,
+                           vdif_globs=[])
+        done.append(out_path)
+    return done
+
+
+if __name__ == "__main__":
+    # base2fil <frb.conf>: split files -> filterbank (mode B); base2fil --raw <frb.conf>: raw recordings -> filterbank (mode C)
+    _args = [a for a in sys.argv[1:] if a != "--raw"]
+    for p in (base2fil_raw if "--raw" in sys.argv[1:] else base2fil)(_args[0]):
+        print(p)

@@ -122,7 +122,7 @@ def make_raw_mark5b(codes: np.ndarray, word_bits: int, bits, *, bw_mhz: float, m
 
 
 def make_raw_vdif(codes: np.ndarray, word_bits: int, bits, *, bw_mhz: float, payload_bytes: int = 8000,
-                  ref_epoch: int = 40, sec0: int = 0) -> np.ndarray:
+                  ref_epoch: int = 40, sec0: int = 0, frame0: int = 0) -> np.ndarray:
     """Raw multi-BBC VDIF stream (what the recorder holds): codes[if, pol, t] in 0..3 are scattered to
     the bit positions `bits[if] = [pol0 lsb, pol0 msb, pol1 lsb, pol1 msb]` of one word_bits-bit word per
     time sample -- the inverse of the spif2file recipe."""
@@ -138,7 +138,7 @@ def make_raw_vdif(codes: np.ndarray, word_bits: int, bits, *, bw_mhz: float, pay
     nframes = nsamp // spf
     fps = int(round(2 * abs(bw_mhz) * 1e6 / spf))
     hdr = vdif.make_headers(nframes, frames_per_sec=fps, payload_bytes=payload_bytes, nbit=sample_bits,
-                            log2_nchan=int(np.log2(max(1, word_bits // sample_bits))), ref_epoch=ref_epoch, sec0=sec0)
+                            log2_nchan=int(np.log2(max(1, word_bits // sample_bits))), ref_epoch=ref_epoch, sec0=sec0, frame0=frame0)
     out = np.empty((nframes, vdif.HEADER_BYTES + payload_bytes), dtype=np.uint8)
     out[:, : vdif.HEADER_BYTES] = hdr.view(np.uint8).reshape(nframes, vdif.HEADER_BYTES)
     out[:, vdif.HEADER_BYTES:] = w[: nframes * spf].view(np.uint8).reshape(nframes, payload_bytes)

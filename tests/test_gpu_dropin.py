@@ -94,6 +94,39 @@ def test_base2fil_conf_to_spliced_file(gpu, tmp_path):
     assert np.abs(d[:, 0, :].astype(int) - ref["data"].astype(int)).max() <= 1
 
 
+def test_base2fil_raw_conf_to_spliced_file(gpu, tmp_path):
+    """Mode C from a frb.conf: the raw multi-BBC recording is the only input; window, recipe and frequency plan as
+    base2fil.sh / spif2file.sh derive them.  Checked against oracle(corner turn -> digifil per IF -> splice)."""
+    from frb_baseband_b200 import spif
+    nif, bw, nchan, D = 4, 2.0, 8, 4
+    vbs = tmp_path / "vbs" / "rawtest"
+    vbs.mkdir(parents=True)
+    W, bits = spif.recipe_for_mode("VDIF_8000-64-8-2", nif, flip_if=True)
+    spf, fps, nfr = 8000 * 8 // W, 1000, 3000
+    rng = np.random.default_rng(29)
+    codes = synth.quantise_2bit(rng.standard_normal((nif, 2, nfr * spf)) + 0.5 * np.cos(0.7 * np.arange(nfr * spf)))
+    raw = synth.make_raw_vdif(codes, W, bits, bw_mhz=bw, sec0=5, frame0=37)
+    raw.tofile(vbs / "rawtest_ef_no0012")
+    c = tmp_path / "frb.conf"
+    c.write_text(f"experiment=rawtest\ntarget=\"R3 --ra 01:58:00.75 --dec +65:43:00.3\"\nscans=( 012 )\nskips=( 1 )\nlengths=( 1 )\n"
+                 f"scannames=( 012 )\nbw={bw}\nnif={nif}\nfreqLSB_0=1300.0\nstation=effelsberg\nnchan={nchan}\ntscrunch={D}\nflipIF=1\n"
+                 f"nbit=-32\nkeepBP=1\nvbsdir_base={tmp_path}/vbs\noutdir_base={tmp_path}/out\n")
+    done = base2fil.base2fil_raw(str(c), verbose=False)
+    assert done == [str(tmp_path / "out" / "rawtest" / "rawtest_ef_no0012_IFall_vdif_pol2.fil")]
+    h, d = sigproc.read_fil(done[0])
+    f0 = (fps - 37 - 1) + fps                                             # spif2file.sh:144-149
+    x = o.corner_turn(raw, W, bits)[:, :, f0 * spf:(f0 + fps) * spf]
+    freqs = [1300.0 + (i - 1) * bw for i in range(1, nif + 1)]
+    bws = [bw if i % 2 == 0 else -bw for i in range(1, nif + 1)]
+    parts = [o.digifil(np.zeros(8032, np.uint8), freq_mhz=freqs[i], bw_mhz=bws[i], nchan=nchan, tscrunch_factor=D, out_nbit=-32,
+                       keep_bandpass=True, x=x[i], frame_bytes=8032) for i in sorted(range(nif), key=lambda k: -freqs[k])]
+    ref = o.splice(parts)["data"]
+    assert h.nchans == nif * nchan and h.nbits == 32 and h.source_name == "R3" and d.shape[0] == ref.shape[0] > 0
+    assert h.tstart == pytest.approx(vdif_mjd(raw[f0 * 8032:f0 * 8032 + 32], fps), abs=1e-12)
+    from helpers import REL_TOL, assert_rel
+    assert_rel(d.reshape(d.shape[0], 1, -1), ref.reshape(ref.shape[0], 1, -1).astype(np.float64), REL_TOL, "mode C from a conf")
+
+
 def test_native_runner_equals_streaming_calls(gpu, tmp_path):
     """b2f_run_scan (threaded readers, pinned ring, pipelined push/pull) writes exactly the rows the caller gets
     from b2f_push/b2f_pull chunk by chunk, for a -S/-T window that ends inside a chunk, files of unequal length,
