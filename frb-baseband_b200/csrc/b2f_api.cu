@@ -106,6 +106,9 @@ struct b2f_plan {
     int bps = 1;
     bool smask = false;
     uint8_t* d_carry_mask = nullptr;
+    // JA98 decode on the generic path: levels per window of 512 samples of the index-byte stream (kj_levels_stream)
+    float4* d_levels_stream = nullptr;
+    int64_t levels_stride = 0;
     float2* d_spec = nullptr;
     float2* d_chirp = nullptr;
     uint8_t* d_out_stage[2]{};
@@ -317,7 +320,7 @@ void free_plan(b2f_plan* pl) {
     void* bufs[] = {pl->d_compact, pl->d_wmask, pl->d_fstat, pl->d_blkdirty, pl->d_inter, pl->d_colsum,
                     pl->d_eps, pl->d_F, pl->d_mean, pl->d_scale, pl->d_partial, pl->d_tab_g, pl->d_tab_h,
                     pl->d_tab_w, pl->d_tab_r, pl->d_tab_beta, pl->d_counters, pl->d_sm_slots, pl->d_carry, pl->d_spec, pl->d_chirp, pl->d_tw_col, pl->d_tw_row,
-                    pl->d_tstream, pl->d_fillflag, pl->d_part, pl->d_fsync, pl->d_fprof, pl->d_levels, pl->d_carry_mask};
+                    pl->d_tstream, pl->d_fillflag, pl->d_part, pl->d_fsync, pl->d_fprof, pl->d_levels, pl->d_carry_mask, pl->d_levels_stream};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (pl->d_Fk) cudaFree(pl->d_Fk);
@@ -381,7 +384,15 @@ int push_dedisp(b2f_plan* pl, int64_t nblk, int64_t T) {
         kg.wmask = pl->d_wmask; kg.wmask_stride = pl->wmask_stride; kg.blkdirty = pl->d_blkdirty;
         kg.in8_offset = pl->prm.in8_offset_mode ? 128.0f : 127.5f;
         kg.step = pl->step;
-        const int nbit = pl->prm.in_nbit;
+        kg.levels = pl->d_levels_stream; kg.levels_stride = pl->levels_stride;
+        const int nbit = pl->d_levels_stream ? 22 : pl->prm.in_nbit;          // 22: 2-bit input decoded with JA98 levels
+        if (pl->d_levels_stream) {
+            const int64_t nthreads = ((T + 511) / 512) * nif * 32;
+            kj_levels_stream<<<(unsigned)((nthreads + 255) / 256), 256, 0, pl->stream>>>(pl->d_compact, pl->compact_stride, T, pl->d_levels_stream,
+                                                                                        pl->levels_stride, nif);
+            pl->launches++;
+            CU(cudaGetLastError());
+        }
         kg.inter = pl->d_inter; kg.colsum = pl->d_colsum; kg.eps = pl->d_eps;
         kg.tw_col = pl->d_tw_col; kg.tw_row = pl->d_tw_row;
         kg.F = row_dst(pl); kg.F_if_stride = row_dst_stride(pl); kg.row0 = row_dst_row0(pl);
@@ -395,6 +406,7 @@ int push_dedisp(b2f_plan* pl, int64_t nblk, int64_t T) {
         if (!pl->kgt_lg) {
             CU(cudaFuncSetAttribute(kg_column_pass<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_col));
             CU(cudaFuncSetAttribute(kg_column_pass<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_col));
+            CU(cudaFuncSetAttribute(kg_column_pass<22>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_col));
         }
         if (!pl->kgt_lg || pl->dedisp) {
             CU(cudaFuncSetAttribute(kg_row_pass<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row));
@@ -426,6 +438,7 @@ int push_dedisp(b2f_plan* pl, int64_t nblk, int64_t T) {
                     const int64_t work = nb * (pl->R / kg.C);
                     const unsigned grid = (unsigned)std::min<int64_t>(work, 2 * (int64_t)pl->num_sms);
                     if (nbit == 8) kg_column_pass<8><<<grid, 256, smem_col, pl->stream>>>(kg);
+                    else if (nbit == 22) kg_column_pass<22><<<grid, 256, smem_col, pl->stream>>>(kg);
                     else kg_column_pass<2><<<grid, 256, smem_col, pl->stream>>>(kg);
                 }
             });
@@ -947,10 +960,13 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
         else if (e && !strcmp(e, "split")) want = 1;
         else if (e && !strcmp(e, "fused")) want = 2;
         pl->path = eligible ? want : 0;
-        if (prm->decode_mode == B2F_DECODE_JA98 && (!eligible || want == 0)) {
+        if (prm->decode_mode == B2F_DECODE_JA98 && generic) {
+            // the generic column kernels read the levels per window of 512 stream samples: blocks must start on windows
+            if (pl->step % 512) { delete pl; return fail(B2F_EUNSUPPORTED, "decode_mode JA98 needs FFT blocks that start on multiples of 512 samples"); }
+        } else if (prm->decode_mode == B2F_DECODE_JA98 && (!eligible || want == 0)) {
             delete pl;
-            return fail(B2F_EUNSUPPORTED, "decode_mode JA98 is implemented in the round-2 column kernel only: 2-bit split streams, frames in "
-                                          "order, freq_res 512, nchan <= 256, no dedispersion");
+            return fail(B2F_EUNSUPPORTED, "decode_mode JA98 with freq_res 512 and nchan <= 256 is implemented in the round-2 column kernel only: "
+                                          "2-bit split streams, frames in order, no dedispersion");
         }
         if (pl->path) {
             int occ = 0;
@@ -1046,13 +1062,17 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
     CUB(cudaMalloc(&pl->d_sm_slots, 1024 * sizeof(int)));
     if (pl->carry_mode) CUB(cudaMalloc(&pl->d_carry, (size_t)pl->M * pl->bps * nif));
     if (pl->smask) CUB(cudaMalloc(&pl->d_carry_mask, (size_t)pl->M * pl->bps / 32 * nif));
+    if (prm->decode_mode == B2F_DECODE_JA98 && generic) {
+        pl->levels_stride = (pl->chunk_frames * pl->spf + pl->M) / 512 + 2;
+        CUB(cudaMalloc(&pl->d_levels_stream, (size_t)pl->levels_stride * nif * sizeof(float4)));
+    }
     if (generic && L == R && L >= 1024) {
         // the shapes process_vdif.py:162 produces (-F nchan:2*nchan): kernels with compile-time geometry
         const char* e = getenv("B2F_GENERIC");
         const int lg = 31 - __builtin_clz(L);
         if (!(e && !strcmp(e, "runtime") && L <= 4096)) {
             int cc = 0, rc2 = 0;
-            if (b2f_launch_kgt_col(lg, prm->in_nbit, KGParams{}, 0, nullptr, &cc) != cudaSuccess || cc < 1 ||
+            if (b2f_launch_kgt_col(lg, prm->decode_mode == B2F_DECODE_JA98 ? 22 : prm->in_nbit, KGParams{}, 0, nullptr, &cc) != cudaSuccess || cc < 1 ||
                 b2f_launch_kgt_row(lg, prm->pol_mode, KGParams{}, 0, nullptr, &rc2) != cudaSuccess || rc2 < 1) {
                 cudaGetLastError();
                 if (L > 4096) { g_err = "generic kernels for nchan 4096 do not fit this device"; return bail(B2F_EUNSUPPORTED); }

@@ -53,7 +53,8 @@ __device__ __forceinline__ int kgt_rev16(int seg) {
 // outermost inverse pass stays inside those points, so with this mapping a warp only reads what it wrote itself and
 // the stages are separated by __syncwarp instead of a block barrier: 3 block barriers per strip instead of 6 (8 for
 // N = 8192), and the warps of a CTA drift into different stages (load burst / butterflies / store burst overlap).
-// SRC: 0 shared, 1 index bytes of the 2-bit decode, 2 8-bit sample pairs (KG8: offset and stream-coordinate word masks).
+// SRC: 0 shared, 1 index bytes of the 2-bit decode, 2 8-bit sample pairs (KG8: offset and stream-coordinate word masks),
+// 3 index bytes with JA98 levels per window of 512 samples (KG8::levels).
 template <int LG, int LGN, bool INV, int SRC, int DST, bool WM = false>
 __device__ __forceinline__ void kgt_col_pass16(float2* sm, const float2* tw, const uint8_t* gsrc_b, float2* gdst, const float2* lut,
                                                const KG8* s8 = nullptr) {
@@ -80,6 +81,12 @@ __device__ __forceinline__ void kgt_col_pass16(float2* sm, const float2* tw, con
             } else if (SRC == 2) {
                 const int64_t o = ((int64_t)idx * G::N + c2) * 2;
                 kg_decode8(*reinterpret_cast<const uint32_t*>(gsrc_b + o), *s8, o, a[j], b[j]);
+            } else if (SRC == 3) {                                   // index bytes, JA98 levels of the sample's window
+                const int64_t o = (int64_t)idx * G::N + c2;
+                const uint32_t two = *reinterpret_cast<const uint16_t*>(gsrc_b + o);
+                const float4 lv = __ldg(s8->levels + ((s8->byte0 + o) >> 9));
+                a[j] = kg_ja98(*reinterpret_cast<const float2*>(reinterpret_cast<const uint8_t*>(lut) + (two & 255u)), lv);
+                b[j] = kg_ja98(*reinterpret_cast<const float2*>(reinterpret_cast<const uint8_t*>(lut) + (two >> 8)), lv);
             } else {
                 const float4 v4 = *reinterpret_cast<const float4*>(&sm[kg_phys<false>((idx << G::LGC) + c2)]);
                 a[j] = make_float2(v4.x, v4.y);
@@ -218,11 +225,12 @@ __global__ void __launch_bounds__(KGT<LG>::kColThreads, KGT<LG>::kColCtas) kgt_c
         constexpr int BPS = NBIT == 8 ? 2 : 1;                            // stream bytes per time sample
         const int64_t off = (blk * p.step + (int64_t)strip * C) * BPS;           // step = M without overlap-save
         const uint8_t* src = p.compact + ifi * p.compact_stride + off;
-        const KG8 s8{p.wmask + ifi * p.wmask_stride, off, p.in8_offset, NBIT == 8 && p.blkdirty[gb] != 0};
+        const KG8 s8{p.wmask + ifi * p.wmask_stride, off, p.in8_offset, NBIT == 8 && p.blkdirty[gb] != 0,
+                     NBIT == 22 ? p.levels + ifi * p.levels_stride : nullptr};            // NBIT 22 = 2-bit input, JA98 levels
         float2* dst = p.inter + (lb << (2 * LG)) + strip * C;
         float2* colsum = p.colsum + gb * N + strip * C;
         // forward, outermost first
-        kgt_col_pass16<LG, LG, false, NBIT == 8 ? 2 : 1, 0>(data, tw, src, nullptr, lut, &s8);
+        kgt_col_pass16<LG, LG, false, NBIT == 8 ? 2 : (NBIT == 22 ? 3 : 1), 0>(data, tw, src, nullptr, lut, &s8);
         __syncthreads();
         kgt_col_pass16<LG, LG - 4, false, 0, 0, true>(data, tw + kg_tw_offset(LG, 1), nullptr, nullptr, lut);
         __syncwarp();

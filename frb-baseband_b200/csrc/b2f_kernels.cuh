@@ -502,6 +502,53 @@ static __global__ void k0b_finish_slots(const K0bParams p) {
 #endif
 
 #ifdef B2F_API_TU
+// JA98 decode on the generic path (NBIT = 22 in the column kernels): one warp per window of 512 samples of the index-byte
+// stream (carried samples in front, so windows count from the start of the scan as long as blocks start on multiples of
+// 512) counts, per polarisation, the samples between the thresholds among those that are not masked, and turns the
+// fraction into the two output magnitudes -- the arithmetic of kj_ja98_levels (b2f_fused.cuh) and of the oracle's ja98_levels.
+static __global__ void kj_levels_stream(const uint8_t* compact, size_t compact_stride, int64_t T, float4* levels, int64_t levels_stride, int nif) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwin = (T + 511) >> 9;
+    if (w >= nwin * nif) return;
+    const int ifi = (int)(w / nwin);
+    const int64_t wi = w % nwin, pos = wi * 512 + lane * 16;
+    const uint8_t* src = compact + ifi * compact_stride + pos;
+    unsigned lowP = 0, lowQ = 0, nval = 0;
+    uint32_t x[4] = {0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u};
+    if (pos + 16 <= T) {
+        const uint4 v = *reinterpret_cast<const uint4*>(src);
+        x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+    } else {
+        for (int k = 0; k < 16 && pos + k < T; ++k) x[k >> 2] = (x[k >> 2] & ~(0xFFu << (8 * (k & 3)))) | ((uint32_t)src[k] << (8 * (k & 3)));
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {                                  // index byte = (c1 << 2 | c0) << 3, 0x80 = masked
+        const uint32_t ok = (~x[k] >> 7) & 0x01010101u;
+        lowP += __popc(((x[k] >> 3) ^ (x[k] >> 4)) & ok);           // code 1 or 2: the two bits differ
+        lowQ += __popc(((x[k] >> 5) ^ (x[k] >> 6)) & ok);
+        nval += __popc(ok);
+    }
+    for (int m = 16; m; m >>= 1) {
+        lowP += __shfl_xor_sync(0xffffffffu, lowP, m);
+        lowQ += __shfl_xor_sync(0xffffffffu, lowQ, m);
+        nval += __shfl_xor_sync(0xffffffffu, nval, m);
+    }
+    if (lane == 0) {
+        float lv[4];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            double phi = nval ? (double)(q ? lowQ : lowP) / (double)nval : 0.5;
+            phi = fmin(fmax(phi, 1.0 / 512.0), 1.0 - 1.0 / 512.0);
+            const double t = 1.4142135623730951 * erfinv(phi);
+            const double e = exp(-0.5 * t * t);
+            lv[2 * q] = (float)(0.7978845608028654 * (1.0 - e) / phi);
+            lv[2 * q + 1] = (float)(0.7978845608028654 * e / (1.0 - phi));
+        }
+        levels[ifi * levels_stride + wi] = make_float4(lv[0], lv[1], lv[2], lv[3]);
+    }
+}
+
 // 8-bit input in carry mode keeps its word masks by stream position (b2f_plan::smask): a block is dirty when any mask
 // byte of its M samples is set.  step32 / blk32: block stride and block length in mask bytes.
 static __global__ void k8_blkdirty(const uint8_t* wmask, size_t wmask_stride, uint8_t* blkdirty, int nblk, int64_t step32, int64_t blk32) {
@@ -1544,6 +1591,7 @@ struct KGParams {
     const uint8_t* blkdirty;
     float in8_offset;
     int64_t step;                // samples between the starts of consecutive blocks (M, or less with overlap-save)
+    const float4* levels; int64_t levels_stride;   // JA98 decode: (lo0, hi0, lo1, hi1) per window of 512 stream samples and IF
     float2* volt;                // mode kModeVolt: [gb - gb_begin][L][2][R/2] un-detected channel samples (P, Q)
 };
 // kg_row_pass mode: no detection, the two polarisations of every channel sample go to KGParams::volt (dedispersion)
@@ -1551,7 +1599,12 @@ constexpr int kModeVolt = 101;
 
 // One 32-bit word of an 8-bit stream = two time samples x (pol 0, pol 1).  `o` = byte offset of the word from s.byte0,
 // which in turn counts from the start of the IF's de-framed stream of this push (carried samples included).
-struct KG8 { const uint8_t* wm; int64_t byte0; float off; bool dirty; };
+struct KG8 { const uint8_t* wm; int64_t byte0; float off; bool dirty; const float4* levels; };
+// JA98 decode of a 2-bit sample pair: sign and size class from the static lookup, magnitude from the window's levels
+__device__ __forceinline__ float2 kg_ja98(float2 v, float4 lv) {
+    const float ax = fabsf(v.x), ay = fabsf(v.y);
+    return make_float2(ax == 0.f ? 0.f : copysignf(ax > 2.f ? lv.y : lv.x, v.x), ay == 0.f ? 0.f : copysignf(ay > 2.f ? lv.w : lv.z, v.y));
+}
 __device__ __forceinline__ void kg_decode8(uint32_t four, const KG8& s, int64_t o, float2& a, float2& b) {
     a = make_float2((float)(four & 255u) - s.off, (float)((four >> 8) & 255u) - s.off);
     b = make_float2((float)((four >> 16) & 255u) - s.off, (float)(four >> 24) - s.off);
@@ -1672,6 +1725,12 @@ __device__ __forceinline__ void kg_pass16_pair(float2* sm, const float2* tw, int
             } else if (SRC == 2) {                                   // 8-bit sample pairs
                 const int64_t o = ((int64_t)idx * gstride + c2) * 2;
                 kg_decode8(*reinterpret_cast<const uint32_t*>(gsrc_b + o), *s8, o, a[j], b[j]);
+            } else if (SRC == 3) {                                   // index bytes, JA98 levels of the sample's window
+                const int64_t o = (int64_t)idx * gstride + c2;
+                const uint32_t two = *reinterpret_cast<const uint16_t*>(gsrc_b + o);
+                const float4 lv = __ldg(s8->levels + ((s8->byte0 + o) >> 9));
+                a[j] = kg_ja98(*reinterpret_cast<const float2*>(reinterpret_cast<const uint8_t*>(lut) + (two & 255u)), lv);
+                b[j] = kg_ja98(*reinterpret_cast<const float2*>(reinterpret_cast<const uint8_t*>(lut) + (two >> 8)), lv);
             } else {
                 const float4 v4 = *reinterpret_cast<const float4*>(&sm[kg_phys<false>((idx << lgC) + c2)]);
                 a[j] = make_float2(v4.x, v4.y);
@@ -1763,7 +1822,10 @@ __device__ __forceinline__ void kg_column_inner(float2* sm, const KGParams& p, i
 #pragma unroll
         for (int q = 0; q < RM; ++q) {
             const int idx = seg * RM + q;
-            if (GLOBAL && s8) {                                     // 8-bit: one (pol 0, pol 1) pair = half a stream word
+            if (GLOBAL && s8 && s8->levels) {                       // 2-bit, JA98 levels
+                const int64_t o = (int64_t)idx * p.R + cl;
+                v[q] = kg_ja98(*reinterpret_cast<const float2*>(reinterpret_cast<const uint8_t*>(lut) + gsrc_b[o]), __ldg(s8->levels + ((s8->byte0 + o) >> 9)));
+            } else if (GLOBAL && s8) {                              // 8-bit: one (pol 0, pol 1) pair = half a stream word
                 const int64_t o = ((int64_t)idx * p.R + cl) * 2;
                 float2 lo, hi;
                 kg_decode8(*reinterpret_cast<const uint32_t*>(gsrc_b + (o & ~(int64_t)3)), *s8, o & ~(int64_t)3, lo, hi);
@@ -1820,16 +1882,17 @@ static __global__ void __launch_bounds__(256, 2) kg_column_pass(const KGParams p
         const int64_t blk = gb % p.nblk;
         const int64_t off = (blk * p.step + (int64_t)strip * C) * (NBIT == 8 ? 2 : 1);
         const uint8_t* src = p.compact + ifi * p.compact_stride + off;
-        const KG8 s8{p.wmask + ifi * p.wmask_stride, off, p.in8_offset, NBIT == 8 && p.blkdirty[gb] != 0};
+        const KG8 s8{p.wmask + ifi * p.wmask_stride, off, p.in8_offset, NBIT == 8 && p.blkdirty[gb] != 0,
+                     NBIT == 22 ? p.levels + ifi * p.levels_stride : nullptr};
         float2* dst = p.inter + lb * (int64_t)L * R + strip * C;
         float2* colsum = p.colsum + gb * R + strip * C;
         if (nf == 0) {                                       // L = 16: one register-resident step, no shared memory
-            kg_column_inner<16, true>(data, p, strip * C, colsum, src, dst, lut, NBIT == 8 ? &s8 : nullptr);
+            kg_column_inner<16, true>(data, p, strip * C, colsum, src, dst, lut, NBIT != 2 ? &s8 : nullptr);
             continue;
         }
         const int cnt2 = cnt16 >> 1;                         // two neighbouring columns per thread
         for (int f = 0; f < nf; ++f) {                       // forward, outermost first
-            if (f == 0) kg_pass16_pair<false, NBIT == 8 ? 2 : 1, 0>(data, tw, lgL, lgL, lgC, cnt2, src, nullptr, R, lut, &s8);
+            if (f == 0) kg_pass16_pair<false, NBIT == 8 ? 2 : (NBIT == 22 ? 3 : 1), 0>(data, tw, lgL, lgL, lgC, cnt2, src, nullptr, R, lut, &s8);
             else kg_pass16_pair<false, 0, 0>(data, tw + kg_tw_offset(lgL, f), lgL, lgL - 4 * f, lgC, cnt2, nullptr, nullptr, 0, lut);
             __syncthreads();
         }

@@ -35,7 +35,8 @@ static cudaError_t col_go(const KGParams& p, int grid, cudaStream_t st, int* cta
 }
 
 cudaError_t KG_CAT(b2f_launch_kgt_col_, B2F_KG_LG)(int in_nbit, const KGParams& p, int grid, cudaStream_t st, int* ctas) {
-    return in_nbit == 8 ? col_go<8>(p, grid, st, ctas) : col_go<2>(p, grid, st, ctas);
+    // in_nbit: 8, 2 (1-bit input arrives as the same index bytes), or 22 = 2-bit input with JA98 levels
+    return in_nbit == 8 ? col_go<8>(p, grid, st, ctas) : (in_nbit == 22 ? col_go<22>(p, grid, st, ctas) : col_go<2>(p, grid, st, ctas));
 }
 
 cudaError_t KG_CAT(b2f_launch_kgt_row_, B2F_KG_LG)(int mode, const KGParams& p, int grid, cudaStream_t st, int* ctas) {

@@ -53,6 +53,35 @@ def test_ja98_dynamic_levels(gpu, monkeypatch, path, nchan, bw, D):
     assert np.abs(static / ref - 1).max() > 0.5              # and it is a different result from the static levels
 
 
+@pytest.mark.parametrize("nchan,freq_res,D,nframes,chunk,dm", [(512, 0, 4, 300, 100, 0.0), (64, 256, 8, 120, 50, 0.0), (16, 32, 2, 40, 15, 0.0),
+                                                                (1024, 0, 2, 700, 300, 560.0)])
+def test_ja98_generic_shapes(gpu, nchan, freq_res, D, nframes, chunk, dm):
+    """decode_mode = JA98 on the generic channeliser (the CLI default --nchan 512 among it): levels per window of 512 samples of
+    the de-framed stream, windows counted through the samples carried from push to push; also under the generic dedispersion."""
+    bw, fc = 32.0, 1254.0
+    L = freq_res or 2 * nchan
+    v = synth.make_vdif(nframes, seed=4300 + nchan, bw_mhz=bw, tone_frac=0.31, invalid_frac=0.02, fill_frac=0.02)
+    cfg = PlanConfig(nchan=nchan, bw_mhz=[-bw], freq_mhz=[fc], freq_res=freq_res, tscrunch=D, out_nbit=-32, keep_bandpass=True,
+                     decode_mode=_lib.DECODE_JA98, chunk_units=chunk, dm=dm, coherent=dm > 0)
+    out = []
+    with Plan(cfg) as pl:
+        nf = (int(pl.geometry.nfilt_pos), int(pl.geometry.nfilt_neg))
+        cf, fb = int(pl.chunk_frames), cfg.frame_bytes
+        assert cf == chunk and int(pl.geometry.freq_res) == L
+        for f0 in range(0, nframes, cf):
+            n = min(cf, nframes - f0)
+            pl.push([v[f0 * fb:(f0 + n) * fb]])
+            out.append(pl.pull().copy())
+        pl.flush()
+        out.append(pl.pull().copy())
+        rows = pl.view_rows(np.concatenate(out))
+    kw = dict(freq_mhz=fc, bw_mhz=-bw, nchan=nchan, freq_res=L, tscrunch_factor=D, out_nbit=-32, keep_bandpass=True, dm=dm, coherent=dm > 0, nfilt=nf)
+    ref = o.digifil(v, decode_mode="ja98", **kw)["data"].astype(np.float64)
+    assert rows.shape[0] == ref.shape[0] > 0
+    assert_rel(rows.reshape(ref.shape), ref, REL_TOL, f"JA98 generic nchan {nchan} L {L}")
+    assert np.abs(o.digifil(v, **kw)["data"] / ref - 1).max() > 0.5      # not the static levels
+
+
 def test_ja98_needs_the_round2_kernels(gpu, monkeypatch):
     monkeypatch.setenv("B2F_PATH", "legacy")
     with pytest.raises(_lib.B2FError) as e:
