@@ -211,7 +211,7 @@ int launch_kb(b2f_plan* pl, const KBParams& kp, int grid) {
 
 int launch_ka(b2f_plan* pl, const KAParams& ka, unsigned grid) {
     cudaError_t e = cudaSuccess;
-    int rc = timed(pl, B2F_K_COLUMN, [&] { e = b2f_launch_ka(pl->prm.in_nbit, pl->R, ka, grid, pl->stream); });
+    int rc = timed(pl, B2F_K_COLUMN, [&] { e = b2f_launch_ka(pl->d_levels_stream ? 22 : pl->prm.in_nbit, pl->R, ka, grid, pl->stream); });
     if (rc) return rc;
     if (e != cudaSuccess) return fail(B2F_ECUDA, std::string("column pass launch: ") + cudaGetErrorString(e));
     return 0;
@@ -490,6 +490,14 @@ int push_dedisp(b2f_plan* pl, int64_t nblk, int64_t T) {
         ka.payload_bytes = (int)pl->payload; ka.groups_per_slot = (int)pl->groups_per_slot;
         ka.blk_step_bytes = pl->step * pl->bps;                   // 2-bit: 1 index byte per sample; 8-bit: 2 bytes, masks by stream position
         ka.in8_offset = pl->prm.in8_offset_mode ? 128.0f : 127.5f;
+        ka.levels = pl->d_levels_stream; ka.levels_stride = pl->levels_stride;
+        if (pl->d_levels_stream) {                                // JA98: levels per window of 512 stream samples
+            const int64_t nthreads = ((T + 511) / 512) * nif * 32;
+            kj_levels_stream<<<(unsigned)((nthreads + 255) / 256), 256, 0, pl->stream>>>(pl->d_compact, pl->compact_stride, T, pl->d_levels_stream,
+                                                                                        pl->levels_stride, nif);
+            pl->launches++;
+            CU(cudaGetLastError());
+        }
         ka.sm_slots = pl->d_sm_slots; ka.stagger_cycles = 0; ka.variant = 32;      // forward only
         KBParams kb{};
         kb.inter = pl->d_inter; kb.eps = nullptr; kb.tab_r = pl->d_tab_r; kb.spec = pl->d_spec;
@@ -539,6 +547,7 @@ int push_dedisp(b2f_plan* pl, int64_t nblk, int64_t T) {
 }
 
 cudaError_t b2f_launch_ka(int in_nbit, int R, const KAParams& p, unsigned grid, cudaStream_t st) {
+    if (in_nbit == 22) return b2f_launch_ka_22(R, p, grid, st);                               // 2-bit input, JA98 levels
     return in_nbit == 8 ? b2f_launch_ka_8(R, p, grid, st) : b2f_launch_ka_2(R, p, grid, st);   // 1- and 2-bit: index-byte stream
 }
 cudaError_t b2f_launch_kr(int R, int mode, const KBParams& p, int grid, cudaStream_t st) {
@@ -960,13 +969,13 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
         else if (e && !strcmp(e, "split")) want = 1;
         else if (e && !strcmp(e, "fused")) want = 2;
         pl->path = eligible ? want : 0;
-        if (prm->decode_mode == B2F_DECODE_JA98 && generic) {
-            // the generic column kernels read the levels per window of 512 stream samples: blocks must start on windows
-            if (pl->step % 512) { delete pl; return fail(B2F_EUNSUPPORTED, "decode_mode JA98 needs FFT blocks that start on multiples of 512 samples"); }
-        } else if (prm->decode_mode == B2F_DECODE_JA98 && (!eligible || want == 0)) {
+        // JA98 decode: the round-2 column kernel has its own implementation (levels per block from the frames); every other
+        // kernel family (generic, round-1 tuned, dedispersion, raw input) reads levels per window of 512 samples of the
+        // de-framed stream (kj_levels_stream).  The generic kernels address windows from the block start: blocks must start
+        // on multiples of 512 samples.
+        if (prm->decode_mode == B2F_DECODE_JA98 && generic && pl->step % 512) {
             delete pl;
-            return fail(B2F_EUNSUPPORTED, "decode_mode JA98 with freq_res 512 and nchan <= 256 is implemented in the round-2 column kernel only: "
-                                          "2-bit split streams, frames in order, no dedispersion");
+            return fail(B2F_EUNSUPPORTED, "decode_mode JA98 needs FFT blocks that start on multiples of 512 samples");
         }
         if (pl->path) {
             int occ = 0;
@@ -974,11 +983,7 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
             if (prm->decode_mode == B2F_DECODE_JA98) dummy.levels = reinterpret_cast<const float4*>(&dummy);   // selects the instantiation
             if (b2f_launch_kf(R, prm->pol_mode, dummy, 0, 0, nullptr, &occ) != cudaSuccess || occ < 1) {
                 cudaGetLastError();
-                pl->path = 0;
-                if (prm->decode_mode == B2F_DECODE_JA98) {
-                    delete pl;
-                    return fail(B2F_EUNSUPPORTED, "decode_mode JA98 is built for the detection products I, coherence and IQUV");
-                }
+                pl->path = 0;            // JA98 with the other detection products: the round-1 column kernel with stream levels
             } else {
                 const int npair = R / 2;                                   // warps per lane (one block per lane and round)
                 pl->f_grid = pl->num_sms;                                  // one 16-warp CTA per SM
@@ -1062,7 +1067,7 @@ int b2f_plan_create(const b2f_params* prm, b2f_plan** out) {
     CUB(cudaMalloc(&pl->d_sm_slots, 1024 * sizeof(int)));
     if (pl->carry_mode) CUB(cudaMalloc(&pl->d_carry, (size_t)pl->M * pl->bps * nif));
     if (pl->smask) CUB(cudaMalloc(&pl->d_carry_mask, (size_t)pl->M * pl->bps / 32 * nif));
-    if (prm->decode_mode == B2F_DECODE_JA98 && generic) {
+    if (prm->decode_mode == B2F_DECODE_JA98 && (generic || pl->path == 0)) {
         pl->levels_stride = (pl->chunk_frames * pl->spf + pl->M) / 512 + 2;
         CUB(cudaMalloc(&pl->d_levels_stream, (size_t)pl->levels_stride * nif * sizeof(float4)));
     }
@@ -1351,6 +1356,14 @@ int b2f_push(b2f_plan* pl, const void* const* frames, int64_t nframes, int on_de
         ka.blk_step_bytes = pl->M * pl->bps;
         ka.sm_slots = pl->d_sm_slots; ka.stagger_cycles = pl->stagger_cycles;
         ka.in8_offset = pl->prm.in8_offset_mode ? 128.0f : 127.5f;
+        ka.levels = pl->d_levels_stream; ka.levels_stride = pl->levels_stride;
+        if (pl->d_levels_stream) {                                // JA98: levels per window of 512 stream samples
+            const int64_t nthreads = ((T + 511) / 512) * nif * 32;
+            kj_levels_stream<<<(unsigned)((nthreads + 255) / 256), 256, 0, pl->stream>>>(pl->d_compact, pl->compact_stride, T, pl->d_levels_stream,
+                                                                                        pl->levels_stride, nif);
+            pl->launches++;
+            CU(cudaGetLastError());
+        }
         {
             const char* e = getenv("B2F_KA_VARIANT");      // timing ablations only (tools/ablate.py)
             ka.variant = e ? atoi(e) : 0;

@@ -1,4 +1,4 @@
-// Column-pass instantiations for one input bit depth (-DB2F_NBIT=2|8).
+// Column-pass instantiations for one input bit depth (-DB2F_NBIT=2|8|22; 22 = 2-bit input decoded with JA98 levels).
 #include "b2f_launch.h"
 
 using namespace b2f;

@@ -599,6 +599,12 @@ __global__ void k_decode(const uint8_t* __restrict__ compact, const uint8_t* __r
     }
 }
 
+// JA98 decode of a 2-bit sample pair: sign and size class from the static lookup, magnitude from the window's levels
+__device__ __forceinline__ float2 kg_ja98(float2 v, float4 lv) {
+    const float ax = fabsf(v.x), ay = fabsf(v.y);
+    return make_float2(ax == 0.f ? 0.f : copysignf(ax > 2.f ? lv.y : lv.x, v.x), ay == 0.f ? 0.f : copysignf(ay > 2.f ? lv.w : lv.z, v.y));
+}
+
 // ================================================================== kernel 3a: column pass
 // A block of M = R*512 dual-pol samples z[n] = xP[n] + i xQ[n] is viewed as a 512 x R matrix
 // (n = n1 + R n2).  One CTA owns a strip of 16 columns: lane = column, so every shared-memory
@@ -645,13 +651,14 @@ struct KAParams {
     int stagger_cycles;
     int variant;             // 0 = product kernel; else a timing ablation
     float in8_offset;        // 8-bit samples: value = code - in8_offset (127.5, or 128: SURVEY D3)
+    const float4* levels; int64_t levels_stride;   // NBIT 22 (JA98): levels per window of 512 stream samples and IF (kj_levels_stream)
 };
 
 template <int NBIT>
 struct KASmem {
-    static constexpr int kPiece = (NBIT == 2 ? 1 : 2) * kStripCols;   // staged bytes per (row, strip)
+    static constexpr int kPiece = (NBIT != 8 ? 1 : 2) * kStripCols;   // staged bytes per (row, strip); NBIT 22 = 2-bit with JA98 levels
     static constexpr int kRawBytes = kL * kPiece;
-    static constexpr int kLutEntries = NBIT == 2 ? 32 : 0;      // index byte >> 3 -> (pol0, pol1); 16 = zero
+    static constexpr int kLutEntries = NBIT != 8 ? 32 : 0;      // index byte >> 3 -> (pol0, pol1); 16 = zero
     static constexpr size_t kBytes =
         (size_t)(kL * kStripCols + 512 + 512 + 32 * kStripCols + 16 * kStripCols + kLutEntries) * sizeof(float2) + 2 * kRawBytes;
 };
@@ -701,7 +708,7 @@ __global__ void __launch_bounds__(kKAThreads, kKACtasPerSM) ka_column_pass(const
         const int q = i / C, ln = i % C;
         s_g[((q & 7) * C + ln) * 2 + (q >> 3)] = p.tab_g[q * R + strip * C + ln];
     }
-    if (NBIT == 2 && tid < 32) {
+    if (NBIT != 8 && tid < 32) {
         // 16 entries span exactly the 32 banks once (conflict-free for any index pattern);
         // entry 16 = (0, 0) is what masked samples point at
         const int c0 = tid & 3, c1 = (tid >> 2) & 3;
@@ -736,7 +743,7 @@ __global__ void __launch_bounds__(kKAThreads, kKACtasPerSM) ka_column_pass(const
     const int64_t nbt = p.gb_end;
     const int64_t first = p.gb_begin + blockIdx.x / p.nstrips;
     const int64_t step = gridDim.x / p.nstrips;
-    const int64_t row_bytes = (int64_t)R * (NBIT == 2 ? 1 : 2);   // stream bytes per time sample: 1 index / 2 raw
+    const int64_t row_bytes = (int64_t)R * (NBIT != 8 ? 1 : 2);   // stream bytes per time sample: 1 index / 2 raw
     const int64_t blk_bytes = row_bytes * kL;
 
     auto issue_raw = [&](int64_t gb, int buf) {
@@ -791,7 +798,7 @@ __global__ void __launch_bounds__(kKAThreads, kKACtasPerSM) ka_column_pass(const
 #pragma unroll
             for (int r = 0; r < 16; ++r) {
                 const int rowA = 32 * r + item, rowB = rowA + 16;
-                if (NBIT == 2) {
+                if (NBIT != 8) {
                     vA[r] = *reinterpret_cast<const float2*>(reinterpret_cast<const uint8_t*>(s_lut) + raw[rowA * C + lane16]);
                     vB[r] = *reinterpret_cast<const float2*>(reinterpret_cast<const uint8_t*>(s_lut) + raw[rowB * C + lane16]);
                 } else {
@@ -799,6 +806,16 @@ __global__ void __launch_bounds__(kKAThreads, kKACtasPerSM) ka_column_pass(const
                     const uint32_t b = *reinterpret_cast<const uint16_t*>(raw + rowB * 2 * C + lane16 * 2);
                     vA[r] = make_float2((float)(a & 255u) - p.in8_offset, (float)(a >> 8) - p.in8_offset);
                     vB[r] = make_float2((float)(b & 255u) - p.in8_offset, (float)(b >> 8) - p.in8_offset);
+                }
+            }
+            if (NBIT == 22) {       // JA98: a row of R <= 512 samples lies in one window of 512 stream samples
+                const float4* lvb = p.levels + ifi * p.levels_stride;
+                const int64_t s0 = blk * p.blk_step_bytes;           // index bytes = samples
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    const int rowA = 32 * r + item;
+                    vA[r] = kg_ja98(vA[r], __ldg(lvb + ((s0 + (int64_t)rowA * R) >> 9)));
+                    vB[r] = kg_ja98(vB[r], __ldg(lvb + ((s0 + (int64_t)(rowA + 16) * R) >> 9)));
                 }
             }
             if (NBIT == 8 && dirty) {
@@ -1600,11 +1617,7 @@ constexpr int kModeVolt = 101;
 // One 32-bit word of an 8-bit stream = two time samples x (pol 0, pol 1).  `o` = byte offset of the word from s.byte0,
 // which in turn counts from the start of the IF's de-framed stream of this push (carried samples included).
 struct KG8 { const uint8_t* wm; int64_t byte0; float off; bool dirty; const float4* levels; };
-// JA98 decode of a 2-bit sample pair: sign and size class from the static lookup, magnitude from the window's levels
-__device__ __forceinline__ float2 kg_ja98(float2 v, float4 lv) {
-    const float ax = fabsf(v.x), ay = fabsf(v.y);
-    return make_float2(ax == 0.f ? 0.f : copysignf(ax > 2.f ? lv.y : lv.x, v.x), ay == 0.f ? 0.f : copysignf(ay > 2.f ? lv.w : lv.z, v.y));
-}
+
 __device__ __forceinline__ void kg_decode8(uint32_t four, const KG8& s, int64_t o, float2& a, float2& b) {
     a = make_float2((float)(four & 255u) - s.off, (float)((four >> 8) & 255u) - s.off);
     b = make_float2((float)((four >> 16) & 255u) - s.off, (float)(four >> 24) - s.off);

@@ -4,6 +4,7 @@
 #include "b2f_kernels.cuh"
 
 cudaError_t b2f_launch_ka(int in_nbit, int R, const b2f::KAParams& p, unsigned grid, cudaStream_t st);
+cudaError_t b2f_launch_ka_22(int R, const b2f::KAParams& p, unsigned grid, cudaStream_t st);
 cudaError_t b2f_launch_kb(int R, int mode, const b2f::KBParams& p, int grid, cudaStream_t st);
 cudaError_t b2f_launch_kr(int R, int mode, const b2f::KBParams& p, int grid, cudaStream_t st);     // [pair][row][2] blocks
 cudaError_t b2f_launch_kr_part0(int R, int mode, const b2f::KBParams& p, int grid, cudaStream_t st);

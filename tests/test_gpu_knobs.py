@@ -82,11 +82,41 @@ def test_ja98_generic_shapes(gpu, nchan, freq_res, D, nframes, chunk, dm):
     assert np.abs(o.digifil(v, **kw)["data"] / ref - 1).max() > 0.5      # not the static levels
 
 
-def test_ja98_needs_the_round2_kernels(gpu, monkeypatch):
-    monkeypatch.setenv("B2F_PATH", "legacy")
+@pytest.mark.parametrize("nchan,D,mode,name,dm,force_legacy", [(128, 16, _lib.POL_P0, "P0", 0.0, False), (64, 8, _lib.POL_I2, "I2", 0.0, False),
+                                                               (128, 16, _lib.POL_I, "I", 0.0, True), (128, 16, _lib.POL_COHERENCE, "coherence", 560.0, False)])
+def test_ja98_round1_kernels(gpu, monkeypatch, nchan, D, mode, name, dm, force_legacy):
+    """decode_mode = JA98 where the round-2 column kernel does not apply (the other detection products, dedispersion,
+    B2F_PATH=legacy): the round-1 column kernel reads the levels per window of 512 samples of the de-framed stream."""
+    if force_legacy:
+        monkeypatch.setenv("B2F_PATH", "legacy")
+    bw, fc = 32.0, 1254.0
+    cfg = PlanConfig(nchan=nchan, bw_mhz=[-bw], freq_mhz=[fc], tscrunch=D, pol_mode=mode, out_nbit=-32, keep_bandpass=True,
+                     decode_mode=_lib.DECODE_JA98, dm=dm, coherent=dm > 0, chunk_units=8 if dm > 0 else 0)
+    out = []
+    with Plan(cfg) as pl:
+        assert pl.path == 0
+        nf = (int(pl.geometry.nfilt_pos), int(pl.geometry.nfilt_neg))
+        cf, fb = int(pl.chunk_frames), cfg.frame_bytes
+        nframes = cf + (cf // 2 if dm > 0 else 0)
+        v = synth.make_vdif(nframes, seed=4400 + nchan, bw_mhz=bw, tone_frac=0.31, rho=0.3, invalid_frac=0.01, fill_frac=0.01)
+        for f0 in range(0, nframes, cf):
+            n = min(cf, nframes - f0)
+            pl.push([v[f0 * fb:(f0 + n) * fb]])
+            out.append(pl.pull().copy())
+        pl.flush()
+        out.append(pl.pull().copy())
+        rows = pl.view_rows(np.concatenate(out))
+    ref = o.digifil(v, freq_mhz=fc, bw_mhz=-bw, nchan=nchan, tscrunch_factor=D, pol_mode=name, out_nbit=-32, keep_bandpass=True,
+                    decode_mode="ja98", dm=dm, coherent=dm > 0, nfilt=nf)["data"].astype(np.float64)
+    assert rows.shape[0] == ref.shape[0] > 0
+    power = ref[:, 0] + ref[:, 1] if name == "coherence" else None
+    assert_rel(rows.reshape(ref.shape), ref, REL_TOL, f"JA98 round-1 kernels {name}", power=power)
+
+
+def test_ja98_is_a_2bit_unpacker(gpu):
     with pytest.raises(_lib.B2FError) as e:
-        Plan(PlanConfig(nchan=128, bw_mhz=[-32.0], decode_mode=_lib.DECODE_JA98))
-    assert e.value.code == _lib.EUNSUPPORTED
+        Plan(PlanConfig(nchan=128, bw_mhz=[-32.0], in_nbit=8, decode_mode=_lib.DECODE_JA98))
+    assert e.value.code == _lib.EINVAL
 
 
 def test_8bit_offset_128(gpu):
