@@ -67,7 +67,8 @@ enum b2f_frame_time_mode {
  * optimal levels.  Both are selectable; static is the default. */
 enum b2f_decode_mode {
     B2F_DECODE_STATIC = 0,         /* -hi, -lo, +lo, +hi with lo = 1, hi = 3.3359 */
-    B2F_DECODE_JA98 = 1            /* per window of 512 samples: lo, hi = conditional means of |x| for the observed fraction */
+    B2F_DECODE_JA98 = 1            /* per window of 512 samples: lo, hi = conditional means of |x| for the observed fraction;
+                                      2-bit input, FFT blocks starting on multiples of 512 samples */
 };
 
 /* what `-c` freezes */
@@ -90,11 +91,13 @@ typedef struct b2f_params {
     int32_t nif;                   /* dual-pol IFs (subbands) processed together, 1..B2F_MAX_IF */
     int32_t nchan;                 /* channels per IF        (--nchan, digifil -F<nchan>:..)  */
     int32_t freq_res;              /* digifil -F ..:<freq_res>; 0 = reference rule
-                                      512 if nchan<=128 else 2*nchan (process_vdif.py:162) */
+                                      512 if nchan<=128 else 2*nchan (process_vdif.py:162); with `coherent` the
+                                      dedispersion kernel may lengthen it (next power of two >= 4 nfilt, up to 4096)
+                                      when the smearing does not fit: b2f_geometry.freq_res is what was chosen */
     int32_t tscrunch;              /* digifil -t             (--tscrunch)                     */
     int32_t pol_mode;              /* enum b2f_pol_mode                                       */
     int32_t out_nbit;              /* digifil -b: 2, 8, 16, -32 (process_vdif.py:153)         */
-    int32_t in_nbit;               /* VDIF bits/sample: 2 or 8 (frb.conf nbits)               */
+    int32_t in_nbit;               /* VDIF bits/sample: 1, 2 or 8 (frb.conf nbits; digifil reads it from the header) */
     int32_t frame_bytes;           /* VDIF frame size incl. header (base2fil.sh:130-136)      */
     int32_t header_bytes;          /* 32, or 16 for legacy (base2fil.sh:137-147)              */
     int32_t frame_time_mode;       /* enum b2f_frame_time_mode                                */
@@ -109,7 +112,8 @@ typedef struct b2f_params {
     int32_t if_order[B2F_MAX_IF];  /* output tile s <- IF index if_order[s]; descending sky
                                       frequency for base2fil's plan                           */
     double dm;                     /* digifil -D dm (process_vdif.py:177-178)                 */
-    int32_t coherent;              /* digifil -F nchan:D: in-channel coherent dedispersion by overlap-save (:179-180) */
+    int32_t coherent;              /* digifil -F nchan:D: in-channel coherent dedispersion by overlap-save (:179-180);
+                                      nchan <= 2048, smearing up to what 4096 points hold */
     int32_t profile;               /* 1: time every kernel launch with CUDA events            */
     void* stream;                  /* cudaStream_t to launch on; NULL = plan-owned stream     */
     int32_t raw_word_bits;         /* 0: frames[i] is the split 2-channel VDIF stream of IF i (what jive5ab's
