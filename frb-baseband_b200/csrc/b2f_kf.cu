@@ -1,4 +1,6 @@
-// Fused column + row kernel instantiations for one row length (-DB2F_FR=16|32|64|128|256|512).
+// Fused column + row kernel instantiations for one row length (-DB2F_FR=16|32|64|128|256|512).  Two translation units per
+// row length halve the longest compile of the build (kf512: 7 minutes in one piece): -DB2F_KF_PART=1 holds the JA98
+// instantiations behind b2f_launch_kfj_<R>, the default part the static-level ones and the dispatch.
 #include "b2f_fused.cuh"
 #include "b2f_launch.h"
 
@@ -26,13 +28,23 @@ static cudaError_t go2(const FParams& p, int grid, int cooperative, cudaStream_t
 }
 
 // the dynamic-level decode is instantiated for the products the north star names (I, coherence, IQUV)
+#if defined(B2F_KF_PART) && B2F_KF_PART == 1
+cudaError_t B2F_CAT(b2f_launch_kfj_, B2F_FR)(int mode, const FParams& p, int grid, int cooperative, cudaStream_t st, int* max_ctas_per_sm) {
+    switch (mode) {
+        case B2F_POL_I: return go2<B2F_POL_I, true>(p, grid, cooperative, st, max_ctas_per_sm);
+#ifndef B2F_KF_ONLY_I
+        case B2F_POL_COHERENCE: return go2<B2F_POL_COHERENCE, true>(p, grid, cooperative, st, max_ctas_per_sm);
+        case B2F_POL_IQUV: return go2<B2F_POL_IQUV, true>(p, grid, cooperative, st, max_ctas_per_sm);
+#endif
+    }
+    return cudaErrorInvalidValue;
+}
+#else
+cudaError_t B2F_CAT(b2f_launch_kfj_, B2F_FR)(int mode, const FParams& p, int grid, int cooperative, cudaStream_t st, int* max_ctas_per_sm);
+
 template <int MODE>
 static cudaError_t go(const FParams& p, int grid, int cooperative, cudaStream_t st, int* max_ctas_per_sm) {
-    if (p.levels) {
-        if (MODE == B2F_POL_I || MODE == B2F_POL_COHERENCE || MODE == B2F_POL_IQUV)
-            return go2<(MODE == B2F_POL_I || MODE == B2F_POL_COHERENCE || MODE == B2F_POL_IQUV) ? MODE : B2F_POL_I, true>(p, grid, cooperative, st, max_ctas_per_sm);
-        return cudaErrorInvalidValue;
-    }
+    if (p.levels) return B2F_CAT(b2f_launch_kfj_, B2F_FR)(MODE, p, grid, cooperative, st, max_ctas_per_sm);
     return go2<MODE, false>(p, grid, cooperative, st, max_ctas_per_sm);
 }
 
@@ -55,3 +67,4 @@ cudaError_t B2F_CAT(b2f_launch_kf_, B2F_FR)(int mode, const FParams& p, int grid
     }
     return cudaErrorInvalidValue;
 }
+#endif
