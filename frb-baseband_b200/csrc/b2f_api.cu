@@ -364,9 +364,24 @@ int init_state(b2f_plan* pl) {
 
 }  // namespace
 
-// Dedispersion path of one push: forward column pass -> row FFT (spectrum) -> un-mix, chirp, backward
-// column FFT, overlap discard, detect, integrate.  Leaves the unconsumed tail of the sample stream in
-// d_carry for the next push ("time-chunked coherent dedispersion carries its overlap halo").
+// JA98 decode outside the round-2 column kernel: levels per window of 512 samples of the de-framed stream of this push
+// (T samples per IF, carried samples included); no-op for the static levels.
+int stream_levels(b2f_plan* pl, int64_t T) {
+    if (!pl->d_levels_stream) return 0;
+    const int nif = pl->prm.nif;
+    const int64_t nthreads = ((T + 511) / 512) * nif * 32;
+    kj_levels_stream<<<(unsigned)((nthreads + 255) / 256), 256, 0, pl->stream>>>(pl->d_compact, pl->compact_stride, T, pl->d_levels_stream,
+                                                                                pl->levels_stride, nif);
+    pl->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// Carry-mode path of one push (dedispersion and / or the generic channeliser).  Tuned dedispersion: forward column pass ->
+// row FFT (spectrum) -> un-mix, chirp, backward column FFT, overlap discard, detect, integrate; generic shapes: generic
+// column and row kernels, with dedispersion the row pass leaves channel samples and kx_dedisp_generic finishes.  Leaves the
+// unconsumed tail of the sample stream (and, for 8-bit input, of its word masks) in d_carry for the next push
+// ("time-chunked coherent dedispersion carries its overlap halo").
 int push_dedisp(b2f_plan* pl, int64_t nblk, int64_t T) {
     const int nif = pl->prm.nif;
     const int64_t nbt = (int64_t)nif * nblk;
@@ -386,13 +401,7 @@ int push_dedisp(b2f_plan* pl, int64_t nblk, int64_t T) {
         kg.step = pl->step;
         kg.levels = pl->d_levels_stream; kg.levels_stride = pl->levels_stride;
         const int nbit = pl->d_levels_stream ? 22 : pl->prm.in_nbit;          // 22: 2-bit input decoded with JA98 levels
-        if (pl->d_levels_stream) {
-            const int64_t nthreads = ((T + 511) / 512) * nif * 32;
-            kj_levels_stream<<<(unsigned)((nthreads + 255) / 256), 256, 0, pl->stream>>>(pl->d_compact, pl->compact_stride, T, pl->d_levels_stream,
-                                                                                        pl->levels_stride, nif);
-            pl->launches++;
-            CU(cudaGetLastError());
-        }
+        if ((rc = stream_levels(pl, T))) return rc;
         kg.inter = pl->d_inter; kg.colsum = pl->d_colsum; kg.eps = pl->d_eps;
         kg.tw_col = pl->d_tw_col; kg.tw_row = pl->d_tw_row;
         kg.F = row_dst(pl); kg.F_if_stride = row_dst_stride(pl); kg.row0 = row_dst_row0(pl);
@@ -491,13 +500,7 @@ int push_dedisp(b2f_plan* pl, int64_t nblk, int64_t T) {
         ka.blk_step_bytes = pl->step * pl->bps;                   // 2-bit: 1 index byte per sample; 8-bit: 2 bytes, masks by stream position
         ka.in8_offset = pl->prm.in8_offset_mode ? 128.0f : 127.5f;
         ka.levels = pl->d_levels_stream; ka.levels_stride = pl->levels_stride;
-        if (pl->d_levels_stream) {                                // JA98: levels per window of 512 stream samples
-            const int64_t nthreads = ((T + 511) / 512) * nif * 32;
-            kj_levels_stream<<<(unsigned)((nthreads + 255) / 256), 256, 0, pl->stream>>>(pl->d_compact, pl->compact_stride, T, pl->d_levels_stream,
-                                                                                        pl->levels_stride, nif);
-            pl->launches++;
-            CU(cudaGetLastError());
-        }
+        if (int rcl = stream_levels(pl, T)) return rcl;
         ka.sm_slots = pl->d_sm_slots; ka.stagger_cycles = 0; ka.variant = 32;      // forward only
         KBParams kb{};
         kb.inter = pl->d_inter; kb.eps = nullptr; kb.tab_r = pl->d_tab_r; kb.spec = pl->d_spec;
@@ -1357,13 +1360,7 @@ int b2f_push(b2f_plan* pl, const void* const* frames, int64_t nframes, int on_de
         ka.sm_slots = pl->d_sm_slots; ka.stagger_cycles = pl->stagger_cycles;
         ka.in8_offset = pl->prm.in8_offset_mode ? 128.0f : 127.5f;
         ka.levels = pl->d_levels_stream; ka.levels_stride = pl->levels_stride;
-        if (pl->d_levels_stream) {                                // JA98: levels per window of 512 stream samples
-            const int64_t nthreads = ((T + 511) / 512) * nif * 32;
-            kj_levels_stream<<<(unsigned)((nthreads + 255) / 256), 256, 0, pl->stream>>>(pl->d_compact, pl->compact_stride, T, pl->d_levels_stream,
-                                                                                        pl->levels_stride, nif);
-            pl->launches++;
-            CU(cudaGetLastError());
-        }
+        if (int rcl = stream_levels(pl, T)) return rcl;
         {
             const char* e = getenv("B2F_KA_VARIANT");      // timing ablations only (tools/ablate.py)
             ka.variant = e ? atoi(e) : 0;
