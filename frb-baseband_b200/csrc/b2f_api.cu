@@ -430,7 +430,7 @@ int push_dedisp(b2f_plan* pl, int64_t nblk, int64_t T) {
             kx.L = pl->L; kx.lgL = kg.lgL; kx.N = pl->N; kx.CH = std::max(1, std::min(4, 8192 / pl->L));
             kx.nblk = (int)nblk; kx.nif = nif; kx.D = pl->D; kx.mode = pl->prm.pol_mode;
             kx.nfilt_pos = pl->nfilt_pos; kx.keep = pl->keep;
-            smem_kx = ((size_t)pl->L / 2 + (size_t)kx.CH * 2 * pl->L) * sizeof(float2);
+            smem_kx = ((size_t)pl->L / 2 + (size_t)kx.CH * 2 * (pl->L + pl->L / 16)) * sizeof(float2);     // one pad element per 16 (kx_ph)
             CU(cudaFuncSetAttribute(kx_dedisp_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kx));
         }
         if (pl->R * sizeof(float2) > 48 * 1024)

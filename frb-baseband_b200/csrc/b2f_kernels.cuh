@@ -2087,12 +2087,16 @@ struct KXParams {
     int64_t gb_begin, gb_end;
 };
 #ifdef B2F_API_TU
+// shared-memory position of element e of a sequence: one pad element per 16, so that the passes with small spans (a thread's
+// four points 1, 2, 4 ... elements apart, neighbouring threads 4, 8, 16 ... apart) spread over the banks
+__device__ __forceinline__ int kx_ph(int e) { return e + (e >> 4); }
 constexpr int kKXThreads = 1024;              // one CTA per SM (up to 147 KiB of shared memory): 32 warps hide the shared-memory latency
 static __global__ void __launch_bounds__(kKXThreads) kx_dedisp_generic(const KXParams p) {
     extern __shared__ __align__(16) uint8_t kx_smem[];
     const int tid = threadIdx.x, NT = kKXThreads, L = p.L, lgL = p.lgL, N = p.N, CH = p.CH, nseq = 2 * CH, H2 = L >> 1, Q4 = L >> 2;
     float2* tw = reinterpret_cast<float2*>(kx_smem);                // [L / 2]  W_L^t
-    float2* data = tw + H2;                                         // [CH][2][L]
+    float2* data = tw + H2;                                         // [CH][2][LP], one pad element per 16 (kx_ph)
+    const int LP = L + (L >> 4);
     for (int t = tid; t < H2; t += NT) {
         float sn, cs;
         sincospif(-(float)(2 * t) / (float)L, &sn, &cs);
@@ -2103,16 +2107,19 @@ static __global__ void __launch_bounds__(kKXThreads) kx_dedisp_generic(const KXP
     const float inv_l = 1.0f / (float)L;
     const int64_t nwork = (p.gb_end - p.gb_begin) * ngroups;
     // two radix-2 stages (spans 2q and q) per pass over the data: points base + {0, q, 2q, 3q} of one sequence
-    auto quad = [&](int b, int lgq, float2*& x, int& j) {
+    auto quad = [&](int b, int lgq, float2*& x, int& j, int& base) {
         const int seq = b >> (lgL - 2), i = b & (Q4 - 1);
         j = i & ((1 << lgq) - 1);
-        x = data + seq * L + ((i >> lgq) << (lgq + 2)) + j;
+        x = data + seq * LP;
+        base = ((i >> lgq) << (lgq + 2)) + j;
     };
     auto span1 = [&]() {                                            // the stage of span 1 (odd log2 L): no twiddle
         for (int b = tid; b < nseq * H2; b += NT) {
-            const float2 u = data[2 * b], v = data[2 * b + 1];
-            data[2 * b] = cadd(u, v);
-            data[2 * b + 1] = csub(u, v);
+            float2* x = data + (b >> (lgL - 1)) * LP;
+            const int e = 2 * (b & (H2 - 1));
+            const float2 u = x[kx_ph(e)], v = x[kx_ph(e + 1)];
+            x[kx_ph(e)] = cadd(u, v);
+            x[kx_ph(e + 1)] = csub(u, v);
         }
         __syncthreads();
     };
@@ -2124,7 +2131,7 @@ static __global__ void __launch_bounds__(kKXThreads) kx_dedisp_generic(const KXP
         const float2* V = p.volt + lb * (int64_t)L * 2 * N;
         for (int e = tid; e < L * nseq; e += NT) {                  // channel fastest: CH neighbouring float2 per access
             const int ch = e % CH, pol = (e / CH) & 1, m = e / nseq;
-            data[(ch * 2 + pol) * L + m] = V[((int64_t)m * 2 + pol) * N + c0 + ch];
+            data[(ch * 2 + pol) * LP + kx_ph(m)] = V[((int64_t)m * 2 + pol) * N + c0 + ch];
         }
         __syncthreads();
         int lgh = lgL - 1;
@@ -2132,16 +2139,17 @@ static __global__ void __launch_bounds__(kKXThreads) kx_dedisp_generic(const KXP
             const int lgq = lgh - 1, q = 1 << lgq, sh = lgL - 1 - lgh;       // W_4q^t = tw[t << sh], W_2q^t = tw[t << (sh + 1)]
             for (int b = tid; b < nseq * Q4; b += NT) {
                 float2* x;
-                int j;
-                quad(b, lgq, x, j);
-                const float2 x0 = x[0], x1 = x[q], x2 = x[2 * q], x3 = x[3 * q];
+                int j, e;
+                quad(b, lgq, x, j, e);
+                const int p0 = kx_ph(e), p1 = kx_ph(e + q), p2 = kx_ph(e + 2 * q), p3 = kx_ph(e + 3 * q);
+                const float2 x0 = x[p0], x1 = x[p1], x2 = x[p2], x3 = x[p3];
                 const float2 u0 = cadd(x0, x2), u2 = cmul(csub(x0, x2), tw[j << sh]);
                 const float2 u1 = cadd(x1, x3), u3 = cmul(csub(x1, x3), tw[(j + q) << sh]);
                 const float2 wq = tw[j << (sh + 1)];
-                x[0] = cadd(u0, u1);
-                x[q] = cmul(csub(u0, u1), wq);
-                x[2 * q] = cadd(u2, u3);
-                x[3 * q] = cmul(csub(u2, u3), wq);
+                x[p0] = cadd(u0, u1);
+                x[p1] = cmul(csub(u0, u1), wq);
+                x[p2] = cadd(u2, u3);
+                x[p3] = cmul(csub(u2, u3), wq);
             }
             __syncthreads();
         }
@@ -2151,8 +2159,9 @@ static __global__ void __launch_bounds__(kKXThreads) kx_dedisp_generic(const KXP
             const int seq = e >> lgL, pos = e & (L - 1);
             const int k = (int)(__brev((unsigned)pos) >> (32 - lgL));
             const float2 h = H[(int64_t)k * N + c0 + (seq >> 1)];
-            const float2 y = cmul(data[e], h);
-            data[e] = make_float2(y.x * inv_l, y.y * inv_l);
+            float2* x = data + seq * LP + kx_ph(pos);
+            const float2 y = cmul(*x, h);
+            *x = make_float2(y.x * inv_l, y.y * inv_l);
         }
         __syncthreads();
         int lgq = 0;
@@ -2161,27 +2170,29 @@ static __global__ void __launch_bounds__(kKXThreads) kx_dedisp_generic(const KXP
             const int q = 1 << lgq, sh = lgL - 2 - lgq;
             for (int b = tid; b < nseq * Q4; b += NT) {
                 float2* x;
-                int j;
-                quad(b, lgq, x, j);
-                const float2 x0 = x[0], x1 = x[q], x2 = x[2 * q], x3 = x[3 * q];
+                int j, e;
+                quad(b, lgq, x, j, e);
+                const int p0 = kx_ph(e), p1 = kx_ph(e + q), p2 = kx_ph(e + 2 * q), p3 = kx_ph(e + 3 * q);
+                const float2 x0 = x[p0], x1 = x[p1], x2 = x[p2], x3 = x[p3];
                 const float2 wq = tw[j << (sh + 1)];
                 const float2 v1 = cmul_conj(x1, wq), v3 = cmul_conj(x3, wq);
                 const float2 y0 = cadd(x0, v1), y1 = csub(x0, v1), y2 = cadd(x2, v3), y3 = csub(x2, v3);
                 const float2 w2 = cmul_conj(y2, tw[j << sh]), w3 = cmul_conj(y3, tw[(j + q) << sh]);
-                x[0] = cadd(y0, w2);
-                x[2 * q] = csub(y0, w2);
-                x[q] = cadd(y1, w3);
-                x[3 * q] = csub(y1, w3);
+                x[p0] = cadd(y0, w2);
+                x[p2] = csub(y0, w2);
+                x[p1] = cadd(y1, w3);
+                x[p3] = csub(y1, w3);
             }
             __syncthreads();
         }
         for (int o = tid; o < CH * nout; o += NT) {                 // detect + integrate D samples
             const int ch = o % CH, sidx = o / CH;
-            const float2* xp = data + (ch * 2) * L + p.nfilt_pos + sidx * p.D;
-            const float2* xq = xp + L;
+            const float2* xp = data + (ch * 2) * LP;
+            const float2* xq = xp + LP;
+            const int m0 = p.nfilt_pos + sidx * p.D;
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
             for (int d = 0; d < p.D; ++d) {
-                const float2 P = xp[d], Q = xq[d];
+                const float2 P = xp[kx_ph(m0 + d)], Q = xq[kx_ph(m0 + d)];
                 const float pp = 0.25f * (P.x * P.x + P.y * P.y), qq = 0.25f * (Q.x * Q.x + Q.y * Q.y);
                 const float xr = P.x * Q.x + P.y * Q.y, xi = P.y * Q.x - P.x * Q.y;
                 const float re = -0.25f * xi, im = 0.25f * xr;
