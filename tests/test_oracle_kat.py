@@ -22,6 +22,32 @@ def test_decode_lut_exhaustive():
         assert x[0, 2 * k + 1] == lev[(b >> 4) & 3] and x[1, 2 * k + 1] == lev[(b >> 6) & 3]
 
 
+def test_decode_1bit_and_8bit_known_answers():
+    """1-bit (spif2file.sh:58-61 mode): bit 2t = channel 0, bit 2t + 1 = channel 1 of time sample t, 0 -> -1, 1 -> +1;
+    8-bit: offset binary, code - 127.5 (128 as the alternative)."""
+    pay = np.resize(np.arange(256, dtype=np.uint8), 8000)
+    fr = np.zeros(8032, np.uint8)
+    fr[:32] = vdif.make_headers(1, frames_per_sec=2000, nbit=1).view(np.uint8)
+    fr[32:] = pay
+    x = o.decode_vdif(fr, nbit=1)
+    assert x.shape == (2, 32000)
+    for k in range(0, 8000, 37):
+        b = int(pay[k])
+        for t in range(4):
+            assert x[0, 4 * k + t] == (1.0 if (b >> (2 * t)) & 1 else -1.0)
+            assert x[1, 4 * k + t] == (1.0 if (b >> (2 * t + 1)) & 1 else -1.0)
+    fr[:32] = vdif.make_headers(1, frames_per_sec=16000, nbit=8).view(np.uint8)
+    x8 = o.decode_vdif(fr, nbit=8)
+    assert x8.shape == (2, 4000) and x8[0, 0] == pay[0] - 127.5 and x8[1, 0] == pay[1] - 127.5 and x8[0, 3] == pay[6] - 127.5
+    assert o.decode_vdif(fr, nbit=8, offset8=128.0)[1, 1] == pay[3] - 128.0
+    # a fill word blanks the 16 time samples it holds (1-bit) / the 2 it holds (8-bit)
+    fr[32 + 40:32 + 44] = np.frombuffer(np.uint32(vdif.FILL_WORD).tobytes(), np.uint8)
+    assert np.all(o.decode_vdif(fr, nbit=8)[:, 20:22] == 0) and o.decode_vdif(fr, nbit=8)[0, 22] != 0
+    fr[:32] = vdif.make_headers(1, frames_per_sec=2000, nbit=1).view(np.uint8)
+    x1 = o.decode_vdif(fr, nbit=1)
+    assert np.all(x1[:, 160:176] == 0) and np.all(np.abs(x1[:, 176:192]) == 1)
+
+
 def test_decode_faults_zeroed():
     v = synth.make_vdif(64, seed=3, invalid_frac=0.2, fill_frac=0.2)
     x, fl = o.decode_vdif(v, return_flags=True)
